@@ -1,0 +1,189 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes wrapper over oracle/_ref/libcfref.so + input generator G.
+
+encode()/decode() run the reference's CPU encoders/decoders (see oracle/cfref.cpp for the
+file:line map).  gen_image() is generator G of SURVEY.md section 8(d): the synthetic inputs
+every BASELINE.md number was measured on.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libcfref.so")
+
+# cuttlefish::Texture::Format values (lib/include/cuttlefish/Texture.h:59-130)
+FORMATS = {
+    "BC1_RGB": 29, "BC1_RGBA": 30, "BC2": 31, "BC3": 32, "BC4": 33, "BC5": 34, "BC6H": 35, "BC7": 36,
+    "ETC1": 37, "ETC2_R8G8B8": 38, "ETC2_R8G8B8A1": 39, "ETC2_R8G8B8A8": 40, "EAC_R11": 41,
+    "EAC_R11G11": 42, "ASTC_4x4": 43, "ASTC_5x4": 44, "ASTC_5x5": 45, "ASTC_6x5": 46, "ASTC_6x6": 47,
+    "ASTC_8x5": 48, "ASTC_8x6": 49, "ASTC_8x8": 50, "ASTC_10x5": 51, "ASTC_10x6": 52, "ASTC_10x8": 53,
+    "ASTC_10x10": 54, "ASTC_12x10": 55, "ASTC_12x12": 56,
+}
+TYPES = {"UNorm": 0, "SNorm": 1, "UInt": 2, "Int": 3, "UFloat": 4, "Float": 5}
+QUALITY = {"Lowest": 0, "Low": 1, "Normal": 2, "High": 3, "Highest": 4}
+ALPHA = {"None": 0, "Standard": 1, "PreMultiplied": 2, "Encoded": 3}
+
+
+class Desc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in
+                ("format", "type", "quality", "alpha_type", "color_mask", "color_space", "width", "height")]
+
+
+_lib = None
+
+
+def build(quiet=True):
+    """Build oracle/_ref/libcfref.so from /root/reference (only possible where it is mounted)."""
+    ref = os.environ.get("CFX_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "lib", "bc7enc_rdo")):
+        return os.path.exists(_LIB_PATH)
+    r = subprocess.run(["make", "-C", _HERE, "-j8", "REF=" + ref], capture_output=quiet, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return True
+
+
+def available():
+    return os.path.exists(_LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.cfref_encoded_size.restype = ctypes.c_size_t
+        L.cfref_encoded_size.argtypes = [ctypes.POINTER(Desc)]
+        L.cfref_encode.restype = ctypes.c_int
+        L.cfref_encode.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_size_t,
+                                   ctypes.c_void_p, ctypes.c_uint]
+        L.cfref_decode.restype = ctypes.c_int
+        L.cfref_decode.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_void_p]
+        L.cfref_hardware_threads.restype = ctypes.c_uint
+        _lib = L
+    return _lib
+
+
+def make_desc(fmt, width, height, type="UNorm", quality="Normal", alpha="Standard", color_mask=15,
+              srgb=False):
+    g = lambda table, v: table[v] if isinstance(v, str) else int(v)
+    return Desc(g(FORMATS, fmt), g(TYPES, type), g(QUALITY, quality), g(ALPHA, alpha),
+                int(color_mask), 1 if srgb else 0, int(width), int(height))
+
+
+def encode(img, fmt, threads=0, **kw):
+    """img: float32 [H,W,4] RGBAF (row 0 = top).  Returns uint8 packed blocks (row-major blocks)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w, c = img.shape
+    assert c == 4
+    d = make_desc(fmt, w, h, **kw)
+    n = lib().cfref_encoded_size(ctypes.byref(d))
+    if n == 0:
+        raise ValueError("unsupported format %r" % (fmt,))
+    out = np.empty(n, dtype=np.uint8)
+    rc = lib().cfref_encode(ctypes.byref(d), img.ctypes.data, w * 4, out.ctypes.data, threads)
+    if rc != 0:
+        raise RuntimeError("cfref_encode failed: %d" % rc)
+    return out
+
+
+def decode(blocks, fmt, width, height, **kw):
+    """Decode packed blocks with the reference's decoders -> float32 [H,W,4]."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+    d = make_desc(fmt, width, height, **kw)
+    assert blocks.size == lib().cfref_encoded_size(ctypes.byref(d))
+    out = np.zeros((height, width, 4), dtype=np.float32)
+    rc = lib().cfref_decode(ctypes.byref(d), blocks.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("cfref_decode failed: %d" % rc)
+    return out
+
+
+def hardware_threads():
+    return int(lib().cfref_hardware_threads())
+
+
+# ---- generator G -------------------------------------------------------------
+
+def _lcg_noise(n_values, seed=12345):
+    """n = (s>>24)/255 for s = s*1664525+1013904223 (uint32), vectorised by jump-ahead blocks."""
+    a, c = np.uint64(1664525), np.uint64(1013904223)
+    mask = np.uint64(0xFFFFFFFF)
+    # affine powers: s_{k} = A_k s_0 + C_k
+    blk = 1 << 16
+    A = np.empty(blk, dtype=np.uint64)
+    C = np.empty(blk, dtype=np.uint64)
+    ak, ck = np.uint64(1), np.uint64(0)
+    for i in range(blk):
+        ak = (ak * a) & mask
+        ck = (ck * a + c) & mask
+        A[i], C[i] = ak, ck
+    out = np.empty(n_values, dtype=np.uint32)
+    s = np.uint64(seed)
+    pos = 0
+    while pos < n_values:
+        m = min(blk, n_values - pos)
+        vals = (A[:m] * s + C[:m]) & mask
+        out[pos:pos + m] = vals.astype(np.uint32)
+        s = vals[m - 1]
+        pos += m
+    return (out >> np.uint32(24)).astype(np.float32) / np.float32(255.0)
+
+
+def gen_image(kind, width, height, seed=12345):
+    """Generator G.  Returns float32 [H,W,4], row 0 = top, alpha 1.
+
+    gradient:   r = x/(w-1), g = y/(h-1), b = (w-1-x)/(w-1)
+    noise+grad: 0.75*gradient + 0.25*LCG noise (three draws per texel, r,g,b order, row-major)
+    both LDR kinds snapped to 8 bit: v = round(v*255)/255
+    hdr:        t = (x+y*w)/(w*h); r = 64t, g = 8x/(w-1), b = 0.5y/(h-1)   (not snapped)
+    """
+    w, h = int(width), int(height)
+    x = np.arange(w, dtype=np.float32)[None, :]
+    y = np.arange(h, dtype=np.float32)[:, None]
+    dx = np.float32(max(w - 1, 1))
+    dy = np.float32(max(h - 1, 1))
+    img = np.empty((h, w, 4), dtype=np.float32)
+    img[..., 3] = 1.0
+    if kind == "hdr":
+        t = (x + y * np.float32(w)) / np.float32(w * h)
+        img[..., 0] = np.float32(64.0) * t
+        img[..., 1] = np.broadcast_to(np.float32(8.0) * x / dx, (h, w))
+        img[..., 2] = np.broadcast_to(np.float32(0.5) * y / dy, (h, w))
+        return img
+    gr = np.broadcast_to(x / dx, (h, w))
+    gg = np.broadcast_to(y / dy, (h, w))
+    gb = np.broadcast_to((np.float32(w - 1) - x) / dx, (h, w))
+    if kind == "gradient":
+        img[..., 0], img[..., 1], img[..., 2] = gr, gg, gb
+    elif kind in ("noise+grad", "noise"):
+        n = _lcg_noise(w * h * 3, seed).reshape(h, w, 3)
+        img[..., 0] = np.float32(0.75) * gr + np.float32(0.25) * n[..., 0]
+        img[..., 1] = np.float32(0.75) * gg + np.float32(0.25) * n[..., 1]
+        img[..., 2] = np.float32(0.75) * gb + np.float32(0.25) * n[..., 2]
+    else:
+        raise ValueError(kind)
+    img[..., :3] = np.floor(img[..., :3] * np.float32(255.0) + np.float32(0.5)) / np.float32(255.0)
+    return img
+
+
+def to_rgba8(img):
+    """round(clamp01(v)*255) -> uint8 (lib/src/S3tcConverter.cpp:97-111; half away from zero)."""
+    v = np.clip(img, 0.0, 1.0).astype(np.float32) * np.float32(255.0)
+    return np.floor(v + np.float32(0.5)).astype(np.uint8)
+
+
+def psnr_rgb(a, b, peak=1.0):
+    d = (a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64))
+    mse = float(np.mean(d * d))
+    return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def fnv1a64(data):
+    h = 0xcbf29ce484222325
+    for b in bytes(data):
+        h = ((h ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
