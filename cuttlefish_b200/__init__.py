@@ -1,0 +1,13 @@
+"""cuttlefish_b200 -- B200-native block texture encoding behind Cuttlefish's Texture::convert().
+
+Host-side mirror (Python) of the reference's convert surface over the C-ABI in include/cfx.h:
+
+    Texture.convert(format, type, quality, alphaType, colorMask)   lib/include/cuttlefish/Texture.h:740-742
+    Texture.data(mip, depth) / dataSize(...)                        lib/include/cuttlefish/Texture.h:780-807
+
+plus array-level helpers `encode()` (host buffers) and `encode_device()` (torch CUDA tensors).
+All encoding happens in hand-written sm_100a kernels inside lib/libcfx.so; there is no CPU path.
+"""
+from .api import (ALPHA, FORMATS, QUALITY, SRC_FORMATS, TYPES, CfxError, ColorMask, Texture,  # noqa: F401
+                  block_info, encode, encode_device, encoded_size, format_supported, init,
+                  kernel_launches, last_error, shard_block_rows, version)

@@ -1,0 +1,223 @@
+"""Host API over libcfx.so: enums (same numeric values as cuttlefish::Texture), array-level
+encode calls, block-row sharding for multi-GPU runs, and a Texture class mirroring the part of
+cuttlefish::Texture that the convert path touches."""
+import ctypes
+
+import numpy as np
+
+from ._lib import SurfaceDesc, load
+
+# cuttlefish::Texture::Format (lib/include/cuttlefish/Texture.h:59-130)
+FORMATS = {
+    "BC1_RGB": 29, "BC1_RGBA": 30, "BC2": 31, "BC3": 32, "BC4": 33, "BC5": 34, "BC6H": 35, "BC7": 36,
+    "ETC1": 37, "ETC2_R8G8B8": 38, "ETC2_R8G8B8A1": 39, "ETC2_R8G8B8A8": 40, "EAC_R11": 41,
+    "EAC_R11G11": 42, "ASTC_4x4": 43, "ASTC_5x4": 44, "ASTC_5x5": 45, "ASTC_6x5": 46, "ASTC_6x6": 47,
+    "ASTC_8x5": 48, "ASTC_8x6": 49, "ASTC_8x8": 50, "ASTC_10x5": 51, "ASTC_10x6": 52, "ASTC_10x8": 53,
+    "ASTC_10x10": 54, "ASTC_12x10": 55, "ASTC_12x12": 56,
+}
+TYPES = {"UNorm": 0, "SNorm": 1, "UInt": 2, "Int": 3, "UFloat": 4, "Float": 5}
+QUALITY = {"Lowest": 0, "Low": 1, "Normal": 2, "High": 3, "Highest": 4}
+ALPHA = {"None": 0, "Standard": 1, "PreMultiplied": 2, "Encoded": 3}
+SRC_FORMATS = {"RGBA8": 0, "RGBA16F": 1, "RGBA32F": 2}
+
+CFX_ERR_UNSUPPORTED = -2
+
+
+class CfxError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("cfx error %d: %s" % (code, message))
+        self.code = code
+
+
+class ColorMask:
+    """cuttlefish::Texture::ColorMask (Texture.h:216-237)."""
+
+    def __init__(self, r=True, g=True, b=True, a=True):
+        self.r, self.g, self.b, self.a = bool(r), bool(g), bool(b), bool(a)
+
+    def bits(self):
+        return (1 if self.r else 0) | (2 if self.g else 0) | (4 if self.b else 0) | (8 if self.a else 0)
+
+
+def _enum(table, v):
+    return table[v] if isinstance(v, str) else int(v)
+
+
+def _mask_bits(m):
+    return m.bits() if isinstance(m, ColorMask) else int(m)
+
+
+def _check(rc):
+    if rc != 0:
+        raise CfxError(rc, load().cfx_last_error().decode())
+
+
+def init(device=-1):
+    _check(load().cfx_init(int(device)))
+
+
+def version():
+    return load().cfx_version().decode()
+
+
+def last_error():
+    return load().cfx_last_error().decode()
+
+
+def kernel_launches():
+    return int(load().cfx_kernel_launches())
+
+
+def format_supported(fmt, type="UNorm"):
+    return bool(load().cfx_format_supported(_enum(FORMATS, fmt), _enum(TYPES, type)))
+
+
+def block_info(fmt):
+    bw, bh, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    rc = load().cfx_block_info(_enum(FORMATS, fmt), ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(nb))
+    if rc != 0:
+        raise CfxError(rc, "format %r is not block compressed" % (fmt,))
+    return bw.value, bh.value, nb.value
+
+
+def make_desc(fmt, width, height, src_format, row_pitch, type="UNorm", quality="Normal", alpha="Standard",
+              color_mask=15, srgb=False):
+    return SurfaceDesc(_enum(FORMATS, fmt), _enum(TYPES, type), _enum(QUALITY, quality), _enum(ALPHA, alpha),
+                       _mask_bits(color_mask), 1 if srgb else 0, int(width), int(height),
+                       _enum(SRC_FORMATS, src_format), 0, int(row_pitch))
+
+
+def encoded_size(fmt, width, height):
+    d = make_desc(fmt, width, height, "RGBA8", width * 4)
+    return int(load().cfx_encoded_size(ctypes.byref(d)))
+
+
+def _src_format_of(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.uint8:
+        return "RGBA8", 4
+    if dtype == np.float16:
+        return "RGBA16F", 8
+    if dtype == np.float32:
+        return "RGBA32F", 16
+    raise TypeError("source texels must be uint8, float16 or float32 RGBA, got %s" % dtype)
+
+
+def encode(img, fmt, out=None, **kw):
+    """Encode a HOST image [H,W,4] (uint8 / float16 / float32, row 0 = top) -> uint8 block bytes.
+
+    Goes through cfx_encode: host->device copy, kernels, device->host copy."""
+    img = np.asarray(img)
+    if img.ndim != 3 or img.shape[2] != 4:
+        raise ValueError("expected [H,W,4] RGBA texels")
+    if not img.flags["C_CONTIGUOUS"]:
+        img = np.ascontiguousarray(img)
+    h, w, _ = img.shape
+    src_format, texel = _src_format_of(img.dtype)
+    d = make_desc(fmt, w, h, src_format, w * texel, **kw)
+    n = int(load().cfx_encoded_size(ctypes.byref(d)))
+    if n == 0:
+        raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
+    if out is None:
+        out = np.empty(n, dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.size >= n and out.flags["C_CONTIGUOUS"]
+    _check(load().cfx_encode(ctypes.byref(d), img.ctypes.data, out.ctypes.data, out.size))
+    return out[:n]
+
+
+def encode_device(src, fmt, out=None, stream=None, **kw):
+    """Encode a torch CUDA tensor [H,W,4] (uint8/float16/float32) into a CUDA uint8 tensor,
+    asynchronously on `stream` (default: torch's current stream). Goes through cfx_encode_device."""
+    import torch
+    if not src.is_cuda:
+        raise ValueError("encode_device needs a CUDA tensor; use encode() for host arrays")
+    if src.dim() != 3 or src.shape[2] != 4 or src.stride(2) != 1 or src.stride(1) != 4:
+        raise ValueError("expected [H,W,4] texels with contiguous rows")
+    h, w, _ = src.shape
+    table = {torch.uint8: ("RGBA8", 4), torch.float16: ("RGBA16F", 8), torch.float32: ("RGBA32F", 16)}
+    if src.dtype not in table:
+        raise TypeError("unsupported texel dtype %s" % src.dtype)
+    src_format, texel = table[src.dtype]
+    pitch = src.stride(0) * src.element_size()
+    d = make_desc(fmt, w, h, src_format, pitch, **kw)
+    n = int(load().cfx_encoded_size(ctypes.byref(d)))
+    if n == 0:
+        raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
+    if out is None:
+        out = torch.empty(n, dtype=torch.uint8, device=src.device)
+    assert out.is_cuda and out.dtype == torch.uint8 and out.numel() >= n and out.is_contiguous()
+    with torch.cuda.device(src.device):
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        _check(load().cfx_init(src.device.index))
+        _check(load().cfx_encode_device(ctypes.byref(d), src.data_ptr(), out.data_ptr(), out.numel(),
+                                        ctypes.c_void_p(stream.cuda_stream)))
+    return out[:n]
+
+
+def shard_block_rows(height, block_h, rank, world):
+    """Contiguous block-row range [r0, r1) owned by `rank` out of `world`, and the source rows
+    [y0, y1) it needs. Slabs end on block-row boundaries, so each rank encodes its slab as an
+    independent surface and the packed outputs concatenate."""
+    rows = (int(height) + block_h - 1) // block_h
+    r0 = rows * rank // world
+    r1 = rows * (rank + 1) // world
+    return r0, r1, r0 * block_h, min(int(height), r1 * block_h)
+
+
+class Texture:
+    """The slice of cuttlefish::Texture the convert path uses (lib/include/cuttlefish/Texture.h).
+
+    Images are float32/uint8 [H,W,4] arrays per (mip, depth); convert() replaces them by packed
+    block bytes exactly like Texture::convert -> Converter::convert (lib/src/Texture.cpp:1536-1561,
+    lib/src/Converter.cpp:508-593): returns False and leaves the texture unconverted when the
+    (format, type) pair has no encoder."""
+
+    def __init__(self, width, height, depth=1, mip_levels=1, srgb=False):
+        self.width, self.height, self.depth, self.mip_levels = int(width), int(height), int(depth), int(mip_levels)
+        self.srgb = bool(srgb)
+        self._images = [[None] * self.depth for _ in range(self.mip_levels)]
+        self._data = None
+        self.format = None
+        self.type = None
+
+    def mip_size(self, mip):
+        return max(1, self.width >> mip), max(1, self.height >> mip)
+
+    def setImage(self, image, mip=0, depth=0):
+        image = np.asarray(image)
+        w, h = self.mip_size(mip)
+        if image.shape != (h, w, 4):
+            return False
+        self._images[mip][depth] = image
+        return True
+
+    def imagesComplete(self):
+        return all(im is not None for level in self._images for im in level)
+
+    def converted(self):
+        return self._data is not None
+
+    def convert(self, format, type="UNorm", quality="Normal", alphaType="Standard", colorMask=None, threads=None):
+        if not self.imagesComplete() or self.converted():
+            return False
+        if not format_supported(format, type):
+            return False
+        mask = colorMask if colorMask is not None else ColorMask()
+        data = []
+        for level in self._images:
+            row = []
+            for image in level:
+                row.append(encode(image, format, type=type, quality=quality, alpha=alphaType, color_mask=mask,
+                                  srgb=self.srgb))
+            data.append(row)
+        self._data = data
+        self._images = None
+        self.format, self.type = format, type
+        return True
+
+    def dataSize(self, mip=0, depth=0):
+        return 0 if self._data is None else int(self._data[mip][depth].size)
+
+    def data(self, mip=0, depth=0):
+        return None if self._data is None else self._data[mip][depth]

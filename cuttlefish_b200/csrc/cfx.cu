@@ -1,0 +1,374 @@
+// C-ABI of the encoder library (include/cfx.h): descriptor validation, device context
+// (streams, device and pinned buffers), the chunked H2D -> kernel -> D2H pipeline of
+// cfx_encode(), and dispatch to the per-format kernel launchers.
+//
+// This file is the device-side stand-in for Converter::convert()'s per-surface job loop
+// (lib/src/Converter.cpp:508-593): where the reference enumerates jobsX x jobsY process(x,y)
+// calls over a std::thread pool, this enqueues one persistent kernel per chunk of block rows.
+#include "../../include/cfx.h"
+#include "kernels.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace cfx {
+
+static thread_local char t_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CFX_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(CFX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));         \
+    } while (0)
+
+static const uint32_t kAstcDims[14][2] = {{4,4},{5,4},{5,5},{6,5},{6,6},{8,5},{8,6},{8,8},{10,5},
+    {10,6},{10,8},{10,10},{12,10},{12,12}};
+
+static bool block_info(uint32_t format, uint32_t& bw, uint32_t& bh, uint32_t& bytes)
+{
+    bw = bh = 4;
+    switch (format) {
+        case CFX_FORMAT_BC1_RGB: case CFX_FORMAT_BC1_RGBA: case CFX_FORMAT_BC4: case CFX_FORMAT_ETC1:
+        case CFX_FORMAT_ETC2_R8G8B8: case CFX_FORMAT_ETC2_R8G8B8A1: case CFX_FORMAT_EAC_R11:
+            bytes = 8; return true;
+        case CFX_FORMAT_BC2: case CFX_FORMAT_BC3: case CFX_FORMAT_BC5: case CFX_FORMAT_BC6H:
+        case CFX_FORMAT_BC7: case CFX_FORMAT_ETC2_R8G8B8A8: case CFX_FORMAT_EAC_R11G11:
+            bytes = 16; return true;
+        default:
+            if (format >= CFX_FORMAT_ASTC_4x4 && format <= CFX_FORMAT_ASTC_12x12) {
+                bw = kAstcDims[format - CFX_FORMAT_ASTC_4x4][0];
+                bh = kAstcDims[format - CFX_FORMAT_ASTC_4x4][1];
+                bytes = 16;
+                return true;
+            }
+            return false;
+    }
+}
+
+typedef int (*Launcher)(const EncodeParams&, cudaStream_t);
+
+// (format,type) -> launcher. Mirrors the compressed cases of createConverter(),
+// lib/src/Converter.cpp:339-502; anything absent here is CFX_ERR_UNSUPPORTED.
+static Launcher find_launcher(uint32_t format, uint32_t type)
+{
+    switch (format) {
+        case CFX_FORMAT_BC4: case CFX_FORMAT_BC5:
+            return type == CFX_TYPE_UNORM ? launch_bc45 : nullptr;
+#ifdef CFX_HAVE_BC7
+        case CFX_FORMAT_BC7:
+            return type == CFX_TYPE_UNORM ? launch_bc7 : nullptr;
+#endif
+#ifdef CFX_HAVE_BC1
+        case CFX_FORMAT_BC1_RGB: case CFX_FORMAT_BC1_RGBA: case CFX_FORMAT_BC2: case CFX_FORMAT_BC3:
+            return type == CFX_TYPE_UNORM ? launch_bc123 : nullptr;
+#endif
+#ifdef CFX_HAVE_ETC
+        case CFX_FORMAT_ETC1: case CFX_FORMAT_ETC2_R8G8B8: case CFX_FORMAT_ETC2_R8G8B8A8:
+            return type == CFX_TYPE_UNORM ? launch_etc : nullptr;
+#endif
+#ifdef CFX_HAVE_BC6H
+        case CFX_FORMAT_BC6H:
+            return type == CFX_TYPE_UFLOAT ? launch_bc6h : nullptr;
+#endif
+        default:
+#ifdef CFX_HAVE_ASTC
+            if (format >= CFX_FORMAT_ASTC_4x4 && format <= CFX_FORMAT_ASTC_12x12)
+                return type == CFX_TYPE_UNORM ? launch_astc : nullptr;
+#endif
+            return nullptr;
+    }
+}
+
+static uint32_t src_texel_bytes(uint32_t src_format)
+{
+    return src_format == CFX_SRC_RGBA8 ? 4u : src_format == CFX_SRC_RGBA16F ? 8u : 16u;
+}
+
+// ---- device context ---------------------------------------------------------------------------
+
+constexpr int kStreams = 3;
+
+struct Context {
+    std::mutex mutex;
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t streams[kStreams] = {};
+    uint8_t* d_src = nullptr; size_t d_src_cap = 0;
+    uint8_t* d_dst = nullptr; size_t d_dst_cap = 0;
+};
+static Context g_ctx;
+
+uint32_t persistent_ctas(const void* kernel, int threads, size_t dyn_smem)
+{
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    int sms = g_ctx.sm_count > 0 ? g_ctx.sm_count : 148;
+    return static_cast<uint32_t>(sms*per_sm);
+}
+
+static int ensure_init(int device)
+{
+    if (g_ctx.ready && (device < 0 || device == g_ctx.device)) {
+        CFX_CUDA(cudaSetDevice(g_ctx.device));
+        return CFX_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(CFX_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) return fail(CFX_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+    if (g_ctx.ready) {
+        // switching device: drop the old context's resources
+        cudaSetDevice(g_ctx.device);
+        for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
+        if (g_ctx.d_src) cudaFree(g_ctx.d_src);
+        if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
+        g_ctx.d_src = g_ctx.d_dst = nullptr; g_ctx.d_src_cap = g_ctx.d_dst_cap = 0;
+        g_ctx.ready = false;
+    }
+    cudaDeviceProp prop;
+    CFX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CFX_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+            device, prop.major, prop.minor);
+    CFX_CUDA(cudaSetDevice(device));
+    for (auto& s : g_ctx.streams) CFX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.ready = true;
+    return CFX_OK;
+}
+
+static int reserve(uint8_t*& ptr, size_t& cap, size_t bytes)
+{
+    if (bytes <= cap) return CFX_OK;
+    if (ptr) { CFX_CUDA(cudaDeviceSynchronize()); CFX_CUDA(cudaFree(ptr)); ptr = nullptr; cap = 0; }
+    size_t want = bytes + bytes/8 + 4096;
+    CFX_CUDA(cudaMalloc(&ptr, want));
+    cap = want;
+    return CFX_OK;
+}
+
+static int validate(const cfx_surface_desc* d, EncodeParams& p, Launcher& launcher)
+{
+    if (!d) return fail(CFX_ERR_INVALID, "null descriptor");
+    uint32_t bw, bh, bytes;
+    if (!block_info(d->format, bw, bh, bytes))
+        return fail(CFX_ERR_UNSUPPORTED, "format %u is not a block-compressed format", d->format);
+    launcher = find_launcher(d->format, d->type);
+    if (!launcher)
+        return fail(CFX_ERR_UNSUPPORTED, "no GPU encoder for format %u type %u", d->format, d->type);
+    if (d->width == 0 || d->height == 0) return fail(CFX_ERR_INVALID, "empty surface %ux%u", d->width, d->height);
+    if (d->quality > CFX_QUALITY_HIGHEST) return fail(CFX_ERR_INVALID, "quality %u out of range", d->quality);
+    if (d->alpha_type > CFX_ALPHA_ENCODED) return fail(CFX_ERR_INVALID, "alpha type %u out of range", d->alpha_type);
+    if (d->src_format > CFX_SRC_RGBA32F) return fail(CFX_ERR_INVALID, "source format %u out of range", d->src_format);
+    if (d->reserved != 0) return fail(CFX_ERR_INVALID, "reserved field must be 0");
+    uint64_t min_pitch = static_cast<uint64_t>(d->width)*src_texel_bytes(d->src_format);
+    if (d->src_row_pitch < min_pitch)
+        return fail(CFX_ERR_INVALID, "row pitch %llu < %llu", (unsigned long long)d->src_row_pitch,
+            (unsigned long long)min_pitch);
+    if (d->src_row_pitch % src_texel_bytes(d->src_format))
+        return fail(CFX_ERR_INVALID, "row pitch must be a multiple of the texel size");
+    uint64_t bx = (d->width + bw - 1)/bw, by = (d->height + bh - 1)/bh;
+    if (bx*by > 0x7FFFFFFFull) return fail(CFX_ERR_INVALID, "surface too large");
+    memset(&p, 0, sizeof(p));
+    p.pitch = d->src_row_pitch;
+    p.width = d->width; p.height = d->height; p.src_format = d->src_format;
+    p.blocks_x = static_cast<uint32_t>(bx); p.blocks_y = static_cast<uint32_t>(by);
+    p.total_blocks = static_cast<uint32_t>(bx*by);
+    p.block_w = bw; p.block_h = bh; p.block_bytes = bytes;
+    p.format = d->format; p.type = d->type; p.quality = d->quality; p.alpha_type = d->alpha_type;
+    p.color_mask = d->color_mask & 15u; p.color_space = d->color_space ? 1u : 0u;
+    return CFX_OK;
+}
+
+static int launch(Launcher launcher, EncodeParams& p, cudaStream_t stream)
+{
+    p.aligned16 = ((reinterpret_cast<uintptr_t>(p.src) | p.pitch) & 15) == 0;
+    int n = launcher(p, stream);
+    if (n < 0) return n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CFX_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches += static_cast<uint64_t>(n);
+    return CFX_OK;
+}
+
+static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst, size_t dst_size)
+{
+    EncodeParams p; Launcher launcher;
+    int rc = validate(desc, p, launcher);
+    if (rc != CFX_OK) return rc;
+    if (!src || !dst) return fail(CFX_ERR_INVALID, "null buffer");
+    size_t out_bytes = static_cast<size_t>(p.total_blocks)*p.block_bytes;
+    if (dst_size < out_bytes) return fail(CFX_ERR_INVALID, "dst_size %zu < %zu", dst_size, out_bytes);
+    rc = ensure_init(-1);
+    if (rc != CFX_OK) return rc;
+
+    const size_t row_bytes = static_cast<size_t>(p.width)*src_texel_bytes(p.src_format);
+    const size_t d_pitch = (row_bytes + 255) & ~static_cast<size_t>(255);
+    rc = reserve(g_ctx.d_src, g_ctx.d_src_cap, d_pitch*p.height);
+    if (rc != CFX_OK) return rc;
+    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, out_bytes);
+    if (rc != CFX_OK) return rc;
+
+    // Chunk by block rows so that copy-in, encode and copy-out of neighbouring chunks overlap
+    // on the three streams. ~8 M texels per chunk keeps every kernel a few full waves.
+    uint32_t rows_per_chunk = p.blocks_y;
+    {
+        uint64_t texels_per_row = static_cast<uint64_t>(p.width)*p.block_h;
+        uint64_t want = (8ull << 20)/(texels_per_row ? texels_per_row : 1);
+        if (want < 1) want = 1;
+        if (want < rows_per_chunk) rows_per_chunk = static_cast<uint32_t>(want);
+    }
+    int k = 0;
+    for (uint32_t r0 = 0; r0 < p.blocks_y; r0 += rows_per_chunk, ++k) {
+        uint32_t r1 = min(p.blocks_y, r0 + rows_per_chunk);
+        uint32_t y0 = r0*p.block_h, y1 = min(p.height, r1*p.block_h);
+        cudaStream_t s = g_ctx.streams[k % kStreams];
+        CFX_CUDA(cudaMemcpy2DAsync(g_ctx.d_src + static_cast<size_t>(y0)*d_pitch, d_pitch,
+            static_cast<const uint8_t*>(src) + static_cast<size_t>(y0)*desc->src_row_pitch,
+            desc->src_row_pitch, row_bytes, y1 - y0, cudaMemcpyHostToDevice, s));
+        EncodeParams c = p;
+        c.src = g_ctx.d_src + static_cast<size_t>(y0)*d_pitch;
+        c.pitch = d_pitch;
+        c.height = y1 - y0;   // interior chunks end on a block-row boundary, so the clamp is unchanged
+        c.blocks_y = r1 - r0;
+        c.total_blocks = c.blocks_x*c.blocks_y;
+        size_t off = static_cast<size_t>(r0)*p.blocks_x*p.block_bytes;
+        c.dst = g_ctx.d_dst + off;
+        rc = launch(launcher, c, s);
+        if (rc != CFX_OK) return rc;
+        CFX_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, c.dst,
+            static_cast<size_t>(c.total_blocks)*p.block_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    for (auto& s : g_ctx.streams) CFX_CUDA(cudaStreamSynchronize(s));
+    return CFX_OK;
+}
+
+} // namespace cfx
+
+using namespace cfx;
+
+extern "C" {
+
+int cfx_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    t_error[0] = 0;
+    return ensure_init(device);
+}
+
+void cfx_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    if (!g_ctx.ready) return;
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
+    if (g_ctx.d_src) cudaFree(g_ctx.d_src);
+    if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
+    g_ctx.d_src = g_ctx.d_dst = nullptr; g_ctx.d_src_cap = g_ctx.d_dst_cap = 0;
+    g_ctx.ready = false;
+}
+
+int cfx_format_supported(uint32_t format, uint32_t type) { return find_launcher(format, type) != nullptr; }
+
+int cfx_block_info(uint32_t format, uint32_t* bw, uint32_t* bh, uint32_t* bytes)
+{
+    uint32_t w, h, b;
+    if (!block_info(format, w, h, b)) return CFX_ERR_UNSUPPORTED;
+    if (bw) *bw = w;
+    if (bh) *bh = h;
+    if (bytes) *bytes = b;
+    return CFX_OK;
+}
+
+size_t cfx_encoded_size(const cfx_surface_desc* d)
+{
+    uint32_t bw, bh, bytes;
+    if (!d || !block_info(d->format, bw, bh, bytes)) return 0;
+    return static_cast<size_t>((d->width + bw - 1)/bw)*((d->height + bh - 1)/bh)*bytes;
+}
+
+int cfx_encode(const cfx_surface_desc* desc, const void* src, void* dst, size_t dst_size)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    t_error[0] = 0;
+    return encode_host(desc, src, dst, dst_size);
+}
+
+int cfx_encode_batch(int n, const cfx_surface_desc* descs, const void* const* srcs, void* const* dsts,
+    const size_t* dst_sizes)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    t_error[0] = 0;
+    if (n < 0 || (n > 0 && (!descs || !srcs || !dsts || !dst_sizes))) return fail(CFX_ERR_INVALID, "bad batch arguments");
+    // Validate everything first so a bad surface fails the batch before any work is queued
+    // (Converter::convert only tolerates a missing converter on the first surface).
+    for (int i = 0; i < n; ++i) {
+        EncodeParams p; Launcher l;
+        int rc = validate(&descs[i], p, l);
+        if (rc != CFX_OK) return rc;
+    }
+    for (int i = 0; i < n; ++i) {
+        int rc = encode_host(&descs[i], srcs[i], dsts[i], dst_sizes[i]);
+        if (rc != CFX_OK) return rc;
+    }
+    return CFX_OK;
+}
+
+int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_dst, size_t dst_size,
+    void* cuda_stream)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    t_error[0] = 0;
+    EncodeParams p; Launcher launcher;
+    int rc = validate(desc, p, launcher);
+    if (rc != CFX_OK) return rc;
+    if (!d_src || !d_dst) return fail(CFX_ERR_INVALID, "null buffer");
+    size_t out_bytes = static_cast<size_t>(p.total_blocks)*p.block_bytes;
+    if (dst_size < out_bytes) return fail(CFX_ERR_INVALID, "dst_size %zu < %zu", dst_size, out_bytes);
+    rc = ensure_init(-1);
+    if (rc != CFX_OK) return rc;
+    p.src = static_cast<const uint8_t*>(d_src);
+    p.dst = static_cast<uint8_t*>(d_dst);
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g_ctx.streams[0];
+    return launch(launcher, p, s);
+}
+
+void* cfx_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { fail(CFX_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+
+void cfx_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+uint64_t cfx_kernel_launches(void) { return g_launches.load(); }
+const char* cfx_last_error(void) { return t_error; }
+const char* cfx_version(void) { return "cuttlefish-b200 0.1 (sm_100a)"; }
+
+} // extern "C"

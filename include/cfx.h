@@ -1,0 +1,120 @@
+/*
+ * cfx.h -- C-ABI of the B200 block-texture encoder that drops in behind Cuttlefish's
+ * Texture::convert() / Converter interface.
+ *
+ * Every entry point is plain C: pointers, sizes and ints.  No C++/torch types cross it.
+ * The library owns device memory, streams and pinned staging; the caller owns host buffers.
+ * There is NO CPU fallback: if no sm_100 device is usable every encode call fails with
+ * CFX_ERR_NO_DEVICE / CFX_ERR_CUDA and cfx_last_error() says why.
+ *
+ * Which reference interface each entry point replaces (paths relative to the Cuttlefish tree):
+ *   cfx_format_supported  <- createConverter() returning nullptr for an unsupported (format,type)
+ *                            lib/src/Converter.cpp:32-506, failure contract :530-536
+ *   cfx_block_info /
+ *   cfx_encoded_size      <- Texture::blockWidth/blockHeight/blockSize, lib/src/Texture.cpp:529-773;
+ *                            S3tcConverter ctor data().resize(), lib/src/S3tcConverter.cpp:230-240
+ *   cfx_encode            <- the whole per-surface job loop of Converter::convert(),
+ *                            lib/src/Converter.cpp:538-587, i.e. every Converter::process(x,y)
+ *                            call for one surface (lib/src/S3tcConverter.cpp:242-255,
+ *                            lib/src/EtcConverter.cpp:120-152, lib/src/AstcConverter.cpp:208-230)
+ *   cfx_encode_batch      <- the mip/depth/face loop around it, lib/src/Converter.cpp:521-527
+ *   cfx_encode_device     <- same as cfx_encode for callers that already hold the surface in HBM
+ *   cfx_init/cfx_shutdown <- the one-time encoder table inits (rgbcx::init, bc7enc_compress_block_init,
+ *                            astcenc context alloc), lib/src/S3tcConverter.cpp:54-64,158-168
+ */
+#ifndef CFX_H
+#define CFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cuttlefish::Texture::Format, lib/include/cuttlefish/Texture.h:59-130 (same numeric values). */
+enum {
+    CFX_FORMAT_BC1_RGB = 29, CFX_FORMAT_BC1_RGBA = 30, CFX_FORMAT_BC2 = 31, CFX_FORMAT_BC3 = 32,
+    CFX_FORMAT_BC4 = 33, CFX_FORMAT_BC5 = 34, CFX_FORMAT_BC6H = 35, CFX_FORMAT_BC7 = 36,
+    CFX_FORMAT_ETC1 = 37, CFX_FORMAT_ETC2_R8G8B8 = 38, CFX_FORMAT_ETC2_R8G8B8A1 = 39,
+    CFX_FORMAT_ETC2_R8G8B8A8 = 40, CFX_FORMAT_EAC_R11 = 41, CFX_FORMAT_EAC_R11G11 = 42,
+    CFX_FORMAT_ASTC_4x4 = 43, CFX_FORMAT_ASTC_5x4 = 44, CFX_FORMAT_ASTC_5x5 = 45,
+    CFX_FORMAT_ASTC_6x5 = 46, CFX_FORMAT_ASTC_6x6 = 47, CFX_FORMAT_ASTC_8x5 = 48,
+    CFX_FORMAT_ASTC_8x6 = 49, CFX_FORMAT_ASTC_8x8 = 50, CFX_FORMAT_ASTC_10x5 = 51,
+    CFX_FORMAT_ASTC_10x6 = 52, CFX_FORMAT_ASTC_10x8 = 53, CFX_FORMAT_ASTC_10x10 = 54,
+    CFX_FORMAT_ASTC_12x10 = 55, CFX_FORMAT_ASTC_12x12 = 56
+};
+/* Texture::Type :135-143, Texture::Alpha :161-167, Texture::Quality :181-188. */
+enum { CFX_TYPE_UNORM = 0, CFX_TYPE_SNORM = 1, CFX_TYPE_UINT = 2, CFX_TYPE_INT = 3,
+       CFX_TYPE_UFLOAT = 4, CFX_TYPE_FLOAT = 5 };
+enum { CFX_ALPHA_NONE = 0, CFX_ALPHA_STANDARD = 1, CFX_ALPHA_PREMULTIPLIED = 2, CFX_ALPHA_ENCODED = 3 };
+enum { CFX_QUALITY_LOWEST = 0, CFX_QUALITY_LOW = 1, CFX_QUALITY_NORMAL = 2, CFX_QUALITY_HIGH = 3,
+       CFX_QUALITY_HIGHEST = 4 };
+/* Texel layout of the source surface handed to the encoder. RGBA32F is what Cuttlefish's
+ * Converter holds (Image::Format::RGBAF, lib/src/Converter.h:52-56); the kernels do the
+ * float->u8 / float->half step of lib/src/S3tcConverter.cpp:97-129 themselves. */
+enum { CFX_SRC_RGBA8 = 0, CFX_SRC_RGBA16F = 1, CFX_SRC_RGBA32F = 2 };
+
+enum {
+    CFX_OK = 0,
+    CFX_ERR_INVALID = -1,      /* bad descriptor / null pointer / dst too small          */
+    CFX_ERR_UNSUPPORTED = -2,  /* (format,type) has no GPU encoder: host should treat it
+                                  like createConverter() == nullptr                       */
+    CFX_ERR_NO_DEVICE = -3,    /* no CUDA device, or not compute capability 10.x         */
+    CFX_ERR_CUDA = -4          /* a CUDA runtime call failed; see cfx_last_error()       */
+};
+
+typedef struct cfx_surface_desc {
+    uint32_t format;        /* CFX_FORMAT_*                                           */
+    uint32_t type;          /* CFX_TYPE_*                                             */
+    uint32_t quality;       /* CFX_QUALITY_*                                          */
+    uint32_t alpha_type;    /* CFX_ALPHA_*                                            */
+    uint32_t color_mask;    /* bit0..3 = r,g,b,a enabled (Texture::ColorMask)         */
+    uint32_t color_space;   /* 0 linear, 1 sRGB (image().colorSpace())                */
+    uint32_t width, height; /* texels                                                 */
+    uint32_t src_format;    /* CFX_SRC_*                                              */
+    uint32_t reserved;      /* must be 0                                              */
+    uint64_t src_row_pitch; /* bytes between rows; rows are top-down (row 0 = top).
+                               Cuttlefish images are stored bottom-up: pass scanline(y)
+                               order, i.e. point at the last stored row and use the
+                               library's helper in INTEGRATION.md, or flip on upload.  */
+} cfx_surface_desc;
+
+/* Select the CUDA device this thread's context encodes on and create its streams/buffers.
+ * device < 0 keeps the current device. Idempotent. Returns CFX_OK or an error. */
+int cfx_init(int device);
+void cfx_shutdown(void);
+
+/* 1 if the (format,type) pair has a GPU encoder, else 0. */
+int cfx_format_supported(uint32_t format, uint32_t type);
+/* Block footprint and bytes per block; returns CFX_OK or CFX_ERR_UNSUPPORTED. */
+int cfx_block_info(uint32_t format, uint32_t* block_w, uint32_t* block_h, uint32_t* block_bytes);
+/* ceil(w/bw)*ceil(h/bh)*block_bytes, 0 if the format is unknown. */
+size_t cfx_encoded_size(const cfx_surface_desc* desc);
+
+/* Encode one surface held in HOST memory into HOST memory (blocks row-major, y*blocksX+x).
+ * Does H2D, kernels, D2H; returns when dst is complete. */
+int cfx_encode(const cfx_surface_desc* desc, const void* src, void* dst, size_t dst_size);
+/* Encode n surfaces (a mip chain / array layers); same semantics per surface. */
+int cfx_encode_batch(int n, const cfx_surface_desc* descs, const void* const* srcs,
+                     void* const* dsts, const size_t* dst_sizes);
+/* Encode one surface already resident in DEVICE memory into DEVICE memory, asynchronously on
+ * cuda_stream (a cudaStream_t cast to void*; NULL = the library's stream). src must be
+ * 16-byte aligned with a 16-byte-multiple pitch for the fast path; otherwise a slower path runs. */
+int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_dst, size_t dst_size,
+                      void* cuda_stream);
+
+/* Pinned host memory helpers for callers that want zero-copy staging. */
+void* cfx_host_alloc(size_t bytes);
+void cfx_host_free(void* p);
+
+/* Number of encoder kernel launches issued by this process so far. */
+uint64_t cfx_kernel_launches(void);
+/* Thread-local description of the last failure ("" if none). */
+const char* cfx_last_error(void);
+const char* cfx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFX_H */
