@@ -354,7 +354,7 @@ int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_d
     if (rc != CFX_OK) return rc;
     p.src = static_cast<const uint8_t*>(d_src);
     p.dst = static_cast<uint8_t*>(d_dst);
-    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g_ctx.streams[0];
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);   // NULL = the CUDA default stream
     return launch(launcher, p, s);
 }
 

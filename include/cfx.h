@@ -99,7 +99,7 @@ int cfx_encode(const cfx_surface_desc* desc, const void* src, void* dst, size_t 
 int cfx_encode_batch(int n, const cfx_surface_desc* descs, const void* const* srcs,
                      void* const* dsts, const size_t* dst_sizes);
 /* Encode one surface already resident in DEVICE memory into DEVICE memory, asynchronously on
- * cuda_stream (a cudaStream_t cast to void*; NULL = the library's stream). src must be
+ * cuda_stream (a cudaStream_t cast to void*; NULL = the CUDA default stream). src must be
  * 16-byte aligned with a 16-byte-multiple pitch for the fast path; otherwise a slower path runs. */
 int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_dst, size_t dst_size,
                       void* cuda_stream);

@@ -38,3 +38,47 @@ def test_device_entry_matches_host_entry(cfx, oracle, fmt):
     dev = cfx.encode_device(torch.from_numpy(img).cuda(), fmt)
     torch.cuda.synchronize()
     assert np.array_equal(dev.cpu().numpy(), host)
+
+
+# ---- search formats: RGB PSNR within 0.1 dB of the reference CPU encoder on the same input ----
+PSNR_TOLERANCE_DB = 0.1     # BASELINE.json north_star: "<= 0.1 dB vs reference"
+
+
+def _psnr_pair(cfx, oracle, fmt, img, **kw):
+    h, w, _ = img.shape
+    got = cfx.encode(oracle.to_rgba8(img), fmt, **kw)
+    ref = oracle.encode(img, fmt, **kw)
+    p_gpu = oracle.psnr_rgb(img, oracle.decode(got, fmt, w, h, **kw))
+    p_ref = oracle.psnr_rgb(img, oracle.decode(ref, fmt, w, h, **kw))
+    return p_gpu, p_ref
+
+
+@pytest.mark.parametrize("kind,w,h", [("noise+grad", 512, 512), ("gradient", 512, 512), ("noise+grad", 97, 61)])
+def test_bc7_psnr_vs_oracle(cfx, oracle, kind, w, h):
+    if not cfx.format_supported("BC7"):
+        pytest.fail("BC7 encoder missing from libcfx.so")
+    img = oracle.gen_image(kind, w, h, seed=99)
+    p_gpu, p_ref = _psnr_pair(cfx, oracle, "BC7", img)
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "BC7 %s: gpu %.3f dB < reference %.3f dB - 0.1" % (kind, p_gpu, p_ref)
+
+
+def test_bc7_alpha_psnr_vs_oracle(cfx, oracle):
+    # decoded RGBA error including alpha must not be worse than the reference's either
+    src, blocks, fmt, kw = load_golden("BC7_alpha_32x32")
+    img = src_as_float(src)
+    got = cfx.encode(src, "BC7")
+    d_gpu = oracle.decode(got, "BC7", 32, 32)
+    d_ref = oracle.decode(blocks, "BC7", 32, 32)
+    mse = lambda d: float(np.mean((d.astype(np.float64) - img) ** 2))
+    assert 10*np.log10(1/mse(d_gpu)) >= 10*np.log10(1/mse(d_ref)) - PSNR_TOLERANCE_DB
+
+
+def test_bc7_solid_blocks_exact(cfx, oracle):
+    # flat colours must decode to within the reference's error (usually exactly)
+    img = np.zeros((16, 16, 4), np.float32)
+    img[..., 3] = 1.0
+    for i, c in enumerate([(0, 0, 0), (1, 1, 1), (0.5, 0.25, 0.75), (1 / 255.0, 254 / 255.0, 128 / 255.0)]):
+        img[(i // 2) * 8:(i // 2) * 8 + 8, (i % 2) * 8:(i % 2) * 8 + 8, :3] = np.float32(c)
+    img = oracle.to_rgba8(img).astype(np.float32) / np.float32(255)
+    p_gpu, p_ref = _psnr_pair(cfx, oracle, "BC7", img)
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
