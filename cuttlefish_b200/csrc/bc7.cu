@@ -20,488 +20,17 @@
 //   phase 4  butterfly argmin over (SSE | lane) picks the winner lane, which packs the 128 bits.
 // Texels come from a shared-memory tile staged with coalesced 16-byte loads; packed blocks go
 // back through shared memory and leave as 16-byte stores.
-#include "bc7_tables.cuh"
+#include "bc7_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
 namespace cfx {
 
+using namespace bc7;
+
 namespace {
 
 constexpr int kTileBc7 = 64;
-
-struct ModeInfo {
-    uint32_t ns, cbits, abits, pmode, ibits;   // pmode: 0 none, 1 unique, 2 shared
-};
-
-__device__ __forceinline__ ModeInfo mode_info(uint32_t mode)
-{
-    ModeInfo m;
-    m.ns = mode == 6 ? 1u : 2u;
-    m.cbits = mode == 1 ? 6u : (mode == 7 ? 5u : 7u);
-    m.abits = mode == 6 ? 7u : (mode == 7 ? 5u : 0u);
-    m.pmode = mode == 1 ? 2u : 1u;
-    m.ibits = mode == 6 ? 4u : (mode == 1 ? 3u : 2u);
-    return m;
-}
-
-// BC7 interpolation weight of index k for an ibits-bit index: {0,21,43,64}, {0,9,...,64},
-// {0,4,9,...,64} == (k*64 + (N-1)/2) / (N-1); the division is done with a 17-bit reciprocal.
-__device__ __forceinline__ uint32_t index_weight(uint32_t k, uint32_t half, uint32_t recip)
-{
-    return ((k*64u + half)*recip) >> 17;
-}
-
-struct Fit {
-    uint32_t e0[2], e1[2];     // quantised endpoints per subset, one byte per channel (incl. p-bit)
-    uint32_t err[2];           // SSE per subset
-    uint32_t sel_lo, sel_hi;   // 16 x 4-bit indices
-};
-
-__device__ __forceinline__ uint32_t nibble_mask8(uint32_t m8)
-{
-    // spread 8 mask bits to 8 nibbles of 0xF
-    uint32_t x = m8 & 0xFFu;
-    x = (x | (x << 12)) & 0x000F000Fu;
-    x = (x | (x << 6)) & 0x03030303u;
-    x = (x | (x << 3)) & 0x11111111u;
-    return x*15u;
-}
-
-// Principal axis of a symmetric 4x4 matrix (upper triangle c[10]: xx xy xz xw yy yz yw zz zw ww).
-__device__ __forceinline__ float4 principal_axis(const float* c, int iters)
-{
-    // start from the row with the largest diagonal so a degenerate start is impossible
-    float4 v = make_float4(c[0], c[1], c[2], c[3]);
-    float best = c[0];
-    if (c[4] > best) { best = c[4]; v = make_float4(c[1], c[4], c[5], c[6]); }
-    if (c[7] > best) { best = c[7]; v = make_float4(c[2], c[5], c[7], c[8]); }
-    if (c[9] > best) { best = c[9]; v = make_float4(c[3], c[6], c[8], c[9]); }
-    for (int it = 0; it < iters; ++it) {
-        float n2 = v.x*v.x + v.y*v.y + v.z*v.z + v.w*v.w;
-        float inv = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
-        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-        float4 r;
-        r.x = c[0]*v.x + c[1]*v.y + c[2]*v.z + c[3]*v.w;
-        r.y = c[1]*v.x + c[4]*v.y + c[5]*v.z + c[6]*v.w;
-        r.z = c[2]*v.x + c[5]*v.y + c[7]*v.z + c[8]*v.w;
-        r.w = c[3]*v.x + c[6]*v.y + c[8]*v.z + c[9]*v.w;
-        v = r;
-    }
-    float n2 = v.x*v.x + v.y*v.y + v.z*v.z + v.w*v.w;
-    float inv = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
-    return make_float4(v.x*inv, v.y*inv, v.z*inv, v.w*inv);
-}
-
-// lambda_max estimate of the same matrix: |C v| for the unit v after `iters` power iterations.
-__device__ __forceinline__ float lambda_max(const float* c)
-{
-    float4 v = principal_axis(c, 3);
-    float4 r;
-    r.x = c[0]*v.x + c[1]*v.y + c[2]*v.z + c[3]*v.w;
-    r.y = c[1]*v.x + c[4]*v.y + c[5]*v.z + c[6]*v.w;
-    r.z = c[2]*v.x + c[5]*v.y + c[7]*v.z + c[8]*v.w;
-    r.w = c[3]*v.x + c[6]*v.y + c[8]*v.z + c[9]*v.w;
-    return v.x*r.x + v.y*r.y + v.z*r.z + v.w*r.w;
-}
-
-// Quantise one float endpoint (0..255 per channel) to tb-bit codes with p-bit p (p = 2: mode has
-// no p-bit), returning the codes packed one per byte and the squared quantisation error.
-__device__ __forceinline__ uint32_t quantize_endpoint(float4 x, uint32_t cbits, uint32_t abits,
-    bool has_p, uint32_t p, float& qerr)
-{
-    float v[4] = {x.x, x.y, x.z, x.w};
-    uint32_t out = 0;
-    qerr = 0.0f;
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        uint32_t bits = ch == 3 ? abits : cbits;
-        if (bits == 0) continue;                       // mode has no alpha: decodes to 255
-        uint32_t tb = bits + (has_p ? 1u : 0u);
-        float maxv = static_cast<float>((1u << tb) - 1u);
-        float f = fminf(fmaxf(v[ch], 0.0f), 255.0f)*(maxv*(1.0f/255.0f));
-        uint32_t code;
-        if (has_p) {
-            int q = __float2int_rn((f - static_cast<float>(p))*0.5f);
-            q = min(max(q, 0), static_cast<int>((1u << bits) - 1u));
-            code = (static_cast<uint32_t>(q) << 1) | p;
-        } else {
-            int q = __float2int_rn(f);
-            code = static_cast<uint32_t>(min(max(q, 0), static_cast<int>((1u << bits) - 1u)));
-        }
-        uint32_t dq = (code << (8u - tb)) | (code >> (2u*tb - 8u));
-        float d = static_cast<float>(dq) - v[ch];
-        qerr += d*d;
-        out |= code << (8*ch);
-    }
-    return out;
-}
-
-// Expand packed tb-bit codes to the 8-bit values the decoder interpolates.
-__device__ __forceinline__ uint32_t dequant_endpoint(uint32_t codes, uint32_t ctb, uint32_t atb)
-{
-    // colour bytes
-    uint32_t c = codes & 0x00FFFFFFu;
-    uint32_t rmask = ((1u << (8u - ctb)) - 1u)*0x010101u;
-    uint32_t rgb = ((c << (8u - ctb)) | ((c >> (2u*ctb - 8u)) & rmask)) & 0x00FFFFFFu;
-    uint32_t a = 0xFFu;
-    if (atb) {
-        uint32_t av = codes >> 24;
-        a = ((av << (8u - atb)) | (av >> (2u*atb - 8u))) & 0xFFu;
-    }
-    return rgb | (a << 24);
-}
-
-// Mixed-sign 2-way dot products: a = two signed 16-bit halves, b = unsigned bytes
-// (lo: bytes 0,1; hi: bytes 2,3).  The CUDA intrinsics only offer same-sign variants.
-__device__ __forceinline__ int dp2a_lo_s16_u8(uint32_t a, uint32_t b, int c)
-{
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp2a_hi_s16_u8(uint32_t a, uint32_t b, int c)
-{
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-struct SubsetEval {
-    uint32_t lo_rg, lo_ba, hi_rg, hi_ba;   // dequantised endpoints as 2x16-bit pairs
-    uint32_t d_rg, d_ba;                   // hi - lo as signed 16-bit pairs
-    int c0;                                // dot(lo, d)
-    float scale;                           // (N-1) / |d|^2
-};
-
-__device__ __forceinline__ SubsetEval make_eval(uint32_t e0, uint32_t e1, uint32_t ctb, uint32_t atb,
-    uint32_t nm1)
-{
-    uint32_t lo = dequant_endpoint(e0, ctb, atb), hi = dequant_endpoint(e1, ctb, atb);
-    SubsetEval s;
-    s.lo_rg = (lo & 0xFFu) | ((lo & 0xFF00u) << 8);
-    s.lo_ba = ((lo >> 16) & 0xFFu) | ((lo >> 8) & 0xFF0000u);
-    s.hi_rg = (hi & 0xFFu) | ((hi & 0xFF00u) << 8);
-    s.hi_ba = ((hi >> 16) & 0xFFu) | ((hi >> 8) & 0xFF0000u);
-    int dr = static_cast<int>(hi & 0xFF) - static_cast<int>(lo & 0xFF);
-    int dg = static_cast<int>((hi >> 8) & 0xFF) - static_cast<int>((lo >> 8) & 0xFF);
-    int db = static_cast<int>((hi >> 16) & 0xFF) - static_cast<int>((lo >> 16) & 0xFF);
-    int da = static_cast<int>(hi >> 24) - static_cast<int>(lo >> 24);
-    s.d_rg = (static_cast<uint32_t>(dr) & 0xFFFFu) | (static_cast<uint32_t>(dg) << 16);
-    s.d_ba = (static_cast<uint32_t>(db) & 0xFFFFu) | (static_cast<uint32_t>(da) << 16);
-    s.c0 = dr*static_cast<int>(lo & 0xFF) + dg*static_cast<int>((lo >> 8) & 0xFF) +
-        db*static_cast<int>((lo >> 16) & 0xFF) + da*static_cast<int>(lo >> 24);
-    int len2 = dr*dr + dg*dg + db*db + da*da;
-    s.scale = len2 > 0 ? static_cast<float>(nm1)/static_cast<float>(len2) : 0.0f;
-    return s;
-}
-
-// Exact SSE of texel x against palette entry k of the subset (weights 1 on enabled channels).
-__device__ __forceinline__ uint32_t entry_error(const SubsetEval& s, uint32_t x, uint32_t w, uint32_t chmask)
-{
-    uint32_t iw = 64u - w;
-    uint32_t rg = ((s.lo_rg*iw + s.hi_rg*w + 0x00200020u) >> 6) & 0x00FF00FFu;
-    uint32_t ba = ((s.lo_ba*iw + s.hi_ba*w + 0x00200020u) >> 6) & 0x00FF00FFu;
-    uint32_t pal = __byte_perm(rg, ba, 0x6420);          // R G B A
-    uint32_t d = __vabsdiffu4(pal, x) & chmask;
-    return __dp4a(d, d, 0u);
-}
-
-// Assign indices and accumulate per-subset SSE for the lane's candidate.
-__device__ __forceinline__ void evaluate(const uint32_t* s_x, uint32_t m1, const SubsetEval& s0,
-    const SubsetEval& s1, uint32_t nm1, uint32_t half, uint32_t recip, uint32_t chmask, uint32_t err[2],
-    uint32_t& sel_lo, uint32_t& sel_hi)
-{
-    uint32_t e0 = 0, e1 = 0;
-    uint64_t sel = 0;
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        uint32_t x = s_x[i];
-        bool in1 = (m1 >> i) & 1u;
-        SubsetEval s;
-        s.lo_rg = in1 ? s1.lo_rg : s0.lo_rg; s.lo_ba = in1 ? s1.lo_ba : s0.lo_ba;
-        s.hi_rg = in1 ? s1.hi_rg : s0.hi_rg; s.hi_ba = in1 ? s1.hi_ba : s0.hi_ba;
-        s.d_rg = in1 ? s1.d_rg : s0.d_rg; s.d_ba = in1 ? s1.d_ba : s0.d_ba;
-        s.c0 = in1 ? s1.c0 : s0.c0; s.scale = in1 ? s1.scale : s0.scale;
-        int dot = dp2a_lo_s16_u8(s.d_rg, x, 0);        // dR*R + dG*G
-        dot = dp2a_hi_s16_u8(s.d_ba, x, dot);          // + dB*B + dA*A
-        int k = __float2int_rn(static_cast<float>(dot - s.c0)*s.scale);
-        k = min(max(k, 0), static_cast<int>(nm1));
-        int ka = max(k - 1, 0), kb = min(k + 1, static_cast<int>(nm1));
-        uint32_t er = entry_error(s, x, index_weight(k, half, recip), chmask);
-        uint32_t era = entry_error(s, x, index_weight(ka, half, recip), chmask);
-        uint32_t erb = entry_error(s, x, index_weight(kb, half, recip), chmask);
-        uint32_t bk = k;
-        if (era < er) { er = era; bk = ka; }
-        if (erb < er) { er = erb; bk = kb; }
-        if (in1) e1 += er; else e0 += er;
-        sel |= static_cast<uint64_t>(bk) << (4*i);
-    }
-    err[0] = e0; err[1] = e1;
-    sel_lo = static_cast<uint32_t>(sel); sel_hi = static_cast<uint32_t>(sel >> 32);
-}
-
-// Choose p-bits + quantise both endpoints of one subset.
-__device__ __forceinline__ void quantize_pair(float4 lo, float4 hi, const ModeInfo& mi, uint32_t& e0,
-    uint32_t& e1)
-{
-    float q00, q01, q10, q11;
-    uint32_t a0 = quantize_endpoint(lo, mi.cbits, mi.abits, true, 0, q00);
-    uint32_t a1 = quantize_endpoint(lo, mi.cbits, mi.abits, true, 1, q01);
-    uint32_t b0 = quantize_endpoint(hi, mi.cbits, mi.abits, true, 0, q10);
-    uint32_t b1 = quantize_endpoint(hi, mi.cbits, mi.abits, true, 1, q11);
-    if (mi.pmode == 2) {          // shared p-bit
-        bool one = (q01 + q11) < (q00 + q10);
-        e0 = one ? a1 : a0; e1 = one ? b1 : b0;
-    } else {
-        e0 = q01 < q00 ? a1 : a0;
-        e1 = q11 < q10 ? b1 : b0;
-    }
-}
-
-// Quantise the least-squares endpoints of one subset with the indices held fixed.  With fixed
-// indices the SSE of channel c is the quadratic  A l^2 + 2B l h + C h^2 - 2 P_c l - 2 Q_c h  in the
-// decoded endpoint values (l, h), so for every p-bit choice each channel independently tries the
-// two representable values below/above the real-valued optimum for l and for h (4 pairs) and the
-// p-bit combination with the smallest total wins.  This is what makes p-bit and rounding
-// decisions exact instead of nearest-value guesses.
-__device__ __forceinline__ void quantize_ls(float A, float B, float C, const float* P, const float* Q,
-    const float* lo, const float* hi, const ModeInfo& mi, uint32_t& e0, uint32_t& e1)
-{
-    float bestE = 3.4e38f;
-    uint32_t b0 = 0, b1 = 0;
-    const int combos = mi.pmode == 2 ? 2 : 4;
-#pragma unroll 1
-    for (int pc = 0; pc < combos; ++pc) {
-        const uint32_t pl = mi.pmode == 2 ? pc : (pc & 1), ph = mi.pmode == 2 ? pc : (pc >> 1);
-        float E = 0.0f;
-        uint32_t c0 = 0, c1 = 0;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t bits = ch == 3 ? mi.abits : mi.cbits;
-            if (bits == 0) continue;
-            const uint32_t tb = bits + 1u;
-            const float scale = static_cast<float>((1u << tb) - 1u)*(1.0f/255.0f);
-            const int qmax = static_cast<int>((1u << bits) - 1u);
-            // two codes around each optimum, on the lattice of codes with the required parity
-            int ql = static_cast<int>(floorf((fminf(fmaxf(lo[ch], 0.0f), 255.0f)*scale - static_cast<float>(pl))*0.5f));
-            int qh = static_cast<int>(floorf((fminf(fmaxf(hi[ch], 0.0f), 255.0f)*scale - static_cast<float>(ph))*0.5f));
-            float bestc = 3.4e38f;
-            uint32_t bl = 0, bh = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int a = min(max(ql + (k & 1), 0), qmax), b = min(max(qh + (k >> 1), 0), qmax);
-                uint32_t ca = (static_cast<uint32_t>(a) << 1) | pl, cb = (static_cast<uint32_t>(b) << 1) | ph;
-                float l = static_cast<float>((ca << (8u - tb)) | (ca >> (2u*tb - 8u)));
-                float h = static_cast<float>((cb << (8u - tb)) | (cb >> (2u*tb - 8u)));
-                float e = l*(A*l + 2.0f*(B*h - P[ch])) + h*(C*h - 2.0f*Q[ch]);
-                if (e < bestc) { bestc = e; bl = ca; bh = cb; }
-            }
-            E += bestc;
-            c0 |= bl << (8*ch); c1 |= bh << (8*ch);
-        }
-        if (E < bestE) { bestE = E; b0 = c0; b1 = c1; }
-    }
-    e0 = b0; e1 = b1;
-}
-
-// The whole fit of one (mode, shape) candidate by one lane.
-__device__ __forceinline__ void fit_candidate(const float4* s_xf, const uint32_t* s_x, uint32_t mode,
-    uint32_t m1, uint32_t variant, uint32_t chmask, Fit& best)
-{
-    const ModeInfo mi = mode_info(mode);
-    const uint32_t ctb = mi.cbits + 1u, atb = mi.abits ? mi.abits + 1u : 0u;
-    const uint32_t nm1 = (1u << mi.ibits) - 1u;
-    const uint32_t half = nm1 >> 1;
-    const uint32_t recip = nm1 == 3 ? 43691u : (nm1 == 7 ? 18725u : 8739u);
-
-    // ---- statistics: totals and subset 1; subset 0 = total - subset 1
-    float nT = 16.0f, n1 = 0.0f;
-    float sT[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
-    float cT[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, c1[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 2
-    for (int i = 0; i < 16; ++i) {
-        float4 x = s_xf[i];
-        float f = ((m1 >> i) & 1u) ? 1.0f : 0.0f;
-        float o[10] = {x.x*x.x, x.x*x.y, x.x*x.z, x.x*x.w, x.y*x.y, x.y*x.z, x.y*x.w, x.z*x.z, x.z*x.w, x.w*x.w};
-        sT[0] += x.x; sT[1] += x.y; sT[2] += x.z; sT[3] += x.w;
-        s1[0] += f*x.x; s1[1] += f*x.y; s1[2] += f*x.z; s1[3] += f*x.w;
-        n1 += f;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) { cT[k] += o[k]; c1[k] += f*o[k]; }
-    }
-    float4 mean[2], axis[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        float n = s ? n1 : nT - n1;
-        float sm[4], cc[10];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sm[k] = s ? s1[k] : sT[k] - s1[k];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) cc[k] = s ? c1[k] : cT[k] - c1[k];
-        float inv = n > 0.0f ? 1.0f/n : 0.0f;
-        float m[4] = {sm[0]*inv, sm[1]*inv, sm[2]*inv, sm[3]*inv};
-        cc[0] -= sm[0]*m[0]; cc[1] -= sm[0]*m[1]; cc[2] -= sm[0]*m[2]; cc[3] -= sm[0]*m[3];
-        cc[4] -= sm[1]*m[1]; cc[5] -= sm[1]*m[2]; cc[6] -= sm[1]*m[3];
-        cc[7] -= sm[2]*m[2]; cc[8] -= sm[2]*m[3]; cc[9] -= sm[3]*m[3];
-        mean[s] = make_float4(m[0], m[1], m[2], m[3]);
-        axis[s] = principal_axis(cc, 4);
-    }
-
-    // ---- extent of each subset along its axis
-    float tmin[2] = {1e30f, 1e30f}, tmax[2] = {-1e30f, -1e30f};
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        float4 x = s_xf[i];
-        bool in1 = (m1 >> i) & 1u;
-        float4 mu = in1 ? mean[1] : mean[0];
-        float4 ax = in1 ? axis[1] : axis[0];
-        float t = (x.x - mu.x)*ax.x + (x.y - mu.y)*ax.y + (x.z - mu.z)*ax.z + (x.w - mu.w)*ax.w;
-        if (in1) { tmin[1] = fminf(tmin[1], t); tmax[1] = fmaxf(tmax[1], t); }
-        else { tmin[0] = fminf(tmin[0], t); tmax[0] = fmaxf(tmax[0], t); }
-    }
-
-    uint32_t e0[2], e1[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        float lo_t = tmin[s] < 1e29f ? tmin[s] : 0.0f, hi_t = tmax[s] > -1e29f ? tmax[s] : 0.0f;
-        float4 lo = make_float4(mean[s].x + lo_t*axis[s].x, mean[s].y + lo_t*axis[s].y,
-            mean[s].z + lo_t*axis[s].z, mean[s].w + lo_t*axis[s].w);
-        float4 hi = make_float4(mean[s].x + hi_t*axis[s].x, mean[s].y + hi_t*axis[s].y,
-            mean[s].z + hi_t*axis[s].z, mean[s].w + hi_t*axis[s].w);
-        quantize_pair(lo, hi, mi, e0[s], e1[s]);
-    }
-
-    SubsetEval ev0 = make_eval(e0[0], e1[0], ctb, atb, nm1);
-    SubsetEval ev1 = make_eval(e0[1], e1[1], ctb, atb, nm1);
-    evaluate(s_x, m1, ev0, ev1, nm1, half, recip, chmask, best.err, best.sel_lo, best.sel_hi);
-    best.e0[0] = e0[0]; best.e0[1] = e0[1]; best.e1[0] = e1[0]; best.e1[1] = e1[1];
-
-    // ---- least-squares refinement: solve for endpoints given the indices, keep per-subset wins
-    uint32_t cur_lo = best.sel_lo, cur_hi = best.sel_hi;
-    for (int round = 0; round < 2; ++round) {
-        // normal equations per subset: [A B; B C] [lo hi]^T = [P Q]^T
-        float AT = 0, BT = 0, CT = 0, A1 = 0, B1 = 0, C1 = 0;
-        float PT[4] = {0, 0, 0, 0}, QT[4] = {0, 0, 0, 0}, P1[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0};
-#pragma unroll 2
-        for (int i = 0; i < 16; ++i) {
-            float4 x = s_xf[i];
-            uint32_t k = ((i < 8 ? cur_lo : cur_hi) >> (4*(i & 7))) & 15u;
-            // variant 1, first round: pull the extreme indices inwards so the solved endpoints
-            // extrapolate beyond the texel range (finds the wide-endpoint encodings that make
-            // near-flat blocks exact)
-            if (variant == 1 && round == 0) k = min(max(k, 1u), nm1 - 1u);
-            float w = static_cast<float>(index_weight(k, half, recip))*(1.0f/64.0f);
-            float iw = 1.0f - w;
-            float f = ((m1 >> i) & 1u) ? 1.0f : 0.0f;
-            float a = iw*iw, b = iw*w, c = w*w;
-            AT += a; BT += b; CT += c; A1 += f*a; B1 += f*b; C1 += f*c;
-            float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                float p = iw*xs[ch], q = w*xs[ch];
-                PT[ch] += p; QT[ch] += q; P1[ch] += f*p; Q1[ch] += f*q;
-            }
-        }
-        uint32_t n0[2], n1e[2];
-        bool ok[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            float A = s ? A1 : AT - A1, B = s ? B1 : BT - B1, C = s ? C1 : CT - C1;
-            float det = A*C - B*B;
-            ok[s] = fabsf(det) > 1e-4f;
-            float id = ok[s] ? 1.0f/det : 0.0f;
-            float lo[4], hi[4], Ps[4], Qs[4];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                Ps[ch] = s ? P1[ch] : PT[ch] - P1[ch]; Qs[ch] = s ? Q1[ch] : QT[ch] - Q1[ch];
-                lo[ch] = (C*Ps[ch] - B*Qs[ch])*id;
-                hi[ch] = (A*Qs[ch] - B*Ps[ch])*id;
-            }
-            quantize_ls(A, B, C, Ps, Qs, lo, hi, mi, n0[s], n1e[s]);
-            if (!ok[s]) { n0[s] = best.e0[s]; n1e[s] = best.e1[s]; }
-        }
-        ev0 = make_eval(n0[0], n1e[0], ctb, atb, nm1);
-        ev1 = make_eval(n0[1], n1e[1], ctb, atb, nm1);
-        uint32_t nerr[2], nlo, nhi;
-        evaluate(s_x, m1, ev0, ev1, nm1, half, recip, chmask, nerr, nlo, nhi);
-        cur_lo = nlo; cur_hi = nhi;
-        uint32_t take = 0;                      // texel mask of subsets that improved
-        if (nerr[0] < best.err[0]) { best.err[0] = nerr[0]; best.e0[0] = n0[0]; best.e1[0] = n1e[0]; take |= ~m1 & 0xFFFFu; }
-        if (nerr[1] < best.err[1]) { best.err[1] = nerr[1]; best.e0[1] = n0[1]; best.e1[1] = n1e[1]; take |= m1; }
-        uint32_t tl = nibble_mask8(take), th = nibble_mask8(take >> 8);
-        best.sel_lo = (best.sel_lo & ~tl) | (nlo & tl);
-        best.sel_hi = (best.sel_hi & ~th) | (nhi & th);
-    }
-}
-
-struct BitWriter {
-    uint64_t lo, hi;
-    uint32_t pos;
-    __device__ __forceinline__ void init() { lo = hi = 0; pos = 0; }
-    __device__ __forceinline__ void put(uint32_t v, uint32_t bits)
-    {
-        uint64_t vv = v;
-        if (pos < 64) {
-            lo |= vv << pos;
-            if (pos + bits > 64) hi |= vv >> (64u - pos);
-        } else {
-            hi |= vv << (pos - 64u);
-        }
-        pos += bits;
-    }
-};
-
-// Pack modes 1, 3, 6, 7 (one index set, p-bits).
-__device__ __noinline__ uint4 pack_block(uint32_t mode, uint32_t part, uint32_t m1, Fit f)
-{
-    const ModeInfo mi = mode_info(mode);
-    const uint32_t nm1 = (1u << mi.ibits) - 1u;
-    uint64_t sel = (static_cast<uint64_t>(f.sel_hi) << 32) | f.sel_lo;
-    uint32_t anchor1 = mi.ns == 2 ? kBc7Anchor2[part] : 0u;
-    // anchor indices must have a clear MSB: swap that subset's endpoints and invert its indices
-    uint32_t msb = 1u << (mi.ibits - 1u);
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (s >= static_cast<int>(mi.ns)) continue;
-        uint32_t a = s ? anchor1 : 0u;
-        if ((static_cast<uint32_t>(sel >> (4*a)) & 15u) & msb) {
-            uint32_t t = f.e0[s]; f.e0[s] = f.e1[s]; f.e1[s] = t;
-            uint32_t mask = s ? m1 : (~m1 & 0xFFFFu);
-            uint64_t nm = (static_cast<uint64_t>(nibble_mask8(mask >> 8)) << 32) | nibble_mask8(mask);
-            // idx -> nm1 - idx on that subset's texels
-            uint64_t inv = (0x1111111111111111ull*nm1) & nm;
-            sel = (sel & ~nm) | ((inv - (sel & nm)) & nm);
-        }
-    }
-    BitWriter bw; bw.init();
-    bw.put(1u << mode, mode + 1u);
-    if (mi.ns == 2) bw.put(part, 6);
-    const uint32_t pshift = 1u;   // every mode handled here has p-bits
-#pragma unroll 1
-    for (uint32_t ch = 0; ch < 4; ++ch) {
-        uint32_t bits = ch == 3 ? mi.abits : mi.cbits;
-        if (!bits) continue;
-#pragma unroll 1
-        for (uint32_t s = 0; s < mi.ns; ++s) {
-            bw.put(((f.e0[s] >> (8*ch)) & 0xFFu) >> pshift, bits);
-            bw.put(((f.e1[s] >> (8*ch)) & 0xFFu) >> pshift, bits);
-        }
-    }
-#pragma unroll 1
-    for (uint32_t s = 0; s < mi.ns; ++s) {
-        if (mi.pmode == 2) bw.put(f.e0[s] & 1u, 1);
-        else { bw.put(f.e0[s] & 1u, 1); bw.put(f.e1[s] & 1u, 1); }
-    }
-#pragma unroll 1
-    for (uint32_t i = 0; i < 16; ++i) {
-        uint32_t k = static_cast<uint32_t>(sel >> (4*i)) & 15u;
-        bool is_anchor = i == 0 || (mi.ns == 2 && i == anchor1);
-        bw.put(k, is_anchor ? mi.ibits - 1u : mi.ibits);
-    }
-    return make_uint4(static_cast<uint32_t>(bw.lo), static_cast<uint32_t>(bw.lo >> 32),
-        static_cast<uint32_t>(bw.hi), static_cast<uint32_t>(bw.hi >> 32));
-}
 
 template <int G>
 __device__ __forceinline__ uint32_t group_min(uint32_t v)
@@ -554,7 +83,6 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
             const bool has_alpha = amin < 255 && (p.color_mask & 8u);
 
             // ---- phase 1: score 64/G two-subset shapes per lane
-            float nT = 16.0f;
             float sT[4] = {0, 0, 0, 0};
             float cT[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 2
@@ -569,36 +97,7 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
 #pragma unroll 1
             for (int j = 0; j < kShapes; ++j) {
                 const uint32_t shape = sub*kShapes + j;
-                const uint32_t m1 = kBc7Part2[shape];
-                float n1 = 0, s1[4] = {0, 0, 0, 0}, c1[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    if ((m1 >> i) & 1u) {
-                        float4 x = bxf[i];
-                        n1 += 1.0f;
-                        s1[0] += x.x; s1[1] += x.y; s1[2] += x.z; s1[3] += x.w;
-                        c1[0] += x.x*x.x; c1[1] += x.x*x.y; c1[2] += x.x*x.z; c1[3] += x.x*x.w;
-                        c1[4] += x.y*x.y; c1[5] += x.y*x.z; c1[6] += x.y*x.w;
-                        c1[7] += x.z*x.z; c1[8] += x.z*x.w; c1[9] += x.w*x.w;
-                    }
-                }
-                float score = 0.0f;
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    float nn = s ? n1 : nT - n1;
-                    float sm[4], cc[10];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) sm[k] = s ? s1[k] : sT[k] - s1[k];
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) cc[k] = s ? c1[k] : cT[k] - c1[k];
-                    float inv = 1.0f/nn;     // every BC7 shape has both subsets non-empty
-                    cc[0] -= sm[0]*sm[0]*inv; cc[1] -= sm[0]*sm[1]*inv; cc[2] -= sm[0]*sm[2]*inv; cc[3] -= sm[0]*sm[3]*inv;
-                    cc[4] -= sm[1]*sm[1]*inv; cc[5] -= sm[1]*sm[2]*inv; cc[6] -= sm[1]*sm[3]*inv;
-                    cc[7] -= sm[2]*sm[2]*inv; cc[8] -= sm[2]*sm[3]*inv; cc[9] -= sm[3]*sm[3]*inv;
-                    score += (cc[0] + cc[4] + cc[7] + cc[9]) - lambda_max(cc);
-                }
-                score = fmaxf(score, 0.0f);
-                const uint32_t key = (__float_as_uint(score) & ~63u) | shape;
+                const uint32_t key = score_shape(bxf, sT, cT, shape);
 #pragma unroll
                 for (int jj = 0; jj < kShapes; ++jj) if (jj == j) keys[jj] = key;
             }
@@ -607,8 +106,7 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
             // lanes 0,1: mode 6 (plain / extrapolating variant). Remaining lanes j = l-2:
             //   opaque: rank j/4, (mode 1, mode 3) x (plain, extrapolating) by j%4
             //   alpha : rank j/2, mode 7 x (plain, extrapolating)
-            const uint32_t j = sub >= 2 ? sub - 2 : 0;
-            uint32_t my_rank = sub < 2 ? 0xFFFFFFFFu : (has_alpha ? j >> 1 : j >> 2);
+            const uint32_t my_rank = candidate_rank(sub, has_alpha);
             uint32_t my_shape = 0;
             // trip count must be warp-uniform (shuffles inside)
             const uint32_t need = __any_sync(0xFFFFFFFFu, has_alpha) ? (G - 2 + 1)/2 : (G - 2 + 3)/4;
@@ -622,9 +120,7 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
                 if (my_rank == r) my_shape = win & 63u;
             }
             uint32_t mode, m1, variant;
-            if (sub < 2) { mode = 6; m1 = 0; variant = sub; }
-            else if (has_alpha) { mode = 7; m1 = kBc7Part2[my_shape]; variant = j & 1u; }
-            else { mode = (j & 1u) ? 3u : 1u; m1 = kBc7Part2[my_shape]; variant = (j >> 1) & 1u; }
+            candidate_of(sub, has_alpha, my_shape, mode, m1, variant);
 
             Fit fit;
             fit_candidate(bxf, bx, mode, m1, variant, chmask, fit);
