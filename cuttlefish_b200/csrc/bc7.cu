@@ -42,9 +42,34 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v)
 
 } // namespace
 
+// Candidate sets per lanes-per-block G (index 0: G=4, 1: G=8, 2: G=16, 3: G=32) and per opaque / alpha.
+#define C CFX_BC7_CAND
+__device__ __constant__ uint16_t kBc7Cand[4][2][32] = {
+    {{C(6,0,0,2), C(1,0,0,2), C(3,0,0,2), C(6,0,1,2)},
+     {C(6,0,0,2), C(7,0,0,2), C(7,1,0,2), C(6,0,1,2)}},
+    {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2)},
+     {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(7,1,1,2), C(7,2,0,2), C(7,2,1,2)}},
+    {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2),
+      C(1,1,1,2), C(3,1,1,2), C(1,2,0,2), C(3,2,0,2), C(1,2,1,2), C(3,2,1,2), C(1,3,0,2), C(3,3,0,2)},
+     {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(7,1,1,2), C(7,2,0,2), C(7,2,1,2),
+      C(7,3,0,2), C(7,3,1,2), C(7,4,0,2), C(7,4,1,2), C(7,5,0,2), C(7,5,1,2), C(7,6,0,2), C(7,6,1,2)}},
+    {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2),
+      C(1,1,1,2), C(3,1,1,2), C(1,2,0,2), C(3,2,0,2), C(1,2,1,2), C(3,2,1,2), C(1,3,0,2), C(3,3,0,2),
+      C(1,3,1,2), C(3,3,1,2), C(1,4,0,2), C(3,4,0,2), C(1,4,1,2), C(3,4,1,2), C(1,5,0,2), C(3,5,0,2),
+      C(1,5,1,2), C(3,5,1,2), C(1,6,0,2), C(3,6,0,2), C(1,6,1,2), C(3,6,1,2), C(1,7,0,2), C(3,7,0,2)},
+     {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(7,1,1,2), C(7,2,0,2), C(7,2,1,2),
+      C(7,3,0,2), C(7,3,1,2), C(7,4,0,2), C(7,4,1,2), C(7,5,0,2), C(7,5,1,2), C(7,6,0,2), C(7,6,1,2),
+      C(7,7,0,2), C(7,7,1,2), C(7,8,0,2), C(7,8,1,2), C(7,9,0,2), C(7,9,1,2), C(7,10,0,2), C(7,10,1,2),
+      C(7,11,0,2), C(7,11,1,2), C(7,12,0,2), C(7,12,1,2), C(7,13,0,2), C(7,13,1,2), C(7,14,0,2), C(7,14,1,2)}},
+};
+#undef C
+// number of ranked shapes each set needs (opaque, alpha)
+__device__ __constant__ uint8_t kBc7Ranks[4][2] = {{1, 2}, {2, 3}, {4, 7}, {8, 15}};
+
 template <int G>
 __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
 {
+    constexpr int kCandSet = G == 4 ? 0 : (G == 8 ? 1 : (G == 16 ? 2 : 3));
     constexpr int kPerWarp = 32/G;            // blocks a warp encodes at once
     constexpr int kShapes = 64/G;             // partition shapes scored per lane
     __shared__ __align__(16) uint32_t s_px[kTileBc7*16];
@@ -106,10 +131,11 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
             // lanes 0,1: mode 6 (plain / extrapolating variant). Remaining lanes j = l-2:
             //   opaque: rank j/4, (mode 1, mode 3) x (plain, extrapolating) by j%4
             //   alpha : rank j/2, mode 7 x (plain, extrapolating)
-            const uint32_t my_rank = candidate_rank(sub, has_alpha);
+            const uint32_t desc = kBc7Cand[kCandSet][has_alpha ? 1 : 0][sub];
+            const uint32_t my_rank = cand_rank(desc);
             uint32_t my_shape = 0;
             // trip count must be warp-uniform (shuffles inside)
-            const uint32_t need = __any_sync(0xFFFFFFFFu, has_alpha) ? (G - 2 + 1)/2 : (G - 2 + 3)/4;
+            const uint32_t need = __any_sync(0xFFFFFFFFu, has_alpha) ? kBc7Ranks[kCandSet][1] : kBc7Ranks[kCandSet][0];
             for (uint32_t r = 0; r < need; ++r) {
                 uint32_t local = keys[0];
 #pragma unroll
@@ -119,11 +145,11 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
                 for (int jj = 0; jj < kShapes; ++jj) if (keys[jj] == win) keys[jj] = 0xFFFFFFFFu;
                 if (my_rank == r) my_shape = win & 63u;
             }
-            uint32_t mode, m1, variant;
-            candidate_of(sub, has_alpha, my_shape, mode, m1, variant);
+            const uint32_t mode = cand_mode(desc);
+            const uint32_t m1 = mode == 6 ? 0u : kBc7Part2[my_shape];
 
             Fit fit;
-            fit_candidate(bxf, bx, mode, m1, variant, chmask, fit);
+            fit_candidate(bxf, bx, mode, m1, cand_variant(desc), cand_rounds(desc), chmask, fit);
 
             // ---- phase 4: winner
             uint32_t total = fit.err[0] + fit.err[1];
@@ -143,16 +169,16 @@ int launch_bc7(const EncodeParams& p, cudaStream_t stream)
 {
     uint32_t tiles = (p.total_blocks + kTileBc7 - 1)/kTileBc7;
     // lanes per block by quality: more lanes = more (mode, shape) candidates refined per block
-    if (p.quality <= 1) {
-        uint32_t grid = min(tiles, persistent_ctas(reinterpret_cast<const void*>(&bc7_kernel<8>), kThreads));
-        bc7_kernel<8><<<grid, kThreads, 0, stream>>>(p);
-    } else if (p.quality == 2) {
-        uint32_t grid = min(tiles, persistent_ctas(reinterpret_cast<const void*>(&bc7_kernel<16>), kThreads));
-        bc7_kernel<16><<<grid, kThreads, 0, stream>>>(p);
-    } else {
-        uint32_t grid = min(tiles, persistent_ctas(reinterpret_cast<const void*>(&bc7_kernel<32>), kThreads));
-        bc7_kernel<32><<<grid, kThreads, 0, stream>>>(p);
+    const void* k;
+    switch (p.quality) {
+        case 0: case 1: k = reinterpret_cast<const void*>(&bc7_kernel<4>); break;
+        case 2: k = reinterpret_cast<const void*>(&bc7_kernel<8>); break;
+        case 3: k = reinterpret_cast<const void*>(&bc7_kernel<16>); break;
+        default: k = reinterpret_cast<const void*>(&bc7_kernel<32>); break;
     }
+    uint32_t grid = min(tiles, persistent_ctas(k, kThreads));
+    void* args[] = {const_cast<EncodeParams*>(&p)};
+    if (cudaLaunchKernel(k, dim3(grid), dim3(kThreads), args, 0, stream) != cudaSuccess) return -4;
     return 1;
 }
 

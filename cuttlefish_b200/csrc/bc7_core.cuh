@@ -122,22 +122,14 @@ CFX_HD uint32_t score_shape(const float4* bxf, const float* sT, const float* cT,
     return (__float_as_uint(score) & ~63u) | shape;
 }
 
-// Which candidate lane `sub` of a group fits.  Lanes 0,1: mode 6 (plain / extrapolating variant).
-// Remaining lanes j = sub-2:  opaque: rank j/4, (mode 1, mode 3) x (plain, extrapolating) by j%4;
-// alpha: rank j/2, mode 7 x (plain, extrapolating).
-CFX_HD uint32_t candidate_rank(uint32_t sub, bool has_alpha)
-{
-    const uint32_t j = sub >= 2 ? sub - 2 : 0;
-    return sub < 2 ? 0xFFFFFFFFu : (has_alpha ? j >> 1 : j >> 2);
-}
-CFX_HD void candidate_of(uint32_t sub, bool has_alpha, uint32_t shape, uint32_t& mode, uint32_t& m1,
-    uint32_t& variant)
-{
-    const uint32_t j = sub >= 2 ? sub - 2 : 0;
-    if (sub < 2) { mode = 6; m1 = 0; variant = sub; }
-    else if (has_alpha) { mode = 7; m1 = kBc7Part2[shape]; variant = j & 1u; }
-    else { mode = (j & 1u) ? 3u : 1u; m1 = kBc7Part2[shape]; variant = (j >> 1) & 1u; }
-}
+// Candidate descriptor of a lane: mode | rank << 4 | variant << 8 | LS rounds << 12, where rank is
+// the position of the lane's partition shape in the phase-1 ranking (ignored for mode 6), variant 1
+// = "extrapolating" first LS round, and rounds = number of least-squares refinement rounds.
+#define CFX_BC7_CAND(mode, rank, variant, rounds) ((mode) | ((rank) << 4) | ((variant) << 8) | ((rounds) << 12))
+CFX_HD uint32_t cand_mode(uint32_t d) { return d & 15u; }
+CFX_HD uint32_t cand_rank(uint32_t d) { return (d & 15u) == 6u ? 0xFFFFFFFFu : ((d >> 4) & 15u); }
+CFX_HD uint32_t cand_variant(uint32_t d) { return (d >> 8) & 15u; }
+CFX_HD uint32_t cand_rounds(uint32_t d) { return (d >> 12) & 15u; }
 
 // Quantise one float endpoint (0..255 per channel) to tb-bit codes with p-bit p (p = 2: mode has
 // no p-bit), returning the codes packed one per byte and the squared quantisation error.
@@ -267,15 +259,15 @@ CFX_HD void evaluate(const uint32_t* s_x, uint32_t m1, const SubsetEval& s0,
         s.c0 = in1 ? s1.c0 : s0.c0; s.scale = in1 ? s1.scale : s0.scale;
         int dot = dp2a_lo_s16_u8(s.d_rg, x, 0);        // dR*R + dG*G
         dot = dp2a_hi_s16_u8(s.d_ba, x, dot);          // + dB*B + dA*A
-        int k = __float2int_rn(static_cast<float>(dot - s.c0)*s.scale);
+        // nearest index along the endpoint axis, then the neighbour on the side the texel lies on
+        const float t = static_cast<float>(dot - s.c0)*s.scale;
+        int k = __float2int_rn(t);
         k = min(max(k, 0), static_cast<int>(nm1));
-        int ka = max(k - 1, 0), kb = min(k + 1, static_cast<int>(nm1));
+        const int kn = min(max(t > static_cast<float>(k) ? k + 1 : k - 1, 0), static_cast<int>(nm1));
         uint32_t er = entry_error(s, x, index_weight(k, half, recip), chmask);
-        uint32_t era = entry_error(s, x, index_weight(ka, half, recip), chmask);
-        uint32_t erb = entry_error(s, x, index_weight(kb, half, recip), chmask);
+        const uint32_t ern = entry_error(s, x, index_weight(kn, half, recip), chmask);
         uint32_t bk = k;
-        if (era < er) { er = era; bk = ka; }
-        if (erb < er) { er = erb; bk = kb; }
+        if (ern < er) { er = ern; bk = kn; }
         if (in1) e1 += er; else e0 += er;
         sel |= static_cast<uint64_t>(bk) << (4*i);
     }
@@ -310,40 +302,56 @@ CFX_HD void quantize_pair(float4 lo, float4 hi, const ModeInfo& mi, uint32_t& e0
 CFX_HD void quantize_ls(float A, float B, float C, const float* P, const float* Q,
     const float* lo, const float* hi, const ModeInfo& mi, uint32_t& e0, uint32_t& e1)
 {
-    float bestE = 3.4e38f;
-    uint32_t b0 = 0, b1 = 0;
-    const int combos = mi.pmode == 2 ? 2 : 4;
-#pragma unroll 1
-    for (int pc = 0; pc < combos; ++pc) {
-        const uint32_t pl = mi.pmode == 2 ? pc : (pc & 1), ph = mi.pmode == 2 ? pc : (pc >> 1);
-        float E = 0.0f;
-        uint32_t c0 = 0, c1 = 0;
+    // Every mode fitted here has cbits == abits or no alpha at all, so one lattice serves all channels.
+    const uint32_t tb = mi.cbits + 1u;
+    const float scale = static_cast<float>((1u << tb) - 1u)*(1.0f/255.0f);
+    const int qmax = static_cast<int>((1u << mi.cbits) - 1u);
+    const int nch = mi.abits ? 4 : 3;
+    // E[pl + 2 ph] accumulates, over the channels, the best of the 2x2 codes around the optimum
+    float E[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t bits = ch == 3 ? mi.abits : mi.cbits;
-            if (bits == 0) continue;
-            const uint32_t tb = bits + 1u;
-            const float scale = static_cast<float>((1u << tb) - 1u)*(1.0f/255.0f);
-            const int qmax = static_cast<int>((1u << bits) - 1u);
-            // two codes around each optimum, on the lattice of codes with the required parity
-            int ql = static_cast<int>(floorf((fminf(fmaxf(lo[ch], 0.0f), 255.0f)*scale - static_cast<float>(pl))*0.5f));
-            int qh = static_cast<int>(floorf((fminf(fmaxf(hi[ch], 0.0f), 255.0f)*scale - static_cast<float>(ph))*0.5f));
+    for (int ch = 0; ch < 4; ++ch) {
+        if (ch >= nch) continue;
+        const float fl = fminf(fmaxf(lo[ch], 0.0f), 255.0f)*scale, fh = fminf(fmaxf(hi[ch], 0.0f), 255.0f)*scale;
+        // the four codes around each optimum: index = parity*2 + (floor, floor+1)
+        uint32_t lc[4], hc[4];
+        float lb[4], le[4], hv[4], he[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int par = k >> 1;
+            const int ql = static_cast<int>(floorf((fl - static_cast<float>(par))*0.5f)) + (k & 1);
+            const int qh = static_cast<int>(floorf((fh - static_cast<float>(par))*0.5f)) + (k & 1);
+            lc[k] = (static_cast<uint32_t>(min(max(ql, 0), qmax)) << 1) | static_cast<uint32_t>(par);
+            hc[k] = (static_cast<uint32_t>(min(max(qh, 0), qmax)) << 1) | static_cast<uint32_t>(par);
+            const float l = static_cast<float>((lc[k] << (8u - tb)) | (lc[k] >> (2u*tb - 8u)));
+            const float h = static_cast<float>((hc[k] << (8u - tb)) | (hc[k] >> (2u*tb - 8u)));
+            le[k] = l*(A*l - 2.0f*P[ch]); lb[k] = 2.0f*B*l;
+            he[k] = h*(C*h - 2.0f*Q[ch]); hv[k] = h;
+        }
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+            if (mi.pmode == 2 && (pc == 1 || pc == 2)) continue;      // shared p-bit: pl == ph
+            const int pl = pc & 1, ph = pc >> 1;
             float bestc = 3.4e38f;
             uint32_t bl = 0, bh = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                int a = min(max(ql + (k & 1), 0), qmax), b = min(max(qh + (k >> 1), 0), qmax);
-                uint32_t ca = (static_cast<uint32_t>(a) << 1) | pl, cb = (static_cast<uint32_t>(b) << 1) | ph;
-                float l = static_cast<float>((ca << (8u - tb)) | (ca >> (2u*tb - 8u)));
-                float h = static_cast<float>((cb << (8u - tb)) | (cb >> (2u*tb - 8u)));
-                float e = l*(A*l + 2.0f*(B*h - P[ch])) + h*(C*h - 2.0f*Q[ch]);
-                if (e < bestc) { bestc = e; bl = ca; bh = cb; }
+                const int i = pl*2 + (k & 1), j = ph*2 + (k >> 1);
+                const float e = lb[i]*hv[j] + (le[i] + he[j]);
+                if (e < bestc) { bestc = e; bl = lc[i]; bh = hc[j]; }
             }
-            E += bestc;
-            c0 |= bl << (8*ch); c1 |= bh << (8*ch);
+            E[pc] += bestc;
+            c0[pc] |= bl << (8*ch); c1[pc] |= bh << (8*ch);
         }
-        if (E < bestE) { bestE = E; b0 = c0; b1 = c1; }
     }
+    uint32_t b0 = c0[0], b1 = c1[0];
+    float bestE = E[0];
+    if (mi.pmode != 2) {
+        if (E[1] < bestE) { bestE = E[1]; b0 = c0[1]; b1 = c1[1]; }
+        if (E[2] < bestE) { bestE = E[2]; b0 = c0[2]; b1 = c1[2]; }
+    }
+    if (E[3] < bestE) { bestE = E[3]; b0 = c0[3]; b1 = c1[3]; }
     e0 = b0; e1 = b1;
 }
 
@@ -396,7 +404,7 @@ CFX_HD uint32_t flat_fit(uint32_t target, const ModeInfo& mi, uint32_t w, uint32
 
 // The whole fit of one (mode, shape) candidate by one lane.
 CFX_HD void fit_candidate(const float4* s_xf, const uint32_t* s_x, uint32_t mode,
-    uint32_t m1, uint32_t variant, uint32_t chmask, Fit& best)
+    uint32_t m1, uint32_t variant, uint32_t rounds, uint32_t chmask, Fit& best)
 {
     const ModeInfo mi = mode_info(mode);
     const uint32_t ctb = mi.cbits + 1u, atb = mi.abits ? mi.abits + 1u : 0u;
@@ -468,7 +476,7 @@ CFX_HD void fit_candidate(const float4* s_xf, const uint32_t* s_x, uint32_t mode
 
     // ---- least-squares refinement: solve for endpoints given the indices, keep per-subset wins
     uint32_t cur_lo = best.sel_lo, cur_hi = best.sel_hi;
-    for (int round = 0; round < 2; ++round) {
+    for (uint32_t round = 0; round < rounds; ++round) {
         // normal equations per subset: [A B; B C] [lo hi]^T = [P Q]^T
         float AT = 0, BT = 0, CT = 0, A1 = 0, B1 = 0, C1 = 0;
         float PT[4] = {0, 0, 0, 0}, QT[4] = {0, 0, 0, 0}, P1[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0};
@@ -479,7 +487,7 @@ CFX_HD void fit_candidate(const float4* s_xf, const uint32_t* s_x, uint32_t mode
             // variant 1, first round: pull the extreme indices inwards so the solved endpoints
             // extrapolate beyond the texel range (finds the wide-endpoint encodings that make
             // near-flat blocks exact)
-            if (variant == 1 && round == 0) k = min(max(k, 1u), nm1 - 1u);
+            if ((variant & 1u) && round == 0) k = min(max(k, 1u), nm1 - 1u);
             float w = static_cast<float>(index_weight(k, half, recip))*(1.0f/64.0f);
             float iw = 1.0f - w;
             float f = ((m1 >> i) & 1u) ? 1.0f : 0.0f;
@@ -507,7 +515,12 @@ CFX_HD void fit_candidate(const float4* s_xf, const uint32_t* s_x, uint32_t mode
                 lo[ch] = (C*Ps[ch] - B*Qs[ch])*id;
                 hi[ch] = (A*Qs[ch] - B*Ps[ch])*id;
             }
-            quantize_ls(A, B, C, Ps, Qs, lo, hi, mi, n0[s], n1e[s]);
+            // the intermediate rounds only have to produce good indices for the next solve: nearest
+            // endpoint codes are enough there; the last round decides p-bits and rounding exactly
+            if (round + 1 < rounds)
+                quantize_pair(make_float4(lo[0], lo[1], lo[2], lo[3]), make_float4(hi[0], hi[1], hi[2], hi[3]), mi, n0[s], n1e[s]);
+            else
+                quantize_ls(A, B, C, Ps, Qs, lo, hi, mi, n0[s], n1e[s]);
             if (!ok[s]) { n0[s] = best.e0[s]; n1e[s] = best.e1[s]; }
         }
         ev0 = make_eval(n0[0], n1e[0], ctb, atb, nm1);

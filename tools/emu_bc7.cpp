@@ -11,7 +11,8 @@ using namespace cfx;
 using namespace cfx::bc7;
 
 extern "C" int emu_bc7_encode(const uint8_t* rgba, uint32_t w, uint32_t h, uint8_t* out, int G,
-    uint32_t color_mask, uint32_t* dbg /* per block: mode, shape, variant, err */)
+    uint32_t color_mask, uint32_t* dbg /* per block: mode, shape, variant, err */,
+    const uint16_t* cand_opaque, const uint16_t* cand_alpha)
 {
     uint32_t bxn = (w + 3)/4, byn = (h + 3)/4;
     uint32_t chmask = 0;
@@ -45,12 +46,13 @@ extern "C" int emu_bc7_encode(const uint8_t* rgba, uint32_t w, uint32_t h, uint8
             uint4 best_blk = make_uint4(0, 0, 0, 0);
             uint32_t bm = 0, bs = 0, bv = 0, be = 0;
             for (uint32_t sub = 0; sub < uint32_t(G); ++sub) {
-                uint32_t rank = candidate_rank(sub, has_alpha);
+                uint32_t desc = has_alpha ? cand_alpha[sub] : cand_opaque[sub];
+                uint32_t rank = cand_rank(desc);
                 uint32_t shape = rank == 0xFFFFFFFFu ? 0 : (keys[rank] & 63u);
-                uint32_t mode, m1, variant;
-                candidate_of(sub, has_alpha, shape, mode, m1, variant);
+                uint32_t mode = cand_mode(desc), variant = cand_variant(desc);
+                uint32_t m1 = mode == 6 ? 0u : kBc7Part2[shape];
                 Fit fit;
-                fit_candidate(pxf, px, mode, m1, variant, chmask, fit);
+                fit_candidate(pxf, px, mode, m1, variant, cand_rounds(desc), chmask, fit);
                 uint32_t total = fit.err[0] + fit.err[1];
                 uint32_t key = (std::min(total, 0x03FFFFFFu) << 5) | sub;
                 if (key < best_key) {
