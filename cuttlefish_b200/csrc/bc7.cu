@@ -31,6 +31,8 @@ using namespace bc7;
 namespace {
 
 constexpr int kTileBc7 = 64;
+constexpr int kPxStride = 20;     // words per block in s_px: blocks of one warp land in different banks
+constexpr int kPxfStride = 17;    // float4 per block in s_pxf, same reason
 
 template <int G>
 __device__ __forceinline__ uint32_t group_min(uint32_t v)
@@ -72,8 +74,8 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
     constexpr int kCandSet = G == 4 ? 0 : (G == 8 ? 1 : (G == 16 ? 2 : 3));
     constexpr int kPerWarp = 32/G;            // blocks a warp encodes at once
     constexpr int kShapes = 64/G;             // partition shapes scored per lane
-    __shared__ __align__(16) uint32_t s_px[kTileBc7*16];
-    __shared__ __align__(16) float4 s_pxf[kTileBc7*16];
+    __shared__ __align__(16) uint32_t s_px[kTileBc7*kPxStride];
+    __shared__ __align__(16) float4 s_pxf[kTileBc7*kPxfStride];
     __shared__ __align__(16) uint32_t s_out[kTileBc7*4];
 
     const uint32_t lane = lane_id();
@@ -87,19 +89,19 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
         const uint32_t first = tile*kTileBc7;
         const uint32_t n = min(static_cast<uint32_t>(kTileBc7), p.total_blocks - first);
         __syncthreads();
-        stage_tile_u8(s_px, p, first, n);
+        stage_tile_u8(s_px, p, first, n, kPxStride);
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < n*16; i += blockDim.x) {
-            uint32_t x = s_px[i];
-            s_pxf[i] = make_float4(static_cast<float>(x & 0xFF), static_cast<float>((x >> 8) & 0xFF),
+            uint32_t x = s_px[(i >> 4)*kPxStride + (i & 15)];
+            s_pxf[(i >> 4)*kPxfStride + (i & 15)] = make_float4(static_cast<float>(x & 0xFF), static_cast<float>((x >> 8) & 0xFF),
                 static_cast<float>((x >> 16) & 0xFF), static_cast<float>(x >> 24));
         }
         __syncthreads();
 
         for (uint32_t b0 = warp_id()*kPerWarp; b0 < n; b0 += kWarps*kPerWarp) {
             const uint32_t b = min(b0 + grp, n - 1);     // idle groups redo the last block, unstored
-            const uint32_t* bx = s_px + b*16;
-            const float4* bxf = s_pxf + b*16;
+            const uint32_t* bx = s_px + b*kPxStride;
+            const float4* bxf = s_pxf + b*kPxfStride;
 
             // block-level facts
             uint32_t amin = 255;

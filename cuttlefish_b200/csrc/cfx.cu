@@ -87,8 +87,12 @@ static Launcher find_launcher(uint32_t format, uint32_t type)
 #endif
         default:
 #ifdef CFX_HAVE_ASTC
-            if (format >= CFX_FORMAT_ASTC_4x4 && format <= CFX_FORMAT_ASTC_12x12)
-                return type == CFX_TYPE_UNORM ? launch_astc : nullptr;
+            // LDR footprints of up to 64 texels (4x4 ... 8x8, 10x5, 10x6); the four larger ones and the
+            // HDR profiles have no GPU encoder yet
+            if (format >= CFX_FORMAT_ASTC_4x4 && format <= CFX_FORMAT_ASTC_12x12) {
+                const uint32_t* d = kAstcDims[format - CFX_FORMAT_ASTC_4x4];
+                return (type == CFX_TYPE_UNORM && d[0]*d[1] <= 64) ? launch_astc : nullptr;
+            }
 #endif
             return nullptr;
     }

@@ -82,8 +82,10 @@ __device__ __forceinline__ uint32_t load_texel_u8(const EncodeParams& p, uint32_
 // Stage the RGBA8 view of `nblocks` consecutive 4x4 blocks (linear block index first..first+n)
 // into shared memory: s_px[b*16 + r*4 + c].  Work item = (texel row r, block b) so that
 // consecutive threads read consecutive 16-byte pieces of the same image row.
+// `stride` = words between consecutive blocks in s_px (a multiple of 4; 20 keeps the 4 or 8 blocks a
+// warp works on at once in different banks).
 __device__ __forceinline__ void stage_tile_u8(uint32_t* s_px, const EncodeParams& p, uint32_t first,
-    uint32_t nblocks)
+    uint32_t nblocks, uint32_t stride = 16)
 {
     for (uint32_t i = threadIdx.x; i < nblocks*4; i += blockDim.x) {
         uint32_t r = i / nblocks, b = i - r*nblocks;
@@ -101,7 +103,7 @@ __device__ __forceinline__ void stage_tile_u8(uint32_t* s_px, const EncodeParams
             v.z = load_texel_u8(p, min(x0 + 2, xm), y);
             v.w = load_texel_u8(p, min(x0 + 3, xm), y);
         }
-        *reinterpret_cast<uint4*>(s_px + b*16 + r*4) = v;
+        *reinterpret_cast<uint4*>(s_px + b*stride + r*4) = v;
     }
 }
 

@@ -82,3 +82,39 @@ def test_bc7_solid_blocks_exact(cfx, oracle):
     img = oracle.to_rgba8(img).astype(np.float32) / np.float32(255)
     p_gpu, p_ref = _psnr_pair(cfx, oracle, "BC7", img)
     assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
+
+
+ASTC_FORMATS = ["ASTC_4x4", "ASTC_5x5", "ASTC_6x6", "ASTC_8x8", "ASTC_10x6"]
+
+
+@pytest.mark.parametrize("fmt", ASTC_FORMATS)
+@pytest.mark.parametrize("kind,w,h", [("noise+grad", 240, 240), ("gradient", 240, 240), ("noise+grad", 97, 61)])
+def test_astc_psnr_vs_oracle(cfx, oracle, fmt, kind, w, h):
+    if not cfx.format_supported(fmt):
+        pytest.fail("%s encoder missing from libcfx.so" % fmt)
+    img = oracle.gen_image(kind, w, h, seed=31)
+    p_gpu, p_ref = _psnr_pair(cfx, oracle, fmt, img)
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s %s: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, kind, p_gpu, p_ref)
+
+
+def test_astc_float_source_and_constant_blocks(cfx, oracle):
+    # RGBA32F source path + void-extent blocks (flat colour) decode exactly
+    img = np.zeros((24, 24, 4), np.float32)
+    img[..., 3] = 1.0
+    img[:12, :, 0] = 0.25
+    img[12:, :, 1] = 200 / 255.0
+    got = cfx.encode(img, "ASTC_6x6")
+    dec = oracle.decode(got, "ASTC_6x6", 24, 24)
+    assert np.abs(dec - img).max() < 1.5 / 255.0
+    ref = oracle.decode(oracle.encode(img, "ASTC_6x6"), "ASTC_6x6", 24, 24)
+    assert oracle.psnr_rgb(img, dec) >= oracle.psnr_rgb(img, ref) - PSNR_TOLERANCE_DB
+
+
+def test_astc_alpha_psnr_vs_oracle(cfx, oracle):
+    src, blocks, fmt, kw = load_golden("ASTC_6x6_alpha_32x32")
+    img = src_as_float(src)
+    got = cfx.encode(src, "ASTC_6x6")
+    mse = lambda d: float(np.mean((d.astype(np.float64) - img) ** 2))
+    p_gpu = 10*np.log10(1/mse(oracle.decode(got, "ASTC_6x6", 32, 32)))
+    p_ref = 10*np.log10(1/mse(oracle.decode(blocks, "ASTC_6x6", 32, 32)))
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "RGBA PSNR gpu %.3f ref %.3f" % (p_gpu, p_ref)
