@@ -1,0 +1,65 @@
+// BC6H UFloat kernel: ONE LANE OWNS ONE 4x4 BLOCK (bc6h_core.cuh); a warp encodes 32 consecutive
+// blocks, so a warp's texel loads walk 32 x 32 contiguous bytes of each image row (RGBA16F) and its
+// 32 x 16 output bytes are one contiguous 512-byte store.  Texels are converted to the decoder's
+// unquantised integer domain (half bits x 64/31) once and kept in shared memory, lane-interleaved.
+//
+// Replaces Bc6HConverter::compressBlock (lib/src/S3tcConverter.cpp:549-590) for Type::UFloat.
+#include "bc6h_core.cuh"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cfx {
+
+namespace {
+constexpr int kBc6Warps = 4;
+
+__device__ __forceinline__ float half_bits_to_domain(uint32_t h)
+{
+    if (h & 0x8000u) return 0.0f;                 // unsigned format: negatives clamp to 0
+    if (h > 0x7BFFu) h = 0x7BFFu;                 // inf / nan -> largest finite half
+    return static_cast<float>(h)*(64.0f/31.0f);
+}
+} // namespace
+
+__global__ void __launch_bounds__(kBc6Warps*32) bc6h_kernel(const EncodeParams p)
+{
+    __shared__ float s_x[kBc6Warps][16*3*32];
+    const uint32_t lane = lane_id(), warp = warp_id();
+    float* xs = s_x[warp];
+    const uint32_t groups = (p.total_blocks + 31)/32;
+    for (uint32_t grp = blockIdx.x*kBc6Warps + warp; grp < groups; grp += gridDim.x*kBc6Warps) {
+        const uint32_t blk = grp*32 + lane;
+        const bool live = blk < p.total_blocks;
+        const uint32_t b = live ? blk : p.total_blocks - 1;
+        const uint32_t by = b / p.blocks_x, bx = b - by*p.blocks_x;
+        for (uint32_t t = 0; t < 16; ++t) {
+            const uint32_t x = min(bx*4 + (t & 3), p.width - 1), y = min(by*4 + (t >> 2), p.height - 1);
+            uint32_t hr, hg, hb;
+            const uint8_t* row = p.src + static_cast<uint64_t>(y)*p.pitch;
+            if (p.src_format == SRC_RGBA16F) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(row) + x);
+                hr = v.x & 0xFFFFu; hg = v.x >> 16; hb = v.y & 0xFFFFu;
+            } else {
+                const float4 f = load_texel_f32(p, x, y);
+                hr = __half_as_ushort(__float2half_rn(f.x)); hg = __half_as_ushort(__float2half_rn(f.y));
+                hb = __half_as_ushort(__float2half_rn(f.z));
+            }
+            bc6h::px(xs, lane, t, 0) = (p.color_mask & 1u) ? half_bits_to_domain(hr) : 0.0f;
+            bc6h::px(xs, lane, t, 1) = (p.color_mask & 2u) ? half_bits_to_domain(hg) : 0.0f;
+            bc6h::px(xs, lane, t, 2) = (p.color_mask & 4u) ? half_bits_to_domain(hb) : 0.0f;
+        }
+        const uint4 out = bc6h::encode_block(xs, lane, p.quality);
+        if (live) reinterpret_cast<uint4*>(p.dst)[blk] = out;
+    }
+}
+
+int launch_bc6h(const EncodeParams& p, cudaStream_t stream)
+{
+    const uint32_t groups = (p.total_blocks + 31)/32;
+    const uint32_t ctas = (groups + kBc6Warps - 1)/kBc6Warps;
+    const uint32_t grid = min(ctas, persistent_ctas(reinterpret_cast<const void*>(&bc6h_kernel), kBc6Warps*32));
+    bc6h_kernel<<<grid, kBc6Warps*32, 0, stream>>>(p);
+    return 1;
+}
+
+} // namespace cfx

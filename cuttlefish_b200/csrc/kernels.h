@@ -12,5 +12,6 @@ uint32_t persistent_ctas(const void* kernel, int threads, size_t dyn_smem = 0);
 int launch_bc45(const EncodeParams& p, cudaStream_t stream);
 int launch_bc7(const EncodeParams& p, cudaStream_t stream);
 int launch_astc(const EncodeParams& p, cudaStream_t stream);
+int launch_bc6h(const EncodeParams& p, cudaStream_t stream);
 
 } // namespace cfx

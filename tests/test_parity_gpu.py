@@ -118,3 +118,29 @@ def test_astc_alpha_psnr_vs_oracle(cfx, oracle):
     p_gpu = 10*np.log10(1/mse(oracle.decode(got, "ASTC_6x6", 32, 32)))
     p_ref = 10*np.log10(1/mse(oracle.decode(blocks, "ASTC_6x6", 32, 32)))
     assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "RGBA PSNR gpu %.3f ref %.3f" % (p_gpu, p_ref)
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (97, 61)])
+def test_bc6h_psnr_vs_oracle(cfx, oracle, w, h):
+    if not cfx.format_supported("BC6H", "UFloat"):
+        pytest.fail("BC6H encoder missing from libcfx.so")
+    img = oracle.gen_image("hdr", w, h)
+    img16 = img.astype(np.float16)
+    imgf = img16.astype(np.float32)
+    ref = oracle.encode(imgf, "BC6H", type="UFloat")
+    p_ref = oracle.psnr_rgb(imgf, oracle.decode(ref, "BC6H", w, h, type="UFloat"), 64.0)
+    for src in (img16, imgf):                      # RGBA16F and RGBA32F source paths
+        got = cfx.encode(src, "BC6H", type="UFloat")
+        p_gpu = oracle.psnr_rgb(imgf, oracle.decode(got, "BC6H", w, h, type="UFloat"), 64.0)
+        assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "BC6H: gpu %.3f dB < reference %.3f dB - 0.1" % (p_gpu, p_ref)
+
+
+def test_bc6h_golden_inputs(cfx, oracle):
+    for name in golden_cases(["BC6H"]):
+        src, blocks, fmt, kw = load_golden(name)
+        h, w, _ = src.shape
+        imgf = src.astype(np.float32)
+        got = cfx.encode(src, "BC6H", **kw)
+        p_gpu = oracle.psnr_rgb(imgf, oracle.decode(got, "BC6H", w, h, **kw), 64.0)
+        p_ref = oracle.psnr_rgb(imgf, oracle.decode(blocks, "BC6H", w, h, **kw), 64.0)
+        assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
