@@ -25,7 +25,7 @@ UNITS = [
     ("cfx.cu", [], None),
     ("bc4_bc5.cu", [], None),
     ("bc7.cu", [], "CFX_HAVE_BC7"),
-    ("bc1_bc3.cu", ["-fmad=false"], "CFX_HAVE_BC1"),
+    ("bc1_bc3.cu", [], "CFX_HAVE_BC1"),
     ("etc.cu", ["-fmad=false"], "CFX_HAVE_ETC"),
     ("bc6h.cu", [], "CFX_HAVE_BC6H"),
     ("astc.cu", [], "CFX_HAVE_ASTC"),

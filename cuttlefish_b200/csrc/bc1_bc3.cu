@@ -1,0 +1,108 @@
+// BC1_RGB / BC1_RGBA / BC2 / BC3 kernels.  A warp owns 32 consecutive blocks: it stages their
+// texels in shared memory with 16-byte row loads (32 lanes x 16 B = 512 contiguous bytes per image
+// row), every LANE encodes the colour half of ITS block (bc1_core.cuh), and for BC3 the warp then
+// walks the 32 blocks cooperatively for the alpha half with the exact BC4 search of bc4_device.cuh
+// (bit-identical to rgbcx::encode_bc4_hq, as Bc3Converter uses it through encode_bc3_hq).
+//
+// Replaces Bc1Converter / Bc1AConverter / Bc2Converter / Bc3Converter::compressBlock,
+// lib/src/S3tcConverter.cpp:263-376.  Colour halves: PSNR parity (see bc1_core.cuh); BC3/BC2 alpha
+// halves: bit-exact (rgbcx.cpp:2730-2884; packBc2Alpha, S3tcConverter.cpp:131-143).
+#include "bc1_core.cuh"
+#include "bc4_device.cuh"
+#include "kernels.h"
+
+namespace cfx {
+
+namespace {
+constexpr int kBc1Warps = 8;
+constexpr int kBlkStride = 20;     // words per block in shared memory (16 texels + pad: no bank conflicts)
+}
+
+template <int FORMAT>   // 29 BC1_RGB, 30 BC1_RGBA, 31 BC2, 32 BC3
+__global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams p, int descent, uint32_t radius, uint32_t hq)
+{
+    __shared__ __align__(16) uint32_t s_px[kBc1Warps][32*kBlkStride];
+    const uint32_t lane = lane_id(), warp = warp_id();
+    uint32_t* sp = s_px[warp];
+    const uint32_t groups = (p.total_blocks + 31)/32;
+    for (uint32_t grp = blockIdx.x*kBc1Warps + warp; grp < groups; grp += gridDim.x*kBc1Warps) {
+        const uint32_t first = grp*32;
+        const uint32_t nblk = min(32u, p.total_blocks - first);
+        __syncwarp();
+        // stage: row r of block (first + lane)
+        {
+            const uint32_t blk = min(first + lane, p.total_blocks - 1);
+            const uint32_t by = blk / p.blocks_x, bx = blk - by*p.blocks_x;
+#pragma unroll
+            for (uint32_t r = 0; r < 4; ++r) {
+                const uint32_t y = min(by*4 + r, p.height - 1), x0 = bx*4;
+                uint4 v;
+                if (p.src_format == SRC_RGBA8 && p.aligned16 && x0 + 3 < p.width) {
+                    v = __ldg(reinterpret_cast<const uint4*>(p.src + static_cast<uint64_t>(y)*p.pitch) + bx);
+                } else {
+                    const uint32_t xm = p.width - 1;
+                    v.x = load_texel_u8(p, min(x0, xm), y); v.y = load_texel_u8(p, min(x0 + 1, xm), y);
+                    v.z = load_texel_u8(p, min(x0 + 2, xm), y); v.w = load_texel_u8(p, min(x0 + 3, xm), y);
+                }
+                *reinterpret_cast<uint4*>(sp + lane*kBlkStride + r*4) = v;
+            }
+        }
+        __syncwarp();
+        uint32_t px[16];
+        uint32_t keep = 0xFF000000u;
+        if (p.color_mask & 1u) keep |= 0xFFu;
+        if (p.color_mask & 2u) keep |= 0xFF00u;
+        if (p.color_mask & 4u) keep |= 0xFF0000u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) px[i] = sp[lane*kBlkStride + i] & keep;
+        uint32_t flags = 0;
+        if (FORMAT == 29) flags = bc1::kAllow3 | bc1::kAllowBlack;
+        if (FORMAT == 30) flags = bc1::kAllow3 | bc1::kPunchThrough;
+        const uint2 color = bc1::encode_color_block(px, flags, descent);
+        if (FORMAT == 29 || FORMAT == 30) {
+            if (lane < nblk) reinterpret_cast<uint2*>(p.dst)[first + lane] = color;
+        } else if (FORMAT == 31) {
+            // explicit 4-bit alpha: round(a * 15/255), half away from zero (packBc2Alpha)
+            uint32_t a_lo = 0, a_hi = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t a = (p.color_mask & 8u) ? (px[i] >> 24) : 0u;
+                const uint32_t q = static_cast<uint32_t>(roundf(__fmul_rn(static_cast<float>(a), 15.0f/255.0f))) & 15u;
+                if (i < 8) a_lo |= q << (4*i); else a_hi |= q << (4*(i - 8));
+            }
+            if (lane < nblk) reinterpret_cast<uint4*>(p.dst)[first + lane] = make_uint4(a_lo, a_hi, color.x, color.y);
+        } else {
+            uint2 mine = make_uint2(0, 0);
+            for (uint32_t b = 0; b < nblk; ++b) {
+                const uint2 a = bc4_encode_warp(sp + b*kBlkStride, 3, radius, hq != 0);
+                if (b == lane) mine = a;
+            }
+            if (!(p.color_mask & 8u)) mine = make_uint2(0, 0);
+            if (lane < nblk) reinterpret_cast<uint4*>(p.dst)[first + lane] = make_uint4(mine.x, mine.y, color.x, color.y);
+        }
+    }
+}
+
+int launch_bc123(const EncodeParams& p, cudaStream_t stream)
+{
+    static const uint32_t radii[5] = {3, 3, 5, 16, 32};   // getSearchRadius, S3tcConverter.cpp:80-95
+    static const int descents[5] = {0, 1, 2, 3, 4};
+    const uint32_t radius = radii[p.quality], hq = p.quality > 1;
+    const int descent = descents[p.quality];
+    const uint32_t groups = (p.total_blocks + 31)/32;
+    const uint32_t ctas = (groups + kBc1Warps - 1)/kBc1Warps;
+    const void* k;
+    switch (p.format) {
+        case 29: k = reinterpret_cast<const void*>(&bc123_kernel<29>); break;
+        case 30: k = reinterpret_cast<const void*>(&bc123_kernel<30>); break;
+        case 31: k = reinterpret_cast<const void*>(&bc123_kernel<31>); break;
+        default: k = reinterpret_cast<const void*>(&bc123_kernel<32>); break;
+    }
+    const uint32_t grid = min(ctas, persistent_ctas(k, kBc1Warps*32));
+    void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&descent), const_cast<uint32_t*>(&radius),
+        const_cast<uint32_t*>(&hq)};
+    if (cudaLaunchKernel(k, dim3(grid), dim3(kBc1Warps*32), args, 0, stream) != cudaSuccess) return -4;
+    return 1;
+}
+
+} // namespace cfx

@@ -144,3 +144,39 @@ def test_bc6h_golden_inputs(cfx, oracle):
         p_gpu = oracle.psnr_rgb(imgf, oracle.decode(got, "BC6H", w, h, **kw), 64.0)
         p_ref = oracle.psnr_rgb(imgf, oracle.decode(blocks, "BC6H", w, h, **kw), 64.0)
         assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
+
+
+# ---- BC1 family: colour halves PSNR parity (own search, see bc1_core.cuh), alpha halves bit-exact ----
+@pytest.mark.parametrize("fmt", ["BC1_RGB", "BC1_RGBA", "BC2", "BC3"])
+@pytest.mark.parametrize("kind,w,h", [("noise+grad", 256, 256), ("gradient", 512, 512), ("gradient", 1024, 256), ("noise+grad", 97, 61)])
+def test_bc123_psnr_vs_oracle(cfx, oracle, fmt, kind, w, h):
+    if not cfx.format_supported(fmt):
+        pytest.fail("%s encoder missing from libcfx.so" % fmt)
+    img = oracle.gen_image(kind, w, h, seed=17)
+    p_gpu, p_ref = _psnr_pair(cfx, oracle, fmt, img)
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s %s: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, kind, p_gpu, p_ref)
+
+
+@pytest.mark.parametrize("fmt", ["BC2", "BC3"])
+def test_bc23_alpha_half_bit_exact(cfx, oracle, fmt):
+    src, blocks, _, kw = load_golden("%s_alpha_32x32" % fmt)
+    got = cfx.encode(src, fmt, **kw).reshape(-1, 16)
+    assert np.array_equal(got[:, :8], blocks.reshape(-1, 16)[:, :8]), "%s alpha bytes differ from the reference" % fmt
+    img = src_as_float(src)
+    mse = lambda d: float(np.mean((d.astype(np.float64) - img) ** 2))
+    p_gpu = 10*np.log10(1/mse(oracle.decode(got.ravel(), fmt, 32, 32)))
+    p_ref = 10*np.log10(1/mse(oracle.decode(blocks, fmt, 32, 32)))
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
+
+
+def test_bc1_rgba_punch_through(cfx, oracle):
+    src, blocks, _, kw = load_golden("BC1_RGBA_alpha_32x32")
+    got = cfx.encode(src, "BC1_RGBA", **kw)
+    d_gpu = oracle.decode(got, "BC1_RGBA", 32, 32)
+    d_ref = oracle.decode(blocks, "BC1_RGBA", 32, 32)
+    # the same texels are transparent, and the opaque ones are as close to the source as the reference's
+    assert np.array_equal(d_gpu[..., 3] < 0.5, src[..., 3] < 128)
+    opaque = src[..., 3] >= 128
+    img = src_as_float(src)
+    e = lambda d: float(np.mean((d[opaque][:, :3].astype(np.float64) - img[opaque][:, :3]) ** 2))
+    assert 10*np.log10(1/e(d_gpu)) >= 10*np.log10(1/e(d_ref)) - PSNR_TOLERANCE_DB
