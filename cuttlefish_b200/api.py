@@ -125,6 +125,31 @@ def encode(img, fmt, out=None, **kw):
     return out[:n]
 
 
+def encode_batch(images, fmt, **kw):
+    """Encode several HOST surfaces (a mip chain / array layers) with one cfx_encode_batch call.
+    Returns a list of uint8 arrays, one per surface."""
+    lib = load()
+    imgs, descs, outs = [], [], []
+    for img in images:
+        img = np.ascontiguousarray(np.asarray(img))
+        if img.ndim != 3 or img.shape[2] != 4:
+            raise ValueError("expected [H,W,4] RGBA texels")
+        h, w, _ = img.shape
+        src_format, texel = _src_format_of(img.dtype)
+        d = make_desc(fmt, w, h, src_format, w * texel, **kw)
+        n = int(lib.cfx_encoded_size(ctypes.byref(d)))
+        if n == 0:
+            raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
+        imgs.append(img); descs.append(d); outs.append(np.empty(n, dtype=np.uint8))
+    n = len(imgs)
+    c_descs = (SurfaceDesc * n)(*descs)
+    c_srcs = (ctypes.c_void_p * n)(*[im.ctypes.data for im in imgs])
+    c_dsts = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+    c_sizes = (ctypes.c_size_t * n)(*[o.size for o in outs])
+    _check(lib.cfx_encode_batch(n, c_descs, c_srcs, c_dsts, c_sizes))
+    return outs
+
+
 def encode_device(src, fmt, out=None, stream=None, **kw):
     """Encode a torch CUDA tensor [H,W,4] (uint8/float16/float32) into a CUDA uint8 tensor,
     asynchronously on `stream` (default: torch's current stream). Goes through cfx_encode_device."""
@@ -204,14 +229,11 @@ class Texture:
         if not format_supported(format, type):
             return False
         mask = colorMask if colorMask is not None else ColorMask()
-        data = []
-        for level in self._images:
-            row = []
-            for image in level:
-                row.append(encode(image, format, type=type, quality=quality, alpha=alphaType, color_mask=mask,
-                                  srgb=self.srgb))
-            data.append(row)
-        self._data = data
+        # one batch for every surface of the texture (the mip/depth loop of Converter::convert)
+        flat = [image for level in self._images for image in level]
+        outs = encode_batch(flat, format, type=type, quality=quality, alpha=alphaType, color_mask=mask, srgb=self.srgb)
+        it = iter(outs)
+        self._data = [[next(it) for _ in level] for level in self._images]
         self._images = None
         self.format, self.type = format, type
         return True

@@ -1,0 +1,71 @@
+// ETC1 / ETC2 RGB / ETC2 RGBA8 kernels: ONE LANE OWNS ONE 4x4 BLOCK (etc_core.cuh); a warp encodes
+// 32 consecutive blocks, so its texel loads walk contiguous bytes of each image row and its output
+// is one contiguous store.  Texels are kept as floats (0..255) in shared memory, lane-interleaved:
+// like the reference (lib/src/EtcConverter.cpp:145, float RGBA into Etc::Image) the encoder sees
+// unquantised values when the source is RGBA16F / RGBA32F.
+//
+// Replaces EtcConverter::process, lib/src/EtcConverter.cpp:120-152, for ETC1, ETC2_R8G8B8 and
+// ETC2_R8G8B8A8.
+#include "common.cuh"
+#include "etc_core.cuh"
+#include "kernels.h"
+
+namespace cfx {
+
+namespace { constexpr int kEtcWarps = 4; }
+
+template <int FORMAT>   // 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8
+__global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p, int rounds, int alpha_radius)
+{
+    __shared__ float s_x[kEtcWarps][16*4*32];
+    const uint32_t lane = lane_id(), warp = warp_id();
+    float* xs = s_x[warp];
+    const uint32_t groups = (p.total_blocks + 31)/32;
+    for (uint32_t grp = blockIdx.x*kEtcWarps + warp; grp < groups; grp += gridDim.x*kEtcWarps) {
+        const uint32_t blk = grp*32 + lane;
+        const bool live = blk < p.total_blocks;
+        const uint32_t b = live ? blk : p.total_blocks - 1;
+        const uint32_t by = b / p.blocks_x, bx = b - by*p.blocks_x;
+        for (uint32_t t = 0; t < 16; ++t) {
+            const uint32_t x = min(bx*4 + (t & 3), p.width - 1), y = min(by*4 + (t >> 2), p.height - 1);
+            float4 v;
+            if (p.src_format == SRC_RGBA8) {
+                const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(p.src + static_cast<uint64_t>(y)*p.pitch) + x);
+                v = make_float4(static_cast<float>(q & 0xFF), static_cast<float>((q >> 8) & 0xFF), static_cast<float>((q >> 16) & 0xFF),
+                    static_cast<float>(q >> 24));
+            } else {
+                const float4 f = load_texel_f32(p, x, y);
+                v = make_float4(fminf(fmaxf(f.x, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.y, 0.0f), 1.0f)*255.0f,
+                    fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
+            }
+            etc::px(xs, lane, t, 0) = (p.color_mask & 1u) ? v.x : 0.0f;
+            etc::px(xs, lane, t, 1) = (p.color_mask & 2u) ? v.y : 0.0f;
+            etc::px(xs, lane, t, 2) = (p.color_mask & 4u) ? v.z : 0.0f;
+            etc::px(xs, lane, t, 3) = (p.color_mask & 8u) ? (p.alpha_type == 0 ? 255.0f : v.w) : 0.0f;
+        }
+        const uint2 color = etc::encode_color(xs, lane, FORMAT != 37, rounds);
+        if (FORMAT == 40) {
+            const uint2 alpha = etc::encode_eac_alpha(xs, lane, alpha_radius);
+            if (live) reinterpret_cast<uint4*>(p.dst)[blk] = make_uint4(alpha.x, alpha.y, color.x, color.y);
+        } else {
+            if (live) reinterpret_cast<uint2*>(p.dst)[blk] = color;
+        }
+    }
+}
+
+int launch_etc(const EncodeParams& p, cudaStream_t stream)
+{
+    static const int rounds_by_quality[5] = {0, 1, 1, 2, 3};
+    static const int radius_by_quality[5] = {0, 1, 2, 3, 4};
+    const int rounds = rounds_by_quality[p.quality], radius = radius_by_quality[p.quality];
+    const uint32_t groups = (p.total_blocks + 31)/32;
+    const uint32_t ctas = (groups + kEtcWarps - 1)/kEtcWarps;
+    const void* k = p.format == 37 ? reinterpret_cast<const void*>(&etc_kernel<37>) :
+        (p.format == 38 ? reinterpret_cast<const void*>(&etc_kernel<38>) : reinterpret_cast<const void*>(&etc_kernel<40>));
+    const uint32_t grid = min(ctas, persistent_ctas(k, kEtcWarps*32));
+    void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&rounds), const_cast<int*>(&radius)};
+    if (cudaLaunchKernel(k, dim3(grid), dim3(kEtcWarps*32), args, 0, stream) != cudaSuccess) return -4;
+    return 1;
+}
+
+} // namespace cfx

@@ -1,0 +1,496 @@
+// Lane-local ETC1 / ETC2 RGB / ETC2 RGBA8 (EAC alpha) encoder: ONE LANE OWNS ONE BLOCK.
+//
+// PARITY STATUS: our own search, held to "RGB(A) PSNR >= reference - 0.1 dB" against etc2comp as
+// EtcConverter::process drives it (lib/src/EtcConverter.cpp:120-152: one Etc::Image::Encode per
+// block; at Quality::Normal only encoding iteration 0 runs, lib/etc2comp/EtcLib/Etc/EtcImage.cpp:282).
+// It is NOT bit-identical to etc2comp's float pipeline (Block4x4Encoding_ETC1::PerformFirstIteration,
+// EtcBlock4x4Encoding_ETC1.cpp:311-338); see DESIGN.md.
+//
+// Search: both flips x {differential 555+333, individual 444+444}, each half fitted by a +-1
+// descent around its mean over all 8 modifier tables with exact decoded error; ETC2 adds the planar
+// mode (least-squares plane per channel, 676 quantisation, +-1 descent) and the T / H modes
+// (two-colour clustering); EAC alpha searches table x multiplier x base around the block's range.
+// Compiles for the device and, through hostdev.h, for tools/emu_etc.cpp.
+#pragma once
+#include "hostdev.h"
+
+namespace cfx {
+namespace etc {
+
+CFX_CONST int16_t kMod[8][2] = {{2, 8}, {5, 17}, {9, 29}, {13, 42}, {18, 60}, {24, 80}, {33, 106}, {47, 183}};
+CFX_CONST uint8_t kDist[8] = {3, 6, 11, 16, 23, 32, 41, 64};
+CFX_CONST int8_t kEac[16][8] = {
+    {-3, -6, -9, -15, 2, 5, 8, 14}, {-3, -7, -10, -13, 2, 6, 9, 12}, {-2, -5, -8, -13, 1, 4, 7, 12}, {-2, -4, -6, -13, 1, 3, 5, 12},
+    {-3, -6, -8, -12, 2, 5, 7, 11}, {-3, -7, -9, -11, 2, 6, 8, 10}, {-4, -7, -8, -11, 3, 6, 7, 10}, {-3, -5, -8, -11, 2, 4, 7, 10},
+    {-2, -6, -8, -10, 1, 5, 7, 9}, {-2, -5, -8, -10, 1, 4, 7, 9}, {-2, -4, -8, -10, 1, 3, 7, 9}, {-2, -5, -7, -10, 1, 4, 6, 9},
+    {-3, -4, -7, -10, 2, 3, 6, 9}, {-1, -2, -3, -10, 0, 1, 2, 9}, {-4, -6, -8, -9, 3, 5, 7, 8}, {-3, -5, -7, -9, 2, 4, 6, 8}};
+
+// texel t = y*4 + x, channel c (0..3), values 0..255 as floats
+CFX_HD float& px(float* xs, uint32_t lane, uint32_t t, uint32_t c) { return xs[(t*4u + c)*32u + lane]; }
+
+CFX_HD int clamp255(int v) { return min(max(v, 0), 255); }
+CFX_HD int expand5(int v) { return (v << 3) | (v >> 2); }
+CFX_HD int expand4(int v) { return (v << 4) | v; }
+CFX_HD int expand6(int v) { return (v << 2) | (v >> 4); }
+CFX_HD int expand7(int v) { return (v << 1) | (v >> 6); }
+
+struct HalfFit { float err; uint32_t table; uint32_t sel; };   // sel: 2 bits per texel t (only the half's texels)
+
+// Best modifier table and selectors of one half (texel mask) for an 8-bit base colour.
+CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out)
+{
+    out.err = 3.0e38f; out.table = 0; out.sel = 0;
+#pragma unroll 1
+    for (uint32_t tb = 0; tb < 8; ++tb) {
+        float err = 0.0f;
+        uint32_t sel = 0;
+        for (uint32_t t = 0; t < 16; ++t) {
+            if (!((mask >> t) & 1u)) continue;
+            const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
+            float be = 3.0e38f;
+            uint32_t bk = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const int m = (k & 2u) ? -static_cast<int>(kMod[tb][k & 1u]) : static_cast<int>(kMod[tb][k & 1u]);
+                const float d0 = static_cast<float>(clamp255(base[0] + m)) - x0, d1 = static_cast<float>(clamp255(base[1] + m)) - x1,
+                    d2 = static_cast<float>(clamp255(base[2] + m)) - x2;
+                const float e = d0*d0 + d1*d1 + d2*d2;
+                if (e < be) { be = e; bk = k; }
+            }
+            err += be;
+            sel |= bk << (2*t);
+            if (err >= out.err || err >= limit) break;
+        }
+        if (err < out.err) { out.err = err; out.table = tb; out.sel = sel; }
+    }
+}
+
+// Descent of one half's quantised base colour (bits = 4 or 5) within [lo, hi] per channel.
+CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* q /* in/out */, const int* lo, const int* hi,
+    int rounds, HalfFit& best)
+{
+    int base[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { q[c] = min(max(q[c], lo[c]), hi[c]); base[c] = bits == 5 ? expand5(q[c]) : expand4(q[c]); }
+    half_fit(xs, lane, mask, base, 3.0e38f, best);
+    for (int round = 0; round < rounds && best.err > 0.0f; ++round) {
+        bool improved = false;
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            // k 0,1: all channels -1 / +1 (luma); k 2..7: one channel -1 / +1
+            int t[3] = {q[0], q[1], q[2]};
+            const int d = (k & 1) ? 1 : -1;
+            if (k < 2) { t[0] += d; t[1] += d; t[2] += d; } else t[(k - 2) >> 1] += d;
+            if (t[0] < lo[0] || t[0] > hi[0] || t[1] < lo[1] || t[1] > hi[1] || t[2] < lo[2] || t[2] > hi[2]) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) base[c] = bits == 5 ? expand5(t[c]) : expand4(t[c]);
+            HalfFit f;
+            half_fit(xs, lane, mask, base, best.err, f);
+            if (f.err < best.err) { best = f; q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; improved = true; }
+        }
+        if (!improved) break;
+    }
+}
+
+CFX_HD void put_be(uint32_t& hi, uint32_t& lo, int bit /* 63..0 */, uint32_t v, int n)
+{
+    // field occupies bits [bit, bit-n+1] of the 64-bit big-endian word (hi = bits 63..32)
+    for (int i = 0; i < n; ++i) {
+        const int b = bit - i;
+        const uint32_t one = (v >> (n - 1 - i)) & 1u;
+        if (b >= 32) hi |= one << (b - 32); else lo |= one << b;
+    }
+}
+
+// pixel index bits: selector k of texel t=(y*4+x) goes to pixel p = x*4 + y: MSB at bit 16+p, LSB at bit p
+CFX_HD uint32_t pixel_bits(uint32_t sel)
+{
+    uint32_t out = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < 16; ++t) {
+        const uint32_t k = (sel >> (2*t)) & 3u, p = (t & 3u)*4u + (t >> 2);
+        out |= ((k >> 1) & 1u) << (16u + p);
+        out |= (k & 1u) << p;
+    }
+    return out;
+}
+
+CFX_HD uint2 to_bytes(uint32_t hi, uint32_t lo)
+{
+    // the block is stored big-endian: byte 0 = bits 63..56
+    return make_uint2(__byte_perm(hi, 0, 0x0123), __byte_perm(lo, 0, 0x0123));
+}
+
+struct ColorResult { float err; uint32_t hi, lo; };
+
+// ---- ETC1 part: both flips, differential and individual -----------------------------------------
+CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out)
+{
+    out.err = 3.0e38f; out.hi = out.lo = 0;
+#pragma unroll 1
+    for (uint32_t flip = 0; flip < 2; ++flip) {
+        const uint32_t maskA = flip ? 0x00FFu : 0x3333u, maskB = ~maskA & 0xFFFFu;
+        float mA[3] = {0, 0, 0}, mB[3] = {0, 0, 0};
+        for (uint32_t t = 0; t < 16; ++t) {
+            const bool a = (maskA >> t) & 1u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float v = px(xs, lane, t, c); if (a) mA[c] += v; else mB[c] += v; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { mA[c] *= 0.125f; mB[c] *= 0.125f; }
+#pragma unroll 1
+        for (int diff = 1; diff >= 0; --diff) {
+            const int bits = diff ? 5 : 4, maxq = diff ? 31 : 15;
+            int qA[3], qB[3], lo[3] = {0, 0, 0}, hi[3] = {maxq, maxq, maxq};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                qA[c] = __float2int_rn(mA[c]*static_cast<float>(maxq)*(1.0f/255.0f));
+                qB[c] = __float2int_rn(mB[c]*static_cast<float>(maxq)*(1.0f/255.0f));
+            }
+            if (diff) {
+                // pull the two bases together until every delta fits in [-4, 3]
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    int d = qB[c] - qA[c];
+                    while (d > 3) { if ((d & 1) == 0) ++qA[c]; else --qB[c]; d = qB[c] - qA[c]; }
+                    while (d < -4) { if ((d & 1) == 0) --qA[c]; else ++qB[c]; d = qB[c] - qA[c]; }
+                }
+            }
+            HalfFit fA, fB;
+            half_search(xs, lane, maskA, bits, qA, lo, hi, rounds, fA);
+            if (diff) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { lo[c] = max(qA[c] - 4, 0); hi[c] = min(qA[c] + 3, 31); }
+            }
+            half_search(xs, lane, maskB, bits, qB, lo, hi, rounds, fB);
+            const float err = fA.err + fB.err;
+            if (err < out.err) {
+                uint32_t h = 0, l = 0;
+                if (diff) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        put_be(h, l, 63 - 8*c, static_cast<uint32_t>(qA[c]), 5);
+                        put_be(h, l, 58 - 8*c, static_cast<uint32_t>(qB[c] - qA[c]) & 7u, 3);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        put_be(h, l, 63 - 8*c, static_cast<uint32_t>(qA[c]), 4);
+                        put_be(h, l, 59 - 8*c, static_cast<uint32_t>(qB[c]), 4);
+                    }
+                }
+                put_be(h, l, 39, fA.table, 3);
+                put_be(h, l, 36, fB.table, 3);
+                put_be(h, l, 33, static_cast<uint32_t>(diff), 1);
+                put_be(h, l, 32, flip, 1);
+                l = pixel_bits((fA.sel & (maskA*0 + 0xFFFFFFFFu)) | fB.sel);
+                out.err = err; out.hi = h; out.lo = l;
+            }
+        }
+    }
+}
+
+// ---- ETC2 planar ---------------------------------------------------------------------------------
+CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, const int* V)
+{
+    float err = 0.0f;
+    for (uint32_t t = 0; t < 16; ++t) {
+        const int x = t & 3, y = t >> 2;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int v = clamp255((x*(H[c] - O[c]) + y*(V[c] - O[c]) + 4*O[c] + 2) >> 2);
+            const float d = static_cast<float>(v) - px(xs, lane, t, c);
+            err += d*d;
+        }
+    }
+    return err;
+}
+
+CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out)
+{
+    int q[9];     // RO GO BO RH GH BH RV GV BV (6/7/6 bits)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float m = 0, sx = 0, sy = 0;
+        for (uint32_t t = 0; t < 16; ++t) {
+            const float v = px(xs, lane, t, c);
+            m += v; sx += (static_cast<float>(t & 3) - 1.5f)*v; sy += (static_cast<float>(t >> 2) - 1.5f)*v;
+        }
+        m *= (1.0f/16.0f); sx *= (1.0f/20.0f); sy *= (1.0f/20.0f);
+        const float o = m - 1.5f*sx - 1.5f*sy, h = o + 4.0f*sx, v = o + 4.0f*sy;
+        const float scale = c == 1 ? 127.0f/255.0f : 63.0f/255.0f;
+        const int maxq = c == 1 ? 127 : 63;
+        q[c] = min(max(__float2int_rn(o*scale), 0), maxq);
+        q[3 + c] = min(max(__float2int_rn(h*scale), 0), maxq);
+        q[6 + c] = min(max(__float2int_rn(v*scale), 0), maxq);
+    }
+    int O[3], H[3], V[3];
+    auto expand_all = [&]() {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            O[c] = c == 1 ? expand7(q[c]) : expand6(q[c]);
+            H[c] = c == 1 ? expand7(q[3 + c]) : expand6(q[3 + c]);
+            V[c] = c == 1 ? expand7(q[6 + c]) : expand6(q[6 + c]);
+        }
+    };
+    expand_all();
+    float best = planar_error(xs, lane, O, H, V);
+    for (int round = 0; round < rounds && best > 0.0f; ++round) {
+        bool improved = false;
+#pragma unroll 1
+        for (int k = 0; k < 18; ++k) {
+            const int i = k >> 1, d = (k & 1) ? 1 : -1;
+            const int maxq = (i % 3) == 1 ? 127 : 63;
+            if (q[i] + d < 0 || q[i] + d > maxq) continue;
+            q[i] += d;
+            expand_all();
+            const float e = planar_error(xs, lane, O, H, V);
+            if (e < best) { best = e; improved = true; } else q[i] -= d;
+        }
+        if (!improved) break;
+    }
+    out.err = best;
+    const uint32_t RO = q[0], GO = q[1], BO = q[2], RH = q[3], GH = q[4], BH = q[5], RV = q[6], GV = q[7], BV = q[8];
+    uint32_t h = 0, l = 0;
+    // R: bits 62..57 = RO; no overflow of (63..59) + signed(58..56)
+    put_be(h, l, 62, RO, 6);
+    put_be(h, l, 56, GO >> 6, 1);
+    {
+        const int dr = static_cast<int>(((RO & 3u) << 1) | (GO >> 6));          // bits 58..56 as signed 3
+        put_be(h, l, 63, (dr & 4) ? 1u : 0u, 1);
+    }
+    put_be(h, l, 54, GO & 63u, 6);
+    put_be(h, l, 48, BO >> 5, 1);
+    {
+        const int dg = static_cast<int>(((GO & 3u) << 1) | (BO >> 5));
+        put_be(h, l, 55, (dg & 4) ? 1u : 0u, 1);
+    }
+    put_be(h, l, 44, (BO >> 3) & 3u, 2);
+    put_be(h, l, 41, BO & 7u, 3);
+    {
+        // B must overflow: 5-bit (47..43) + signed 3-bit (42..40)
+        const uint32_t a = (BO >> 3) & 3u, b = (BO >> 1) & 3u;
+        if (a + b < 4) { put_be(h, l, 47, 0u, 3); put_be(h, l, 42, 1u, 1); }
+        else { put_be(h, l, 47, 7u, 3); put_be(h, l, 42, 0u, 1); }
+    }
+    put_be(h, l, 38, RH >> 1, 5);
+    put_be(h, l, 33, 1u, 1);
+    put_be(h, l, 32, RH & 1u, 1);
+    put_be(h, l, 31, GH, 7);
+    put_be(h, l, 24, BH, 6);
+    put_be(h, l, 18, RV, 6);
+    put_be(h, l, 12, GV, 7);
+    put_be(h, l, 5, BV, 6);
+    out.hi = h; out.lo = l;
+}
+
+// ---- ETC2 T and H modes --------------------------------------------------------------------------
+// Two 444 colours from a 2-means split of the block along its principal axis.
+CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out)
+{
+    out.err = 3.0e38f; out.hi = out.lo = 0;
+    float m[3] = {0, 0, 0};
+    for (uint32_t t = 0; t < 16; ++t) { m[0] += px(xs, lane, t, 0); m[1] += px(xs, lane, t, 1); m[2] += px(xs, lane, t, 2); }
+    m[0] *= (1.0f/16.0f); m[1] *= (1.0f/16.0f); m[2] *= (1.0f/16.0f);
+    float cv[6] = {0, 0, 0, 0, 0, 0};
+    for (uint32_t t = 0; t < 16; ++t) {
+        const float d0 = px(xs, lane, t, 0) - m[0], d1 = px(xs, lane, t, 1) - m[1], d2 = px(xs, lane, t, 2) - m[2];
+        cv[0] += d0*d0; cv[1] += d0*d1; cv[2] += d0*d2; cv[3] += d1*d1; cv[4] += d1*d2; cv[5] += d2*d2;
+    }
+    float v[3] = {cv[0], cv[1], cv[2]};
+    float bestd = cv[0];
+    if (cv[3] > bestd) { bestd = cv[3]; v[0] = cv[1]; v[1] = cv[3]; v[2] = cv[4]; }
+    if (cv[5] > bestd) { bestd = cv[5]; v[0] = cv[2]; v[1] = cv[4]; v[2] = cv[5]; }
+    for (int it = 0; it < 4; ++it) {
+        const float n2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2];
+        const float s = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+        const float a0 = v[0]*s, a1 = v[1]*s, a2 = v[2]*s;
+        v[0] = cv[0]*a0 + cv[1]*a1 + cv[2]*a2; v[1] = cv[1]*a0 + cv[3]*a1 + cv[4]*a2; v[2] = cv[2]*a0 + cv[4]*a1 + cv[5]*a2;
+    }
+    // split at the mean projection, two Lloyd iterations
+    uint32_t side = 0;
+    for (uint32_t t = 0; t < 16; ++t) {
+        const float p = (px(xs, lane, t, 0) - m[0])*v[0] + (px(xs, lane, t, 1) - m[1])*v[1] + (px(xs, lane, t, 2) - m[2])*v[2];
+        if (p > 0.0f) side |= 1u << t;
+    }
+    float cA[3] = {m[0], m[1], m[2]}, cB[3] = {m[0], m[1], m[2]};
+    for (int it = 0; it < 3; ++it) {
+        float sA[3] = {0, 0, 0}, sB[3] = {0, 0, 0}, nA = 0, nB = 0;
+        for (uint32_t t = 0; t < 16; ++t) {
+            const bool b = (side >> t) & 1u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float x = px(xs, lane, t, c); if (b) sB[c] += x; else sA[c] += x; }
+            if (b) nB += 1.0f; else nA += 1.0f;
+        }
+        if (nA == 0.0f || nB == 0.0f) return;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { cA[c] = sA[c]/nA; cB[c] = sB[c]/nB; }
+        side = 0;
+        for (uint32_t t = 0; t < 16; ++t) {
+            float dA = 0, dB = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float x = px(xs, lane, t, c); dA += (x - cA[c])*(x - cA[c]); dB += (x - cB[c])*(x - cB[c]); }
+            if (dB < dA) side |= 1u << t;
+        }
+    }
+    int qA[3], qB[3], eA[3], eB[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        qA[c] = min(max(__float2int_rn(cA[c]*(15.0f/255.0f)), 0), 15); qB[c] = min(max(__float2int_rn(cB[c]*(15.0f/255.0f)), 0), 15);
+        eA[c] = expand4(qA[c]); eB[c] = expand4(qB[c]);
+    }
+    // kind 0: T with A single, B +-d; kind 1: T with B single, A +-d; kind 2: H
+    float best = 3.0e38f;
+    uint32_t best_kind = 0, best_d = 0, best_sel = 0;
+#pragma unroll 1
+    for (uint32_t kind = 0; kind < 3; ++kind) {
+#pragma unroll 1
+        for (uint32_t di = 0; di < 8; ++di) {
+            const int d = kDist[di];
+            int pal[4][3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int s = kind == 1 ? eB[c] : eA[c], o = kind == 1 ? eA[c] : eB[c];
+                if (kind < 2) { pal[0][c] = s; pal[1][c] = clamp255(o + d); pal[2][c] = o; pal[3][c] = clamp255(o - d); }
+                else { pal[0][c] = clamp255(eA[c] + d); pal[1][c] = clamp255(eA[c] - d); pal[2][c] = clamp255(eB[c] + d); pal[3][c] = clamp255(eB[c] - d); }
+            }
+            float err = 0.0f;
+            uint32_t sel = 0;
+            for (uint32_t t = 0; t < 16 && err < best; ++t) {
+                float be = 3.0e38f;
+                uint32_t bk = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const float d0 = static_cast<float>(pal[k][0]) - px(xs, lane, t, 0), d1 = static_cast<float>(pal[k][1]) - px(xs, lane, t, 1),
+                        d2 = static_cast<float>(pal[k][2]) - px(xs, lane, t, 2);
+                    const float e = d0*d0 + d1*d1 + d2*d2;
+                    if (e < be) { be = e; bk = k; }
+                }
+                err += be; sel |= bk << (2*t);
+            }
+            if (err < best) { best = err; best_kind = kind; best_d = di; best_sel = sel; }
+        }
+    }
+    if (best >= 3.0e38f) return;
+    out.err = best;
+    uint32_t h = 0, l = 0;
+    if (best_kind < 2) {
+        const int* s = best_kind == 1 ? qB : qA;
+        const int* o = best_kind == 1 ? qA : qB;
+        const uint32_t R1 = s[0], a = R1 >> 2, b = R1 & 3u;
+        if (a + b < 4) { put_be(h, l, 63, 0u, 3); put_be(h, l, 58, 1u, 1); } else { put_be(h, l, 63, 7u, 3); put_be(h, l, 58, 0u, 1); }
+        put_be(h, l, 60, a, 2); put_be(h, l, 57, b, 2);
+        put_be(h, l, 55, static_cast<uint32_t>(s[1]), 4); put_be(h, l, 51, static_cast<uint32_t>(s[2]), 4);
+        put_be(h, l, 47, static_cast<uint32_t>(o[0]), 4); put_be(h, l, 43, static_cast<uint32_t>(o[1]), 4); put_be(h, l, 39, static_cast<uint32_t>(o[2]), 4);
+        put_be(h, l, 35, best_d >> 1, 2); put_be(h, l, 33, 1u, 1); put_be(h, l, 32, best_d & 1u, 1);
+        l = pixel_bits(best_sel);
+    } else {
+        // H: the low bit of the distance index is carried by the ORDER of the two colours
+        int c1[3] = {qA[0], qA[1], qA[2]}, c2[3] = {qB[0], qB[1], qB[2]};
+        uint32_t sel = best_sel;
+        const uint32_t v1 = (c1[0] << 8) | (c1[1] << 4) | c1[2], v2 = (c2[0] << 8) | (c2[1] << 4) | c2[2];
+        const bool want_ge = best_d & 1u;
+        if (v1 == v2 && !want_ge) { out.err = 3.0e38f; return; }        // cannot express an even index with equal colours
+        if ((v1 >= v2) != want_ge) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const int tmp = c1[c]; c1[c] = c2[c]; c2[c] = tmp; }
+            // colours swapped: selectors 0,1 <-> 2,3
+            sel ^= 0xAAAAAAAAu;
+        }
+        const uint32_t R1 = c1[0], G1 = c1[1], B1 = c1[2];
+        put_be(h, l, 62, R1, 4);
+        put_be(h, l, 58, G1 >> 1, 3);
+        put_be(h, l, 63, (G1 & 8u) ? 1u : 0u, 1);          // keep R + dR in range
+        put_be(h, l, 52, G1 & 1u, 1);
+        put_be(h, l, 51, B1 >> 3, 1);
+        put_be(h, l, 49, B1 & 7u, 3);
+        {
+            const uint32_t a = ((G1 & 1u) << 1) | (B1 >> 3), b = (B1 >> 1) & 3u;
+            if (a + b < 4) { put_be(h, l, 55, 0u, 3); put_be(h, l, 50, 1u, 1); } else { put_be(h, l, 55, 7u, 3); put_be(h, l, 50, 0u, 1); }
+        }
+        put_be(h, l, 46, static_cast<uint32_t>(c2[0]), 4); put_be(h, l, 42, static_cast<uint32_t>(c2[1]), 4); put_be(h, l, 38, static_cast<uint32_t>(c2[2]), 4);
+        put_be(h, l, 34, best_d >> 2, 1); put_be(h, l, 33, 1u, 1); put_be(h, l, 32, (best_d >> 1) & 1u, 1);
+        l = pixel_bits(sel);
+    }
+    out.hi = h; out.lo = l;
+}
+
+// ---- EAC alpha (ETC2 RGBA8) ----------------------------------------------------------------------
+CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius)
+{
+    float lo = 3.0e38f, hi = -3.0e38f;
+    for (uint32_t t = 0; t < 16; ++t) { const float a = px(xs, lane, t, 3); lo = fminf(lo, a); hi = fmaxf(hi, a); }
+    uint32_t best_base = 255, best_mul = 1, best_tab = 13;
+    float best = 3.0e38f;
+    if (lo == hi && lo == 255.0f) {
+        best = 0.0f;                 // opaque: base 255, table 13 has a zero modifier at selector 4
+    } else {
+#pragma unroll 1
+        for (uint32_t tab = 0; tab < 16; ++tab) {
+            const float tmin = static_cast<float>(kEac[tab][3]), tmax = static_cast<float>(kEac[tab][7]);
+            const float range = tmax - tmin;
+            const int mul0 = min(max(__float2int_rn((hi - lo)/range), 1), 15);
+#pragma unroll 1
+            for (int dm = -1; dm <= 1; ++dm) {
+                const int mul = mul0 + dm;
+                if (mul < 1 || mul > 15) continue;
+                // centre the table's span on the block's alpha range
+                const int base0 = __float2int_rn(0.5f*(lo + hi) - 0.5f*(tmin + tmax)*static_cast<float>(mul));
+#pragma unroll 1
+                for (int db = -radius; db <= radius; ++db) {
+                    const int base = base0 + db;
+                    if (base < 0 || base > 255) continue;
+                    float err = 0.0f;
+                    for (uint32_t t = 0; t < 16 && err < best; ++t) {
+                        const float a = px(xs, lane, t, 3);
+                        float be = 3.0e38f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float d = static_cast<float>(clamp255(base + kEac[tab][k]*mul)) - a;
+                            be = fminf(be, d*d);
+                        }
+                        err += be;
+                    }
+                    if (err < best) { best = err; best_base = base; best_mul = mul; best_tab = tab; }
+                }
+            }
+        }
+    }
+    // selectors for the winner; 48 bits, pixel p = x*4 + y first (most significant)
+    uint64_t bits = 0;
+    for (uint32_t p = 0; p < 16; ++p) {
+        const uint32_t t = (p & 3u)*4u + (p >> 2);
+        const float a = px(xs, lane, t, 3);
+        float be = 3.0e38f;
+        uint32_t bk = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            const float d = static_cast<float>(clamp255(static_cast<int>(best_base) + kEac[best_tab][k]*static_cast<int>(best_mul))) - a;
+            if (d*d < be) { be = d*d; bk = k; }
+        }
+        bits = (bits << 3) | bk;
+    }
+    const uint32_t hi32 = (best_base << 24) | (best_mul << 20) | (best_tab << 16) | static_cast<uint32_t>(bits >> 32);
+    const uint32_t lo32 = static_cast<uint32_t>(bits);
+    return to_bytes(hi32, lo32);
+}
+
+// format: 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8 (colour part); returns the 8 colour bytes
+CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds)
+{
+    ColorResult best;
+    encode_etc1(xs, lane, rounds, best);
+    if (etc2 && best.err > 0.0f) {
+        ColorResult r;
+        encode_planar(xs, lane, rounds, r);
+        if (r.err < best.err) best = r;
+        if (best.err > 0.0f) {
+            encode_th(xs, lane, r);
+            if (r.err < best.err) best = r;
+        }
+    }
+    return to_bytes(best.hi, best.lo);
+}
+
+} // namespace etc
+} // namespace cfx

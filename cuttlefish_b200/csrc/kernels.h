@@ -14,5 +14,6 @@ int launch_bc7(const EncodeParams& p, cudaStream_t stream);
 int launch_astc(const EncodeParams& p, cudaStream_t stream);
 int launch_bc6h(const EncodeParams& p, cudaStream_t stream);
 int launch_bc123(const EncodeParams& p, cudaStream_t stream);
+int launch_etc(const EncodeParams& p, cudaStream_t stream);
 
 } // namespace cfx

@@ -180,3 +180,68 @@ def test_bc1_rgba_punch_through(cfx, oracle):
     img = src_as_float(src)
     e = lambda d: float(np.mean((d[opaque][:, :3].astype(np.float64) - img[opaque][:, :3]) ** 2))
     assert 10*np.log10(1/e(d_gpu)) >= 10*np.log10(1/e(d_ref)) - PSNR_TOLERANCE_DB
+
+
+# ---- ETC family: PSNR parity (own search, see etc_core.cuh) ----
+@pytest.mark.parametrize("fmt", ["ETC1", "ETC2_R8G8B8", "ETC2_R8G8B8A8"])
+@pytest.mark.parametrize("kind,w,h", [("noise+grad", 256, 256), ("gradient", 256, 256), ("noise+grad", 97, 61)])
+def test_etc_psnr_vs_oracle(cfx, oracle, fmt, kind, w, h):
+    if not cfx.format_supported(fmt):
+        pytest.fail("%s encoder missing from libcfx.so" % fmt)
+    img = oracle.gen_image(kind, w, h, seed=23)
+    p_gpu, p_ref = _psnr_pair(cfx, oracle, fmt, img)
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s %s: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, kind, p_gpu, p_ref)
+
+
+def test_etc2_rgba8_alpha_vs_oracle(cfx, oracle):
+    src, blocks, fmt, kw = load_golden("ETC2_R8G8B8A8_alpha_32x32")
+    img = src_as_float(src)
+    got = cfx.encode(src, fmt, **kw)
+    d_gpu, d_ref = oracle.decode(got, fmt, 32, 32), oracle.decode(blocks, fmt, 32, 32)
+    a = lambda d: 10*np.log10(1/max(float(np.mean((d[..., 3].astype(np.float64) - img[..., 3]) ** 2)), 1e-12))
+    assert a(d_gpu) >= a(d_ref) - PSNR_TOLERANCE_DB, "alpha PSNR gpu %.3f ref %.3f" % (a(d_gpu), a(d_ref))
+    # colour error weighted by alpha (the metric the reference optimises for RGBA8), must not be worse
+    wgt = img[..., 3:4].astype(np.float64)
+    c = lambda d: float(np.mean(((d[..., :3].astype(np.float64) - img[..., :3]) * wgt) ** 2))
+    assert 10*np.log10(1/c(d_gpu)) >= 10*np.log10(1/c(d_ref)) - PSNR_TOLERANCE_DB
+
+
+def test_etc_float_source_mip_like(cfx, oracle):
+    # non-8-bit floats (what mip levels > 0 hold): the encoder must see the unquantised values
+    img = oracle.gen_image("gradient", 64, 64)
+    img[..., :3] = np.clip(img[..., :3] * np.float32(0.737) + np.float32(0.0123), 0, 1)
+    for fmt in ("ETC1", "ETC2_R8G8B8A8"):
+        got = cfx.encode(img, fmt)
+        ref = oracle.encode(img, fmt)
+        assert oracle.psnr_rgb(img, oracle.decode(got, fmt, 64, 64)) >= oracle.psnr_rgb(img, oracle.decode(ref, fmt, 64, 64)) - PSNR_TOLERANCE_DB
+
+
+def test_texture_convert_mip_chain(cfx, oracle):
+    """cuttlefish_b200.Texture mirrors Texture::convert over a mip chain (BASELINE config 5 shape:
+    ETC2_R8G8B8A8 + full chain) through cfx_encode_batch; every level must match the per-surface
+    call and hold PSNR parity with the oracle."""
+    base = oracle.gen_image("noise+grad", 64, 64, seed=3)
+    tex = cfx.Texture(64, 64, mip_levels=7)
+    levels = []
+    img = base
+    for m in range(7):
+        levels.append(img)
+        assert tex.setImage(img, mip=m)
+        if img.shape[0] > 1:
+            img = img.reshape(img.shape[0] // 2, 2, img.shape[1] // 2, 2, 4).mean(axis=(1, 3)).astype(np.float32)
+    assert tex.imagesComplete()
+    assert tex.convert("ETC2_R8G8B8A8", "UNorm", "Normal")
+    for m, img in enumerate(levels):
+        h, w, _ = img.shape
+        assert tex.dataSize(m) == cfx.encoded_size("ETC2_R8G8B8A8", w, h)
+        assert np.array_equal(tex.data(m), cfx.encode(img, "ETC2_R8G8B8A8"))
+        if w >= 8:
+            ref = oracle.encode(img, "ETC2_R8G8B8A8")
+            p_gpu = oracle.psnr_rgb(img, oracle.decode(tex.data(m), "ETC2_R8G8B8A8", w, h))
+            p_ref = oracle.psnr_rgb(img, oracle.decode(ref, "ETC2_R8G8B8A8", w, h))
+            assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
+    # unsupported pair: convert() returns False and the texture stays unconverted
+    tex2 = cfx.Texture(8, 8)
+    tex2.setImage(base[:8, :8])
+    assert not tex2.convert("EAC_R11", "UNorm")
+    assert not tex2.converted()
