@@ -29,6 +29,7 @@ UNITS = [
     ("etc.cu", [], "CFX_HAVE_ETC"),
     ("bc6h.cu", [], "CFX_HAVE_BC6H"),
     ("astc.cu", [], "CFX_HAVE_ASTC"),
+    ("astc2.cu", [], None),
 ]
 
 

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -136,6 +137,8 @@ __global__ void __launch_bounds__(kAstcWarps*32) astc_kernel(const EncodeParams 
     }
 }
 
+int launch_astc2(const EncodeParams& p, const Ctx& ctx, cudaStream_t stream);   // astc2.cu: warp-cooperative search
+
 int launch_astc(const EncodeParams& p, cudaStream_t stream)
 {
     if (p.block_w*p.block_h > static_cast<uint32_t>(kMaxTexels)) return -2;
@@ -157,6 +160,10 @@ int launch_astc(const EncodeParams& p, cudaStream_t stream)
         }
         ctx = it->second.ctx;
     }
+    // The lane-per-candidate kernel below is the first implementation, kept as a cross-check
+    // (CFX_ASTC_V1=1); the default is the warp-cooperative kernel of astc2.cu.
+    static const bool use_v1 = getenv("CFX_ASTC_V1") != nullptr;
+    if (!use_v1) return launch_astc2(p, ctx, stream);
     const Plan plan = make_plan(p.quality, ctx.tab);
     const size_t smem = kAstcWarps*kWarpBytes;
     static bool attr_set = false;

@@ -648,8 +648,9 @@ CFX_HD uint64_t bitrev64(uint64_t v)
 }
 
 // Physical 128-bit block for (slot, mode, encoding) with grid weights in u_scr.
+// u_scr: grid weights in bit-stream order, lane-interleaved scratch (linear == false) or a plain array.
 CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const Slot& slot, const ModeInfo& m, const Enc& e, bool has_alpha,
-    const uint8_t* u_scr, uint32_t lane)
+    const uint8_t* u_scr, uint32_t lane, bool linear = false)
 {
     Bits128 b; b.lo = b.hi = 0;
     const uint32_t pc = slot.pc;
@@ -673,7 +674,7 @@ CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const Slot& slot, const ModeInfo&
     const uint32_t planes = slot.dual_ch >= 0 ? 2u : 1u;
     if (planes == 2) b.put(128u - m.wbits - 2u, static_cast<uint32_t>(slot.dual_ch), 2);
     ise_encode(c, w, 0, m.nw*planes, kWqBits[L], kWqTrits[L] != 0, kWqQuints[L] != 0, [&](uint32_t j) {
-        const uint32_t u = u_scr[scr_index(j, lane)];
+        const uint32_t u = linear ? u_scr[j] : u_scr[scr_index(j, lane)];
         uint32_t k = 0;
         while (k + 1u < kWqN[L] && tab_u8(c, c.tab.off_wq_val + L*32u + k) != u) ++k;
         return tab_u8(c, c.tab.off_wq_enc + L*32u + k);
@@ -721,10 +722,8 @@ CFX_HD uint32_t slot_type(uint32_t slot) { return slot == 0 ? 0u : (slot < 3 ? 1
 // Lowest/Low/Normal/High/Highest -> fastest/fast/medium/thorough/exhaustive).
 inline Plan make_plan(uint32_t quality, const AstcTab& t)
 {
-    static const uint32_t counts[5][4] = {{24, 16, 0, 16}, {40, 32, 16, 32}, {64, 64, 32, 64}, {128, 128, 64, 128},
-        {4096, 4096, 4096, 4096}};
     Plan p;
-    for (int i = 0; i < 4; ++i) p.n_cand[i] = counts[quality][i] < t.n_cand[i] ? counts[quality][i] : t.n_cand[i];
+    for (int i = 0; i < 4; ++i) p.n_cand[i] = kPlanCounts[quality][i] < t.n_cand[i] ? kPlanCounts[quality][i] : t.n_cand[i];
     p.refine = quality >= 3 ? 3 : 2;
     p.slots = 9;
     return p;

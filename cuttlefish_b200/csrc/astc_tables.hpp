@@ -27,6 +27,12 @@ constexpr int kMaxTexels = 64;      // footprints up to 8x8 / 10x6
 constexpr int kWeightLevels = 12;   // 2 3 4 5 6 8 10 12 16 20 24 32
 constexpr int kColorLevels = 17;    // 6 8 10 12 16 20 24 32 40 48 64 80 96 128 160 192 256
 
+// Candidates evaluated per slot of each type (1 / 2 / 3 subsets, dual plane) by Texture::Quality
+// (Lowest .. Highest; AstcConverter maps them to astcenc's fastest .. exhaustive presets,
+// lib/src/AstcConverter.cpp:174-195).
+static const uint32_t kPlanCounts[5][4] = {{24, 16, 0, 16}, {40, 32, 16, 32}, {64, 64, 32, 64}, {128, 128, 64, 128},
+    {4096, 4096, 4096, 4096}};
+
 struct Quant { uint16_t n; uint8_t bits, trits, quints; };
 
 static const Quant kWeightQuant[kWeightLevels] = {
@@ -250,6 +256,8 @@ struct AstcTab {
     uint32_t n_part2, n_part3;  // usable seeds
     uint32_t off_cand[4];       // per slot type (1 / 2 / 3 subsets, dual plane): uint16 mode indices, likeliest first
     uint32_t n_cand[4];
+    uint32_t off_cand_q[5][4];  // per quality: the first kPlanCounts[q][type] of those, re-ordered so that modes
+    uint32_t n_cand_q[5][4];    // sharing a weight grid are adjacent (one decimation per grid)
     uint32_t blob_bytes;
 };
 
@@ -444,6 +452,7 @@ inline Built build_tables(int bw, int bh)
     {
         const ModeInfo* all = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes]);
         const GridInfo* gr = reinterpret_cast<const GridInfo*>(&blob[t.off_grids]);
+        (void)gr;
         for (int type = 0; type < 4; ++type) {
             const uint32_t first = type == 3 ? t.n_modes1 : 0, count = type == 3 ? t.n_modes2 : t.n_modes1;
             std::vector<uint16_t> order;
@@ -459,6 +468,21 @@ inline Built build_tables(int bw, int bh)
             t.n_cand[type] = static_cast<uint32_t>(order.size());
             t.off_cand[type] = reserve(order.size()*2, 4);
             std::memcpy(&blob[t.off_cand[type]], order.data(), order.size()*2);
+            all = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes]);       // reserve() may have moved the blob
+            gr = reinterpret_cast<const GridInfo*>(&blob[t.off_grids]);
+            for (int q = 0; q < 5; ++q) {
+                const size_t n = std::min<size_t>(order.size(), kPlanCounts[q][type]);
+                std::vector<uint16_t> sub(order.begin(), order.begin() + n);
+                std::stable_sort(sub.begin(), sub.end(), [&](uint16_t a, uint16_t b) {
+                    if (all[a].grid != all[b].grid) return all[a].grid < all[b].grid;
+                    return all[a].level > all[b].level;
+                });
+                t.n_cand_q[q][type] = static_cast<uint32_t>(n);
+                t.off_cand_q[q][type] = reserve(n*2 + 2, 4);
+                if (n) std::memcpy(&blob[t.off_cand_q[q][type]], sub.data(), n*2);
+                all = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes]);
+                gr = reinterpret_cast<const GridInfo*>(&blob[t.off_grids]);
+            }
         }
     }
     t.blob_bytes = static_cast<uint32_t>(blob.size());

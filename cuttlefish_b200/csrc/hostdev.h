@@ -7,7 +7,7 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define CFX_HD __device__ __forceinline__
-#define CFX_HD_NOINLINE __device__ __noinline__
+#define CFX_HD_NOINLINE static __device__ __noinline__
 #define CFX_CONST __device__ __constant__
 #else
 #include <algorithm>
