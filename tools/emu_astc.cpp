@@ -2,6 +2,7 @@
 // the warp replaced by a loop over 32 "lanes".  Not part of libcfx.so and never a fallback.
 #include "../cuttlefish_b200/csrc/astc_core.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -52,6 +53,10 @@ extern "C" int emu_astc_encode(const float* rgba /* 0..1 floats */, uint32_t w, 
             for (uint32_t lane = 0; lane < 32; ++lane) { best_err[lane] = 3.0e38f; best_mode[lane] = 0; best_slot[lane] = 0; }
             Plan plan = make_plan(quality, c.tab);
             if (slots < plan.slots) plan.slots = slots;
+            if (const char* ev = getenv("EMU_COUNTS")) {
+                unsigned a, b, cc, d;
+                if (sscanf(ev, "%u,%u,%u,%u", &a, &b, &cc, &d) == 4) { plan.n_cand[0] = a; plan.n_cand[1] = b; plan.n_cand[2] = cc; plan.n_cand[3] = d; }
+            }
             for (uint32_t s = 0; s < plan.slots; ++s) {
                 if (!st.slots[s].valid) continue;
                 const uint32_t type = slot_type(s);

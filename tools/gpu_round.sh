@@ -1,5 +1,4 @@
 set -x
-python -m pytest tests -m gpu -q -k astc 2>&1 | tail -8
-python tools/eval_format.py ASTC_6x6 --size 516 --big 4096 2>&1 | tail -3
-CFX_ASTC_V1=1 python tools/eval_format.py ASTC_6x6 --size 516 --big 1024 --no-oracle 2>&1 | tail -3
-compute-sanitizer --tool memcheck python tools/prof_one.py ASTC_6x6 192 noise+grad 1 2>&1 | tail -5
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 2>&1 | tail -2 | tee gpurun_out/bench_bc7_2gpu.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --format ASTC_6x6 2>&1 | tail -1 | tee gpurun_out/bench_astc_2gpu.json
+python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_ref.json
