@@ -40,9 +40,11 @@ struct WarpState {
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t redux_addu(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
-// Decimate the ideal weights `tt` (per texel) onto grid `gi`: ws.g[plane][j].
-__device__ __forceinline__ void decimate(const Ctx& c, WarpState& ws, uint32_t gi, uint32_t nw, const float* tt, uint32_t plane,
-    uint32_t lane)
+// Decimate the ideal weights `tt` (per texel) onto grid `gi`: ws.g[plane][j].  Returns the sum over
+// texels of (infill of the decimated weights - ideal weight)^2, i.e. what no quantisation level of this
+// grid can undo.
+__device__ __forceinline__ float decimate(const Ctx& c, WarpState& ws, uint32_t gi, uint32_t nw, const float* tt, uint32_t plane,
+    uint32_t lane, const Slot* bound_slot = nullptr)
 {
     const uint32_t T = c.tab.texels;
     const uint32_t start_off = c.tab.off_csr_start + gi*(kMaxTexels + 2)*2u;
@@ -59,7 +61,7 @@ __device__ __forceinline__ void decimate(const Ctx& c, WarpState& ws, uint32_t g
         ws.g[plane][j] = s*tab_f32(c, norm_off + j*4u);
     }
     __syncwarp();
-    if (nw >= T) return;
+    if (nw >= T) return 0.0f;
     for (uint32_t i = lane; i < T; i += 32) {
         const uint2 inf = tab_u32x2(c, inf_off + i*8u);
         float r = 0.0f;
@@ -79,6 +81,20 @@ __device__ __forceinline__ void decimate(const Ctx& c, WarpState& ws, uint32_t g
         ws.g[plane][j] = fminf(fmaxf(ws.g[plane][j] + (s2 > 0.0f ? kDecimationGain*s/s2 : 0.0f), 0.0f), 1.0f);
     }
     __syncwarp();
+    if (!bound_slot) return 0.0f;
+    float d2 = 0.0f;
+    for (uint32_t i = lane; i < T; i += 32) {
+        const uint2 inf = tab_u32x2(c, inf_off + i*8u);
+        float r = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r += static_cast<float>((inf.y >> (8*k)) & 0xFFu)*ws.g[plane][(inf.x >> (8*k)) & 0xFFu];
+        const float d = tt[i] - r*(1.0f/16.0f);
+        const uint32_t q = bound_slot->part[i];
+        d2 += d*d*(q == 0 ? bound_slot->len2[0] : (q == 1 ? bound_slot->len2[1] : bound_slot->len2[2]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, o);
+    return d2;
 }
 
 struct Best { float err; uint32_t slot, mode, cl; };
@@ -281,22 +297,34 @@ __global__ void __launch_bounds__(kWarps2*32) astc2_kernel(const EncodeParams p,
 
         // ---- search: candidates one after another, every step warp-uniform
         Best best; best.err = 3.0e38f; best.slot = 0; best.mode = 0; best.cl = 0;
-        for (uint32_t s = 0; s < plan.slots; ++s) {
+        // good enough: astcenc's own medium-preset quality target for this footprint
+        // (astcenc_entry.cpp:546-552: max(95 - 35 log10 T, 70 - 19 log10 T) dB) plus a 12 dB margin ends the search
+        const float stop_db = fmaxf(95.0f - 35.0f*log10f(static_cast<float>(T)), 70.0f - 19.0f*log10f(static_cast<float>(T))) + 12.0f;
+        const float stop_err = 65025.0f*exp10f(-0.1f*stop_db)*static_cast<float>(T*(has_alpha ? 4u : 3u))*static_cast<float>(FX*FX);
+        for (uint32_t s = 0; s < plan.slots && best.err > stop_err; ++s) {
             const Slot& slot = st.slots[s];
             if (!slot.valid) continue;
             const uint32_t type = slot_type(s);
             const uint32_t n = ctx.tab.n_cand_q[quality][type];
             const uint32_t list = ctx.tab.off_cand_q[quality][type];
             const uint32_t planes = slot.dual_ch >= 0 ? 2u : 1u;
+            // nothing on this slot's lines can beat what we already have
+            const float fx2 = static_cast<float>(FX*FX);
+            if (0.9f*fx2*slot.e_line > best.err) continue;
             uint32_t cur_grid = 0xFFFFFFFFu;
-            for (uint32_t ci = 0; ci < n; ++ci) {
+            bool skip_grid = false;
+            for (uint32_t ci = 0; ci < n && best.err > stop_err; ++ci) {
                 const uint32_t mi = tab_u16(ctx, list + ci*2u);
                 const ModeInfo m = tab_mode(ctx, mi);
                 if (m.grid != cur_grid) {
                     cur_grid = m.grid;
-                    decimate(ctx, ws, cur_grid, m.nw, slot.t, 0, lane);
+                    // lower bound of this grid's error: the slot's line residual plus what decimation alone loses
+                    const bool bound = best.err < 3.0e38f && planes == 1 && m.nw < T;
+                    const float d2 = decimate(ctx, ws, cur_grid, m.nw, slot.t, 0, lane, bound ? &slot : nullptr);
                     if (planes == 2) decimate(ctx, ws, cur_grid, m.nw, slot.t2, 1, lane);
+                    skip_grid = bound && 0.8f*fx2*(slot.e_line + d2) > best.err;
                 }
+                if (skip_grid) continue;
                 uint32_t cl = 0;
                 const float err = evaluate2<K>(ctx, ws, slot, m, has_alpha, lane, cl);
                 if (err < best.err) {

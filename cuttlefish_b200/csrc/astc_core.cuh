@@ -72,6 +72,9 @@ struct Slot {
     float4 e0[3], e1[3];         // line end points (0..255 per channel), sum(e1.rgb) >= sum(e0.rgb)
     uint32_t pc, seed, valid;
     int32_t dual_ch;             // channel that gets its own weight plane, or -1
+    float e_line;                // squared distance of the texels from their subsets' lines (8-bit units):
+                                 // the error left with ideal weights and end points
+    float len2[3];               // squared length of each subset's line (first plane)
 };
 constexpr int kSlots = 9;        // 0: one subset; 1,2: two subsets; 3,4: three subsets; 5..8: dual plane on R,G,B,A
 
@@ -377,6 +380,7 @@ CFX_HD void evaluate(const Ctx& c, const float4* cf, const Slot& slot, const Mod
 // ---- building a slot: per-subset mean, principal axis, projections ----------------------------
 CFX_HD void build_slot(const float4* cf, uint32_t T, bool has_alpha, Slot& slot)
 {
+    slot.e_line = 0.0f;
     for (uint32_t s = 0; s < slot.pc; ++s) {
         float n = 0, m[4] = {0, 0, 0, 0};
         for (uint32_t i = 0; i < T; ++i) {
@@ -420,16 +424,19 @@ CFX_HD void build_slot(const float4* cf, uint32_t T, bool has_alpha, Slot& slot)
             if (n2 <= 1e-20f) { v[0] = v[1] = v[2] = 0.57735f; v[3] = 0.0f; }
             if (v[0] + v[1] + v[2] < 0.0f) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; v[3] = -v[3]; }
         }
-        float tmin = 1e30f, tmax = -1e30f;
+        float tmin = 1e30f, tmax = -1e30f, proj2 = 0.0f;
         for (uint32_t i = 0; i < T; ++i) {
             if (slot.part[i] != s) continue;
             const float4 x = cf[i];
             const float t = (x.x - m[0])*v[0] + (x.y - m[1])*v[1] + (x.z - m[2])*v[2] + (x.w - m[3])*v[3];
             slot.t[i] = t;
+            proj2 += t*t;
             tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
         }
+        slot.e_line += fmaxf(cv[0] + cv[4] + cv[7] + cv[9] - proj2, 0.0f);
         if (!(tmax > tmin)) { tmin = 0.0f; tmax = 0.0f; }
         const float range = tmax - tmin;
+        slot.len2[s] = range*range;
         const float ir = range > 1e-6f ? 1.0f/range : 0.0f;
         for (uint32_t i = 0; i < T; ++i)
             if (slot.part[i] == s) slot.t[i] = (slot.t[i] - tmin)*ir;

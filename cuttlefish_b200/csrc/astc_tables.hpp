@@ -473,7 +473,9 @@ inline Built build_tables(int bw, int bh)
             for (int q = 0; q < 5; ++q) {
                 const size_t n = std::min<size_t>(order.size(), kPlanCounts[q][type]);
                 std::vector<uint16_t> sub(order.begin(), order.begin() + n);
+                // densest grids first: they set a low error early, which lets coarse grids be skipped
                 std::stable_sort(sub.begin(), sub.end(), [&](uint16_t a, uint16_t b) {
+                    if (all[a].nw != all[b].nw) return all[a].nw > all[b].nw;
                     if (all[a].grid != all[b].grid) return all[a].grid < all[b].grid;
                     return all[a].level > all[b].level;
                 });

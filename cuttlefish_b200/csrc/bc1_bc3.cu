@@ -49,12 +49,9 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
         }
         __syncwarp();
         uint32_t px[16];
-        uint32_t keep = 0xFF000000u;
-        if (p.color_mask & 1u) keep |= 0xFFu;
-        if (p.color_mask & 2u) keep |= 0xFF00u;
-        if (p.color_mask & 4u) keep |= 0xFF0000u;
+        // like the reference (Bc1/Bc2/Bc3Converter never look at the colour mask) all channels are encoded
 #pragma unroll
-        for (int i = 0; i < 16; ++i) px[i] = sp[lane*kBlkStride + i] & keep;
+        for (int i = 0; i < 16; ++i) px[i] = sp[lane*kBlkStride + i];
         uint32_t flags = 0;
         if (FORMAT == 29) flags = bc1::kAllow3 | bc1::kAllowBlack;
         if (FORMAT == 30) flags = bc1::kAllow3 | bc1::kPunchThrough;
@@ -66,7 +63,7 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
             uint32_t a_lo = 0, a_hi = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const uint32_t a = (p.color_mask & 8u) ? (px[i] >> 24) : 0u;
+                const uint32_t a = px[i] >> 24;
                 const uint32_t q = static_cast<uint32_t>(roundf(__fmul_rn(static_cast<float>(a), 15.0f/255.0f))) & 15u;
                 if (i < 8) a_lo |= q << (4*i); else a_hi |= q << (4*(i - 8));
             }
@@ -77,7 +74,6 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
                 const uint2 a = bc4_encode_warp(sp + b*kBlkStride, 3, radius, hq != 0);
                 if (b == lane) mine = a;
             }
-            if (!(p.color_mask & 8u)) mine = make_uint2(0, 0);
             if (lane < nblk) reinterpret_cast<uint4*>(p.dst)[first + lane] = make_uint4(mine.x, mine.y, color.x, color.y);
         }
     }

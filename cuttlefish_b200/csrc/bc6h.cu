@@ -44,9 +44,10 @@ __global__ void __launch_bounds__(kBc6Warps*32) bc6h_kernel(const EncodeParams p
                 hr = __half_as_ushort(__float2half_rn(f.x)); hg = __half_as_ushort(__float2half_rn(f.y));
                 hb = __half_as_ushort(__float2half_rn(f.z));
             }
-            bc6h::px(xs, lane, t, 0) = (p.color_mask & 1u) ? half_bits_to_domain(hr) : 0.0f;
-            bc6h::px(xs, lane, t, 1) = (p.color_mask & 2u) ? half_bits_to_domain(hg) : 0.0f;
-            bc6h::px(xs, lane, t, 2) = (p.color_mask & 4u) ? half_bits_to_domain(hb) : 0.0f;
+            // Bc6HConverter does not look at the colour mask
+            bc6h::px(xs, lane, t, 0) = half_bits_to_domain(hr);
+            bc6h::px(xs, lane, t, 1) = half_bits_to_domain(hg);
+            bc6h::px(xs, lane, t, 2) = half_bits_to_domain(hb);
         }
         const uint4 out = bc6h::encode_block(xs, lane, p.quality);
         if (live) reinterpret_cast<uint4*>(p.dst)[blk] = out;

@@ -38,10 +38,8 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
                 v = make_float4(fminf(fmaxf(f.x, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.y, 0.0f), 1.0f)*255.0f,
                     fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
             }
-            etc::px(xs, lane, t, 0) = (p.color_mask & 1u) ? v.x : 0.0f;
-            etc::px(xs, lane, t, 1) = (p.color_mask & 2u) ? v.y : 0.0f;
-            etc::px(xs, lane, t, 2) = (p.color_mask & 4u) ? v.z : 0.0f;
-            etc::px(xs, lane, t, 3) = (p.color_mask & 8u) ? (p.alpha_type == 0 ? 255.0f : v.w) : 0.0f;
+            // EtcConverter never looks at the colour mask or the alpha type: all four channels as they are
+            etc::px(xs, lane, t, 0) = v.x; etc::px(xs, lane, t, 1) = v.y; etc::px(xs, lane, t, 2) = v.z; etc::px(xs, lane, t, 3) = v.w;
         }
         const uint2 color = etc::encode_color(xs, lane, FORMAT != 37, rounds);
         if (FORMAT == 40) {
