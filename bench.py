@@ -130,17 +130,20 @@ def cpu_reference(a, wl, size, steps, warmup):
     img = synth.gen_image(wl["kind"], size, size, rows=(0, s))[:, :s].copy()
     threads = oracle.hardware_threads()
     kw = dict(type=wl["type"], quality=a.quality)
+    # the reference's own Converter::convert (std::thread pool, real converter glue, real encoders) when
+    # oracle/_ref/libcfglue.so was built; else the same encoders under our byte-identical glue restatement
+    enc = oracle.encode_glue if oracle.glue_available() else oracle.encode
     for _ in range(warmup):
-        oracle.encode(img[: max(64, s // 8)], a.format, threads=0, **kw)
+        enc(img[: max(64, s // 8)], a.format, threads=0, **kw)
     times = []
     for _ in range(steps):
         t = time.perf_counter()
-        oracle.encode(img, a.format, threads=0, **kw)
+        enc(img, a.format, threads=0, **kw)
         times.append(time.perf_counter() - t)
     dt = float(np.mean(times))
     return {"value": s * s / dt / 1e6, "unit": "Mtexels/s", "cores": threads, "kind": "reference",
             "sample": "%dx%d top-left crop of the %dx%d %s image, %s quality=%s, oracle/_ref "
-                      "(reference encoders compiled from source), %d threads, %.2f s/step" %
+                      "(reference Converter::convert + encoders compiled from source), %d threads, %.2f s/step" %
                       (s, s, size, size, wl["kind"], a.format, a.quality, threads, dt)}, dt
 
 

@@ -90,6 +90,35 @@ def encode(img, fmt, threads=0, **kw):
     return out
 
 
+_GLUE_PATH = os.path.join(_HERE, "_ref", "libcfglue.so")
+_glue = None
+
+
+def glue_available():
+    return os.path.exists(_GLUE_PATH)
+
+
+def encode_glue(img, fmt, threads=0, **kw):
+    """Same as encode(), but through the reference's REAL converter glue (lib/src/Converter.cpp and the
+    *Converter.cpp files compiled from /root/reference over oracle/glue_stub.cpp) instead of our
+    restatement in cfref.cpp.  Used only to pin the restatement."""
+    global _glue
+    if _glue is None:
+        _glue = ctypes.CDLL(_GLUE_PATH)
+        _glue.cfglue_encode.restype = ctypes.c_int
+        _glue.cfglue_encode.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                        ctypes.c_size_t, ctypes.c_uint]
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w, _ = img.shape
+    d = make_desc(fmt, w, h, **kw)
+    n = lib().cfref_encoded_size(ctypes.byref(d))
+    out = np.empty(n, dtype=np.uint8)
+    rc = _glue.cfglue_encode(ctypes.byref(d), img.ctypes.data, w * 4, out.ctypes.data, n, threads)
+    if rc != n:
+        raise RuntimeError("cfglue_encode failed: %d" % rc)
+    return out
+
+
 def decode(blocks, fmt, width, height, **kw):
     """Decode packed blocks with the reference's decoders -> float32 [H,W,4]."""
     blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
