@@ -21,6 +21,7 @@ SYMBOLS = [
     ("cfx_init", ctypes.c_int, [ctypes.c_int]),
     ("cfx_shutdown", None, []),
     ("cfx_format_supported", ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32]),
+    ("cfx_format_is_exact", ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     ("cfx_block_info", ctypes.c_int, [ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32),
                                       ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     ("cfx_encoded_size", ctypes.c_size_t, [ctypes.POINTER(SurfaceDesc)]),

@@ -72,6 +72,11 @@ def format_supported(fmt, type="UNorm"):
     return bool(load().cfx_format_supported(_enum(FORMATS, fmt), _enum(TYPES, type)))
 
 
+def format_is_exact(fmt, type="UNorm", quality="Normal"):
+    """True if the GPU bytes are identical to the reference CPU encoder's (else: PSNR parity)."""
+    return bool(load().cfx_format_is_exact(_enum(FORMATS, fmt), _enum(TYPES, type), _enum(QUALITY, quality)))
+
+
 def block_info(fmt):
     bw, bh, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
     rc = load().cfx_block_info(_enum(FORMATS, fmt), ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(nb))

@@ -25,7 +25,7 @@ UNITS = [
     ("cfx.cu", [], None),
     ("bc4_bc5.cu", [], None),
     ("bc7.cu", [], "CFX_HAVE_BC7"),
-    ("bc1_bc3.cu", [], "CFX_HAVE_BC1"),
+    ("bc1_bc3.cu", ["-fmad=false"], "CFX_HAVE_BC1"),
     ("etc.cu", [], "CFX_HAVE_ETC"),
     ("bc6h.cu", [], "CFX_HAVE_BC6H"),
     ("astc.cu", [], "CFX_HAVE_ASTC"),
@@ -66,16 +66,38 @@ def _compile(src, flags, defines, headers, verbose):
     return obj, (r.stdout + r.stderr) if verbose else ""
 
 
+GENERATED = os.path.join(CSRC, "generated", "rgbcx_tables.inc")
+
+
+def _generate_tables():
+    """The byte-exact BC1 path needs rgbcx's data tables, dumped from the reference at build time
+    (never committed). Without /root/reference and without a previously generated file, BC1 falls back
+    to our own search (PSNR parity) and cfx_format_is_exact() says so."""
+    if os.path.exists(GENERATED):
+        return True
+    ref = os.environ.get("CFX_REFERENCE", "/root/reference")
+    tool = os.path.join(HERE, "..", "tools", "gen_rgbcx_tables.py")
+    if os.path.exists(os.path.join(ref, "lib", "bc7enc_rdo", "rgbcx.cpp")) and os.path.exists(tool):
+        r = subprocess.run([sys.executable, tool, ref], capture_output=True, text=True)
+        if r.returncode != 0:
+            print("warning: rgbcx table generation failed:\n" + r.stdout + r.stderr)
+    return os.path.exists(GENERATED)
+
+
 def build(verbose=False):
     os.makedirs(OBJ, exist_ok=True)
+    have_tables = _generate_tables()
     units = [(s, f, m) for (s, f, m) in UNITS if os.path.exists(os.path.join(CSRC, s))]
     defines = ["-D%s=1" % m for (_, _, m) in units if m]
     headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "cfx.h"))
+    if have_tables:
+        headers.append(GENERATED)
     ref = os.environ.get("CFX_REFERENCE", "/root/reference")
     objs = []
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
-        futs = [ex.submit(_compile, s, f + ["-DCFX_REFERENCE_DIR=\"%s\"" % ref], defines if s == "cfx.cu" else [],
+        extra = ["-DCFX_HAVE_RGBCX_TABLES=1"] if have_tables else []
+        futs = [ex.submit(_compile, s, f + extra + ["-DCFX_REFERENCE_DIR=\"%s\"" % ref], defines if s == "cfx.cu" else [],
                           headers, verbose) for (s, f, _) in units]
         for fu in futs:
             obj, log = fu.result()

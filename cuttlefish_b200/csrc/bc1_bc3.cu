@@ -8,6 +8,9 @@
 // lib/src/S3tcConverter.cpp:263-376.  Colour halves: PSNR parity (see bc1_core.cuh); BC3/BC2 alpha
 // halves: bit-exact (rgbcx.cpp:2730-2884; packBc2Alpha, S3tcConverter.cpp:131-143).
 #include "bc1_core.cuh"
+#ifdef CFX_HAVE_RGBCX_TABLES
+#include "bc1_exact.cuh"
+#endif
 #include "bc4_device.cuh"
 #include "kernels.h"
 
@@ -19,7 +22,8 @@ constexpr int kBlkStride = 20;     // words per block in shared memory (16 texel
 }
 
 template <int FORMAT>   // 29 BC1_RGB, 30 BC1_RGBA, 31 BC2, 32 BC3
-__global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams p, int descent, uint32_t radius, uint32_t hq)
+__global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams p, int descent, uint32_t radius, uint32_t hq,
+    bool exact)
 {
     __shared__ __align__(16) uint32_t s_px[kBc1Warps][32*kBlkStride];
     const uint32_t lane = lane_id(), warp = warp_id();
@@ -55,7 +59,21 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
         uint32_t flags = 0;
         if (FORMAT == 29) flags = bc1::kAllow3 | bc1::kAllowBlack;
         if (FORMAT == 30) flags = bc1::kAllow3 | bc1::kPunchThrough;
-        const uint2 color = bc1::encode_color_block(px, flags, descent);
+        uint2 color;
+#ifdef CFX_HAVE_RGBCX_TABLES
+        // Quality::Normal: byte-exact rgbcx level 9 (bc1_exact.cuh).  BC1_RGBA blocks with a texel of
+        // alpha < 0.5 go through libsquish in the reference (S3tcConverter.cpp:283-330); those keep our
+        // punch-through search.
+        bool transparent = false;
+        if (FORMAT == 30) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) transparent = transparent || (px[i] >> 24) < 128u;
+        }
+        if (exact && !transparent)
+            color = rgbcx9::encode_bc1_level9(px, FORMAT == 29 || FORMAT == 30, FORMAT == 29);
+        else
+#endif
+            color = bc1::encode_color_block(px, flags, descent);
         if (FORMAT == 29 || FORMAT == 30) {
             if (lane < nblk) reinterpret_cast<uint2*>(p.dst)[first + lane] = color;
         } else if (FORMAT == 31) {
@@ -79,6 +97,18 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
     }
 }
 
+// Whether BC1-family colour blocks are byte-identical to rgbcx at this quality: only Normal (rgbcx level
+// 9) is restated, and only when the reference's tables were generated into the build.
+bool bc1_color_is_exact(uint32_t quality)
+{
+#ifdef CFX_HAVE_RGBCX_TABLES
+    return quality == 2;
+#else
+    (void)quality;
+    return false;
+#endif
+}
+
 int launch_bc123(const EncodeParams& p, cudaStream_t stream)
 {
     static const uint32_t radii[5] = {3, 3, 5, 16, 32};   // getSearchRadius, S3tcConverter.cpp:80-95
@@ -95,8 +125,9 @@ int launch_bc123(const EncodeParams& p, cudaStream_t stream)
         default: k = reinterpret_cast<const void*>(&bc123_kernel<32>); break;
     }
     const uint32_t grid = min(ctas, persistent_ctas(k, kBc1Warps*32));
+    bool exact = bc1_color_is_exact(p.quality);
     void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&descent), const_cast<uint32_t*>(&radius),
-        const_cast<uint32_t*>(&hq)};
+        const_cast<uint32_t*>(&hq), &exact};
     if (cudaLaunchKernel(k, dim3(grid), dim3(kBc1Warps*32), args, 0, stream) != cudaSuccess) return -4;
     return 1;
 }

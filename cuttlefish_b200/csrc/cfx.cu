@@ -299,6 +299,19 @@ void cfx_shutdown(void)
 
 int cfx_format_supported(uint32_t format, uint32_t type) { return find_launcher(format, type) != nullptr; }
 
+int cfx_format_is_exact(uint32_t format, uint32_t type, uint32_t quality)
+{
+    if (!find_launcher(format, type) || quality > CFX_QUALITY_HIGHEST) return 0;
+    switch (format) {
+        case CFX_FORMAT_BC4: case CFX_FORMAT_BC5: return 1;
+#ifdef CFX_HAVE_BC1
+        // BC1_RGBA: exact for blocks without transparent texels (the others go through libsquish in the reference)
+        case CFX_FORMAT_BC1_RGB: case CFX_FORMAT_BC2: case CFX_FORMAT_BC3: return bc1_color_is_exact(quality) ? 1 : 0;
+#endif
+        default: return 0;
+    }
+}
+
 int cfx_block_info(uint32_t format, uint32_t* bw, uint32_t* bh, uint32_t* bytes)
 {
     uint32_t w, h, b;

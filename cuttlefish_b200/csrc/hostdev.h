@@ -9,6 +9,7 @@
 #define CFX_HD __device__ __forceinline__
 #define CFX_HD_NOINLINE static __device__ __noinline__
 #define CFX_CONST __device__ __constant__
+#define CFX_TABLE static __device__ const
 #else
 #include <algorithm>
 #include <cmath>
@@ -16,6 +17,7 @@
 #define CFX_HD inline
 #define CFX_HD_NOINLINE inline
 #define CFX_CONST static const
+#define CFX_TABLE static const
 struct float4 { float x, y, z, w; };
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };

@@ -87,6 +87,11 @@ void cfx_shutdown(void);
 
 /* 1 if the (format,type) pair has a GPU encoder, else 0. */
 int cfx_format_supported(uint32_t format, uint32_t type);
+/* 1 if the GPU encoder's bytes are IDENTICAL to the reference CPU encoder's for this (format, type,
+ * quality) -- BC4/BC5 always; BC1_RGB/BC2/BC3 at CFX_QUALITY_NORMAL when the library was built with the
+ * reference's rgbcx tables (tools/gen_rgbcx_tables.py) -- else 0: the format is held to PSNR parity.
+ * No reference analogue; lets an integrator (and the tests) know which guarantee applies. */
+int cfx_format_is_exact(uint32_t format, uint32_t type, uint32_t quality);
 /* Block footprint and bytes per block; returns CFX_OK or CFX_ERR_UNSUPPORTED. */
 int cfx_block_info(uint32_t format, uint32_t* block_w, uint32_t* block_h, uint32_t* block_bytes);
 /* ceil(w/bw)*ceil(h/bh)*block_bytes, 0 if the format is unknown. */

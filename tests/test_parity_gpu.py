@@ -306,3 +306,40 @@ def test_color_mask_and_quality_levels(cfx, oracle):
             got = cfx.encode(src, fmt, quality=q)
             psnr.append(oracle.psnr_rgb(img, oracle.decode(got, fmt, 64, 64)))
         assert psnr[4] >= psnr[0] - 0.05 and psnr[2] >= psnr[0] - 0.05, "%s %s" % (fmt, psnr)
+
+
+# ---- BC1 family at Quality::Normal: byte-exact rgbcx level 9 when the build has the reference tables ----
+@pytest.mark.parametrize("fmt", ["BC1_RGB", "BC1_RGBA", "BC2", "BC3"])
+def test_bc123_bit_exact_at_normal(cfx, oracle, fmt):
+    if not cfx.format_is_exact("BC1_RGB", quality="Normal"):
+        pytest.skip("libcfx.so was built without the reference's rgbcx tables: BC1 is held to PSNR parity only")
+    for kind, w, h in [("noise+grad", 256, 256), ("gradient", 512, 512), ("gradient", 1024, 64), ("noise+grad", 97, 61)]:
+        img = oracle.gen_image(kind, w, h, seed=41)
+        ref = oracle.encode(img, fmt)
+        for src in (oracle.to_rgba8(img), img):                   # RGBA8 and RGBA32F source paths
+            got = cfx.encode(src, fmt)
+            bad = block_mismatches(got, ref, cfx.block_info(fmt)[2])
+            assert bad.size == 0, "%s %s %dx%d: %d blocks differ, first %s" % (fmt, kind, w, h, bad.size, bad[:8])
+    # committed goldens (64x64 noise+grad, gradient, 30x22) are reference outputs too
+    for name in golden_cases([fmt]):
+        src, blocks, f, kw = load_golden(name)
+        if kw.get("quality", "Normal") != "Normal" or "alpha" in name:
+            continue
+        assert np.array_equal(cfx.encode(src, f, **kw), blocks), name
+
+
+def test_bc1_rgb_dark_and_gray_blocks_exact(cfx, oracle):
+    """rgbcx special cases: grayscale blocks, near-black texels (3-colour + black), solid blocks."""
+    if not cfx.format_is_exact("BC1_RGB", quality="Normal"):
+        pytest.skip("built without the reference's rgbcx tables")
+    rng = np.random.default_rng(5)
+    img = np.zeros((64, 64, 4), np.float32); img[..., 3] = 1
+    gray = rng.integers(0, 256, (32, 64, 1)).astype(np.float32) / 255
+    img[:32, :, :3] = gray                                         # grayscale noise
+    dark = rng.integers(0, 12, (16, 64, 3)).astype(np.float32) / 255
+    img[32:48, :, :3] = dark                                       # near-black texels
+    img[48:, :, :3] = (rng.integers(0, 256, (4, 16, 3)).repeat(4, axis=0).repeat(4, axis=1) / 255).astype(np.float32)  # solid blocks
+    for fmt in ("BC1_RGB", "BC3"):
+        got = cfx.encode(oracle.to_rgba8(img), fmt)
+        bad = block_mismatches(got, oracle.encode(img, fmt), cfx.block_info(fmt)[2])
+        assert bad.size == 0, "%s: %d blocks differ, first %s" % (fmt, bad.size, bad[:8])
