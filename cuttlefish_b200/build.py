@@ -26,7 +26,7 @@ UNITS = [
     ("bc4_bc5.cu", [], None),
     ("bc7.cu", [], "CFX_HAVE_BC7"),
     ("bc1_bc3.cu", ["-fmad=false"], "CFX_HAVE_BC1"),
-    ("etc.cu", [], "CFX_HAVE_ETC"),
+    ("etc.cu", ["-fmad=false"], "CFX_HAVE_ETC"),
     ("bc6h.cu", [], "CFX_HAVE_BC6H"),
     ("astc.cu", [], "CFX_HAVE_ASTC"),
     ("astc2.cu", [], None),

@@ -308,6 +308,9 @@ int cfx_format_is_exact(uint32_t format, uint32_t type, uint32_t quality)
         // BC1_RGBA: exact for blocks without transparent texels (the others go through libsquish in the reference)
         case CFX_FORMAT_BC1_RGB: case CFX_FORMAT_BC2: case CFX_FORMAT_BC3: return bc1_color_is_exact(quality) ? 1 : 0;
 #endif
+#ifdef CFX_HAVE_ETC
+        case CFX_FORMAT_ETC1: return etc1_is_exact(quality) ? 1 : 0;       // linear colour space
+#endif
         default: return 0;
     }
 }

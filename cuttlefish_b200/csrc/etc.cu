@@ -8,6 +8,7 @@
 // ETC2_R8G8B8A8.
 #include "common.cuh"
 #include "etc_core.cuh"
+#include "etc1_exact.cuh"
 #include "kernels.h"
 
 namespace cfx {
@@ -15,7 +16,7 @@ namespace cfx {
 namespace { constexpr int kEtcWarps = 4; }
 
 template <int FORMAT>   // 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8
-__global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p, int rounds, int alpha_radius)
+__global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p, int rounds, int alpha_radius, bool exact)
 {
     __shared__ float s_x[kEtcWarps][16*4*32];
     const uint32_t lane = lane_id(), warp = warp_id();
@@ -26,6 +27,27 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
         const bool live = blk < p.total_blocks;
         const uint32_t b = live ? blk : p.total_blocks - 1;
         const uint32_t by = b / p.blocks_x, bx = b - by*p.blocks_x;
+        if (FORMAT == 37 && exact) {
+            // byte-exact etc2comp iteration 0 (etc1_exact.cuh): texels in the reference's column-major
+            // block order, [0,1] floats, alpha forced to 1, texels outside the image marked with NaN alpha
+            etc1x::Px src[16];
+#pragma unroll
+            for (uint32_t x = 0; x < 4; ++x)
+#pragma unroll
+                for (uint32_t y = 0; y < 4; ++y) {
+                    const uint32_t sx = bx*4 + x, sy = by*4 + y;
+                    etc1x::Px q;
+                    if (sx >= p.width || sy >= p.height) { q.r = q.g = q.b = 0.0f; q.a = __int_as_float(0x7FC00000); }
+                    else {
+                        const float4 f = load_texel_f32(p, sx, sy);
+                        q.r = etc1x::clamp01(f.x); q.g = etc1x::clamp01(f.y); q.b = etc1x::clamp01(f.z); q.a = 1.0f;
+                    }
+                    src[x*4 + y] = q;
+                }
+            const uint2 color = etc1x::encode_etc1_exact(src);
+            if (live) reinterpret_cast<uint2*>(p.dst)[blk] = color;
+            continue;
+        }
         for (uint32_t t = 0; t < 16; ++t) {
             const uint32_t x = min(bx*4 + (t & 3), p.width - 1), y = min(by*4 + (t >> 2), p.height - 1);
             float4 v;
@@ -51,6 +73,8 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
     }
 }
 
+bool etc1_is_exact(uint32_t quality) { return quality <= 2; }
+
 int launch_etc(const EncodeParams& p, cudaStream_t stream)
 {
     static const int rounds_by_quality[5] = {0, 1, 1, 2, 3};
@@ -61,7 +85,9 @@ int launch_etc(const EncodeParams& p, cudaStream_t stream)
     const void* k = p.format == 37 ? reinterpret_cast<const void*>(&etc_kernel<37>) :
         (p.format == 38 ? reinterpret_cast<const void*>(&etc_kernel<38>) : reinterpret_cast<const void*>(&etc_kernel<40>));
     const uint32_t grid = min(ctas, persistent_ctas(k, kEtcWarps*32));
-    void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&rounds), const_cast<int*>(&radius)};
+    // ETC1 at effort <= 40 (Lowest/Low/Normal) in linear colour space is the byte-exact restatement
+    bool exact = etc1_is_exact(p.quality) && p.color_space == 0;
+    void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&rounds), const_cast<int*>(&radius), &exact};
     if (cudaLaunchKernel(k, dim3(grid), dim3(kEtcWarps*32), args, 0, stream) != cudaSuccess) return -4;
     return 1;
 }

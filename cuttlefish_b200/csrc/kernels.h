@@ -16,5 +16,6 @@ int launch_bc6h(const EncodeParams& p, cudaStream_t stream);
 int launch_bc123(const EncodeParams& p, cudaStream_t stream);
 int launch_etc(const EncodeParams& p, cudaStream_t stream);
 bool bc1_color_is_exact(uint32_t quality);
+bool etc1_is_exact(uint32_t quality);
 
 } // namespace cfx

@@ -89,7 +89,8 @@ void cfx_shutdown(void);
 int cfx_format_supported(uint32_t format, uint32_t type);
 /* 1 if the GPU encoder's bytes are IDENTICAL to the reference CPU encoder's for this (format, type,
  * quality) -- BC4/BC5 always; BC1_RGB/BC2/BC3 at CFX_QUALITY_NORMAL when the library was built with the
- * reference's rgbcx tables (tools/gen_rgbcx_tables.py) -- else 0: the format is held to PSNR parity.
+ * reference's rgbcx tables (tools/gen_rgbcx_tables.py); ETC1 at CFX_QUALITY_LOWEST..NORMAL in linear
+ * colour space -- else 0: the format is held to PSNR parity.
  * No reference analogue; lets an integrator (and the tests) know which guarantee applies. */
 int cfx_format_is_exact(uint32_t format, uint32_t type, uint32_t quality);
 /* Block footprint and bytes per block; returns CFX_OK or CFX_ERR_UNSUPPORTED. */

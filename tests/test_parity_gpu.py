@@ -343,3 +343,25 @@ def test_bc1_rgb_dark_and_gray_blocks_exact(cfx, oracle):
         got = cfx.encode(oracle.to_rgba8(img), fmt)
         bad = block_mismatches(got, oracle.encode(img, fmt), cfx.block_info(fmt)[2])
         assert bad.size == 0, "%s: %d blocks differ, first %s" % (fmt, bad.size, bad[:8])
+
+
+def test_etc1_bit_exact(cfx, oracle):
+    """ETC1 at Lowest/Low/Normal (etc2comp effort <= 40: only encoding iteration 0 runs) is byte-exact,
+    including ragged edges (the reference hands edge blocks to etc2comp as smaller images) and
+    non-8-bit float sources."""
+    assert cfx.format_is_exact("ETC1", quality="Normal")
+    for kind, w, h in [("noise+grad", 256, 256), ("gradient", 512, 512), ("noise+grad", 97, 61), ("gradient", 30, 22), ("noise+grad", 3, 5)]:
+        img = oracle.gen_image(kind, w, h, seed=59)
+        for q in ("Normal", "Lowest"):
+            ref = oracle.encode(img, "ETC1", quality=q)
+            for src in (oracle.to_rgba8(img), img):
+                bad = block_mismatches(cfx.encode(src, "ETC1", quality=q), ref, 8)
+                assert bad.size == 0, "ETC1 %s %dx%d %s: %d blocks differ, first %s" % (kind, w, h, q, bad.size, bad[:8])
+    img = oracle.gen_image("gradient", 64, 64)
+    img[..., :3] = np.clip(img[..., :3] * np.float32(0.737) + np.float32(0.0123), 0, 1)
+    img[..., 3] = 0.3                                                  # alpha is ignored by ETC1
+    assert np.array_equal(cfx.encode(img, "ETC1"), oracle.encode(img, "ETC1"))
+    for name in golden_cases(["ETC1"]):
+        src, blocks, f, kw = load_golden(name)
+        if kw.get("quality", "Normal") in ("Normal", "Low", "Lowest"):
+            assert np.array_equal(cfx.encode(src, f, **kw), blocks), name
