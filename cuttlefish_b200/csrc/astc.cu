@@ -16,6 +16,7 @@
 // ASTC specification (astc_tables.hpp) once per footprint and live in global memory (L1/L2 resident).
 //
 // Replaces AstcConverter::process (lib/src/AstcConverter.cpp:208-230) for LDR profiles.
+#include "astc3_tables.hpp"
 #include "astc_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -37,6 +38,7 @@ constexpr uint32_t kWarpBytes = (sizeof(BlockState) + 15)/16*16 + kUScr + kWScr;
 
 struct DeviceTables {
     Ctx ctx;
+    Astc3Tab t3;
 };
 
 std::mutex g_mutex;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kAstcWarps*32) astc_kernel(const EncodeParams 
 }
 
 int launch_astc2(const EncodeParams& p, const Ctx& ctx, cudaStream_t stream);   // astc2.cu: warp-cooperative search
+int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cudaStream_t stream);   // astc3.cu: two-phase search
 
 int launch_astc(const EncodeParams& p, cudaStream_t stream)
 {
@@ -145,25 +148,31 @@ int launch_astc(const EncodeParams& p, cudaStream_t stream)
     int device = 0;
     cudaGetDevice(&device);
     Ctx ctx;
+    Astc3Tab t3;
     {
         std::lock_guard<std::mutex> lock(g_mutex);
         auto key = std::make_pair(device, static_cast<int>(p.block_w*16 + p.block_h));
         auto it = g_tables.find(key);
         if (it == g_tables.end()) {
             Built b = build_tables(static_cast<int>(p.block_w), static_cast<int>(p.block_h));
+            const Astc3Tab b3 = build_tables3(b);
+            if (b.tab.n_grids > static_cast<uint32_t>(kMaxGrids3)) return -2;
             uint8_t* d = nullptr;
             if (cudaMalloc(&d, b.blob.size()) != cudaSuccess) return -4;
             if (cudaMemcpy(d, b.blob.data(), b.blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) return -4;
             DeviceTables dt;
-            dt.ctx.blob = d; dt.ctx.tab = b.tab;
+            dt.ctx.blob = d; dt.ctx.tab = b.tab; dt.t3 = b3;
             it = g_tables.insert(std::make_pair(key, dt)).first;
         }
         ctx = it->second.ctx;
+        t3 = it->second.t3;
     }
-    // The lane-per-candidate kernel below is the first implementation, kept as a cross-check
-    // (CFX_ASTC_V1=1); the default is the warp-cooperative kernel of astc2.cu.
-    static const bool use_v1 = getenv("CFX_ASTC_V1") != nullptr;
-    if (!use_v1) return launch_astc2(p, ctx, stream);
+    // Default: the two-phase tensor-core kernel of astc3.cu.  The earlier implementations are kept as
+    // cross-checks: CFX_ASTC_V=2 (exhaustive warp-cooperative search, astc2.cu), CFX_ASTC_V=1 (lane per
+    // candidate, below).
+    static const int version = getenv("CFX_ASTC_V") ? atoi(getenv("CFX_ASTC_V")) : (getenv("CFX_ASTC_V1") ? 1 : 3);
+    if (version >= 3) return launch_astc3(p, ctx, t3, stream);
+    if (version == 2) return launch_astc2(p, ctx, stream);
     const Plan plan = make_plan(p.quality, ctx.tab);
     const size_t smem = kAstcWarps*kWarpBytes;
     static bool attr_set = false;

@@ -1,0 +1,187 @@
+// Extra per-footprint tables of the two-phase ASTC search (astc3.cu), appended to the blob that
+// astc_tables.hpp builds.  For every weight grid g of the footprint, with P_g the bilinear infill
+// matrix (texels x grid weights, ASTC spec "Weight Infill"):
+//   M_g = pinv(P_g)      least-squares decimation: ideal texel weights -> ideal grid weights
+//   R_g = I - P_g M_g    what decimation to grid g cannot represent
+// Both are stored as fp16 in the register layout of the B operand of mma.sync.m16n8k16, so that a warp
+// gets decimated weights / decimation residuals of all its partition hypotheses ("slot planes", the
+// A operand rows) from a handful of tensor-core instructions.
+//
+// What these tables replace in the reference: astcenc's per-decimation-mode ideal-weight computation and
+// its error estimate, compute_ideal_weights_for_decimation / compute_error_of_weight_set_1plane
+// (lib/astc-encoder/Source/astcenc_ideal_endpoints_and_weights.cpp:845, :688).
+//
+// Plain C++ (no CUDA): used by astc3.cu's host side and by the host tools.
+#pragma once
+#include "astc_tables.hpp"
+
+#include <cmath>
+
+namespace cfx {
+namespace astc {
+
+constexpr int kMaxGrids3 = 52;
+constexpr int kRows3 = 16;          // slot planes (A operand rows): 9 first planes, 4 second planes, 3 spare
+
+struct Astc3Tab {
+    uint32_t NT, KS;                // texel n-tiles (8 wide), texel k-steps (16 deep)
+    uint32_t off_rfrag_idx;         // [n_grids] uint32: byte offset of grid's R fragments, 0 = full-resolution grid (R = 0)
+    uint32_t off_mfrag_idx;         // [n_grids] uint32: byte offset of grid's M fragments
+    uint32_t off_kappa;             // [n_grids][kMaxTexels] float: kappa_gi = sum_j P_ij^2
+    uint32_t off_ksum;              // [n_grids] float: sum_i kappa_gi
+    uint32_t off_modecl;            // [2 alpha][4 slot type][n_modes1 + n_modes2] u8 colour level, 0xFF = does not fit
+    uint32_t n_modes;               // n_modes1 + n_modes2
+};
+
+inline uint16_t f32_to_f16_bits(float f)
+{
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x47800000u) return static_cast<uint16_t>(sign | 0x7BFFu);            // clamp to max finite
+    if (x < 0x38800000u) {                                                         // subnormal / zero
+        if (x < 0x33000000u) return static_cast<uint16_t>(sign);
+        const int shift = 113 - static_cast<int>(x >> 23);
+        const uint32_t mant = (x & 0x7FFFFFu) | 0x800000u;
+        uint32_t h = mant >> (shift + 13);
+        const uint32_t rem = mant & ((1u << (shift + 13)) - 1u), half = 1u << (shift + 12);
+        if (rem > half || (rem == half && (h & 1u))) ++h;
+        return static_cast<uint16_t>(sign | h);
+    }
+    uint32_t h = ((x - 0x38000000u) >> 13);
+    const uint32_t rem = x & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+    return static_cast<uint16_t>(sign | h);
+}
+
+// Solves (P^T P) M = P^T in double precision (Gauss-Jordan with partial pivoting).
+inline void pinv_infill(const std::vector<double>& P, int T, int nw, std::vector<double>& M)
+{
+    std::vector<double> A(static_cast<size_t>(nw)*nw, 0.0);
+    M.assign(static_cast<size_t>(nw)*T, 0.0);
+    for (int a = 0; a < nw; ++a) {
+        for (int b = 0; b < nw; ++b) {
+            double s = 0;
+            for (int i = 0; i < T; ++i) s += P[i*nw + a]*P[i*nw + b];
+            A[a*nw + b] = s + (a == b ? 1e-9 : 0.0);
+        }
+        for (int i = 0; i < T; ++i) M[a*T + i] = P[i*nw + a];
+    }
+    for (int col = 0; col < nw; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < nw; ++r) if (std::fabs(A[r*nw + col]) > std::fabs(A[piv*nw + col])) piv = r;
+        if (piv != col) {
+            for (int k = 0; k < nw; ++k) std::swap(A[piv*nw + k], A[col*nw + k]);
+            for (int k = 0; k < T; ++k) std::swap(M[piv*T + k], M[col*T + k]);
+        }
+        const double inv = 1.0/A[col*nw + col];
+        for (int k = 0; k < nw; ++k) A[col*nw + k] *= inv;
+        for (int k = 0; k < T; ++k) M[col*T + k] *= inv;
+        for (int r = 0; r < nw; ++r) {
+            if (r == col) continue;
+            const double f = A[r*nw + col];
+            if (f == 0.0) continue;
+            for (int k = 0; k < nw; ++k) A[r*nw + k] -= f*A[col*nw + k];
+            for (int k = 0; k < T; ++k) M[r*T + k] -= f*M[col*T + k];
+        }
+    }
+}
+
+// Appends the tables to b.blob and returns their offsets.
+inline Astc3Tab build_tables3(Built& b)
+{
+    Astc3Tab t3;
+    std::memset(&t3, 0, sizeof(t3));
+    AstcTab& t = b.tab;
+    std::vector<uint8_t>& blob = b.blob;
+    const int T = static_cast<int>(t.texels);
+    const int G = static_cast<int>(t.n_grids);
+    auto reserve = [&](size_t bytes, size_t align) {
+        size_t off = (blob.size() + align - 1)/align*align;
+        blob.resize(off + bytes, 0);
+        return static_cast<uint32_t>(off);
+    };
+    t3.NT = static_cast<uint32_t>((T + 7)/8);
+    t3.KS = static_cast<uint32_t>((T + 15)/16);
+    t3.n_modes = t.n_modes1 + t.n_modes2;
+    t3.off_rfrag_idx = reserve(static_cast<size_t>(G)*4, 4);
+    t3.off_mfrag_idx = reserve(static_cast<size_t>(G)*4, 4);
+    t3.off_kappa = reserve(static_cast<size_t>(G)*kMaxTexels*4, 4);
+    t3.off_ksum = reserve(static_cast<size_t>(G)*4, 4);
+    const int KS = static_cast<int>(t3.KS), NT = static_cast<int>(t3.NT);
+    for (int g = 0; g < G; ++g) {
+        const GridInfo gi = reinterpret_cast<const GridInfo*>(&blob[t.off_grids])[g];
+        const int nw = gi.nw;
+        std::vector<double> P(static_cast<size_t>(T)*nw, 0.0), M;
+        for (int i = 0; i < T; ++i) {
+            const uint8_t* inf = &blob[t.off_infill + (static_cast<size_t>(g)*T + i)*8];
+            for (int k = 0; k < 4; ++k) P[i*nw + inf[k]] += inf[4 + k]/16.0;
+        }
+        double ksum = 0;
+        for (int i = 0; i < T; ++i) {
+            double kap = 0;
+            for (int j = 0; j < nw; ++j) kap += P[i*nw + j]*P[i*nw + j];
+            reinterpret_cast<float*>(&blob[t3.off_kappa])[g*kMaxTexels + i] = static_cast<float>(kap);
+            ksum += kap;
+        }
+        reinterpret_cast<float*>(&blob[t3.off_ksum])[g] = static_cast<float>(ksum);
+        pinv_infill(P, T, nw, M);
+        // M fragments: B[k = texel][n = grid weight] = M[n][k]
+        const int NTW = (nw + 7)/8;
+        {
+            const uint32_t off = reserve(static_cast<size_t>(NTW)*KS*32*8, 16);
+            reinterpret_cast<uint32_t*>(&blob[t3.off_mfrag_idx])[g] = off;
+            uint16_t* dst = reinterpret_cast<uint16_t*>(&blob[off]);
+            for (int nt = 0; nt < NTW; ++nt)
+                for (int ks = 0; ks < KS; ++ks)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int n = nt*8 + (lane >> 2), k0 = ks*16 + 2*(lane & 3);
+                        uint16_t* d = dst + ((static_cast<size_t>(nt)*KS + ks)*32 + lane)*4;
+                        const int ks4[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
+                        for (int e = 0; e < 4; ++e)
+                            d[e] = (n < nw && ks4[e] < T) ? f32_to_f16_bits(static_cast<float>(M[n*T + ks4[e]])) : 0;
+                    }
+        }
+        // R fragments: B[k = texel][n = texel i] = R[i][k]
+        if (nw < T) {
+            std::vector<double> R(static_cast<size_t>(T)*T);
+            for (int i = 0; i < T; ++i)
+                for (int k = 0; k < T; ++k) {
+                    double s = i == k ? 1.0 : 0.0;
+                    for (int j = 0; j < nw; ++j) s -= P[i*nw + j]*M[j*T + k];
+                    R[i*T + k] = s;
+                }
+            const uint32_t off = reserve(static_cast<size_t>(NT)*KS*32*8, 16);
+            reinterpret_cast<uint32_t*>(&blob[t3.off_rfrag_idx])[g] = off;
+            uint16_t* dst = reinterpret_cast<uint16_t*>(&blob[off]);
+            for (int nt = 0; nt < NT; ++nt)
+                for (int ks = 0; ks < KS; ++ks)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int n = nt*8 + (lane >> 2), k0 = ks*16 + 2*(lane & 3);
+                        uint16_t* d = dst + ((static_cast<size_t>(nt)*KS + ks)*32 + lane)*4;
+                        const int ks4[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
+                        for (int e = 0; e < 4; ++e)
+                            d[e] = (n < T && ks4[e] < T) ? f32_to_f16_bits(static_cast<float>(R[n*T + ks4[e]])) : 0;
+                    }
+        }
+    }
+    // colour level of every (alpha, slot type, mode)
+    t3.off_modecl = reserve(static_cast<size_t>(2)*4*t3.n_modes, 4);
+    for (int alpha = 0; alpha < 2; ++alpha)
+        for (int type = 0; type < 4; ++type)
+            for (uint32_t mi = 0; mi < t3.n_modes; ++mi) {
+                const ModeInfo m = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes])[mi];
+                const int pc = type == 1 ? 2 : (type == 2 ? 3 : 1);
+                const int n_ints = pc*(alpha ? 8 : 6);
+                const int avail = 128 - static_cast<int>(m.wbits) - (pc == 1 ? 17 : 29) - (type == 3 ? 2 : 0);
+                uint8_t cl = 0xFF;
+                if ((m.dual != 0) == (type == 3) && n_ints <= 18 && avail >= 0) cl = blob[t.off_clevel + (n_ints >> 1)*128 + avail];
+                blob[t3.off_modecl + (static_cast<size_t>(alpha)*4 + type)*t3.n_modes + mi] = cl;
+            }
+    t.blob_bytes = static_cast<uint32_t>(blob.size());
+    return t3;
+}
+
+} // namespace astc
+} // namespace cfx

@@ -656,7 +656,8 @@ CFX_HD uint64_t bitrev64(uint64_t v)
 
 // Physical 128-bit block for (slot, mode, encoding) with grid weights in u_scr.
 // u_scr: grid weights in bit-stream order, lane-interleaved scratch (linear == false) or a plain array.
-CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const Slot& slot, const ModeInfo& m, const Enc& e, bool has_alpha,
+template <typename SlotT>
+CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo& m, const Enc& e, bool has_alpha,
     const uint8_t* u_scr, uint32_t lane, bool linear = false)
 {
     Bits128 b; b.lo = b.hi = 0;
