@@ -30,7 +30,7 @@ UNITS = [
     ("bc6h.cu", [], "CFX_HAVE_BC6H"),
     ("astc.cu", [], "CFX_HAVE_ASTC"),
     ("astc2.cu", [], None),
-    ("astc3.cu", [], None),
+    ("astc3.cu", ["-DCFX_ASTC3_TUNE=1"] if os.environ.get("CFX_ASTC3_TUNE") else [], None),
 ]
 
 

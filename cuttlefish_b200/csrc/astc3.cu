@@ -22,15 +22,21 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 namespace cfx {
 
 using namespace astc;
 
 namespace {
 
-constexpr int kWarps3 = 8;
+// Launch shape: W warps per CTA, CTAS resident CTAs per SM (register budget = 64K/(W*32*CTAS)).  The kernel is ~9k SASS
+// instructions, far beyond the 32 KB instruction cache, so the warps of a CTA are kept in the same phase of the
+// search by CTA-wide barriers at the phase boundaries: one fetched instruction line then serves all of them.
+constexpr int kDefaultWarps = 12;
+constexpr int kDefaultCtasPerSm = 2;
+#define PHASE_SYNC() do { if (LOCK) __syncthreads(); else __syncwarp(); } while (0)
 constexpr int FX = 8;                          // texel fixed point scale
-constexpr int kTaStride = kMaxTexels + 8;      // halfs; 36 words: conflict-free A fragment loads
 constexpr int kMaxCand = 16;
 
 struct Slot3 {
@@ -42,19 +48,40 @@ struct Slot3 {
     int32_t dual_ch;
 };
 
-struct Warp3 {
-    int4 v[kMaxTexels];                     // texels, FX fixed point
+// Moments of a set of texels about the block centre (FX units): count, sums, upper triangle of products.
+struct Mom { float n, s[4], p[10]; };
+struct LineFit { float m[4], v[4], resid, pad[3]; };     // mean (about the centre), unit direction, trace - lambda
+
+// Per-warp working set, sized by the footprint: TP = texel capacity (NT*8), GP = weight grid capacity.
+constexpr int grid_capacity(int NT) { return NT <= 3 ? 12 : (NT == 4 ? 20 : (NT == 5 ? 28 : (NT <= 7 ? 36 : kMaxGrids3))); }
+constexpr int ta_stride(int TP) { return ((TP + 8)/2) % 8 == 0 ? TP + 16 : TP + 8; }   // halfs; conflict-free A fragment loads
+
+template <int NT>
+struct Warp3T {
+    static constexpr int TP = NT*8;
+    static constexpr int GP = grid_capacity(NT);
+    static constexpr int TS = ta_stride(TP);
+    int4 v[TP];                             // texels, FX fixed point
     Slot3 slots[kSlots];
-    uint8_t part[4][kMaxTexels];            // subset of every texel for slots 1..4
-    __half ta[kRows3][kTaStride];           // A operand: ideal weights per slot plane (rows 0..8 first planes,
+    uint8_t part[4][TP];                    // subset of every texel for slots 1..4
+    __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
                                             // 9..12 second planes of slots 5..8, 13/14 refinement scratch)
-    float D[13][kMaxGrids3];                // decimation loss per slot plane and grid
-    float Sm[4][kMaxGrids3];                // sum_i len2_i kappa_gi for the multi-subset slots 1..4
-    float g[2][kMaxTexels];                 // decimated ideal grid weights of the current candidate, per plane
+    struct Est {
+        float D[13][GP];                    // decimation loss per slot plane and grid
+        float Sm[4][GP];                    // sum_i len2_i kappa_gi for the multi-subset slots 1..4
+    };
+    struct Setup {
+        LineFit lines[15];                  // slot 0, dual-plane slots 5..8, then the 10 subsets of slots 1..4
+        Mom moms[10];                       // moments of those 10 subsets
+    };
+    union { Est est; Setup setup; } u;      // the setup scratch is dead before phase 1 writes D
+    float g[2][TP];                         // decimated ideal grid weights of the current candidate, per plane
     int ep[24];                             // quantised end points of the candidate: [subset][e0 rgba, e1 rgba]
     int best_ep[24];
-    uint8_t su[2*kMaxTexels];               // candidate grid weights (unquantised values 0..64), bit-stream order
-    uint8_t best_su[2*kMaxTexels];
+    uint8_t su[2*TP];                       // candidate grid weights (unquantised values 0..64), bit-stream order
+    uint8_t sk[2*TP];                       // ... and their rank in the quantisation level's value table
+    uint8_t best_su[2*TP];
+    uint8_t best_sk[2*TP];
 };
 
 // model constants (fitted on the host with tools/emu_astc3.py)
@@ -75,8 +102,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
 
-template <int KS>
-__device__ __forceinline__ void load_a(const Warp3& ws, uint32_t (&a)[KS][4], uint32_t lane)
+template <int KS, typename WS>
+__device__ __forceinline__ void load_a(const WS& ws, uint32_t (&a)[KS][4], uint32_t lane)
 {
     const uint32_t gq = lane >> 2, tq = lane & 3u;
 #pragma unroll
@@ -89,8 +116,8 @@ __device__ __forceinline__ void load_a(const Warp3& ws, uint32_t (&a)[KS][4], ui
 }
 
 // g[plane][j] = clamp((M_grid t_row)[j], 0, 1) for the rows (slot planes) row0 / row1 (row1 < 0: single plane).
-template <int KS>
-__device__ __forceinline__ void decimate_mma(const Tab3& tb, Warp3& ws, const uint32_t (&a)[KS][4], uint32_t grid, uint32_t nw,
+template <int KS, typename WS>
+__device__ __forceinline__ void decimate_mma(const Tab3& tb, WS& ws, const uint32_t (&a)[KS][4], uint32_t grid, uint32_t nw,
     int row0, int row1, uint32_t lane)
 {
     const uint32_t gq = lane >> 2, tq = lane & 3u;
@@ -118,8 +145,8 @@ __device__ __forceinline__ void decimate_mma(const Tab3& tb, Warp3& ws, const ui
 
 // Evaluate block mode m on slot s with the decimated weights in ws.g; on success ws.su / ws.ep hold the candidate and
 // its exact decoded error (FX^2 units) is returned.
-template <int K>
-__device__ __forceinline__ float evaluate3(const Ctx& c, Warp3& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
+template <int K, typename WS>
+__device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
     uint32_t lane)
 {
     const uint32_t T = c.tab.texels;
@@ -134,6 +161,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, Warp3& ws, uint32_t s, 
         for (uint32_t j = lane; j < nw; j += 32) {
             const int k = min(max(__float2int_rn(ws.g[pl][j]*nm1), 0), static_cast<int>(kWqN[L]) - 1);
             ws.su[j*planes + pl] = static_cast<uint8_t>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(k)));
+            ws.sk[j*planes + pl] = static_cast<uint8_t>(k);
         }
     __syncwarp();
     // infill (lane = texel)
@@ -237,11 +265,159 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, Warp3& ws, uint32_t s, 
     return static_cast<float>(err);
 }
 
-__device__ __forceinline__ void keep_best3(Warp3& ws, uint32_t nw, uint32_t planes, uint32_t pc, uint32_t lane)
+template <typename WS>
+__device__ __forceinline__ void keep_best3(WS& ws, uint32_t nw, uint32_t planes, uint32_t pc, uint32_t lane)
 {
-    for (uint32_t j = lane; j < nw*planes; j += 32) ws.best_su[j] = ws.su[j];
+    for (uint32_t j = lane; j < nw*planes; j += 32) { ws.best_su[j] = ws.su[j]; ws.best_sk[j] = ws.sk[j]; }
     if (lane < pc*8u) ws.best_ep[lane] = ws.ep[lane];
     __syncwarp();
+}
+
+
+// ---- warp-cooperative setup ----------------------------------------------------------------------
+// Moments of a set of texels about the block centre `ctr` (FX units): count, sums, upper triangle of products.
+
+__device__ __forceinline__ float warp_min_f(float f)
+{
+    int o = __float_as_int(f); o ^= (o >> 31) & 0x7FFFFFFF;
+    o = __reduce_min_sync(0xFFFFFFFFu, o);
+    o ^= (o >> 31) & 0x7FFFFFFF;
+    return __int_as_float(o);
+}
+__device__ __forceinline__ float warp_max_f(float f)
+{
+    int o = __float_as_int(f); o ^= (o >> 31) & 0x7FFFFFFF;
+    o = __reduce_max_sync(0xFFFFFFFFu, o);
+    o ^= (o >> 31) & 0x7FFFFFFF;
+    return __int_as_float(o);
+}
+
+// Principal line of a texel set from its moments; zero_ch (>= 0) is left out (it gets its own weight plane).
+__device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, LineFit& out)
+{
+    const float inv = mo.n > 0.0f ? 1.0f/mo.n : 0.0f;
+    float m[4] = {mo.s[0]*inv, mo.s[1]*inv, mo.s[2]*inv, mo.s[3]*inv};
+    float cv[10];
+    cv[0] = mo.p[0] - mo.s[0]*m[0]; cv[1] = mo.p[1] - mo.s[0]*m[1]; cv[2] = mo.p[2] - mo.s[0]*m[2]; cv[3] = mo.p[3] - mo.s[0]*m[3];
+    cv[4] = mo.p[4] - mo.s[1]*m[1]; cv[5] = mo.p[5] - mo.s[1]*m[2]; cv[6] = mo.p[6] - mo.s[1]*m[3];
+    cv[7] = mo.p[7] - mo.s[2]*m[2]; cv[8] = mo.p[8] - mo.s[2]*m[3]; cv[9] = mo.p[9] - mo.s[3]*m[3];
+    if (zero_ch == 0) { cv[0] = cv[1] = cv[2] = cv[3] = 0.0f; }
+    if (zero_ch == 1) { cv[1] = cv[4] = cv[5] = cv[6] = 0.0f; }
+    if (zero_ch == 2) { cv[2] = cv[5] = cv[7] = cv[8] = 0.0f; }
+    if (zero_ch == 3) { cv[3] = cv[6] = cv[8] = cv[9] = 0.0f; }
+    float v[4] = {cv[0], cv[1], cv[2], cv[3]};
+    float best = cv[0];
+    if (cv[4] > best) { best = cv[4]; v[0] = cv[1]; v[1] = cv[4]; v[2] = cv[5]; v[3] = cv[6]; }
+    if (cv[7] > best) { best = cv[7]; v[0] = cv[2]; v[1] = cv[5]; v[2] = cv[7]; v[3] = cv[8]; }
+    if (cv[9] > best) { best = cv[9]; v[0] = cv[3]; v[1] = cv[6]; v[2] = cv[8]; v[3] = cv[9]; }
+    float lam = 0.0f;
+    for (int it = 0; it < iters; ++it) {
+        const float n2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2] + v[3]*v[3];
+        const float s2 = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+        const float a0 = v[0]*s2, a1 = v[1]*s2, a2 = v[2]*s2, a3 = v[3]*s2;
+        v[0] = cv[0]*a0 + cv[1]*a1 + cv[2]*a2 + cv[3]*a3;
+        v[1] = cv[1]*a0 + cv[4]*a1 + cv[5]*a2 + cv[6]*a3;
+        v[2] = cv[2]*a0 + cv[5]*a1 + cv[7]*a2 + cv[8]*a3;
+        v[3] = cv[3]*a0 + cv[6]*a1 + cv[8]*a2 + cv[9]*a3;
+        lam = a0*v[0] + a1*v[1] + a2*v[2] + a3*v[3];
+    }
+    const float n2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2] + v[3]*v[3];
+    const float s2 = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+    v[0] *= s2; v[1] *= s2; v[2] *= s2; v[3] *= s2;
+    if (n2 <= 1e-20f) { v[0] = v[1] = v[2] = 0.57735f; v[3] = 0.0f; }
+    if (v[0] + v[1] + v[2] < 0.0f) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; v[3] = -v[3]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { out.m[k] = m[k]; out.v[k] = v[k]; }
+    out.resid = fmaxf(cv[0] + cv[4] + cv[7] + cv[9] - lam, 0.0f);
+}
+
+// Lane-local masked moments: texels whose bit is set in `mask`, about `ctr`.
+__device__ __noinline__ void masked_moments(const int4* v, uint32_t T, int4 ctr, uint64_t mask, int (&acc)[15])
+{
+#pragma unroll
+    for (int k = 0; k < 15; ++k) acc[k] = 0;
+    for (uint32_t i = 0; i < T; ++i) {
+        const int4 x = v[i];
+        const int f = static_cast<int>((mask >> i) & 1ull);
+        const int x0 = f*(x.x - ctr.x), x1 = f*(x.y - ctr.y), x2 = f*(x.z - ctr.z), x3 = f*(x.w - ctr.w);
+        acc[0] += f; acc[1] += x0; acc[2] += x1; acc[3] += x2; acc[4] += x3;
+        acc[5] += x0*x0; acc[6] += x0*x1; acc[7] += x0*x2; acc[8] += x0*x3; acc[9] += x1*x1;
+        acc[10] += x1*x2; acc[11] += x1*x3; acc[12] += x2*x2; acc[13] += x2*x3; acc[14] += x3*x3;
+    }
+}
+
+__device__ __forceinline__ void mom_from(const int (&a)[15], Mom& m)
+{
+    m.n = static_cast<float>(a[0]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m.s[k] = static_cast<float>(a[1 + k]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) m.p[k] = static_cast<float>(a[5 + k]);
+}
+
+// k-means clustering of the block's texels (lane = texel) into k = 2 or 3 groups: farthest-point seeds, three
+// Lloyd iterations; returns the texel masks of clusters 1 and 2.
+template <int K>
+__device__ __noinline__ void kmeans_warp(const int4* v, uint32_t T, uint32_t k, int4 mean, uint32_t lane, uint64_t& m1, uint64_t& m2)
+{
+    int4 x[K];
+    bool live[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { const uint32_t i = lane + 32u*r; live[r] = i < T; x[r] = v[live[r] ? i : 0u]; }
+    float4 ctr[3];
+    ctr[0] = make_float4(static_cast<float>(mean.x), static_cast<float>(mean.y), static_cast<float>(mean.z), static_cast<float>(mean.w));
+    ctr[1] = ctr[0]; ctr[2] = ctr[0];
+    for (uint32_t c = 0; c < k; ++c) {
+        uint32_t key = 0;
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            if (!live[r]) continue;
+            float d = 3.0e38f;
+            for (uint32_t q = 0; q < (c == 0 ? 1u : c); ++q) {
+                const float dx = x[r].x - ctr[q].x, dy = x[r].y - ctr[q].y, dz = x[r].z - ctr[q].z, dw = x[r].w - ctr[q].w;
+                d = fminf(d, dx*dx + dy*dy + dz*dz + dw*dw);
+            }
+            // farthest texel, lowest index on ties
+            const uint32_t kk = (__float_as_uint(d) & ~63u) | (63u - (lane + 32u*r));
+            key = max(key, kk);
+        }
+        key = __reduce_max_sync(0xFFFFFFFFu, key);
+        const int4 far = v[63u - (key & 63u)];
+        ctr[c] = make_float4(static_cast<float>(far.x), static_cast<float>(far.y), static_cast<float>(far.z), static_cast<float>(far.w));
+    }
+    uint32_t b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
+    for (int it = 0; it < 3; ++it) {
+        int cnt[3] = {0, 0, 0}, sx[3] = {0, 0, 0}, sy[3] = {0, 0, 0}, sz[3] = {0, 0, 0}, sw[3] = {0, 0, 0};
+        uint32_t lab[K];
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            uint32_t bi = 0;
+            float bd = 3.0e38f;
+            for (uint32_t q = 0; q < k; ++q) {
+                const float dx = x[r].x - ctr[q].x, dy = x[r].y - ctr[q].y, dz = x[r].z - ctr[q].z, dw = x[r].w - ctr[q].w;
+                const float d = dx*dx + dy*dy + dz*dz + dw*dw;
+                if (d < bd) { bd = d; bi = q; }
+            }
+            lab[r] = live[r] ? bi : 3u;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int f = lab[r] == static_cast<uint32_t>(q) ? 1 : 0;
+                cnt[q] += f; sx[q] += f*x[r].x; sy[q] += f*x[r].y; sz[q] += f*x[r].z; sw[q] += f*x[r].w;
+            }
+        }
+        b1lo = __ballot_sync(0xFFFFFFFFu, lab[0] == 1u); b2lo = __ballot_sync(0xFFFFFFFFu, lab[0] == 2u);
+        if (K > 1) { b1hi = __ballot_sync(0xFFFFFFFFu, lab[K - 1] == 1u); b2hi = __ballot_sync(0xFFFFFFFFu, lab[K - 1] == 2u); }
+        for (uint32_t q = 0; q < k; ++q) {
+            const int n = redux_add(cnt[q]);
+            const int ax = redux_add(sx[q]), ay = redux_add(sy[q]), az = redux_add(sz[q]), aw = redux_add(sw[q]);
+            if (n > 0) {
+                const float ic = 1.0f/static_cast<float>(n);
+                ctr[q] = make_float4(ax*ic, ay*ic, az*ic, aw*ic);
+            }
+        }
+    }
+    m1 = static_cast<uint64_t>(b1lo) | (static_cast<uint64_t>(b1hi) << 32);
+    m2 = static_cast<uint64_t>(b2lo) | (static_cast<uint64_t>(b2hi) << 32);
 }
 
 struct SlotView {           // what pack_block needs from a slot
@@ -251,97 +427,287 @@ struct SlotView {           // what pack_block needs from a slot
 
 } // namespace
 
-template <int NT, int KS>
-__global__ void __launch_bounds__(kWarps3*32) astc3_kernel(const EncodeParams p, const Tab3 tb, uint32_t n_exact, uint32_t refine)
+template <int NT, int KS, int W, int CTAS, bool LOCK>
+__global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p, const Tab3 tb, uint32_t n_exact, uint32_t refine)
 {
     constexpr int K = (NT*8 > 32) ? 2 : 1;
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = warp_id();
     const uint32_t gq = lane >> 2, tq = lane & 3u;
-    constexpr size_t kWsBytes = (sizeof(Warp3) + 15)/16*16, kStBytes = (sizeof(BlockState) + 15)/16*16;
-    Warp3& ws = *reinterpret_cast<Warp3*>(smem + warp*(kWsBytes + kStBytes));
-    BlockState& st = *reinterpret_cast<BlockState*>(smem + warp*(kWsBytes + kStBytes) + kWsBytes);
+    using WS = Warp3T<NT>;
+    constexpr size_t kWsBytes = (sizeof(WS) + 15)/16*16;
+    constexpr uint32_t TP = WS::TP;
+    WS& ws = *reinterpret_cast<WS*>(smem + warp*kWsBytes);
+    __syncthreads();
     const Ctx& ctx = tb.ctx;
     const uint32_t T = ctx.tab.texels, bw = ctx.tab.bw, bh = ctx.tab.bh;
     const uint32_t G = ctx.tab.n_grids;
     const bool alpha_off = p.alpha_type == 0;
     const float fx2 = static_cast<float>(FX*FX);
+    const float ifx = 1.0f/static_cast<float>(FX);
+    // setup scratch lives where phase 1 later writes D
+    LineFit* lines = ws.u.setup.lines;
+    Mom* moms = ws.u.setup.moms;
+    // the A operand's padding columns must be finite (they meet zero B entries)
+    for (uint32_t i = lane; i < kRows3*WS::TS; i += 32) (&ws.ta[0][0])[i] = __float2half_rn(0.0f);
 
-    for (uint32_t blk = blockIdx.x*kWarps3 + warp; blk < p.total_blocks; blk += gridDim.x*kWarps3) {
+    for (uint32_t base = blockIdx.x*W; base < p.total_blocks; base += gridDim.x*W) {
+        // every warp of the CTA runs every iteration (the barriers below need that): warps past the end redo the last
+        // block without storing it
+        const uint32_t blk = min(base + warp, p.total_blocks - 1u);
+        bool active = base + warp < p.total_blocks;
         const uint32_t by = blk / p.blocks_x, bx = blk - by*p.blocks_x;
-        __syncwarp();
+        PHASE_SYNC();
         bool differs = false, alpha = false;
-        for (uint32_t i = lane; i < T; i += 32) {
-            const uint32_t ty = i / bw, tx = i - ty*bw;
-            const uint32_t x = min(bx*bw + tx, p.width - 1), y = min(by*bh + ty, p.height - 1);
-            float4 v;
-            if (p.src_format == SRC_RGBA8) {
-                const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(p.src + static_cast<uint64_t>(y)*p.pitch) + x);
-                v = make_float4(static_cast<float>(q & 0xFF), static_cast<float>((q >> 8) & 0xFF), static_cast<float>((q >> 16) & 0xFF),
-                    static_cast<float>(q >> 24));
-            } else {
-                const float4 f = load_texel_f32(p, x, y);
-                v = make_float4(fminf(fmaxf(f.x, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.y, 0.0f), 1.0f)*255.0f,
-                    fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
+        float4 first = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 255.0f);
+            if (i < T) {
+                const uint32_t ty = i / bw, tx = i - ty*bw;
+                const uint32_t x = min(bx*bw + tx, p.width - 1), y = min(by*bh + ty, p.height - 1);
+                if (p.src_format == SRC_RGBA8) {
+                    const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(p.src + static_cast<uint64_t>(y)*p.pitch) + x);
+                    v = make_float4(static_cast<float>(q & 0xFF), static_cast<float>((q >> 8) & 0xFF), static_cast<float>((q >> 16) & 0xFF),
+                        static_cast<float>(q >> 24));
+                } else {
+                    const float4 f = load_texel_f32(p, x, y);
+                    v = make_float4(fminf(fmaxf(f.x, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.y, 0.0f), 1.0f)*255.0f,
+                        fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
+                }
+                if (!(p.color_mask & 1u)) v.x = 0.0f;
+                if (!(p.color_mask & 2u)) v.y = 0.0f;
+                if (!(p.color_mask & 4u)) v.z = 0.0f;
+                if (!(p.color_mask & 8u)) v.w = 0.0f; else if (alpha_off) v.w = 255.0f;
+                ws.v[i] = make_int4(__float2int_rn(v.x*FX), __float2int_rn(v.y*FX), __float2int_rn(v.z*FX), __float2int_rn(v.w*FX));
             }
-            if (!(p.color_mask & 1u)) v.x = 0.0f;
-            if (!(p.color_mask & 2u)) v.y = 0.0f;
-            if (!(p.color_mask & 4u)) v.z = 0.0f;
-            if (!(p.color_mask & 8u)) v.w = 0.0f; else if (alpha_off) v.w = 255.0f;
-            st.cf[i] = v;
-            ws.v[i] = make_int4(__float2int_rn(v.x*FX), __float2int_rn(v.y*FX), __float2int_rn(v.z*FX), __float2int_rn(v.w*FX));
-            alpha |= v.w != 255.0f;
+            if (i0 == 0) {
+                first.x = __shfl_sync(0xFFFFFFFFu, v.x, 0); first.y = __shfl_sync(0xFFFFFFFFu, v.y, 0);
+                first.z = __shfl_sync(0xFFFFFFFFu, v.z, 0); first.w = __shfl_sync(0xFFFFFFFFu, v.w, 0);
+            }
+            if (i < T) {
+                differs |= v.x != first.x || v.y != first.y || v.z != first.z || v.w != first.w;
+                alpha |= v.w != 255.0f;
+            }
         }
         __syncwarp();
-        const float4 first = st.cf[0];
-        for (uint32_t i = lane; i < T; i += 32) {
-            const float4 v = st.cf[i];
-            differs |= v.x != first.x || v.y != first.y || v.z != first.z || v.w != first.w;
-        }
         const bool constant = !__any_sync(0xFFFFFFFFu, differs);
         const bool has_alpha = __any_sync(0xFFFFFFFFu, alpha);
         uint4* dst = reinterpret_cast<uint4*>(p.dst) + blk;
         if (constant) {
-            if (lane == 0) *dst = pack_void_extent(first);
-            continue;
+            if (active && lane == 0) *dst = pack_void_extent(first);
+            active = false;
         }
-        // ---- setup: partition hypotheses (lane-local steps shared with astc.cu)
-        if (lane == 0) st.has_alpha = has_alpha ? 1u : 0u;
-        if (lane < kSlots) st.slots[lane].valid = 0;
-        __syncwarp();
-        step_init(ctx, st, lane);
-        __syncwarp();
-        step_rank(ctx, st, lane);
-        __syncwarp();
-        step_score(ctx, st, lane);
-        __syncwarp();
-        step_slots(ctx, st, lane);
-        __syncwarp();
-        // slots -> compact form + fp16 A operand rows
-        if (lane < kSlots) {
-            const Slot& o = st.slots[lane];
-            Slot3& n = ws.slots[lane];
-            n.valid = o.valid; n.pc = o.pc; n.seed = o.seed; n.dual_ch = o.dual_ch; n.e_line = o.e_line;
-            for (int k = 0; k < 3; ++k) { n.e0[k] = o.e0[k]; n.e1[k] = o.e1[k]; n.len2[k] = o.len2[k]; }
-            float lb = 0.0f;
-            if (o.valid && o.dual_ch >= 0) { const float d = ch(o.e1[0], o.dual_ch) - ch(o.e0[0], o.dual_ch); lb = d*d; }
-            n.len2b = lb;
+        const uint32_t nch = has_alpha ? 4u : 3u;
+
+        // ---- setup 1: block moments about the (integer) mean, channel ranges
+        int4 ctr;
+        int tot[15];
+        int lo4[4], hi4[4];
+        if (active) {
+            int sx = 0, sy = 0, sz = 0, sw = 0;
+            int mn[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, mx[4] = {-(1 << 30), -(1 << 30), -(1 << 30), -(1 << 30)};
+            for (uint32_t i = lane; i < T; i += 32) {
+                const int4 x = ws.v[i];
+                sx += x.x; sy += x.y; sz += x.z; sw += x.w;
+                mn[0] = min(mn[0], x.x); mn[1] = min(mn[1], x.y); mn[2] = min(mn[2], x.z); mn[3] = min(mn[3], x.w);
+                mx[0] = max(mx[0], x.x); mx[1] = max(mx[1], x.y); mx[2] = max(mx[2], x.z); mx[3] = max(mx[3], x.w);
+            }
+            const int it = static_cast<int>(T);
+            ctr = make_int4((redux_add(sx) + it/2)/it, (redux_add(sy) + it/2)/it, (redux_add(sz) + it/2)/it, (redux_add(sw) + it/2)/it);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { lo4[k] = __reduce_min_sync(0xFFFFFFFFu, mn[k]); hi4[k] = __reduce_max_sync(0xFFFFFFFFu, mx[k]); }
+            int acc[15];
+#pragma unroll
+            for (int k = 0; k < 15; ++k) acc[k] = 0;
+            for (uint32_t i = lane; i < T; i += 32) {
+                const int4 x = ws.v[i];
+                const int x0 = x.x - ctr.x, x1 = x.y - ctr.y, x2 = x.z - ctr.z, x3 = x.w - ctr.w;
+                acc[0] += 1; acc[1] += x0; acc[2] += x1; acc[3] += x2; acc[4] += x3;
+                acc[5] += x0*x0; acc[6] += x0*x1; acc[7] += x0*x2; acc[8] += x0*x3; acc[9] += x1*x1;
+                acc[10] += x1*x2; acc[11] += x1*x3; acc[12] += x2*x2; acc[13] += x2*x3; acc[14] += x3*x3;
+            }
+#pragma unroll
+            for (int k = 0; k < 15; ++k) tot[k] = redux_add(acc[k]);
         }
-        for (uint32_t r = 0; r < kRows3; ++r) {
-            const uint32_t s = r < 9 ? r : r - 4;
-            const bool ok = r < 13 && st.slots[s].valid;
-            const float* src = r < 9 ? st.slots[s].t : st.slots[s].t2;
-            for (uint32_t i = lane; i < kMaxTexels; i += 32)
-                ws.ta[r][i] = __float2half_rn(ok && i < T ? src[i] : 0.0f);
+        // ---- setup 2: lines of the single-subset slot (lane 0) and of the four dual-plane slots (lanes 1..4)
+        if (active && lane < 5) {
+            Mom mo;
+            mom_from(tot, mo);
+            subset_line(mo, static_cast<int>(lane) - 1, 6, lines[lane]);
         }
-        for (uint32_t s = 1; s <= 4; ++s)
-            for (uint32_t i = lane; i < kMaxTexels; i += 32) ws.part[s - 1][i] = i < T ? st.slots[s].part[i] : 0;
+        if (active && lane < kSlots) {
+            Slot3& sl = ws.slots[lane];
+            sl.pc = 1; sl.seed = 0; sl.dual_ch = lane >= 5 ? static_cast<int32_t>(lane - 5) : -1;
+            sl.valid = lane == 0 || (lane >= 5 && lane - 5 < nch) ? 1u : 0u;
+        }
+        // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
+        uint64_t km0, km1, km2;
+        km0 = km1 = km2 = 0;
+#pragma unroll 1
+        for (uint32_t kk = 2; active && kk <= 3; ++kk) {
+            uint64_t ka, kb;
+            kmeans_warp<K>(ws.v, T, kk, ctr, lane, ka, kb);
+            if (kk == 2) km0 = ka; else { km1 = ka; km2 = kb; }
+        }
+        uint32_t b2 = 0xFFFFFFFFu, b3 = 0xFFFFFFFFu;
+        if (active) {
+            const uint64_t full = T == 64 ? ~0ull : ((1ull << T) - 1ull);
+            for (uint32_t seed = lane; seed < 1024; seed += 32) {
+                const uint64_t q = tab_u64(ctx, ctx.tab.off_part2 + seed*8u);
+                if (q) b2 = min(b2, (mismatch2(km0, q, T) << 10) | seed);
+                const uint64_t q1 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u), q2 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u + 8u);
+                if (q1) b3 = min(b3, (mismatch3(km1, km2, q1, q2, full) << 10) | seed);
+            }
+        }
+        PHASE_SYNC();
+        // ---- setup 4: exact line-fit residual of every lane's two-subset seed; the two best become slots 1, 2
+        if (active) {
+            float sc = 3.0e38f;
+            int a1[15], a0[15];
+            if (b2 != 0xFFFFFFFFu) {
+                masked_moments(ws.v, T, ctr, tab_u64(ctx, ctx.tab.off_part2 + (b2 & 1023u)*8u), a1);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) a0[k] = tot[k] - a1[k];
+                if (a0[0] >= 1 && a1[0] >= 1) {
+                    Mom m0, m1; LineFit l0, l1;
+                    mom_from(a0, m0); mom_from(a1, m1);
+                    subset_line(m0, -1, 4, l0); subset_line(m1, -1, 4, l1);
+                    sc = l0.resid + l1.resid;
+                }
+            }
+            for (uint32_t rank = 0; rank < 2; ++rank) {
+                const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(sc) & ~31u) | lane);
+                const uint32_t wl = kmin & 31u;
+                const bool ok = __shfl_sync(0xFFFFFFFFu, sc, wl) < 3.0e38f;
+                const uint32_t seed = __shfl_sync(0xFFFFFFFFu, b2, wl) & 1023u;
+                if (lane == wl) {
+                    if (ok) { mom_from(a0, moms[rank*2]); mom_from(a1, moms[rank*2 + 1]); }
+                    sc = 3.0e38f;
+                }
+                if (lane == 0) { Slot3& sl = ws.slots[1 + rank]; sl.pc = 2; sl.seed = seed; sl.dual_ch = -1; sl.valid = ok ? 1u : 0u; }
+                const uint64_t m1 = tab_u64(ctx, ctx.tab.off_part2 + seed*8u);
+                for (uint32_t i = lane; i < TP; i += 32) ws.part[rank][i] = static_cast<uint8_t>((m1 >> i) & 1ull);
+            }
+        }
+        PHASE_SYNC();
+        // ---- setup 5: same for the three-subset seeds -> slots 3, 4
+        if (active) {
+            float sc = 3.0e38f;
+            int a1[15], a2[15], a0[15];
+            if (b3 != 0xFFFFFFFFu) {
+                const uint32_t seed = b3 & 1023u;
+                masked_moments(ws.v, T, ctr, tab_u64(ctx, ctx.tab.off_part3 + seed*16u), a1);
+                masked_moments(ws.v, T, ctr, tab_u64(ctx, ctx.tab.off_part3 + seed*16u + 8u), a2);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) a0[k] = tot[k] - a1[k] - a2[k];
+                if (a0[0] >= 1 && a1[0] >= 1 && a2[0] >= 1) {
+                    Mom m0, m1, m2; LineFit l0, l1, l2;
+                    mom_from(a0, m0); mom_from(a1, m1); mom_from(a2, m2);
+                    subset_line(m0, -1, 4, l0); subset_line(m1, -1, 4, l1); subset_line(m2, -1, 4, l2);
+                    sc = l0.resid + l1.resid + l2.resid;
+                }
+            }
+            for (uint32_t rank = 0; rank < 2; ++rank) {
+                const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(sc) & ~31u) | lane);
+                const uint32_t wl = kmin & 31u;
+                const bool ok = __shfl_sync(0xFFFFFFFFu, sc, wl) < 3.0e38f;
+                const uint32_t seed = __shfl_sync(0xFFFFFFFFu, b3, wl) & 1023u;
+                if (lane == wl) {
+                    if (ok) { mom_from(a0, moms[4 + rank*3]); mom_from(a1, moms[4 + rank*3 + 1]); mom_from(a2, moms[4 + rank*3 + 2]); }
+                    sc = 3.0e38f;
+                }
+                if (lane == 0) { Slot3& sl = ws.slots[3 + rank]; sl.pc = 3; sl.seed = seed; sl.dual_ch = -1; sl.valid = ok ? 1u : 0u; }
+                const uint64_t m1 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u), m2 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u + 8u);
+                for (uint32_t i = lane; i < TP; i += 32)
+                    ws.part[2 + rank][i] = static_cast<uint8_t>(((m1 >> i) & 1ull) ? 1u : (((m2 >> i) & 1ull) ? 2u : 0u));
+            }
+        }
+        PHASE_SYNC();
+        // ---- setup 6: lines of the ten subsets of slots 1..4 (lane = subset)
+        if (active && lane < 10) {
+            const uint32_t sl = lane < 2 ? 1u : (lane < 4 ? 2u : (lane < 7 ? 3u : 4u));
+            if (ws.slots[sl].valid) subset_line(moms[lane], -1, 6, lines[5 + lane]);
+        }
         __syncwarp();
+        // ---- setup 7: per slot, project the texels on their subset's line -> ideal weights (fp16 A operand rows),
+        //      end points, line lengths
+        for (uint32_t s = 0; active && s < kSlots; ++s) {
+            Slot3& slot = ws.slots[s];
+            if (!slot.valid) continue;
+            const uint32_t pc = slot.pc;
+            const uint32_t base = s == 0 ? 0u : (s >= 5 ? s - 4u : (s == 1 ? 5u : (s == 2 ? 7u : (s == 3 ? 9u : 12u))));
+            float tl[K];
+            uint32_t ql[K];
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const uint32_t i = lane + 32u*r;
+                tl[r] = 0.0f; ql[r] = 3u;
+                if (i < T) {
+                    const uint32_t q = pc > 1 ? ws.part[s - 1][i] : 0u;
+                    const LineFit& lf = lines[base + q];
+                    const int4 x = ws.v[i];
+                    tl[r] = (static_cast<float>(x.x - ctr.x) - lf.m[0])*lf.v[0] + (static_cast<float>(x.y - ctr.y) - lf.m[1])*lf.v[1] +
+                        (static_cast<float>(x.z - ctr.z) - lf.m[2])*lf.v[2] + (static_cast<float>(x.w - ctr.w) - lf.m[3])*lf.v[3];
+                    ql[r] = q;
+                }
+            }
+            float eline = 0.0f;
+            for (uint32_t q = 0; q < pc; ++q) {
+                float mn = 3.0e38f, mx = -3.0e38f;
+#pragma unroll
+                for (int r = 0; r < K; ++r) if (ql[r] == q) { mn = fminf(mn, tl[r]); mx = fmaxf(mx, tl[r]); }
+                mn = warp_min_f(mn); mx = warp_max_f(mx);
+                if (!(mx > mn)) { mn = 0.0f; mx = 0.0f; }
+                const float range = mx - mn;
+                const float ir = range > 1e-6f*FX ? 1.0f/range : 0.0f;
+#pragma unroll
+                for (int r = 0; r < K; ++r) if (ql[r] == q) tl[r] = (tl[r] - mn)*ir;
+                const LineFit& lf = lines[base + q];
+                eline += lf.resid;
+                if (lane == 0) {
+                    const float c0 = static_cast<float>(ctr.x) + lf.m[0], c1 = static_cast<float>(ctr.y) + lf.m[1];
+                    const float c2 = static_cast<float>(ctr.z) + lf.m[2], c3 = static_cast<float>(ctr.w) + lf.m[3];
+                    slot.e0[q] = make_float4((c0 + mn*lf.v[0])*ifx, (c1 + mn*lf.v[1])*ifx, (c2 + mn*lf.v[2])*ifx, (c3 + mn*lf.v[3])*ifx);
+                    slot.e1[q] = make_float4((c0 + mx*lf.v[0])*ifx, (c1 + mx*lf.v[1])*ifx, (c2 + mx*lf.v[2])*ifx, (c3 + mx*lf.v[3])*ifx);
+                    slot.len2[q] = range*range*ifx*ifx;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const uint32_t i = lane + 32u*r;
+                if (i < T) ws.ta[s][i] = __float2half_rn(tl[r]);
+            }
+            if (lane == 0) { slot.e_line = eline*ifx*ifx; slot.len2b = 0.0f; }
+            if (s >= 5) {
+                // the dual channel runs on its own plane from its minimum to its maximum
+                const int dc = static_cast<int>(s) - 5;
+                const int lo = lo4[dc], hi = hi4[dc];
+                const float ir2 = hi > lo ? 1.0f/static_cast<float>(hi - lo) : 0.0f;
+                for (uint32_t i = lane; i < T; i += 32) {
+                    const int4 x = ws.v[i];
+                    const int xc = dc == 0 ? x.x : (dc == 1 ? x.y : (dc == 2 ? x.z : x.w));
+                    ws.ta[s + 4][i] = __float2half_rn(static_cast<float>(xc - lo)*ir2);
+                }
+                if (lane == 0) {
+                    float a4[4] = {slot.e0[0].x, slot.e0[0].y, slot.e0[0].z, slot.e0[0].w};
+                    float b4[4] = {slot.e1[0].x, slot.e1[0].y, slot.e1[0].z, slot.e1[0].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (k == dc) { a4[k] = static_cast<float>(lo)*ifx; b4[k] = static_cast<float>(hi)*ifx; }
+                    slot.e0[0] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                    slot.e1[0] = make_float4(b4[0], b4[1], b4[2], b4[3]);
+                    const float d = static_cast<float>(hi - lo)*ifx;
+                    slot.len2b = d*d;
+                }
+            }
+        }
+        PHASE_SYNC();
 
         // ---- phase 1a: decimation loss D[slot plane][grid] on the tensor cores
         uint32_t a[KS][4];
         load_a<KS>(ws, a, lane);
-        {
+        if (active) {
             float lw[NT][2];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
@@ -372,13 +738,13 @@ __global__ void __launch_bounds__(kWarps3*32) astc3_kernel(const EncodeParams p,
                     acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 1); acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 2);
                 }
                 if (tq == 0) {
-                    ws.D[gq][g] = acc0*scale0;
-                    if (gq + 8 < 13) ws.D[gq + 8][g] = acc1*scale1;
+                    ws.u.est.D[gq][g] = acc0*scale0;
+                    if (gq + 8 < 13) ws.u.est.D[gq + 8][g] = acc1*scale1;
                 }
             }
         }
         // ---- phase 1b: S of the multi-subset slots (lane = grid)
-        for (uint32_t g = lane; g < G; g += 32) {
+        for (uint32_t g = lane; active && g < G; g += 32) {
             const float* kap = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_kappa) + g*kMaxTexels;
             float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, s4 = 0.0f;
             for (uint32_t i = 0; i < T; ++i) {
@@ -386,13 +752,13 @@ __global__ void __launch_bounds__(kWarps3*32) astc3_kernel(const EncodeParams p,
                 s1 += k*ws.slots[1].len2[ws.part[0][i]]; s2 += k*ws.slots[2].len2[ws.part[1][i]];
                 s3 += k*ws.slots[3].len2[ws.part[2][i]]; s4 += k*ws.slots[4].len2[ws.part[3][i]];
             }
-            ws.Sm[0][g] = s1; ws.Sm[1][g] = s2; ws.Sm[2][g] = s3; ws.Sm[3][g] = s4;
+            ws.u.est.Sm[0][g] = s1; ws.u.est.Sm[1][g] = s2; ws.u.est.Sm[2][g] = s3; ws.u.est.Sm[3][g] = s4;
         }
-        __syncwarp();
+        PHASE_SYNC();
         // ---- phase 1c: estimate every (slot, mode); each lane keeps its three best
         float be0 = 3.0e38f, be1 = 3.0e38f, be2 = 3.0e38f;
         uint32_t bc0 = 0, bc1 = 0, bc2 = 0;
-        {
+        if (active) {
             const float tn = static_cast<float>(T*(has_alpha ? 4u : 3u));
             const float* ksum = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_ksum);
             for (uint32_t s = 0; s < kSlots; ++s) {
@@ -407,10 +773,10 @@ __global__ void __launch_bounds__(kWarps3*32) astc3_kernel(const EncodeParams p,
                     if (cl == 0xFFu) continue;
                     const ModeInfo m = tab_mode(ctx, mi);
                     const uint32_t g = m.grid;
-                    float dsum = ws.D[s][g], ssum;
-                    if (type == 3) { dsum += ws.D[s + 4][g]; ssum = (slot.len2[0] + slot.len2b)*__ldg(ksum + g); }
+                    float dsum = ws.u.est.D[s][g], ssum;
+                    if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = (slot.len2[0] + slot.len2b)*__ldg(ksum + g); }
                     else if (type == 0) ssum = slot.len2[0]*__ldg(ksum + g);
-                    else ssum = ws.Sm[s - 1][g];
+                    else ssum = ws.u.est.Sm[s - 1][g];
                     const float est = base + kDec*dsum + kQuant*ssum*c_qvar[m.level] + kColor*tn*c_cvar[cl];
                     const uint32_t code = (s << 16) | mi;
                     if (est < be2) {
@@ -423,66 +789,81 @@ __global__ void __launch_bounds__(kWarps3*32) astc3_kernel(const EncodeParams p,
                 }
             }
         }
-        // ---- phase 2: exact evaluation of the n_exact best estimates
+        PHASE_SYNC();
+        // ---- phase 2: exact evaluation of the n_exact best estimates, then refinement rounds on the winner
+        //      (re-project the texels on its quantised end points, re-decimate, re-solve) -- one loop, so that the
+        //      evaluation code exists once
         float best_err = 3.0e38f;
         uint32_t best_code = 0, best_cl = 0;
         const float stop_db = fmaxf(95.0f - 35.0f*log10f(static_cast<float>(T)), 70.0f - 19.0f*log10f(static_cast<float>(T))) + 12.0f;
-        const float stop_err = 65025.0f*exp10f(-0.1f*stop_db)*static_cast<float>(T*(has_alpha ? 4u : 3u))*fx2;
-        for (uint32_t n = 0; n < n_exact && best_err > stop_err; ++n) {
-            const uint32_t key = (__float_as_uint(be0) & ~31u) | lane;
-            const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, key);
-            const uint32_t wl = kmin & 31u;
-            const float est = __shfl_sync(0xFFFFFFFFu, be0, wl);
-            const uint32_t code = __shfl_sync(0xFFFFFFFFu, bc0, wl);
-            if (est >= 3.0e38f) break;
-            if (lane == wl) { be0 = be1; bc0 = bc1; be1 = be2; bc1 = bc2; be2 = 3.0e38f; }
-            if (0.8f*est*fx2 > best_err) break;              // estimates are sorted: nothing later can win
-            const uint32_t s = code >> 16, mi = code & 0xFFFFu;
-            const Slot3& slot = ws.slots[s];
-            const ModeInfo m = tab_mode(ctx, mi);
-            const uint32_t cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 4u : 0u) + slot_type(s))*tb.t3.n_modes + mi);
-            decimate_mma<KS>(tb, ws, a, m.grid, m.nw, static_cast<int>(s), slot.dual_ch >= 0 ? static_cast<int>(s) + 4 : -1, lane);
+        const float stop_err = 65025.0f*exp10f(-0.1f*stop_db)*static_cast<float>(T*nch)*fx2;
+        bool refining = false;
+        uint32_t n = 0, rounds = 0;
+#pragma unroll 1
+        while (active) {
+            uint32_t code = 0, cl = 0;
+            int row0 = 0, row1 = -1;
+            if (!refining) {
+                bool done = n >= n_exact || best_err <= stop_err;
+                if (!done) {
+                    const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(be0) & ~31u) | lane);
+                    const uint32_t wl = kmin & 31u;
+                    const float est = __shfl_sync(0xFFFFFFFFu, be0, wl);
+                    code = __shfl_sync(0xFFFFFFFFu, bc0, wl);
+                    if (lane == wl) { be0 = be1; bc0 = bc1; be1 = be2; bc1 = bc2; be2 = 3.0e38f; }
+                    // estimates come out sorted: stop when nothing later can win
+                    done = est >= 3.0e38f || 0.8f*est*fx2 > best_err;
+                    ++n;
+                }
+                if (done) refining = true;
+                else {
+                    const uint32_t s = code >> 16;
+                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 4u : 0u) + slot_type(s))*tb.t3.n_modes + (code & 0xFFFFu));
+                    row0 = static_cast<int>(s); row1 = ws.slots[s].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
+                }
+            }
+            if (refining) {
+                if (rounds >= refine || best_err <= 0.0f || best_err >= 3.0e38f) break;
+                ++rounds;
+                code = best_code; cl = best_cl;
+                const uint32_t bs = code >> 16;
+                const Slot3& bslot = ws.slots[bs];
+                const int dc = bslot.dual_ch;
+                const uint8_t* parts = ws.part[(bs - 1u) & 3u];
+                for (uint32_t i = lane; i < T; i += 32) {
+                    const int* e = ws.best_ep + (bslot.pc > 1 ? parts[i] : 0u)*8u;
+                    const int4 xi = ws.v[i];
+                    const float xs[4] = {static_cast<float>(xi.x)*ifx, static_cast<float>(xi.y)*ifx, static_cast<float>(xi.z)*ifx,
+                        static_cast<float>(xi.w)*ifx};
+                    float num0 = 0, den0 = 0, num1 = 0, den1 = 0;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        if (c4 == 3 && !has_alpha) continue;
+                        const float a0 = static_cast<float>(e[c4]), d = static_cast<float>(e[4 + c4]) - a0;
+                        if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
+                    }
+                    ws.ta[13][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
+                    ws.ta[14][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
+                }
+                __syncwarp();
+                load_a<KS>(ws, a, lane);             // the candidates' rows are not needed any more
+                row0 = 13; row1 = dc >= 0 ? 14 : -1;
+            }
+            const uint32_t s = code >> 16;
+            const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
+            decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
             const float err = evaluate3<K>(ctx, ws, s, m, cl, has_alpha, lane);
             if (err < best_err) {
                 best_err = err; best_code = code; best_cl = cl;
-                keep_best3(ws, m.nw, slot.dual_ch >= 0 ? 2u : 1u, slot.pc, lane);
-            }
+                keep_best3(ws, m.nw, ws.slots[s].dual_ch >= 0 ? 2u : 1u, ws.slots[s].pc, lane);
+            } else if (refining) break;
             __syncwarp();
         }
-        // ---- refine the winner: re-project on its end points, re-decimate, re-solve
         const uint32_t bs = best_code >> 16;
         const Slot3& bslot = ws.slots[bs];
         const ModeInfo bm = tab_mode(ctx, best_code & 0xFFFFu);
-        const uint32_t bplanes = bslot.dual_ch >= 0 ? 2u : 1u;
-        for (uint32_t r = 0; r < refine && best_err > 0.0f; ++r) {
-            const int dc = bslot.dual_ch;
-            const uint8_t* parts = ws.part[(bs - 1u) & 3u];
-            for (uint32_t i = lane; i < T; i += 32) {
-                const int* e = ws.best_ep + (bslot.pc > 1 ? parts[i] : 0u)*8u;
-                const int4 xi = ws.v[i];
-                const float xs[4] = {static_cast<float>(xi.x)*(1.0f/FX), static_cast<float>(xi.y)*(1.0f/FX),
-                    static_cast<float>(xi.z)*(1.0f/FX), static_cast<float>(xi.w)*(1.0f/FX)};
-                float num0 = 0, den0 = 0, num1 = 0, den1 = 0;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    if (c4 == 3 && !has_alpha) continue;
-                    const float a0 = static_cast<float>(e[c4]), d = static_cast<float>(e[4 + c4]) - a0;
-                    if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
-                }
-                ws.ta[13][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
-                ws.ta[14][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
-            }
-            __syncwarp();
-            uint32_t a2[KS][4];
-            load_a<KS>(ws, a2, lane);
-            decimate_mma<KS>(tb, ws, a2, bm.grid, bm.nw, 13, bplanes == 2 ? 14 : -1, lane);
-            const float err = evaluate3<K>(ctx, ws, bs, bm, best_cl, has_alpha, lane);
-            if (err < best_err) { best_err = err; keep_best3(ws, bm.nw, bplanes, bslot.pc, lane); }
-            else break;
-            __syncwarp();
-        }
-        __syncwarp();
-        if (lane == 0) {
+        PHASE_SYNC();
+        if (active && lane == 0) {
             Enc enc;
             enc.clevel = best_cl; enc.err = best_err;
             for (uint32_t s = 0; s < bslot.pc; ++s) {
@@ -493,24 +874,39 @@ __global__ void __launch_bounds__(kWarps3*32) astc3_kernel(const EncodeParams p,
                     (static_cast<uint32_t>(e[7]) << 24);
             }
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
-            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true);
+            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk);
         }
     }
 }
 
 namespace {
 
+template <int NT, int KS, int W, int CTAS, bool LOCK>
+int launch_cfg(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t refine, cudaStream_t stream)
+{
+    const void* k = reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK>);
+    const size_t smem = W*((sizeof(Warp3T<NT>) + 15)/16*16);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -4;
+    const uint32_t ctas_needed = (p.total_blocks + W - 1)/W;
+    const uint32_t grid = min(ctas_needed, persistent_ctas(k, W*32, smem));
+    void* args[] = {const_cast<EncodeParams*>(&p), const_cast<Tab3*>(&tb), &n_exact, &refine};
+    if (cudaLaunchKernel(k, dim3(grid), dim3(W*32), args, smem, stream) != cudaSuccess) return -4;
+    return 1;
+}
+
 template <int NT, int KS>
 int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t refine, cudaStream_t stream)
 {
-    const void* k = reinterpret_cast<const void*>(&astc3_kernel<NT, KS>);
-    const size_t smem = kWarps3*((sizeof(Warp3) + 15)/16*16 + (sizeof(BlockState) + 15)/16*16);
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -4;
-    const uint32_t ctas_needed = (p.total_blocks + kWarps3 - 1)/kWarps3;
-    const uint32_t grid = min(ctas_needed, persistent_ctas(k, kWarps3*32, smem));
-    void* args[] = {const_cast<EncodeParams*>(&p), const_cast<Tab3*>(&tb), &n_exact, &refine};
-    if (cudaLaunchKernel(k, dim3(grid), dim3(kWarps3*32), args, smem, stream) != cudaSuccess) return -4;
-    return 1;
+#ifdef CFX_ASTC3_TUNE
+    // developer knob: compare launch shapes without rebuilding (CFX_ASTC3_CFG = warps*100 + ctas*10 + lockstep)
+    static const int cfg = getenv("CFX_ASTC3_CFG") ? atoi(getenv("CFX_ASTC3_CFG")) : 0;
+    if (cfg == 830) return launch_cfg<NT, KS, 8, 3, false>(p, tb, n_exact, refine, stream);
+    if (cfg == 831) return launch_cfg<NT, KS, 8, 3, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 1221) return launch_cfg<NT, KS, 12, 2, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 1611) return launch_cfg<NT, KS, 16, 1, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 2410) return launch_cfg<NT, KS, 24, 1, false>(p, tb, n_exact, refine, stream);
+#endif
+    return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
 }
 
 bool g_consts_set[16] = {};

@@ -658,7 +658,7 @@ CFX_HD uint64_t bitrev64(uint64_t v)
 // u_scr: grid weights in bit-stream order, lane-interleaved scratch (linear == false) or a plain array.
 template <typename SlotT>
 CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo& m, const Enc& e, bool has_alpha,
-    const uint8_t* u_scr, uint32_t lane, bool linear = false)
+    const uint8_t* u_scr, uint32_t lane, bool linear = false, const uint8_t* k_lin = nullptr)
 {
     Bits128 b; b.lo = b.hi = 0;
     const uint32_t pc = slot.pc;
@@ -682,6 +682,7 @@ CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo
     const uint32_t planes = slot.dual_ch >= 0 ? 2u : 1u;
     if (planes == 2) b.put(128u - m.wbits - 2u, static_cast<uint32_t>(slot.dual_ch), 2);
     ise_encode(c, w, 0, m.nw*planes, kWqBits[L], kWqTrits[L] != 0, kWqQuints[L] != 0, [&](uint32_t j) {
+        if (k_lin) return tab_u8(c, c.tab.off_wq_enc + L*32u + k_lin[j]);    // the caller kept the ranks
         const uint32_t u = linear ? u_scr[j] : u_scr[scr_index(j, lane)];
         uint32_t k = 0;
         while (k + 1u < kWqN[L] && tab_u8(c, c.tab.off_wq_val + L*32u + k) != u) ++k;
