@@ -90,7 +90,7 @@ def build(verbose=False):
     have_tables = _generate_tables()
     units = [(s, f, m) for (s, f, m) in UNITS if os.path.exists(os.path.join(CSRC, s))]
     defines = ["-D%s=1" % m for (_, _, m) in units if m]
-    headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h", ".inc"))]
+    headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h", ".hpp", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "cfx.h"))
     if have_tables:
         headers.append(GENERATED)

@@ -87,9 +87,6 @@ struct Warp3T {
 // model constants (fitted on the host with tools/emu_astc3.py)
 constexpr float kLine = 1.1f, kDec = 1.0f, kQuant = 0.9f, kColor = 0.5f;
 
-__constant__ float c_qvar[kWeightLevels];     // expected squared quantisation error of a uniform weight, after end point refit
-__constant__ float c_cvar[kColorLevels];      // expected squared error per texel channel from end point quantisation
-
 struct Tab3 { Ctx ctx; Astc3Tab t3; };
 
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -334,16 +331,19 @@ __device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, 
 // Lane-local masked moments: texels whose bit is set in `mask`, about `ctr`.
 __device__ __noinline__ void masked_moments(const int4* v, uint32_t T, int4 ctr, uint64_t mask, int (&acc)[15])
 {
-#pragma unroll
-    for (int k = 0; k < 15; ++k) acc[k] = 0;
+    // accumulate in registers (the caller's array lives in local memory: this function is not inlined)
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0, a10 = 0, a11 = 0, a12 = 0, a13 = 0, a14 = 0;
+#pragma unroll 4
     for (uint32_t i = 0; i < T; ++i) {
         const int4 x = v[i];
         const int f = static_cast<int>((mask >> i) & 1ull);
         const int x0 = f*(x.x - ctr.x), x1 = f*(x.y - ctr.y), x2 = f*(x.z - ctr.z), x3 = f*(x.w - ctr.w);
-        acc[0] += f; acc[1] += x0; acc[2] += x1; acc[3] += x2; acc[4] += x3;
-        acc[5] += x0*x0; acc[6] += x0*x1; acc[7] += x0*x2; acc[8] += x0*x3; acc[9] += x1*x1;
-        acc[10] += x1*x2; acc[11] += x1*x3; acc[12] += x2*x2; acc[13] += x2*x3; acc[14] += x3*x3;
+        a0 += f; a1 += x0; a2 += x1; a3 += x2; a4 += x3;
+        a5 += x0*x0; a6 += x0*x1; a7 += x0*x2; a8 += x0*x3; a9 += x1*x1;
+        a10 += x1*x2; a11 += x1*x3; a12 += x2*x2; a13 += x2*x3; a14 += x3*x3;
     }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3; acc[4] = a4; acc[5] = a5; acc[6] = a6; acc[7] = a7; acc[8] = a8;
+    acc[9] = a9; acc[10] = a10; acc[11] = a11; acc[12] = a12; acc[13] = a13; acc[14] = a14;
 }
 
 __device__ __forceinline__ void mom_from(const int (&a)[15], Mom& m)
@@ -554,6 +554,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         uint32_t b2 = 0xFFFFFFFFu, b3 = 0xFFFFFFFFu;
         if (active) {
             const uint64_t full = T == 64 ? ~0ull : ((1ull << T) - 1ull);
+#pragma unroll 4
             for (uint32_t seed = lane; seed < 1024; seed += 32) {
                 const uint64_t q = tab_u64(ctx, ctx.tab.off_part2 + seed*8u);
                 if (q) b2 = min(b2, (mismatch2(km0, q, T) << 10) | seed);
@@ -720,23 +721,36 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 }
             const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
             const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : 0.0f);
-            const uint32_t* ridx = reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx);
-            for (uint32_t g = 0; g < G; ++g) {
-                const uint32_t off = __ldg(ridx + g);
+            // full-resolution grids lose nothing
+            for (uint32_t g = lane; g < G; g += 32)
+                if (__ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx) + g) == 0u)
+                    for (uint32_t r = 0; r < 13; ++r) ws.u.est.D[r][g] = 0.0f;
+            // the decimated grids' R fragments are one contiguous stream: walk it with a one-tile prefetch
+            const uint2* frag = reinterpret_cast<const uint2*>(ctx.blob + tb.t3.off_rstream) + lane;
+            const uint8_t* dec = ctx.blob + tb.t3.off_dec_list;
+            uint2 bcur[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) bcur[ks] = __ldg(frag + ks*32);
+#pragma unroll 1
+            for (uint32_t k = 0; k < tb.t3.n_dec; ++k) {
+                const uint32_t g = __ldg(dec + k);
                 float acc0 = 0.0f, acc1 = 0.0f;
-                if (off) {
-                    const uint2* frag = reinterpret_cast<const uint2*>(ctx.blob + off) + lane;
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                for (int nt = 0; nt < NT; ++nt) {
+                    frag += KS*32;
+                    uint2 bnext[KS];
 #pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], __ldg(frag + (nt*KS + ks)*32));
-                        acc0 += lw[nt][0]*c[0]*c[0] + lw[nt][1]*c[1]*c[1];
-                        acc1 += c[2]*c[2] + c[3]*c[3];
-                    }
-                    acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 1); acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 2);
-                    acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 1); acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 2);
+                    for (int ks = 0; ks < KS; ++ks) bnext[ks] = __ldg(frag + ks*32);     // the table ends with a pad tile
+                    float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], bcur[ks]);
+                    acc0 += lw[nt][0]*c[0]*c[0] + lw[nt][1]*c[1]*c[1];
+                    acc1 += c[2]*c[2] + c[3]*c[3];
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) bcur[ks] = bnext[ks];
                 }
+                acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 1); acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 2);
+                acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 1); acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 2);
                 if (tq == 0) {
                     ws.u.est.D[gq][g] = acc0*scale0;
                     if (gq + 8 < 13) ws.u.est.D[gq + 8][g] = acc1*scale1;
@@ -765,19 +779,19 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const Slot3& slot = ws.slots[s];
                 if (!slot.valid) continue;
                 const uint32_t type = slot_type(s);
-                const uint32_t first = type == 3 ? ctx.tab.n_modes1 : 0u, count = type == 3 ? ctx.tab.n_modes2 : ctx.tab.n_modes1;
-                const uint8_t* mcl = ctx.blob + tb.t3.off_modecl + ((has_alpha ? 4u : 0u) + type)*tb.t3.n_modes;
+                const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
+                const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
                 const float base = kLine*slot.e_line;
-                for (uint32_t mi = first + lane; mi < first + count; mi += 32) {
-                    const uint32_t cl = __ldg(mcl + mi);
-                    if (cl == 0xFFu) continue;
-                    const ModeInfo m = tab_mode(ctx, mi);
-                    const uint32_t g = m.grid;
+                const float l2sum = slot.len2[0] + slot.len2b;
+#pragma unroll 2
+                for (uint32_t e = lane; e < count; e += 32) {
+                    const uint4 q = __ldg(list + e);
+                    const uint32_t g = (q.z >> 16) & 0xFFu, mi = q.z & 0xFFFFu;
                     float dsum = ws.u.est.D[s][g], ssum;
-                    if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = (slot.len2[0] + slot.len2b)*__ldg(ksum + g); }
-                    else if (type == 0) ssum = slot.len2[0]*__ldg(ksum + g);
+                    if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
+                    else if (type == 0) ssum = l2sum*__ldg(ksum + g);
                     else ssum = ws.u.est.Sm[s - 1][g];
-                    const float est = base + kDec*dsum + kQuant*ssum*c_qvar[m.level] + kColor*tn*c_cvar[cl];
+                    const float est = base + kDec*dsum + kQuant*ssum*__uint_as_float(q.x) + kColor*tn*__uint_as_float(q.y);
                     const uint32_t code = (s << 16) | mi;
                     if (est < be2) {
                         if (est < be1) {
@@ -909,29 +923,12 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
     return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
 }
 
-bool g_consts_set[16] = {};
 
 } // namespace
 
 // t3 must describe tables appended to ctx.blob by build_tables3() (astc.cu owns the per-device table cache).
 int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cudaStream_t stream)
 {
-    int device = 0;
-    cudaGetDevice(&device);
-    if (device >= 0 && device < 16 && !g_consts_set[device]) {
-        float qv[kWeightLevels], cv[kColorLevels];
-        for (int l = 0; l < kWeightLevels; ++l) {
-            const float n1 = static_cast<float>(kWeightQuant[l].n - 1);
-            qv[l] = (1.0f/(n1*n1))*(1.0f/12.0f)*(1.0f - 0.75f/n1);
-        }
-        for (int l = 0; l < kColorLevels; ++l) {
-            const float step = 255.0f/static_cast<float>(kColorQuant[l].n - 1);
-            cv[l] = step*step*(1.0f/18.0f);
-        }
-        if (cudaMemcpyToSymbol(c_qvar, qv, sizeof(qv)) != cudaSuccess) return -4;
-        if (cudaMemcpyToSymbol(c_cvar, cv, sizeof(cv)) != cudaSuccess) return -4;
-        g_consts_set[device] = true;
-    }
     static const uint32_t kExact[5] = {2, 4, 8, 12, 16};
     const uint32_t n_exact = kExact[p.quality < 5 ? p.quality : 2];
     const uint32_t refine = p.quality >= 3 ? 3u : 2u;

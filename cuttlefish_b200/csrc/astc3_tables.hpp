@@ -31,6 +31,11 @@ struct Astc3Tab {
     uint32_t off_ksum;              // [n_grids] float: sum_i kappa_gi
     uint32_t off_modecl;            // [2 alpha][4 slot type][n_modes1 + n_modes2] u8 colour level, 0xFF = does not fit
     uint32_t n_modes;               // n_modes1 + n_modes2
+    uint32_t off_rstream;           // R fragments of the decimated grids, contiguous in off_dec_list order (+1 pad tile)
+    uint32_t off_dec_list;          // [n_dec] u8 grid index
+    uint32_t n_dec;                 // number of decimated grids (nw < texels)
+    uint32_t off_est[2][4];         // [alpha][slot type] -> uint4 list of the modes that fit:
+    uint32_t n_est[2][4];           //   {f32 kq = qvar(level), f32 kc = cvar(colour level), mode | grid << 16 | cl << 24, 0}
 };
 
 inline uint16_t f32_to_f16_bits(float f)
@@ -179,6 +184,42 @@ inline Astc3Tab build_tables3(Built& b)
                 if ((m.dual != 0) == (type == 3) && n_ints <= 18 && avail >= 0) cl = blob[t.off_clevel + (n_ints >> 1)*128 + avail];
                 blob[t3.off_modecl + (static_cast<size_t>(alpha)*4 + type)*t3.n_modes + mi] = cl;
             }
+    // the decimated grids' R fragments again as one contiguous stream (phase 1a walks it with a one-tile prefetch)
+    {
+        std::vector<uint8_t> dec;
+        for (int g = 0; g < G; ++g)
+            if (reinterpret_cast<const uint32_t*>(&blob[t3.off_rfrag_idx])[g]) dec.push_back(static_cast<uint8_t>(g));
+        t3.n_dec = static_cast<uint32_t>(dec.size());
+        t3.off_dec_list = reserve(dec.size() + 4, 4);
+        if (!dec.empty()) std::memcpy(&blob[t3.off_dec_list], dec.data(), dec.size());
+        const size_t per = static_cast<size_t>(NT)*KS*32*8;
+        t3.off_rstream = reserve((dec.size() + 1)*per, 16);
+        for (size_t k = 0; k < dec.size(); ++k) {
+            const uint32_t src = reinterpret_cast<const uint32_t*>(&blob[t3.off_rfrag_idx])[dec[k]];
+            std::memcpy(&blob[t3.off_rstream + k*per], &blob[src], per);
+        }
+    }
+    // estimate lists: per (alpha, slot type) the modes that fit, with their model terms
+    for (int alpha = 0; alpha < 2; ++alpha)
+        for (int type = 0; type < 4; ++type) {
+            std::vector<uint32_t> ent;
+            for (uint32_t mi = 0; mi < t3.n_modes; ++mi) {
+                const uint8_t cl = blob[t3.off_modecl + (static_cast<size_t>(alpha)*4 + type)*t3.n_modes + mi];
+                if (cl == 0xFF) continue;
+                const ModeInfo m = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes])[mi];
+                const float n1 = static_cast<float>(kWeightQuant[m.level].n - 1);
+                const float kq = (1.0f/(n1*n1))*(1.0f/12.0f)*(1.0f - 0.75f/n1);
+                const float step = 255.0f/static_cast<float>(kColorQuant[cl].n - 1);
+                const float kc = step*step*(1.0f/18.0f);
+                uint32_t w[4];
+                std::memcpy(&w[0], &kq, 4); std::memcpy(&w[1], &kc, 4);
+                w[2] = mi | (static_cast<uint32_t>(m.grid) << 16) | (static_cast<uint32_t>(cl) << 24); w[3] = 0;
+                ent.insert(ent.end(), w, w + 4);
+            }
+            t3.n_est[alpha][type] = static_cast<uint32_t>(ent.size()/4);
+            t3.off_est[alpha][type] = reserve(ent.size()*4 + 16, 16);
+            if (!ent.empty()) std::memcpy(&blob[t3.off_est[alpha][type]], ent.data(), ent.size()*4);
+        }
     t.blob_bytes = static_cast<uint32_t>(blob.size());
     return t3;
 }
