@@ -14,6 +14,12 @@
 
 namespace cfx {
 
+// SNORM blocks (Bc4Converter / Bc5Converter with Type::SNorm -> Compressonator's CompressBlockBC4S / BC5S,
+// lib/src/S3tcConverter.cpp:400-429, :453-490; lib/compressonator/cmp_core/shaders/bc4_encode_kernel.cpp:202-229) are
+// searched in a BIASED domain b = s + 128 (s = round(clamp(v,-1,1)*127) in [-127,127] -> b in [1,255]): interpolation
+// is linear, so the unsigned search applies unchanged; only the 6-value mode's two constants differ (-1.0 and +1.0,
+// i.e. b = 1 and 255) and end points stay >= 1.  Our own search (PSNR parity with the reference, not byte parity).
+template <bool SIGNED = false>
 __device__ __forceinline__ void bc4_palette(uint32_t e0, uint32_t e1, uint32_t& lo4, uint32_t& hi4)
 {
     // bc4_block::get_block_values: 8 values when e0 > e1, else 6 values + {0,255}.
@@ -23,12 +29,13 @@ __device__ __forceinline__ void bc4_palette(uint32_t e0, uint32_t e1, uint32_t& 
         v5 = (e0*3 + e1*4)/7; v6 = (e0*2 + e1*5)/7; v7 = (e0 + e1*6)/7;
     } else {
         v2 = (e0*4 + e1)/5; v3 = (e0*3 + e1*2)/5; v4 = (e0*2 + e1*3)/5; v5 = (e0 + e1*4)/5;
-        v6 = 0; v7 = 255;
+        v6 = SIGNED ? 1 : 0; v7 = 255;
     }
     lo4 = e0 | (e1 << 8) | (v2 << 16) | (v3 << 24);
     hi4 = v4 | (v5 << 8) | (v6 << 16) | (v7 << 24);
 }
 
+template <bool SIGNED = false>
 __device__ __forceinline__ void bc4_trial_endpoints(uint32_t t, uint32_t n, int rad, uint32_t mn,
     uint32_t mx, uint32_t& e0, uint32_t& e1, bool& valid)
 {
@@ -37,8 +44,8 @@ __device__ __forceinline__ void bc4_trial_endpoints(uint32_t t, uint32_t n, int 
     uint32_t rem = t - mode*nn;
     int lo_d = static_cast<int>(rem / n) - rad;
     int hi_d = static_cast<int>(rem % n) - rad;
-    e0 = static_cast<uint32_t>(min(max(static_cast<int>(mx) + hi_d, 0), 255));
-    e1 = static_cast<uint32_t>(min(max(static_cast<int>(mn) + lo_d, 0), 255));
+    e0 = static_cast<uint32_t>(min(max(static_cast<int>(mx) + hi_d, SIGNED ? 1 : 0), 255));
+    e1 = static_cast<uint32_t>(min(max(static_cast<int>(mn) + lo_d, SIGNED ? 1 : 0), 255));
     valid = e0 != e1;
     bool alpha6 = e0 <= e1;
     if ((mode == 0) ? alpha6 : !alpha6) { uint32_t tmp = e0; e0 = e1; e1 = tmp; }
@@ -46,9 +53,12 @@ __device__ __forceinline__ void bc4_trial_endpoints(uint32_t t, uint32_t n, int 
 
 // s_blk: 16 RGBA8 texels of the block in shared memory; chan: byte lane of the channel.
 // Returns the 8 block bytes as (lo, hi) words; identical in every lane.
+template <bool SIGNED = false>
 __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t chan, uint32_t radius,
     bool hq)
 {
+    // end point bytes as stored: SNORM blocks hold two's complement s = b - 128
+    auto stored = [](uint32_t e) -> uint32_t { return SIGNED ? ((e - 128u) & 0xFFu) : e; };
     const uint32_t lane = lane_id();
     const uint32_t shift = chan*8;
     uint32_t rep[16];
@@ -60,7 +70,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
         rep[i] = v*0x01010101u;
     }
 
-    if (!hq) {
+    if (!hq && !SIGNED) {
         // encode_bc4: endpoints max/min, threshold selector assignment.
         if (mx == mn) return make_uint2(mx | (mn << 8), 0u);
         int delta = static_cast<int>(mx - mn);
@@ -81,17 +91,17 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
         return make_uint2(mx | (mn << 8) | (lo << 16), (lo >> 16) | (hi << 16));
     }
 
-    if (mx == mn) return make_uint2(mn | (mn << 8), 0u);
+    if (mx == mn) return make_uint2(stored(mn) | (stored(mn) << 8), 0u);
 
     const uint32_t n = 2*radius + 1;
     const uint32_t total = 2*n*n;
     uint32_t best_err = 0xFFFFFFFFu, best_t = 0xFFFFFFFFu;
     for (uint32_t t = lane; t < total; t += 32) {
         uint32_t e0, e1; bool valid;
-        bc4_trial_endpoints(t, n, static_cast<int>(radius), mn, mx, e0, e1, valid);
+        bc4_trial_endpoints<SIGNED>(t, n, static_cast<int>(radius), mn, mx, e0, e1, valid);
         if (!valid) continue;
         uint32_t lo4, hi4;
-        bc4_palette(e0, e1, lo4, hi4);
+        bc4_palette<SIGNED>(e0, e1, lo4, hi4);
         uint32_t err = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -106,9 +116,9 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     uint32_t wt = __reduce_min_sync(0xFFFFFFFFu, best_err == werr ? best_t : 0xFFFFFFFFu);
 
     uint32_t e0, e1; bool valid;
-    bc4_trial_endpoints(wt, n, static_cast<int>(radius), mn, mx, e0, e1, valid);
+    bc4_trial_endpoints<SIGNED>(wt, n, static_cast<int>(radius), mn, mx, e0, e1, valid);
     uint32_t lo4, hi4;
-    bc4_palette(e0, e1, lo4, hi4);
+    bc4_palette<SIGNED>(e0, e1, lo4, hi4);
     uint32_t sel = 0;
     if (lane < 16) {
         uint32_t v = (s_blk[lane] >> shift) & 0xFFu;
@@ -125,7 +135,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     if (lane >= 16) bits = 0;
     uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(bits));
     uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(bits >> 32));
-    return make_uint2(e0 | (e1 << 8) | (lo << 16), (lo >> 16) | (hi << 16));
+    return make_uint2(stored(e0) | (stored(e1) << 8) | (lo << 16), (lo >> 16) | (hi << 16));
 }
 
 } // namespace cfx

@@ -68,7 +68,7 @@ static Launcher find_launcher(uint32_t format, uint32_t type)
 {
     switch (format) {
         case CFX_FORMAT_BC4: case CFX_FORMAT_BC5:
-            return type == CFX_TYPE_UNORM ? launch_bc45 : nullptr;
+            return (type == CFX_TYPE_UNORM || type == CFX_TYPE_SNORM) ? launch_bc45 : nullptr;
 #ifdef CFX_HAVE_BC7
         case CFX_FORMAT_BC7:
             return type == CFX_TYPE_UNORM ? launch_bc7 : nullptr;
@@ -80,6 +80,8 @@ static Launcher find_launcher(uint32_t format, uint32_t type)
 #ifdef CFX_HAVE_ETC
         case CFX_FORMAT_ETC1: case CFX_FORMAT_ETC2_R8G8B8: case CFX_FORMAT_ETC2_R8G8B8A8:
             return type == CFX_TYPE_UNORM ? launch_etc : nullptr;
+        case CFX_FORMAT_EAC_R11: case CFX_FORMAT_EAC_R11G11:
+            return (type == CFX_TYPE_UNORM || type == CFX_TYPE_SNORM) ? launch_etc : nullptr;
 #endif
 #ifdef CFX_HAVE_BC6H
         case CFX_FORMAT_BC6H:

@@ -107,6 +107,29 @@ __device__ __forceinline__ void stage_tile_u8(uint32_t* s_px, const EncodeParams
     }
 }
 
+// SNORM view for BC4S / BC5S: per channel round(clamp(v,-1,1)*127) (std::round, like Bc4Converter::compressBlock,
+// lib/src/S3tcConverter.cpp:404-409) biased by +128 into a byte: s_px[b*stride + r*4 + c].
+__device__ __forceinline__ uint32_t f32_to_snorm8_biased(float v)
+{
+    v = fminf(fmaxf(v, -1.0f), 1.0f);
+    return static_cast<uint32_t>(static_cast<int>(roundf(__fmul_rn(v, 127.0f))) + 128);
+}
+
+__device__ __forceinline__ void stage_tile_s8(uint32_t* s_px, const EncodeParams& p, uint32_t first, uint32_t nblocks)
+{
+    for (uint32_t i = threadIdx.x; i < nblocks*16; i += blockDim.x) {
+        uint32_t t = i / nblocks, b = i - t*nblocks;
+        uint32_t r = t >> 2, c = t & 3;
+        uint32_t blk = first + b;
+        uint32_t by = blk / p.blocks_x, bx = blk - by*p.blocks_x;
+        uint32_t y = min(by*4 + r, p.height - 1);
+        uint32_t x = min(bx*4 + c, p.width - 1);
+        const float4 f = load_texel_f32(p, x, y);
+        s_px[b*16 + t] = f32_to_snorm8_biased(f.x) | (f32_to_snorm8_biased(f.y) << 8) | (f32_to_snorm8_biased(f.z) << 16) |
+            (f32_to_snorm8_biased(f.w) << 24);
+    }
+}
+
 // Same for the float view: s_px[b*16 + r*4 + c] as float4 (ETC / BC6H inputs).
 __device__ __forceinline__ void stage_tile_f32(float4* s_px, const EncodeParams& p, uint32_t first,
     uint32_t nblocks)

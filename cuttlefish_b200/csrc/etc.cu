@@ -4,8 +4,8 @@
 // like the reference (lib/src/EtcConverter.cpp:145, float RGBA into Etc::Image) the encoder sees
 // unquantised values when the source is RGBA16F / RGBA32F.
 //
-// Replaces EtcConverter::process, lib/src/EtcConverter.cpp:120-152, for ETC1, ETC2_R8G8B8 and
-// ETC2_R8G8B8A8.
+// Replaces EtcConverter::process, lib/src/EtcConverter.cpp:120-152, for ETC1, ETC2_R8G8B8,
+// ETC2_R8G8B8A8 and EAC_R11 / EAC_R11G11 (UNorm and SNorm).
 #include "common.cuh"
 #include "etc_core.cuh"
 #include "etc1_exact.cuh"
@@ -15,7 +15,7 @@ namespace cfx {
 
 namespace { constexpr int kEtcWarps = 4; }
 
-template <int FORMAT>   // 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8
+template <int FORMAT, bool SIGNED = false>   // 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8, 41 EAC R11, 42 EAC RG11
 __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p, int rounds, int alpha_radius, bool exact)
 {
     __shared__ float s_x[kEtcWarps][16*4*32];
@@ -57,11 +57,22 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
                     static_cast<float>(q >> 24));
             } else {
                 const float4 f = load_texel_f32(p, x, y);
-                v = make_float4(fminf(fmaxf(f.x, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.y, 0.0f), 1.0f)*255.0f,
+                const float lowest = SIGNED ? -1.0f : 0.0f;      // signed EAC keeps [-1,1] (EtcConverter.cpp:139-143)
+                v = make_float4(fminf(fmaxf(f.x, lowest), 1.0f)*255.0f, fminf(fmaxf(f.y, lowest), 1.0f)*255.0f,
                     fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
             }
             // EtcConverter never looks at the colour mask or the alpha type: all four channels as they are
             etc::px(xs, lane, t, 0) = v.x; etc::px(xs, lane, t, 1) = v.y; etc::px(xs, lane, t, 2) = v.z; etc::px(xs, lane, t, 3) = v.w;
+        }
+        if (FORMAT == 41 || FORMAT == 42) {
+            const uint2 r = etc::encode_eac_r11<SIGNED>(xs, lane, 0, alpha_radius);
+            if (FORMAT == 41) {
+                if (live) reinterpret_cast<uint2*>(p.dst)[blk] = r;
+            } else {
+                const uint2 g = etc::encode_eac_r11<SIGNED>(xs, lane, 1, alpha_radius);
+                if (live) reinterpret_cast<uint4*>(p.dst)[blk] = make_uint4(r.x, r.y, g.x, g.y);
+            }
+            continue;
         }
         const uint2 color = etc::encode_color(xs, lane, FORMAT != 37, rounds);
         if (FORMAT == 40) {
@@ -82,8 +93,16 @@ int launch_etc(const EncodeParams& p, cudaStream_t stream)
     const int rounds = rounds_by_quality[p.quality], radius = radius_by_quality[p.quality];
     const uint32_t groups = (p.total_blocks + 31)/32;
     const uint32_t ctas = (groups + kEtcWarps - 1)/kEtcWarps;
-    const void* k = p.format == 37 ? reinterpret_cast<const void*>(&etc_kernel<37>) :
-        (p.format == 38 ? reinterpret_cast<const void*>(&etc_kernel<38>) : reinterpret_cast<const void*>(&etc_kernel<40>));
+    const bool sn = p.type == 1;                          // Texture::Type::SNorm
+    const void* k = nullptr;
+    switch (p.format) {
+        case 37: k = reinterpret_cast<const void*>(&etc_kernel<37>); break;
+        case 38: k = reinterpret_cast<const void*>(&etc_kernel<38>); break;
+        case 40: k = reinterpret_cast<const void*>(&etc_kernel<40>); break;
+        case 41: k = sn ? reinterpret_cast<const void*>(&etc_kernel<41, true>) : reinterpret_cast<const void*>(&etc_kernel<41, false>); break;
+        case 42: k = sn ? reinterpret_cast<const void*>(&etc_kernel<42, true>) : reinterpret_cast<const void*>(&etc_kernel<42, false>); break;
+        default: return -2;
+    }
     const uint32_t grid = min(ctas, persistent_ctas(k, kEtcWarps*32));
     // ETC1 at effort <= 40 (Lowest/Low/Normal) in linear colour space is the byte-exact restatement
     bool exact = etc1_is_exact(p.quality) && p.color_space == 0;

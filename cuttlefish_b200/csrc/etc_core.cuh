@@ -475,6 +475,72 @@ CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius)
     return to_bytes(hi32, lo32);
 }
 
+
+// ---- EAC R11 / RG11 (one or two 11-bit channels, unsigned or signed) --------------------------------
+// Replaces Block4x4Encoding_R11 / _RG11 (lib/etc2comp/EtcLib/EtcCodec/EtcBlock4x4Encoding_R11.cpp:170-392),
+// which EtcConverter selects for EAC_R11 / EAC_R11G11 (lib/src/EtcConverter.cpp:89-115; signed inputs are remapped
+// to [0,1] there, :139-143).  Same table x multiplier x base search as the alpha block above, but scored against the
+// 11-bit decode of the format: unsigned clamp(base*8 + 4 + modifier*multiplier*8, 0, 2047) / 2047, signed
+// clamp(base*8 + modifier*multiplier*8, -1023, 1023) / 1023 with an int8 base.  Our own search: PSNR parity.
+// xs channel `chan` holds v*255 with v clamped to [0,1] (unsigned) or [-1,1] (signed).
+template <bool SIGNED>
+CFX_HD uint2 encode_eac_r11(float* xs, uint32_t lane, uint32_t chan, int radius)
+{
+    const float scale = SIGNED ? 1023.0f/255.0f : 2047.0f/255.0f;
+    const int off = SIGNED ? 0 : 4, vmin = SIGNED ? -1023 : 0, vmax = SIGNED ? 1023 : 2047;
+    const int bmin = SIGNED ? -127 : 0, bmax = SIGNED ? 127 : 255;
+    float lo = 3.0e38f, hi = -3.0e38f;
+    for (uint32_t t = 0; t < 16; ++t) { const float a = px(xs, lane, t, chan)*scale; lo = fminf(lo, a); hi = fmaxf(hi, a); }
+    int best_base = 0, best_mul = 1;
+    uint32_t best_tab = 13;
+    float best = 3.0e38f;
+#pragma unroll 1
+    for (uint32_t tab = 0; tab < 16; ++tab) {
+        const float tmin = static_cast<float>(kEac[tab][3]), tmax = static_cast<float>(kEac[tab][7]);
+        const float range = (tmax - tmin)*8.0f;
+        const int mul0 = min(max(__float2int_rn((hi - lo)/range), 1), 15);
+#pragma unroll 1
+        for (int dm = -1; dm <= 1; ++dm) {
+            const int mul = mul0 + dm;
+            if (mul < 1 || mul > 15) continue;
+            const int base0 = __float2int_rn((0.5f*(lo + hi) - static_cast<float>(off) - 4.0f*(tmin + tmax)*static_cast<float>(mul))*0.125f);
+#pragma unroll 1
+            for (int db = -radius; db <= radius; ++db) {
+                const int base = base0 + db;
+                if (base < bmin || base > bmax) continue;
+                float err = 0.0f;
+                for (uint32_t t = 0; t < 16 && err < best; ++t) {
+                    const float a = px(xs, lane, t, chan)*scale;
+                    float be = 3.0e38f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float d = static_cast<float>(min(max(base*8 + off + kEac[tab][k]*mul*8, vmin), vmax)) - a;
+                        be = fminf(be, d*d);
+                    }
+                    err += be;
+                }
+                if (err < best) { best = err; best_base = base; best_mul = mul; best_tab = tab; }
+            }
+        }
+    }
+    uint64_t bits = 0;
+    for (uint32_t p = 0; p < 16; ++p) {
+        const uint32_t t = (p & 3u)*4u + (p >> 2);
+        const float a = px(xs, lane, t, chan)*scale;
+        float be = 3.0e38f;
+        uint32_t bk = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            const float d = static_cast<float>(min(max(best_base*8 + off + kEac[best_tab][k]*best_mul*8, vmin), vmax)) - a;
+            if (d*d < be) { be = d*d; bk = k; }
+        }
+        bits = (bits << 3) | bk;
+    }
+    const uint32_t hi32 = ((static_cast<uint32_t>(best_base) & 0xFFu) << 24) | (static_cast<uint32_t>(best_mul) << 20) | (best_tab << 16) |
+        static_cast<uint32_t>(bits >> 32);
+    return to_bytes(hi32, static_cast<uint32_t>(bits));
+}
+
 // format: 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8 (colour part); returns the 8 colour bytes
 CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds)
 {

@@ -365,3 +365,61 @@ def test_etc1_bit_exact(cfx, oracle):
         src, blocks, f, kw = load_golden(name)
         if kw.get("quality", "Normal") in ("Normal", "Low", "Lowest"):
             assert np.array_equal(cfx.encode(src, f, **kw), blocks), name
+
+
+# ---- BC4 / BC5 SNorm (Compressonator in the reference): our own search in a biased domain, PSNR parity ----
+@pytest.mark.parametrize("fmt", ["BC4", "BC5"])
+@pytest.mark.parametrize("w,h", [(256, 256), (97, 61)])
+def test_bc45_snorm_psnr_vs_oracle(cfx, oracle, fmt, w, h):
+    from util import decode_bc4_snorm
+    assert cfx.format_supported(fmt, "SNorm")
+    img = oracle.gen_image("noise+grad", w, h)*2.0 - 1.0        # [-1, 1] in every channel
+    img[..., 3] = 1.0
+    img = img.astype(np.float32)
+    ref = oracle.encode(img, fmt, type="SNorm")
+    got = cfx.encode(img, fmt, type="SNorm")
+    assert got.shape == ref.shape
+    nch = 1 if fmt == "BC4" else 2
+
+    def mse(blocks):
+        b = blocks.reshape(-1, 8*nch)
+        e = 0.0
+        for c in range(nch):
+            dec = decode_bc4_snorm(np.ascontiguousarray(b[:, 8*c:8*c + 8]), w, h)
+            q = np.round(np.clip(img[..., c], -1, 1)*127)/127
+            e += float(np.mean((dec - q)**2))
+        return e/nch
+    p_gpu, p_ref = 10*np.log10(4.0/mse(got)), 10*np.log10(4.0/mse(ref))
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s SNorm: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, p_gpu, p_ref)
+    # a half-float source takes the same path
+    got16 = cfx.encode(img.astype(np.float16), fmt, type="SNorm")
+    assert 10*np.log10(4.0/mse(got16)) >= p_ref - 0.5
+
+
+# ---- EAC R11 / RG11, unsigned and signed (etc2comp's Block4x4Encoding_R11 in the reference): PSNR parity ----
+@pytest.mark.parametrize("fmt", ["EAC_R11", "EAC_R11G11"])
+@pytest.mark.parametrize("typ", ["UNorm", "SNorm"])
+@pytest.mark.parametrize("kind,w,h", [("noise+grad", 128, 128), ("gradient", 128, 128), ("noise+grad", 61, 37)])
+def test_eac_r11_psnr_vs_oracle(cfx, oracle, fmt, typ, kind, w, h):
+    from util import decode_eac_r11
+    assert cfx.format_supported(fmt, typ)
+    img = oracle.gen_image(kind, w, h).astype(np.float32)
+    signed = typ == "SNorm"
+    if signed:
+        img = (img*2.0 - 1.0).astype(np.float32)
+        img[..., 3] = 1.0
+    ref = oracle.encode(img, fmt, type=typ)
+    got = cfx.encode(img, fmt, type=typ)
+    assert got.shape == ref.shape
+    nch = 1 if fmt == "EAC_R11" else 2
+
+    def mse(blocks):
+        b = blocks.reshape(-1, 8*nch)
+        e = 0.0
+        for c in range(nch):
+            dec = decode_eac_r11(np.ascontiguousarray(b[:, 8*c:8*c + 8]), w, h, signed)
+            e += float(np.mean((dec - img[..., c])**2))
+        return e/nch
+    peak2 = 4.0 if signed else 1.0
+    p_gpu, p_ref = 10*np.log10(peak2/mse(got)), 10*np.log10(peak2/mse(ref))
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s %s: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, typ, p_gpu, p_ref)
