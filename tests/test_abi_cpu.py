@@ -49,7 +49,10 @@ def test_unsupported_pairs_report_unsupported():
     assert not cfx.format_supported("BC4", "UInt")
     assert not cfx.format_supported(14, "UNorm")
     with pytest.raises(cfx.CfxError) as e:
-        cfx.encode(np.zeros((4, 4, 4), np.uint8), "EAC_R11")
+        cfx.encode(np.zeros((4, 4, 4), np.uint8), "EAC_R11", type="UInt")
+    assert e.value.code == -2
+    with pytest.raises(cfx.CfxError) as e:
+        cfx.encode(np.zeros((12, 12, 4), np.uint8), "ASTC_12x12")      # footprints above 64 texels: no GPU encoder yet
     assert e.value.code == -2
 
 
