@@ -53,7 +53,7 @@ struct Mom { float n, s[4], p[10]; };
 struct LineFit { float m[4], v[4], resid, pad[3]; };     // mean (about the centre), unit direction, trace - lambda
 
 // Per-warp working set, sized by the footprint: TP = texel capacity (NT*8), GP = weight grid capacity.
-constexpr int grid_capacity(int NT) { return NT <= 3 ? 12 : (NT == 4 ? 20 : (NT == 5 ? 28 : (NT <= 7 ? 36 : kMaxGrids3))); }
+constexpr int grid_capacity(int NT) { return NT <= 3 ? 12 : (NT == 4 ? 20 : (NT == 5 ? 28 : (NT <= 7 ? 36 : (NT == 8 ? 52 : kMaxGrids3)))); }
 constexpr int ta_stride(int TP) { return ((TP + 8)/2) % 8 == 0 ? TP + 16 : TP + 8; }   // halfs; conflict-free A fragment loads
 
 template <int NT>
@@ -328,19 +328,85 @@ __device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, 
     out.resid = fmaxf(cv[0] + cv[4] + cv[7] + cv[9] - lam, 0.0f);
 }
 
+// A set of texels: one bit per texel, MW 64-bit words (footprints above 64 texels need 2 or 3).
+template <int MW> struct TexelMask { uint64_t w[MW]; };
+
+template <int MW>
+__device__ __forceinline__ TexelMask<MW> load_mask(const Ctx& c, uint32_t off)
+{
+    TexelMask<MW> m;
+#pragma unroll
+    for (int k = 0; k < MW; ++k) m.w[k] = tab_u64(c, off + 8u*k);
+    return m;
+}
+template <int MW>
+__device__ __forceinline__ bool mask_empty(const TexelMask<MW>& m)
+{
+    uint64_t o = 0;
+#pragma unroll
+    for (int k = 0; k < MW; ++k) o |= m.w[k];
+    return o == 0;
+}
+template <int MW>
+__device__ __forceinline__ uint32_t mask_bit(const TexelMask<MW>& m, uint32_t i)
+{
+    uint64_t word = m.w[0];
+#pragma unroll
+    for (int k = 1; k < MW; ++k) if ((i >> 6) == static_cast<uint32_t>(k)) word = m.w[k];
+    return static_cast<uint32_t>((word >> (i & 63u)) & 1ull);
+}
+// Number of texels a 2-subset seed assigns differently from the clustering (up to relabelling).
+template <int MW>
+__device__ __forceinline__ uint32_t mask_mismatch2(const TexelMask<MW>& km, const TexelMask<MW>& pm, uint32_t T)
+{
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < MW; ++k) d += popc64(km.w[k] ^ pm.w[k]);
+    return min(d, T - d);
+}
+// Same for three subsets: best of the 6 label permutations.
+template <int MW>
+__device__ __forceinline__ uint32_t mask_mismatch3(const TexelMask<MW>& k1, const TexelMask<MW>& k2, const TexelMask<MW>& p1,
+    const TexelMask<MW>& p2, const TexelMask<MW>& full, uint32_t T)
+{
+    uint32_t m[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+        const uint64_t kk[3] = {full.w[w] ^ k1.w[w] ^ k2.w[w], k1.w[w], k2.w[w]};
+        const uint64_t pp[3] = {full.w[w] ^ p1.w[w] ^ p2.w[w], p1.w[w], p2.w[w]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) m[i][j] += popc64(kk[i] & pp[j]);
+    }
+    uint32_t a = m[0][0] + m[1][1] + m[2][2];
+    a = max(a, m[0][0] + m[1][2] + m[2][1]);
+    a = max(a, m[0][1] + m[1][0] + m[2][2]);
+    a = max(a, m[0][1] + m[1][2] + m[2][0]);
+    a = max(a, m[0][2] + m[1][0] + m[2][1]);
+    a = max(a, m[0][2] + m[1][1] + m[2][0]);
+    return T - a;
+}
+
 // Lane-local masked moments: texels whose bit is set in `mask`, about `ctr`.
-__device__ __noinline__ void masked_moments(const int4* v, uint32_t T, int4 ctr, uint64_t mask, int (&acc)[15])
+template <int MW>
+__device__ __noinline__ void masked_moments(const int4* v, uint32_t T, int4 ctr, TexelMask<MW> mask, int (&acc)[15])
 {
     // accumulate in registers (the caller's array lives in local memory: this function is not inlined)
     int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0, a10 = 0, a11 = 0, a12 = 0, a13 = 0, a14 = 0;
+#pragma unroll
+    for (int wd = 0; wd < MW; ++wd) {
+    const uint64_t word = mask.w[wd];
+    const uint32_t i1 = min(T, 64u*(wd + 1));
 #pragma unroll 4
-    for (uint32_t i = 0; i < T; ++i) {
+    for (uint32_t i = 64u*wd; i < i1; ++i) {
         const int4 x = v[i];
-        const int f = static_cast<int>((mask >> i) & 1ull);
+        const int f = static_cast<int>((word >> (i & 63u)) & 1ull);
         const int x0 = f*(x.x - ctr.x), x1 = f*(x.y - ctr.y), x2 = f*(x.z - ctr.z), x3 = f*(x.w - ctr.w);
         a0 += f; a1 += x0; a2 += x1; a3 += x2; a4 += x3;
         a5 += x0*x0; a6 += x0*x1; a7 += x0*x2; a8 += x0*x3; a9 += x1*x1;
         a10 += x1*x2; a11 += x1*x3; a12 += x2*x2; a13 += x2*x3; a14 += x3*x3;
+    }
     }
     acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3; acc[4] = a4; acc[5] = a5; acc[6] = a6; acc[7] = a7; acc[8] = a8;
     acc[9] = a9; acc[10] = a10; acc[11] = a11; acc[12] = a12; acc[13] = a13; acc[14] = a14;
@@ -357,8 +423,9 @@ __device__ __forceinline__ void mom_from(const int (&a)[15], Mom& m)
 
 // k-means clustering of the block's texels (lane = texel) into k = 2 or 3 groups: farthest-point seeds, three
 // Lloyd iterations; returns the texel masks of clusters 1 and 2.
-template <int K>
-__device__ __noinline__ void kmeans_warp(const int4* v, uint32_t T, uint32_t k, int4 mean, uint32_t lane, uint64_t& m1, uint64_t& m2)
+template <int K, int MW>
+__device__ __noinline__ void kmeans_warp(const int4* v, uint32_t T, uint32_t k, int4 mean, uint32_t lane, TexelMask<MW>& m1,
+    TexelMask<MW>& m2)
 {
     int4 x[K];
     bool live[K];
@@ -378,14 +445,16 @@ __device__ __noinline__ void kmeans_warp(const int4* v, uint32_t T, uint32_t k, 
                 d = fminf(d, dx*dx + dy*dy + dz*dz + dw*dw);
             }
             // farthest texel, lowest index on ties
-            const uint32_t kk = (__float_as_uint(d) & ~63u) | (63u - (lane + 32u*r));
+            const uint32_t kk = (__float_as_uint(d) & ~255u) | (255u - (lane + 32u*r));
             key = max(key, kk);
         }
         key = __reduce_max_sync(0xFFFFFFFFu, key);
-        const int4 far = v[63u - (key & 63u)];
+        const int4 far = v[255u - (key & 255u)];
         ctr[c] = make_float4(static_cast<float>(far.x), static_cast<float>(far.y), static_cast<float>(far.z), static_cast<float>(far.w));
     }
-    uint32_t b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
+    uint32_t b1[2*MW], b2[2*MW];
+#pragma unroll
+    for (int r = 0; r < 2*MW; ++r) b1[r] = b2[r] = 0;
     for (int it = 0; it < 3; ++it) {
         int cnt[3] = {0, 0, 0}, sx[3] = {0, 0, 0}, sy[3] = {0, 0, 0}, sz[3] = {0, 0, 0}, sw[3] = {0, 0, 0};
         uint32_t lab[K];
@@ -405,8 +474,8 @@ __device__ __noinline__ void kmeans_warp(const int4* v, uint32_t T, uint32_t k, 
                 cnt[q] += f; sx[q] += f*x[r].x; sy[q] += f*x[r].y; sz[q] += f*x[r].z; sw[q] += f*x[r].w;
             }
         }
-        b1lo = __ballot_sync(0xFFFFFFFFu, lab[0] == 1u); b2lo = __ballot_sync(0xFFFFFFFFu, lab[0] == 2u);
-        if (K > 1) { b1hi = __ballot_sync(0xFFFFFFFFu, lab[K - 1] == 1u); b2hi = __ballot_sync(0xFFFFFFFFu, lab[K - 1] == 2u); }
+#pragma unroll
+        for (int r = 0; r < K; ++r) { b1[r] = __ballot_sync(0xFFFFFFFFu, lab[r] == 1u); b2[r] = __ballot_sync(0xFFFFFFFFu, lab[r] == 2u); }
         for (uint32_t q = 0; q < k; ++q) {
             const int n = redux_add(cnt[q]);
             const int ax = redux_add(sx[q]), ay = redux_add(sy[q]), az = redux_add(sz[q]), aw = redux_add(sw[q]);
@@ -416,8 +485,11 @@ __device__ __noinline__ void kmeans_warp(const int4* v, uint32_t T, uint32_t k, 
             }
         }
     }
-    m1 = static_cast<uint64_t>(b1lo) | (static_cast<uint64_t>(b1hi) << 32);
-    m2 = static_cast<uint64_t>(b2lo) | (static_cast<uint64_t>(b2hi) << 32);
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+        m1.w[w] = static_cast<uint64_t>(b1[2*w]) | (static_cast<uint64_t>(b1[2*w + 1]) << 32);
+        m2.w[w] = static_cast<uint64_t>(b2[2*w]) | (static_cast<uint64_t>(b2[2*w + 1]) << 32);
+    }
 }
 
 struct SlotView {           // what pack_block needs from a slot
@@ -430,7 +502,9 @@ struct SlotView {           // what pack_block needs from a slot
 template <int NT, int KS, int W, int CTAS, bool LOCK>
 __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p, const Tab3 tb, uint32_t n_exact, uint32_t refine)
 {
-    constexpr int K = (NT*8 > 32) ? 2 : 1;
+    constexpr int K = (NT*8 + 31)/32;            // texels per lane
+    constexpr int MW = (NT*8 + 63)/64;           // words per texel mask
+    static_assert(2*MW >= K, "ballot words");
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = lane_id(), warp = warp_id();
     const uint32_t gq = lane >> 2, tq = lane & 3u;
@@ -543,23 +617,30 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             sl.valid = lane == 0 || (lane >= 5 && lane - 5 < nch) ? 1u : 0u;
         }
         // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
-        uint64_t km0, km1, km2;
-        km0 = km1 = km2 = 0;
+        TexelMask<MW> km0, km1, km2;
+#pragma unroll
+        for (int w = 0; w < MW; ++w) km0.w[w] = km1.w[w] = km2.w[w] = 0;
 #pragma unroll 1
         for (uint32_t kk = 2; active && kk <= 3; ++kk) {
-            uint64_t ka, kb;
-            kmeans_warp<K>(ws.v, T, kk, ctr, lane, ka, kb);
+            TexelMask<MW> ka, kb;
+            kmeans_warp<K, MW>(ws.v, T, kk, ctr, lane, ka, kb);
             if (kk == 2) km0 = ka; else { km1 = ka; km2 = kb; }
         }
         uint32_t b2 = 0xFFFFFFFFu, b3 = 0xFFFFFFFFu;
         if (active) {
-            const uint64_t full = T == 64 ? ~0ull : ((1ull << T) - 1ull);
+            TexelMask<MW> full;
+#pragma unroll
+            for (int w = 0; w < MW; ++w) {
+                const uint32_t left = T > 64u*w ? T - 64u*w : 0u;
+                full.w[w] = left >= 64u ? ~0ull : ((1ull << left) - 1ull);
+            }
 #pragma unroll 4
             for (uint32_t seed = lane; seed < 1024; seed += 32) {
-                const uint64_t q = tab_u64(ctx, ctx.tab.off_part2 + seed*8u);
-                if (q) b2 = min(b2, (mismatch2(km0, q, T) << 10) | seed);
-                const uint64_t q1 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u), q2 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u + 8u);
-                if (q1) b3 = min(b3, (mismatch3(km1, km2, q1, q2, full) << 10) | seed);
+                const TexelMask<MW> q = load_mask<MW>(ctx, tb.t3.off_part2w + seed*(8u*MW));
+                if (!mask_empty<MW>(q)) b2 = min(b2, (mask_mismatch2<MW>(km0, q, T) << 10) | seed);
+                const TexelMask<MW> q1 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW));
+                const TexelMask<MW> q2 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW) + 8u*MW);
+                if (!mask_empty<MW>(q1)) b3 = min(b3, (mask_mismatch3<MW>(km1, km2, q1, q2, full, T) << 10) | seed);
             }
         }
         PHASE_SYNC();
@@ -568,7 +649,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             float sc = 3.0e38f;
             int a1[15], a0[15];
             if (b2 != 0xFFFFFFFFu) {
-                masked_moments(ws.v, T, ctr, tab_u64(ctx, ctx.tab.off_part2 + (b2 & 1023u)*8u), a1);
+                masked_moments<MW>(ws.v, T, ctr, load_mask<MW>(ctx, tb.t3.off_part2w + (b2 & 1023u)*(8u*MW)), a1);
 #pragma unroll
                 for (int k = 0; k < 15; ++k) a0[k] = tot[k] - a1[k];
                 if (a0[0] >= 1 && a1[0] >= 1) {
@@ -588,8 +669,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     sc = 3.0e38f;
                 }
                 if (lane == 0) { Slot3& sl = ws.slots[1 + rank]; sl.pc = 2; sl.seed = seed; sl.dual_ch = -1; sl.valid = ok ? 1u : 0u; }
-                const uint64_t m1 = tab_u64(ctx, ctx.tab.off_part2 + seed*8u);
-                for (uint32_t i = lane; i < TP; i += 32) ws.part[rank][i] = static_cast<uint8_t>((m1 >> i) & 1ull);
+                const TexelMask<MW> m1 = load_mask<MW>(ctx, tb.t3.off_part2w + seed*(8u*MW));
+                for (uint32_t i = lane; i < TP; i += 32) ws.part[rank][i] = static_cast<uint8_t>(mask_bit<MW>(m1, i));
             }
         }
         PHASE_SYNC();
@@ -599,8 +680,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             int a1[15], a2[15], a0[15];
             if (b3 != 0xFFFFFFFFu) {
                 const uint32_t seed = b3 & 1023u;
-                masked_moments(ws.v, T, ctr, tab_u64(ctx, ctx.tab.off_part3 + seed*16u), a1);
-                masked_moments(ws.v, T, ctr, tab_u64(ctx, ctx.tab.off_part3 + seed*16u + 8u), a2);
+                masked_moments<MW>(ws.v, T, ctr, load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW)), a1);
+                masked_moments<MW>(ws.v, T, ctr, load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW) + 8u*MW), a2);
 #pragma unroll
                 for (int k = 0; k < 15; ++k) a0[k] = tot[k] - a1[k] - a2[k];
                 if (a0[0] >= 1 && a1[0] >= 1 && a2[0] >= 1) {
@@ -620,9 +701,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     sc = 3.0e38f;
                 }
                 if (lane == 0) { Slot3& sl = ws.slots[3 + rank]; sl.pc = 3; sl.seed = seed; sl.dual_ch = -1; sl.valid = ok ? 1u : 0u; }
-                const uint64_t m1 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u), m2 = tab_u64(ctx, ctx.tab.off_part3 + seed*16u + 8u);
+                const TexelMask<MW> m1 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW));
+                const TexelMask<MW> m2 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW) + 8u*MW);
                 for (uint32_t i = lane; i < TP; i += 32)
-                    ws.part[2 + rank][i] = static_cast<uint8_t>(((m1 >> i) & 1ull) ? 1u : (((m2 >> i) & 1ull) ? 2u : 0u));
+                    ws.part[2 + rank][i] = static_cast<uint8_t>(mask_bit<MW>(m1, i) ? 1u : (mask_bit<MW>(m2, i) ? 2u : 0u));
             }
         }
         PHASE_SYNC();
@@ -759,7 +841,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         }
         // ---- phase 1b: S of the multi-subset slots (lane = grid)
         for (uint32_t g = lane; active && g < G; g += 32) {
-            const float* kap = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_kappa) + g*kMaxTexels;
+            const float* kap = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_kappa) + g*kMaxTexels3;
             float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, s4 = 0.0f;
             for (uint32_t i = 0; i < T; ++i) {
                 const float k = __ldg(kap + i);
@@ -912,6 +994,7 @@ template <int NT, int KS>
 int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t refine, cudaStream_t stream)
 {
 #ifdef CFX_ASTC3_TUNE
+    if constexpr (NT <= 8) {
     // developer knob: compare launch shapes without rebuilding (CFX_ASTC3_CFG = warps*100 + ctas*10 + lockstep)
     static const int cfg = getenv("CFX_ASTC3_CFG") ? atoi(getenv("CFX_ASTC3_CFG")) : 0;
     if (cfg == 830) return launch_cfg<NT, KS, 8, 3, false>(p, tb, n_exact, refine, stream);
@@ -919,8 +1002,11 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
     if (cfg == 1221) return launch_cfg<NT, KS, 12, 2, true>(p, tb, n_exact, refine, stream);
     if (cfg == 1611) return launch_cfg<NT, KS, 16, 1, true>(p, tb, n_exact, refine, stream);
     if (cfg == 2410) return launch_cfg<NT, KS, 24, 1, false>(p, tb, n_exact, refine, stream);
+    }
 #endif
-    return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
+    // above 64 texels the working set and the register file only allow 8 warps per SM
+    if constexpr (NT > 8) return launch_cfg<NT, KS, 8, 1, true>(p, tb, n_exact, refine, stream);
+    else return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
 }
 
 
@@ -941,6 +1027,10 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     if (NT == 6 && KS == 3) return launch_one<6, 3>(p, tb, n_exact, refine, stream);
     if (NT == 7 && KS == 4) return launch_one<7, 4>(p, tb, n_exact, refine, stream);
     if (NT == 8 && KS == 4) return launch_one<8, 4>(p, tb, n_exact, refine, stream);
+    if (NT == 10 && KS == 5) return launch_one<10, 5>(p, tb, n_exact, refine, stream);
+    if (NT == 13 && KS == 7) return launch_one<13, 7>(p, tb, n_exact, refine, stream);
+    if (NT == 15 && KS == 8) return launch_one<15, 8>(p, tb, n_exact, refine, stream);
+    if (NT == 18 && KS == 9) return launch_one<18, 9>(p, tb, n_exact, refine, stream);
     return -2;
 }
 

@@ -20,20 +20,24 @@
 namespace cfx {
 namespace astc {
 
-constexpr int kMaxGrids3 = 52;
+constexpr int kMaxGrids3 = 96;
+constexpr int kMaxTexels3 = 144;    // up to 12x12
 constexpr int kRows3 = 16;          // slot planes (A operand rows): 9 first planes, 4 second planes, 3 spare
 
 struct Astc3Tab {
     uint32_t NT, KS;                // texel n-tiles (8 wide), texel k-steps (16 deep)
     uint32_t off_rfrag_idx;         // [n_grids] uint32: byte offset of grid's R fragments, 0 = full-resolution grid (R = 0)
     uint32_t off_mfrag_idx;         // [n_grids] uint32: byte offset of grid's M fragments
-    uint32_t off_kappa;             // [n_grids][kMaxTexels] float: kappa_gi = sum_j P_ij^2
+    uint32_t off_kappa;             // [n_grids][kMaxTexels3] float: kappa_gi = sum_j P_ij^2
     uint32_t off_ksum;              // [n_grids] float: sum_i kappa_gi
     uint32_t off_modecl;            // [2 alpha][4 slot type][n_modes1 + n_modes2] u8 colour level, 0xFF = does not fit
     uint32_t n_modes;               // n_modes1 + n_modes2
     uint32_t off_rstream;           // R fragments of the decimated grids, contiguous in off_dec_list order (+1 pad tile)
     uint32_t off_dec_list;          // [n_dec] u8 grid index
     uint32_t n_dec;                 // number of decimated grids (nw < texels)
+    uint32_t MW;                    // 64-bit words per texel mask
+    uint32_t off_part2w;            // [1024][MW] uint64 texel mask of subset 1 (all zero = unusable seed)
+    uint32_t off_part3w;            // [1024][2][MW] uint64 masks of subsets 1 and 2
     uint32_t off_est[2][4];         // [alpha][slot type] -> uint4 list of the modes that fit:
     uint32_t n_est[2][4];           //   {f32 kq = qvar(level), f32 kc = cvar(colour level), mode | grid << 16 | cl << 24, 0}
 };
@@ -112,7 +116,7 @@ inline Astc3Tab build_tables3(Built& b)
     t3.n_modes = t.n_modes1 + t.n_modes2;
     t3.off_rfrag_idx = reserve(static_cast<size_t>(G)*4, 4);
     t3.off_mfrag_idx = reserve(static_cast<size_t>(G)*4, 4);
-    t3.off_kappa = reserve(static_cast<size_t>(G)*kMaxTexels*4, 4);
+    t3.off_kappa = reserve(static_cast<size_t>(G)*kMaxTexels3*4, 4);
     t3.off_ksum = reserve(static_cast<size_t>(G)*4, 4);
     const int KS = static_cast<int>(t3.KS), NT = static_cast<int>(t3.NT);
     for (int g = 0; g < G; ++g) {
@@ -127,7 +131,7 @@ inline Astc3Tab build_tables3(Built& b)
         for (int i = 0; i < T; ++i) {
             double kap = 0;
             for (int j = 0; j < nw; ++j) kap += P[i*nw + j]*P[i*nw + j];
-            reinterpret_cast<float*>(&blob[t3.off_kappa])[g*kMaxTexels + i] = static_cast<float>(kap);
+            reinterpret_cast<float*>(&blob[t3.off_kappa])[g*kMaxTexels3 + i] = static_cast<float>(kap);
             ksum += kap;
         }
         reinterpret_cast<float*>(&blob[t3.off_ksum])[g] = static_cast<float>(ksum);
@@ -197,6 +201,50 @@ inline Astc3Tab build_tables3(Built& b)
         for (size_t k = 0; k < dec.size(); ++k) {
             const uint32_t src = reinterpret_cast<const uint32_t*>(&blob[t3.off_rfrag_idx])[dec[k]];
             std::memcpy(&blob[t3.off_rstream + k*per], &blob[src], per);
+        }
+    }
+    // partition masks, any footprint (spec "Partition Pattern Generation"; duplicates and degenerate seeds dropped,
+    // like astcenc's init_partition_tables, lib/astc-encoder/Source/astcenc_partition_tables.cpp)
+    {
+        const int MW = (T + 63)/64;
+        t3.MW = static_cast<uint32_t>(MW);
+        t3.off_part2w = reserve(static_cast<size_t>(1024)*MW*8, 8);
+        t3.off_part3w = reserve(static_cast<size_t>(1024)*2*MW*8, 8);
+        const bool small_block = T < 31;
+        const int bw = static_cast<int>(t.bw);
+        std::vector<std::vector<uint64_t>> seen2, seen3;
+        std::vector<uint64_t> full(MW, 0);
+        for (int i = 0; i < T; ++i) full[i >> 6] |= 1ull << (i & 63);
+        for (int seed = 0; seed < 1024; ++seed) {
+            std::vector<uint64_t> m1(MW, 0), comp(MW, 0);
+            for (int i = 0; i < T; ++i)
+                if (select_partition(seed, i % bw, i/bw, 0, 2, small_block) == 1) m1[i >> 6] |= 1ull << (i & 63);
+            for (int w = 0; w < MW; ++w) comp[w] = m1[w] ^ full[w];
+            bool ok = m1 != std::vector<uint64_t>(MW, 0) && m1 != full;
+            for (auto& sd : seen2) if (sd == m1 || sd == comp) ok = false;
+            if (ok) {
+                seen2.push_back(m1);
+                std::memcpy(&blob[t3.off_part2w + static_cast<size_t>(seed)*MW*8], m1.data(), MW*8);
+            }
+            std::vector<uint64_t> a(MW, 0), b2(MW, 0), c(MW, 0);
+            for (int i = 0; i < T; ++i) {
+                const int pp = select_partition(seed, i % bw, i/bw, 0, 3, small_block);
+                if (pp == 1) a[i >> 6] |= 1ull << (i & 63);
+                if (pp == 2) b2[i >> 6] |= 1ull << (i & 63);
+            }
+            for (int w = 0; w < MW; ++w) c[w] = full[w] ^ a[w] ^ b2[w];
+            const std::vector<uint64_t> zero(MW, 0);
+            ok = a != zero && b2 != zero && c != zero;
+            std::vector<std::vector<uint64_t>> key = {a, b2, c};
+            std::sort(key.begin(), key.end());
+            std::vector<uint64_t> flat;
+            for (auto& k : key) flat.insert(flat.end(), k.begin(), k.end());
+            for (auto& sd : seen3) if (sd == flat) ok = false;
+            if (ok) {
+                seen3.push_back(flat);
+                std::memcpy(&blob[t3.off_part3w + (static_cast<size_t>(seed)*2)*MW*8], a.data(), MW*8);
+                std::memcpy(&blob[t3.off_part3w + (static_cast<size_t>(seed)*2 + 1)*MW*8], b2.data(), MW*8);
+            }
         }
     }
     // estimate lists: per (alpha, slot type) the modes that fit, with their model terms

@@ -3,7 +3,7 @@
 // 32 x 16 output bytes are one contiguous 512-byte store.  Texels are converted to the decoder's
 // unquantised integer domain (half bits x 64/31) once and kept in shared memory, lane-interleaved.
 //
-// Replaces Bc6HConverter::compressBlock (lib/src/S3tcConverter.cpp:549-590) for Type::UFloat.
+// Replaces Bc6HConverter::compressBlock (lib/src/S3tcConverter.cpp:549-590) for Type::UFloat and Type::Float.
 #include "bc6h_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -13,8 +13,14 @@ namespace cfx {
 namespace {
 constexpr int kBc6Warps = 4;
 
-__device__ __forceinline__ float half_bits_to_domain(uint32_t h)
+__device__ __forceinline__ float half_bits_to_domain(uint32_t h, bool sg)
 {
+    if (sg) {                                     // signed format: sign * magnitude * 32/31
+        uint32_t mag = h & 0x7FFFu;
+        if (mag > 0x7BFFu) mag = 0x7BFFu;
+        const float v = static_cast<float>(mag)*(32.0f/31.0f);
+        return (h & 0x8000u) ? -v : v;
+    }
     if (h & 0x8000u) return 0.0f;                 // unsigned format: negatives clamp to 0
     if (h > 0x7BFFu) h = 0x7BFFu;                 // inf / nan -> largest finite half
     return static_cast<float>(h)*(64.0f/31.0f);
@@ -23,6 +29,7 @@ __device__ __forceinline__ float half_bits_to_domain(uint32_t h)
 
 __global__ void __launch_bounds__(kBc6Warps*32) bc6h_kernel(const EncodeParams p)
 {
+    const bool sg = p.type == 5;                  // Texture::Type::Float -> BC6H SF16
     __shared__ float s_x[kBc6Warps][16*3*32];
     const uint32_t lane = lane_id(), warp = warp_id();
     float* xs = s_x[warp];
@@ -45,11 +52,11 @@ __global__ void __launch_bounds__(kBc6Warps*32) bc6h_kernel(const EncodeParams p
                 hb = __half_as_ushort(__float2half_rn(f.z));
             }
             // Bc6HConverter does not look at the colour mask
-            bc6h::px(xs, lane, t, 0) = half_bits_to_domain(hr);
-            bc6h::px(xs, lane, t, 1) = half_bits_to_domain(hg);
-            bc6h::px(xs, lane, t, 2) = half_bits_to_domain(hb);
+            bc6h::px(xs, lane, t, 0) = half_bits_to_domain(hr, sg);
+            bc6h::px(xs, lane, t, 1) = half_bits_to_domain(hg, sg);
+            bc6h::px(xs, lane, t, 2) = half_bits_to_domain(hb, sg);
         }
-        const uint4 out = bc6h::encode_block(xs, lane, p.quality);
+        const uint4 out = bc6h::encode_block(xs, lane, p.quality, sg);
         if (live) reinterpret_cast<uint4*>(p.dst)[blk] = out;
     }
 }

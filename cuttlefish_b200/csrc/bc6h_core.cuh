@@ -23,25 +23,52 @@ CFX_CONST uint8_t kW3[8] = {0, 9, 18, 27, 37, 46, 55, 64};
 // unquantised domain (half bits * 64 / 31, 0..65535)
 CFX_HD float& px(float* xs, uint32_t lane, uint32_t t, uint32_t c) { return xs[(t*3u + c)*32u + lane]; }
 
-CFX_HD int unquantize(int x, int bits)
+// sg: signed format (BC6H SF16, Texture::Type::Float -> SetSignedBC6, lib/src/S3tcConverter.cpp:566-570): end points are
+// two's complement, the unquantised domain is +-0x7FFF and texels are sign * half magnitude * 32/31.
+CFX_HD int unquantize(int x, int bits, bool sg)
 {
+    if (sg) {
+        if (bits >= 16) return x;
+        const bool neg = x < 0;
+        const int ax = neg ? -x : x;
+        int u;
+        if (ax == 0) u = 0;
+        else if (ax >= (1 << (bits - 1)) - 1) u = 0x7FFF;
+        else u = ((ax << 15) + 0x4000) >> (bits - 1);
+        return neg ? -u : u;
+    }
     if (bits >= 15) return x;
     if (x == 0) return 0;
     if (x == (1 << bits) - 1) return 0xFFFF;
     return ((x << 15) + 0x4000) >> (bits - 1);
 }
 
-CFX_HD int quantize(float u, int bits)
+CFX_HD int quantize(float u, int bits, bool sg)
 {
+    if (sg) {
+        const int maxq = (1 << (bits - 1)) - 1;
+        const bool neg = u < 0.0f;
+        const float au = fminf(fabsf(u), 32767.0f);
+        int best;
+        if (bits >= 16) best = min(__float2int_rn(au), 32767);
+        else {
+            const int x = min(max(static_cast<int>(au*(1.0f/static_cast<float>(1 << (16 - bits)))), 0), maxq);
+            best = x;
+            float bd = fabsf(static_cast<float>(unquantize(x, bits, true)) - au);
+            if (x > 0) { const float d = fabsf(static_cast<float>(unquantize(x - 1, bits, true)) - au); if (d < bd) { bd = d; best = x - 1; } }
+            if (x < maxq) { const float d = fabsf(static_cast<float>(unquantize(x + 1, bits, true)) - au); if (d < bd) { bd = d; best = x + 1; } }
+        }
+        return neg ? -best : best;
+    }
     const int maxq = (1 << bits) - 1;
     u = fminf(fmaxf(u, 0.0f), 65535.0f);
     if (bits >= 15) return min(max(__float2int_rn(u), 0), maxq);
     int x = min(max(static_cast<int>(u*(1.0f/static_cast<float>(1 << (16 - bits)))), 0), maxq);
     // nearest of x-1, x, x+1 under the real unquantiser (the end codes are special-cased by it)
     int best = x;
-    float bd = fabsf(static_cast<float>(unquantize(x, bits)) - u);
-    if (x > 0) { const float d = fabsf(static_cast<float>(unquantize(x - 1, bits)) - u); if (d < bd) { bd = d; best = x - 1; } }
-    if (x < maxq) { const float d = fabsf(static_cast<float>(unquantize(x + 1, bits)) - u); if (d < bd) { bd = d; best = x + 1; } }
+    float bd = fabsf(static_cast<float>(unquantize(x, bits, false)) - u);
+    if (x > 0) { const float d = fabsf(static_cast<float>(unquantize(x - 1, bits, false)) - u); if (d < bd) { bd = d; best = x - 1; } }
+    if (x < maxq) { const float d = fabsf(static_cast<float>(unquantize(x + 1, bits, false)) - u); if (d < bd) { bd = d; best = x + 1; } }
     return best;
 }
 
@@ -53,15 +80,15 @@ struct SubsetFit {
 
 // Exact index search for the texels of `mask` against the palette of (q0, q1); returns the error.
 CFX_HD float assign_indices(float* xs, uint32_t lane, uint32_t mask, const int* q0, const int* q1, int wbits, int ibits,
-    uint64_t& idx_out)
+    uint64_t& idx_out, bool sg)
 {
     const int n = 1 << ibits;
     int a[3], d[3];
     float len2 = 0.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        a[c] = unquantize(q0[c], wbits);
-        d[c] = unquantize(q1[c], wbits) - a[c];
+        a[c] = unquantize(q0[c], wbits, sg);
+        d[c] = unquantize(q1[c], wbits, sg) - a[c];
         len2 += static_cast<float>(d[c])*static_cast<float>(d[c]);
     }
     const float scale = len2 > 0.0f ? static_cast<float>(n - 1)/len2 : 0.0f;
@@ -97,7 +124,7 @@ CFX_HD float assign_indices(float* xs, uint32_t lane, uint32_t mask, const int* 
 }
 
 // Full fit of one subset: PCA -> quantise -> indices -> 2 x least squares.
-CFX_HD void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbits, int ibits, SubsetFit& f)
+CFX_HD void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbits, int ibits, SubsetFit& f, bool sg)
 {
     float n = 0.0f, m[3] = {0, 0, 0};
     for (uint32_t t = 0; t < 16; ++t) {
@@ -138,11 +165,11 @@ CFX_HD void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbits, int i
     if (!(tmax >= tmin)) { tmin = tmax = 0.0f; }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        f.q0[c] = quantize(m[c] + tmin*v[c], wbits);
-        f.q1[c] = quantize(m[c] + tmax*v[c], wbits);
+        f.q0[c] = quantize(m[c] + tmin*v[c], wbits, sg);
+        f.q1[c] = quantize(m[c] + tmax*v[c], wbits, sg);
     }
     f.idx = 0;
-    f.err = assign_indices(xs, lane, mask, f.q0, f.q1, wbits, ibits, f.idx);
+    f.err = assign_indices(xs, lane, mask, f.q0, f.q1, wbits, ibits, f.idx, sg);
     for (int round = 0; round < 2 && f.err > 0.0f; ++round) {
         float A = 0, B = 0, C = 0, P[3] = {0, 0, 0}, Q[3] = {0, 0, 0};
         for (uint32_t t = 0; t < 16; ++t) {
@@ -159,11 +186,11 @@ CFX_HD void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbits, int i
         SubsetFit trial;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            trial.q0[c] = quantize((C*P[c] - B*Q[c])*id, wbits);
-            trial.q1[c] = quantize((A*Q[c] - B*P[c])*id, wbits);
+            trial.q0[c] = quantize((C*P[c] - B*Q[c])*id, wbits, sg);
+            trial.q1[c] = quantize((A*Q[c] - B*P[c])*id, wbits, sg);
         }
         trial.idx = f.idx;
-        trial.err = assign_indices(xs, lane, mask, trial.q0, trial.q1, wbits, ibits, trial.idx);
+        trial.err = assign_indices(xs, lane, mask, trial.q0, trial.q1, wbits, ibits, trial.idx, sg);
         if (trial.err < f.err) f = trial; else break;
     }
 }
@@ -226,7 +253,7 @@ struct Bits128 {
 CFX_HD bool delta_fits(int d, int bits) { const int lim = (1 << (bits - 1)) - 1; return d >= -lim && d <= lim; }
 
 // Encode the lane's block; returns the 16 bytes.
-CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality)
+CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality, bool sg = false)
 {
     // ---- one-region modes: {mode bits, wBits, delta bits}
     const int one_mode[4] = {0x03, 0x07, 0x0B, 0x0F}, one_w[4] = {10, 11, 12, 16}, one_t[4] = {10, 9, 8, 4};
@@ -237,7 +264,7 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality)
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         SubsetFit f;
-        fit_subset(xs, lane, 0xFFFFu, one_w[k], 4, f);
+        fit_subset(xs, lane, 0xFFFFu, one_w[k], 4, f, sg);
         if (k > 0 && !(delta_fits(f.q1[0] - f.q0[0], one_t[k]) && delta_fits(f.q1[1] - f.q0[1], one_t[k]) &&
             delta_fits(f.q1[2] - f.q0[2], one_t[k]))) continue;
         if (f.err < best_err) { best_err = f.err; best_kind = k; bf0 = f; }
@@ -269,8 +296,8 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality)
 #pragma unroll 1
             for (int k = 0; k < 3; ++k) {
                 SubsetFit f0, f1;
-                fit_subset(xs, lane, m0, two_w[k], 3, f0);
-                fit_subset(xs, lane, m1, two_w[k], 3, f1);
+                fit_subset(xs, lane, m0, two_w[k], 3, f0, sg);
+                fit_subset(xs, lane, m1, two_w[k], 3, f1, sg);
                 if (k > 0) {
                     bool ok = true;
 #pragma unroll
@@ -299,7 +326,7 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const uint32_t w = static_cast<uint32_t>(bf0.q0[c]);
-            const uint32_t x = k == 0 ? static_cast<uint32_t>(bf0.q1[c]) : static_cast<uint32_t>(bf0.q1[c] - bf0.q0[c]) & ((1u << tb) - 1u);
+            const uint32_t x = (k == 0 ? static_cast<uint32_t>(bf0.q1[c]) : static_cast<uint32_t>(bf0.q1[c] - bf0.q0[c])) & ((1u << tb) - 1u);
             b.put(5 + 10*c, w & 1023u, 10);
             b.put(35 + 10*c, x, tb);
             // high bits of w, mirrored, fill the rest of the 10-bit field up to bit 44 + 10c
@@ -326,8 +353,8 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality)
         uint32_t w[3], x[3], y[3], z[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            w[c] = static_cast<uint32_t>(bf0.q0[c]);
-            if (k == 0) { x[c] = bf0.q1[c]; y[c] = bf1.q0[c]; z[c] = bf1.q1[c]; }
+            w[c] = static_cast<uint32_t>(bf0.q0[c]) & ((1u << (k == 0 ? 6 : (k == 1 ? 7 : 10))) - 1u);
+            if (k == 0) { x[c] = static_cast<uint32_t>(bf0.q1[c]) & 63u; y[c] = static_cast<uint32_t>(bf1.q0[c]) & 63u; z[c] = static_cast<uint32_t>(bf1.q1[c]) & 63u; }
             else {
                 x[c] = static_cast<uint32_t>(bf0.q1[c] - bf0.q0[c]) & tm;
                 y[c] = static_cast<uint32_t>(bf1.q0[c] - bf0.q0[c]) & tm;

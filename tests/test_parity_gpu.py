@@ -84,7 +84,7 @@ def test_bc7_solid_blocks_exact(cfx, oracle):
     assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
 
 
-ASTC_FORMATS = ["ASTC_4x4", "ASTC_5x5", "ASTC_6x6", "ASTC_8x8", "ASTC_10x6"]
+ASTC_FORMATS = ["ASTC_4x4", "ASTC_5x5", "ASTC_6x6", "ASTC_8x8", "ASTC_10x6", "ASTC_10x8", "ASTC_10x10", "ASTC_12x10", "ASTC_12x12"]
 
 
 @pytest.mark.parametrize("fmt", ASTC_FORMATS)
@@ -243,12 +243,13 @@ def test_texture_convert_mip_chain(cfx, oracle):
     # unsupported pair: convert() returns False and the texture stays unconverted
     tex2 = cfx.Texture(8, 8)
     tex2.setImage(base[:8, :8])
-    assert not tex2.convert("EAC_R11", "UNorm")
+    assert not tex2.convert("ETC2_R8G8B8A1", "UNorm")
     assert not tex2.converted()
 
 
 ALL_LDR = ["BC1_RGB", "BC1_RGBA", "BC2", "BC3", "BC4", "BC5", "BC7", "ETC1", "ETC2_R8G8B8", "ETC2_R8G8B8A8",
-           "ASTC_4x4", "ASTC_5x4", "ASTC_6x5", "ASTC_6x6", "ASTC_8x5", "ASTC_8x6", "ASTC_8x8", "ASTC_10x5", "ASTC_10x6"]
+           "ASTC_4x4", "ASTC_5x4", "ASTC_6x5", "ASTC_6x6", "ASTC_8x5", "ASTC_8x6", "ASTC_8x8", "ASTC_10x5", "ASTC_10x6",
+           "ASTC_10x8", "ASTC_10x10", "ASTC_12x10", "ASTC_12x12"]
 
 
 @pytest.mark.parametrize("fmt", ALL_LDR)
@@ -275,6 +276,9 @@ def test_ragged_and_tiny_surfaces(cfx, oracle, fmt):
             e = lambda d: float(np.mean((d[..., :3].astype(np.float64) - img[..., :3]) ** 2))
             # a surface of one or two blocks is a noisy sample (the encoder also fits the replicated edge texels)
             slack = 1.6 if w * h < 128 else 1.25
+            bw_, bh_, _ = cfx.block_info(fmt)
+            if w * h * 4 < bw_ * bh_:
+                slack = 3.0      # a single block of which under a quarter is visible: both encoders fit the replicas
             assert e(d_gpu) <= e(d_ref) * slack + 1e-5, "%s %dx%d mse %.3g vs reference %.3g" % (fmt, w, h, e(d_gpu), e(d_ref))
         # padded pitch through the raw C-ABI gives the same bytes
         pitch = w * 4 + 20

@@ -3,7 +3,7 @@
 #include <vector>
 using namespace cfx;
 
-extern "C" int emu_bc6h_encode(const uint16_t* rgba16f, uint32_t w, uint32_t h, uint8_t* out, uint32_t quality)
+extern "C" int emu_bc6h_encode(const uint16_t* rgba16f, uint32_t w, uint32_t h, uint8_t* out, uint32_t quality, uint32_t is_signed)
 {
     uint32_t bxn = (w + 3)/4, byn = (h + 3)/4;
     std::vector<float> xs(16*3*32);
@@ -14,10 +14,11 @@ extern "C" int emu_bc6h_encode(const uint16_t* rgba16f, uint32_t w, uint32_t h, 
                 for (uint32_t c = 0; c < 3; ++c) {
                     uint32_t hb = rgba16f[(size_t(y)*w + x)*4 + c];
                     float v = (hb & 0x8000u) ? 0.0f : float(std::min(hb, 0x7BFFu))*(64.0f/31.0f);
+                    if (is_signed) { v = float(std::min(hb & 0x7FFFu, 0x7BFFu))*(32.0f/31.0f); if (hb & 0x8000u) v = -v; }
                     bc6h::px(xs.data(), 0, t, c) = v;
                 }
             }
-            uint4 blk = bc6h::encode_block(xs.data(), 0, quality);
+            uint4 blk = bc6h::encode_block(xs.data(), 0, quality, is_signed != 0);
             memcpy(out + (size_t(by)*bxn + bx)*16, &blk, 16);
         }
     return 0;

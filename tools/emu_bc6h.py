@@ -11,11 +11,11 @@ subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-con
 lib = ctypes.CDLL(so)
 
 
-def encode(img16, quality=2):
+def encode(img16, quality=2, signed=False):
     h, w, _ = img16.shape
     out = np.zeros(((w + 3) // 4) * ((h + 3) // 4) * 16, np.uint8)
     src = np.ascontiguousarray(img16.view(np.uint16))
-    lib.emu_bc6h_encode(src.ctypes.data_as(ctypes.c_void_p), w, h, out.ctypes.data_as(ctypes.c_void_p), quality)
+    lib.emu_bc6h_encode(src.ctypes.data_as(ctypes.c_void_p), w, h, out.ctypes.data_as(ctypes.c_void_p), quality, 1 if signed else 0)
     return out
 
 
@@ -31,13 +31,16 @@ def hdr_noise(n, seed=7):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-    for name, img in [("hdr", oracle.gen_image("hdr", n, n)), ("hdr+noise", hdr_noise(n))]:
+    signed_img = hdr_noise(n)
+    signed_img[..., :3] -= np.array([16.0, 2.0, 0.25], np.float32)
+    for name, img, typ in [("hdr", oracle.gen_image("hdr", n, n), "UFloat"), ("hdr+noise", hdr_noise(n), "UFloat"),
+                           ("signed hdr+noise", signed_img, "Float")]:
         img16 = img.astype(np.float16)
         imgf = img16.astype(np.float32)
-        got = encode(img16)
-        ref = oracle.encode(imgf, "BC6H", type="UFloat")
-        dg = oracle.decode(got, "BC6H", n, n, type="UFloat")
-        dr = oracle.decode(ref, "BC6H", n, n, type="UFloat")
+        got = encode(img16, signed=typ == "Float")
+        ref = oracle.encode(imgf, "BC6H", type=typ)
+        dg = oracle.decode(got, "BC6H", n, n, type=typ)
+        dr = oracle.decode(ref, "BC6H", n, n, type=typ)
         peak = 64.0
         pg, pr = oracle.psnr_rgb(imgf, dg, peak), oracle.psnr_rgb(imgf, dr, peak)
         lg = lambda d: float(np.sqrt(np.mean((np.log2(np.maximum(d[..., :3], 1e-4)) - np.log2(np.maximum(imgf[..., :3], 1e-4))) ** 2)))
