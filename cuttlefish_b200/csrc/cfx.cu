@@ -78,7 +78,7 @@ static Launcher find_launcher(uint32_t format, uint32_t type)
             return type == CFX_TYPE_UNORM ? launch_bc123 : nullptr;
 #endif
 #ifdef CFX_HAVE_ETC
-        case CFX_FORMAT_ETC1: case CFX_FORMAT_ETC2_R8G8B8: case CFX_FORMAT_ETC2_R8G8B8A8:
+        case CFX_FORMAT_ETC1: case CFX_FORMAT_ETC2_R8G8B8: case CFX_FORMAT_ETC2_R8G8B8A1: case CFX_FORMAT_ETC2_R8G8B8A8:
             return type == CFX_TYPE_UNORM ? launch_etc : nullptr;
         case CFX_FORMAT_EAC_R11: case CFX_FORMAT_EAC_R11G11:
             return (type == CFX_TYPE_UNORM || type == CFX_TYPE_SNORM) ? launch_etc : nullptr;

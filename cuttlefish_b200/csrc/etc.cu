@@ -4,7 +4,7 @@
 // like the reference (lib/src/EtcConverter.cpp:145, float RGBA into Etc::Image) the encoder sees
 // unquantised values when the source is RGBA16F / RGBA32F.
 //
-// Replaces EtcConverter::process, lib/src/EtcConverter.cpp:120-152, for ETC1, ETC2_R8G8B8,
+// Replaces EtcConverter::process, lib/src/EtcConverter.cpp:120-152, for ETC1, ETC2_R8G8B8, ETC2_R8G8B8A1,
 // ETC2_R8G8B8A8 and EAC_R11 / EAC_R11G11 (UNorm and SNorm).
 #include "common.cuh"
 #include "etc_core.cuh"
@@ -15,7 +15,7 @@ namespace cfx {
 
 namespace { constexpr int kEtcWarps = 4; }
 
-template <int FORMAT, bool SIGNED = false>   // 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8, 41 EAC R11, 42 EAC RG11
+template <int FORMAT, bool SIGNED = false>   // 37 ETC1, 38 ETC2 RGB, 39 ETC2 RGB8A1, 40 ETC2 RGBA8, 41 EAC R11, 42 EAC RG11
 __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p, int rounds, int alpha_radius, bool exact)
 {
     __shared__ float s_x[kEtcWarps][16*4*32];
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
             }
             continue;
         }
-        const uint2 color = etc::encode_color(xs, lane, FORMAT != 37, rounds);
+        const uint2 color = FORMAT == 39 ? etc::encode_color_a1(xs, lane, rounds) : etc::encode_color(xs, lane, FORMAT != 37, rounds);
         if (FORMAT == 40) {
             const uint2 alpha = etc::encode_eac_alpha(xs, lane, alpha_radius);
             if (live) reinterpret_cast<uint4*>(p.dst)[blk] = make_uint4(alpha.x, alpha.y, color.x, color.y);
@@ -98,6 +98,7 @@ int launch_etc(const EncodeParams& p, cudaStream_t stream)
     switch (p.format) {
         case 37: k = reinterpret_cast<const void*>(&etc_kernel<37>); break;
         case 38: k = reinterpret_cast<const void*>(&etc_kernel<38>); break;
+        case 39: k = reinterpret_cast<const void*>(&etc_kernel<39>); break;
         case 40: k = reinterpret_cast<const void*>(&etc_kernel<40>); break;
         case 41: k = sn ? reinterpret_cast<const void*>(&etc_kernel<41, true>) : reinterpret_cast<const void*>(&etc_kernel<41, false>); break;
         case 42: k = sn ? reinterpret_cast<const void*>(&etc_kernel<42, true>) : reinterpret_cast<const void*>(&etc_kernel<42, false>); break;

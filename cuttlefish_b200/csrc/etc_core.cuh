@@ -37,7 +37,9 @@ CFX_HD int expand7(int v) { return (v << 1) | (v >> 6); }
 struct HalfFit { float err; uint32_t table; uint32_t sel; };   // sel: 2 bits per texel t (only the half's texels)
 
 // Best modifier table and selectors of one half (texel mask) for an 8-bit base colour.
-CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out)
+// tmask != 0: punch-through block (ETC2 RGB8A1 with the opaque bit clear): texels of tmask take selector 2
+// (transparent) at no cost, the others choose among {+0, +big, -big} (selectors 0, 1, 3).
+CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask = 0)
 {
     out.err = 3.0e38f; out.table = 0; out.sel = 0;
 #pragma unroll 1
@@ -46,12 +48,15 @@ CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, f
         uint32_t sel = 0;
         for (uint32_t t = 0; t < 16; ++t) {
             if (!((mask >> t) & 1u)) continue;
+            if ((tmask >> t) & 1u) { sel |= 2u << (2*t); continue; }
             const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
             float be = 3.0e38f;
             uint32_t bk = 0;
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k) {
-                const int m = (k & 2u) ? -static_cast<int>(kMod[tb][k & 1u]) : static_cast<int>(kMod[tb][k & 1u]);
+                if (tmask && k == 2u) continue;
+                int m = (k & 2u) ? -static_cast<int>(kMod[tb][k & 1u]) : static_cast<int>(kMod[tb][k & 1u]);
+                if (tmask && k == 0u) m = 0;
                 const float d0 = static_cast<float>(clamp255(base[0] + m)) - x0, d1 = static_cast<float>(clamp255(base[1] + m)) - x1,
                     d2 = static_cast<float>(clamp255(base[2] + m)) - x2;
                 const float e = d0*d0 + d1*d1 + d2*d2;
@@ -67,12 +72,12 @@ CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, f
 
 // Descent of one half's quantised base colour (bits = 4 or 5) within [lo, hi] per channel.
 CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* q /* in/out */, const int* lo, const int* hi,
-    int rounds, HalfFit& best)
+    int rounds, HalfFit& best, uint32_t tmask = 0)
 {
     int base[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { q[c] = min(max(q[c], lo[c]), hi[c]); base[c] = bits == 5 ? expand5(q[c]) : expand4(q[c]); }
-    half_fit(xs, lane, mask, base, 3.0e38f, best);
+    half_fit(xs, lane, mask, base, 3.0e38f, best, tmask);
     for (int round = 0; round < rounds && best.err > 0.0f; ++round) {
         bool improved = false;
 #pragma unroll 1
@@ -85,7 +90,7 @@ CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* 
 #pragma unroll
             for (int c = 0; c < 3; ++c) base[c] = bits == 5 ? expand5(t[c]) : expand4(t[c]);
             HalfFit f;
-            half_fit(xs, lane, mask, base, best.err, f);
+            half_fit(xs, lane, mask, base, best.err, f, tmask);
             if (f.err < best.err) { best = f; q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; improved = true; }
         }
         if (!improved) break;
@@ -124,22 +129,30 @@ CFX_HD uint2 to_bytes(uint32_t hi, uint32_t lo)
 struct ColorResult { float err; uint32_t hi, lo; };
 
 // ---- ETC1 part: both flips, differential and individual -----------------------------------------
-CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out)
+// diff_only: no individual (444+444) mode -- ETC2 RGB8A1, where that bit is the opaque flag.
+// tmask != 0: punch-through block of RGB8A1 (opaque flag clear, see half_fit).
+CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, bool diff_only = false, uint32_t tmask = 0)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
 #pragma unroll 1
     for (uint32_t flip = 0; flip < 2; ++flip) {
         const uint32_t maskA = flip ? 0x00FFu : 0x3333u, maskB = ~maskA & 0xFFFFu;
-        float mA[3] = {0, 0, 0}, mB[3] = {0, 0, 0};
+        float mA[3] = {0, 0, 0}, mB[3] = {0, 0, 0}, nA = 0.0f, nB = 0.0f;
         for (uint32_t t = 0; t < 16; ++t) {
+            if ((tmask >> t) & 1u) continue;
             const bool a = (maskA >> t) & 1u;
+            if (a) nA += 1.0f; else nB += 1.0f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) { const float v = px(xs, lane, t, c); if (a) mA[c] += v; else mB[c] += v; }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { mA[c] *= 0.125f; mB[c] *= 0.125f; }
+        for (int c = 0; c < 3; ++c) { mA[c] *= nA > 0.0f ? 1.0f/nA : 0.0f; mB[c] *= nB > 0.0f ? 1.0f/nB : 0.0f; }
+        if (tmask) {                 // a half without opaque texels follows the other one
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { if (nA == 0.0f) mA[c] = mB[c]; if (nB == 0.0f) mB[c] = mA[c]; }
+        }
 #pragma unroll 1
-        for (int diff = 1; diff >= 0; --diff) {
+        for (int diff = 1; diff >= (diff_only ? 1 : 0); --diff) {
             const int bits = diff ? 5 : 4, maxq = diff ? 31 : 15;
             int qA[3], qB[3], lo[3] = {0, 0, 0}, hi[3] = {maxq, maxq, maxq};
 #pragma unroll
@@ -157,12 +170,12 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out)
                 }
             }
             HalfFit fA, fB;
-            half_search(xs, lane, maskA, bits, qA, lo, hi, rounds, fA);
+            half_search(xs, lane, maskA, bits, qA, lo, hi, rounds, fA, tmask);
             if (diff) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { lo[c] = max(qA[c] - 4, 0); hi[c] = min(qA[c] + 3, 31); }
             }
-            half_search(xs, lane, maskB, bits, qB, lo, hi, rounds, fB);
+            half_search(xs, lane, maskB, bits, qB, lo, hi, rounds, fB, tmask);
             const float err = fA.err + fB.err;
             if (err < out.err) {
                 uint32_t h = 0, l = 0;
@@ -181,7 +194,7 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out)
                 }
                 put_be(h, l, 39, fA.table, 3);
                 put_be(h, l, 36, fB.table, 3);
-                put_be(h, l, 33, static_cast<uint32_t>(diff), 1);
+                put_be(h, l, 33, tmask ? 0u : static_cast<uint32_t>(diff), 1);      // RGB8A1: this bit is the opaque flag
                 put_be(h, l, 32, flip, 1);
                 l = pixel_bits((fA.sel & (maskA*0 + 0xFFFFFFFFu)) | fB.sel);
                 out.err = err; out.hi = h; out.lo = l;
@@ -475,6 +488,35 @@ CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius)
     return to_bytes(hi32, lo32);
 }
 
+
+// ---- ETC2 RGB8A1 (punch-through alpha) --------------------------------------------------------------
+// Replaces Block4x4Encoding_RGB8A1 / _Opaque / _Transparent (lib/etc2comp/EtcLib/EtcCodec/EtcBlock4x4Encoding_RGB8A1.cpp;
+// EtcConverter picks it for ETC2_R8G8B8A1, lib/src/EtcConverter.cpp:76-88).  Texels with alpha < 0.5 are transparent
+// (same threshold, :96, :754).  Opaque blocks: the ETC2 RGB search without the individual mode (that bit is the
+// opaque flag); mixed blocks: differential mode with the opaque flag clear, transparent texels on selector 2 and the
+// others on {+0, +big, -big}; fully transparent blocks: selector 2 everywhere.  Our own search: PSNR parity.
+CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds)
+{
+    uint32_t tmask = 0;
+    for (uint32_t t = 0; t < 16; ++t) if (px(xs, lane, t, 3) < 127.5f) tmask |= 1u << t;
+    ColorResult best;
+    if (tmask == 0xFFFFu) {
+        uint32_t sel = 0;
+        for (uint32_t t = 0; t < 16; ++t) sel |= 2u << (2*t);
+        return to_bytes(0u, pixel_bits(sel));
+    }
+    encode_etc1(xs, lane, rounds, best, true, tmask);
+    if (tmask == 0 && best.err > 0.0f) {
+        ColorResult r;
+        encode_planar(xs, lane, rounds, r);
+        if (r.err < best.err) best = r;
+        if (best.err > 0.0f) {
+            encode_th(xs, lane, r);
+            if (r.err < best.err) best = r;
+        }
+    }
+    return to_bytes(best.hi, best.lo);
+}
 
 // ---- EAC R11 / RG11 (one or two 11-bit channels, unsigned or signed) --------------------------------
 // Replaces Block4x4Encoding_R11 / _RG11 (lib/etc2comp/EtcLib/EtcCodec/EtcBlock4x4Encoding_R11.cpp:170-392),

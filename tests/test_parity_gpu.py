@@ -243,7 +243,7 @@ def test_texture_convert_mip_chain(cfx, oracle):
     # unsupported pair: convert() returns False and the texture stays unconverted
     tex2 = cfx.Texture(8, 8)
     tex2.setImage(base[:8, :8])
-    assert not tex2.convert("ETC2_R8G8B8A1", "UNorm")
+    assert not tex2.convert("BC7", "SNorm")
     assert not tex2.converted()
 
 
@@ -427,3 +427,31 @@ def test_eac_r11_psnr_vs_oracle(cfx, oracle, fmt, typ, kind, w, h):
     peak2 = 4.0 if signed else 1.0
     p_gpu, p_ref = 10*np.log10(peak2/mse(got)), 10*np.log10(peak2/mse(ref))
     assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s %s: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, typ, p_gpu, p_ref)
+
+
+# ---- ETC2 RGB8A1 (punch-through alpha; etc2comp's Block4x4Encoding_RGB8A1 in the reference) ----
+@pytest.mark.parametrize("kind", ["noise+grad", "gradient"])
+@pytest.mark.parametrize("alpha", ["opaque", "disc", "noise", "clear"])
+def test_etc2_a1_psnr_vs_oracle(cfx, oracle, kind, alpha):
+    assert cfx.format_supported("ETC2_R8G8B8A1", "UNorm")
+    n = 96
+    img = oracle.gen_image(kind, n, n).astype(np.float32)
+    if alpha == "disc":
+        yy, xx = np.mgrid[0:n, 0:n]
+        img[..., 3] = (((xx - n/2)**2 + (yy - n/2)**2) < (n*0.35)**2).astype(np.float32)
+    elif alpha == "noise":
+        img[..., 3] = (np.random.default_rng(1).random((n, n)) > 0.3).astype(np.float32)
+    elif alpha == "clear":
+        img[..., 3] = 0.0
+    ref = oracle.encode(img, "ETC2_R8G8B8A1")
+    got = cfx.encode(img, "ETC2_R8G8B8A1")
+    assert got.shape == ref.shape
+    d_gpu, d_ref = oracle.decode(got, "ETC2_R8G8B8A1", n, n), oracle.decode(ref, "ETC2_R8G8B8A1", n, n)
+    opaque = img[..., 3] >= 0.5
+    # the punch-through decision is exact: alpha < 0.5 <=> transparent (EtcBlock4x4Encoding_RGB8A1.cpp:96, :754)
+    assert np.array_equal(d_gpu[..., 3] >= 0.5, opaque)
+    assert np.array_equal(d_ref[..., 3] >= 0.5, opaque)
+    if opaque.any():
+        mse = lambda d: float(np.mean(((d[..., :3] - img[..., :3])**2)[opaque]))
+        p_gpu, p_ref = 10*np.log10(1/max(mse(d_gpu), 1e-12)), 10*np.log10(1/max(mse(d_ref), 1e-12))
+        assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "A1 %s/%s: gpu %.3f dB < reference %.3f dB - 0.1" % (kind, alpha, p_gpu, p_ref)

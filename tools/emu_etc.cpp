@@ -16,7 +16,7 @@ extern "C" int emu_etc_encode(const float* rgba, uint32_t w, uint32_t h, uint8_t
             }
             uint8_t* dst = out + (size_t(by)*bxn + bx)*bytes;
             if (format == 40) { uint2 a = etc::encode_eac_alpha(xs.data(), 0, 2); memcpy(dst, &a, 8); dst += 8; }
-            uint2 c = etc::encode_color(xs.data(), 0, format != 37, rounds);
+            uint2 c = format == 39 ? etc::encode_color_a1(xs.data(), 0, rounds) : etc::encode_color(xs.data(), 0, format != 37, rounds);
             memcpy(dst, &c, 8);
         }
     return 0;

@@ -8,7 +8,7 @@ so = os.path.join(HERE, "_build", "libemu_etc.so")
 os.makedirs(os.path.dirname(so), exist_ok=True)
 subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "emu_etc.cpp")])
 lib = ctypes.CDLL(so)
-FMT = {"ETC1": 37, "ETC2_R8G8B8": 38, "ETC2_R8G8B8A8": 40}
+FMT = {"ETC1": 37, "ETC2_R8G8B8": 38, "ETC2_R8G8B8A1": 39, "ETC2_R8G8B8A8": 40}
 
 
 def encode(img, fmt, rounds=2):
