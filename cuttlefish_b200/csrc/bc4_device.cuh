@@ -51,12 +51,14 @@ __device__ __forceinline__ void bc4_trial_endpoints(uint32_t t, uint32_t n, int 
     if ((mode == 0) ? alpha6 : !alpha6) { uint32_t tmp = e0; e0 = e1; e1 = tmp; }
 }
 
-// s_blk: 16 RGBA8 texels of the block in shared memory; chan: byte lane of the channel.
-// Returns the 8 block bytes as (lo, hi) words; identical in every lane.
+// s_blk: RGBA8 texels of the block in shared memory, texel (row r, column c) at s_blk[r*row_stride + c] (block-major
+// tiles: row_stride 4; row-major tiles as TMA writes them: row_stride = texels per tile row); chan: byte lane of the
+// channel.  Returns the 8 block bytes as (lo, hi) words; identical in every lane.
 template <bool SIGNED = false>
 __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t chan, uint32_t radius,
-    bool hq)
+    bool hq, uint32_t row_stride = 4)
 {
+    auto texel = [&](uint32_t i) -> uint32_t { return s_blk[(i >> 2)*row_stride + (i & 3u)]; };
     // end point bytes as stored: SNORM blocks hold two's complement s = b - 128
     auto stored = [](uint32_t e) -> uint32_t { return SIGNED ? ((e - 128u) & 0xFFu) : e; };
     const uint32_t lane = lane_id();
@@ -65,7 +67,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     uint32_t mn = 255, mx = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        uint32_t v = (s_blk[i] >> shift) & 0xFFu;
+        uint32_t v = (texel(i) >> shift) & 0xFFu;
         mn = min(mn, v); mx = max(mx, v);
         rep[i] = v*0x01010101u;
     }
@@ -77,7 +79,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
         int bias = 4 - static_cast<int>(mn)*14;
         uint32_t sel = 0;
         if (lane < 16) {
-            int v = static_cast<int>((s_blk[lane] >> shift) & 0xFFu);
+            int v = static_cast<int>((texel(lane) >> shift) & 0xFFu);
             v = v*14 + bias;
             int cnt = (v >= delta*13) + (v >= delta*11) + (v >= delta*9) + (v >= delta*7) +
                 (v >= delta*5) + (v >= delta*3) + (v >= delta);
@@ -121,7 +123,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     bc4_palette<SIGNED>(e0, e1, lo4, hi4);
     uint32_t sel = 0;
     if (lane < 16) {
-        uint32_t v = (s_blk[lane] >> shift) & 0xFFu;
+        uint32_t v = (texel(lane) >> shift) & 0xFFu;
         uint32_t bestd = 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
