@@ -455,3 +455,17 @@ def test_etc2_a1_psnr_vs_oracle(cfx, oracle, kind, alpha):
         mse = lambda d: float(np.mean(((d[..., :3] - img[..., :3])**2)[opaque]))
         p_gpu, p_ref = 10*np.log10(1/max(mse(d_gpu), 1e-12)), 10*np.log10(1/max(mse(d_ref), 1e-12))
         assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "A1 %s/%s: gpu %.3f dB < reference %.3f dB - 0.1" % (kind, alpha, p_gpu, p_ref)
+
+
+# ---- sRGB images: the reference switches to perceptual weights / metrics (S3tcConverter.cpp:196-199,
+# AstcConverter.cpp:171-172, EtcConverter.cpp:61-88); our encoders minimise plain RGB error, so plain RGB PSNR must
+# still hold against the reference's output for the same descriptor ----
+@pytest.mark.parametrize("fmt", ["BC7", "ASTC_6x6", "ETC2_R8G8B8", "BC1_RGB"])
+def test_srgb_surfaces_hold_psnr_parity(cfx, oracle, fmt):
+    img = oracle.gen_image("noise+grad", 128, 128, seed=21)
+    src = oracle.to_rgba8(img)
+    ref = oracle.encode(img, fmt, srgb=True)
+    got = cfx.encode(src, fmt, srgb=True)
+    p_gpu = oracle.psnr_rgb(img, oracle.decode(got, fmt, 128, 128))
+    p_ref = oracle.psnr_rgb(img, oracle.decode(ref, fmt, 128, 128))
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s sRGB: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, p_gpu, p_ref)
