@@ -47,6 +47,10 @@ struct Slot3 {
     uint32_t pc, seed, valid;
     int32_t dual_ch;
 };
+constexpr int kSlots3 = kSlots + 1;     // slot 9: one subset with LUMINANCE end points (CEM 0), opaque blocks only
+constexpr int kLumSlot = 9, kLumRow = 13;
+constexpr int kDataLevels = 6;          // weight levels 2,3,4,5,6,8: their quantisation loss is MEASURED on the slot's ideal
+                                        // weights (text and edges are bimodal: the uniform model is far off there)
 
 // Moments of a set of texels about the block centre (FX units): count, sums, upper triangle of products.
 struct Mom { float n, s[4], p[10]; };
@@ -62,12 +66,14 @@ struct Warp3T {
     static constexpr int GP = grid_capacity(NT);
     static constexpr int TS = ta_stride(TP);
     int4 v[TP];                             // texels, FX fixed point
-    Slot3 slots[kSlots];
+    Slot3 slots[kSlots3];
     uint8_t part[4][TP];                    // subset of every texel for slots 1..4
     __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
-                                            // 9..12 second planes of slots 5..8, 13/14 refinement scratch)
+                                            // 9..12 second planes of slots 5..8, 13 luminance slot,
+                                            // 14/15 refinement scratch)
     struct Est {
-        float D[13][GP];                    // decimation loss per slot plane and grid
+        float qn[kSlots3][kDataLevels];     // measured quantisation loss of the slot's ideal weights at the coarse levels
+        float D[14][GP];                    // decimation loss per slot plane and grid
         float Sm[4][GP];                    // sum_i len2_i kappa_gi for the multi-subset slots 1..4
     };
     struct Setup {
@@ -87,7 +93,7 @@ struct Warp3T {
 // model constants (fitted on the host with tools/emu_astc3.py)
 constexpr float kLine = 1.1f, kDec = 1.0f, kQuant = 0.9f, kColor = 0.5f;
 
-struct Tab3 { Ctx ctx; Astc3Tab t3; };
+struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; };   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
 
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t redux_addu(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -146,6 +152,7 @@ template <int K, typename WS>
 __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
     uint32_t lane)
 {
+    const bool lum = s == static_cast<uint32_t>(kLumSlot);
     const uint32_t T = c.tab.texels;
     const Slot3& slot = ws.slots[s];
     const uint32_t pc = slot.pc;
@@ -224,6 +231,11 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
             } else {
                 val = (which ? (fA*fQ - fB*fP) : (fC*fP - fB*fQ))*(64.0f/static_cast<float>(FX))/det;
             }
+            if (lum) {
+                // gray end points: the least-squares solution is the mean of the per-channel ones (same system matrix)
+                const uint32_t b4 = which*4u;
+                val = (__shfl_sync(0xFFu, val, b4) + __shfl_sync(0xFFu, val, b4 + 1u) + __shfl_sync(0xFFu, val, b4 + 2u))*(1.0f/3.0f);
+            }
             int q = 255;
             if (ch < 3 || has_alpha) {
                 const int iv = min(max(__float2int_rn(val), 0), 255);
@@ -235,7 +247,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     }
     __syncwarp();
     // keep sum(e1.rgb) >= sum(e0.rgb) (otherwise the decoder would blue-contract): swap the end points
-    if (lane < pc) {
+    if (lane < pc && !lum) {
         int* e = ws.ep + lane*8u;
         if (e[4] + e[5] + e[6] < e[0] + e[1] + e[2]) {
 #pragma unroll
@@ -611,10 +623,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             mom_from(tot, mo);
             subset_line(mo, static_cast<int>(lane) - 1, 6, lines[lane]);
         }
-        if (active && lane < kSlots) {
+        if (active && lane < kSlots3) {
             Slot3& sl = ws.slots[lane];
-            sl.pc = 1; sl.seed = 0; sl.dual_ch = lane >= 5 ? static_cast<int32_t>(lane - 5) : -1;
-            sl.valid = lane == 0 || (lane >= 5 && lane - 5 < nch) ? 1u : 0u;
+            sl.pc = 1; sl.seed = 0; sl.dual_ch = (lane >= 5 && lane < 9) ? static_cast<int32_t>(lane - 5) : -1;
+            sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u)) ? 1u : 0u;
         }
         // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
         TexelMask<MW> km0, km1, km2;
@@ -785,6 +797,34 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 }
             }
         }
+        // ---- setup 8: the luminance slot (opaque blocks): weights along the gray axis, the chroma is its error floor
+        if (active && !has_alpha) {
+            int lmin = 1 << 30, lmax = -(1 << 30);
+            float chroma = 0.0f;
+            for (uint32_t i = lane; i < T; i += 32) {
+                const int4 x = ws.v[i];
+                const int l3 = x.x + x.y + x.z;                       // 3 * luminance, FX units
+                lmin = min(lmin, l3); lmax = max(lmax, l3);
+                const float l = static_cast<float>(l3)*(1.0f/3.0f);
+                const float d0 = static_cast<float>(x.x) - l, d1 = static_cast<float>(x.y) - l, d2 = static_cast<float>(x.z) - l;
+                chroma += d0*d0 + d1*d1 + d2*d2;
+            }
+            lmin = __reduce_min_sync(0xFFFFFFFFu, lmin); lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) chroma += __shfl_xor_sync(0xFFFFFFFFu, chroma, o);
+            const float ir = lmax > lmin ? 1.0f/static_cast<float>(lmax - lmin) : 0.0f;
+            for (uint32_t i = lane; i < T; i += 32) {
+                const int4 x = ws.v[i];
+                ws.ta[kLumRow][i] = __float2half_rn(static_cast<float>(x.x + x.y + x.z - lmin)*ir);
+            }
+            if (lane == 0) {
+                Slot3& sl = ws.slots[kLumSlot];
+                const float l0 = static_cast<float>(lmin)*(ifx/3.0f), l1 = static_cast<float>(lmax)*(ifx/3.0f);
+                sl.e0[0] = make_float4(l0, l0, l0, 255.0f); sl.e1[0] = make_float4(l1, l1, l1, 255.0f);
+                sl.len2[0] = 3.0f*(l1 - l0)*(l1 - l0); sl.len2b = 0.0f;
+                sl.e_line = chroma*ifx*ifx;
+            }
+        }
         PHASE_SYNC();
 
         // ---- phase 1a: decimation loss D[slot plane][grid] on the tensor cores
@@ -802,11 +842,11 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     lw[nt][e] = wgt;
                 }
             const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
-            const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : 0.0f);
+            const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 0.0f));
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
                 if (__ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx) + g) == 0u)
-                    for (uint32_t r = 0; r < 13; ++r) ws.u.est.D[r][g] = 0.0f;
+                    for (uint32_t r = 0; r < 14; ++r) ws.u.est.D[r][g] = 0.0f;
             // the decimated grids' R fragments are one contiguous stream: walk it with a one-tile prefetch
             const uint2* frag = reinterpret_cast<const uint2*>(ctx.blob + tb.t3.off_rstream) + lane;
             const uint8_t* dec = ctx.blob + tb.t3.off_dec_list;
@@ -835,7 +875,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 1); acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 2);
                 if (tq == 0) {
                     ws.u.est.D[gq][g] = acc0*scale0;
-                    if (gq + 8 < 13) ws.u.est.D[gq + 8][g] = acc1*scale1;
+                    if (gq + 8 < 14) ws.u.est.D[gq + 8][g] = acc1*scale1;
                 }
             }
         }
@@ -850,17 +890,59 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             }
             ws.u.est.Sm[0][g] = s1; ws.u.est.Sm[1][g] = s2; ws.u.est.Sm[2][g] = s3; ws.u.est.Sm[3][g] = s4;
         }
+        // ---- phase 1b': measured weight-quantisation loss of every slot at the coarse levels (lane = texel):
+        //      qn[s][L] = sum_i len2_i (t_i - Q_L(t_i))^2 / sum_i len2_i, with the end point refit gain folded in
+        if (active) {
+            for (uint32_t s = 0; s < kSlots3; ++s) {
+                const Slot3& slot = ws.slots[s];
+                if (!slot.valid) continue;
+                const uint32_t row0 = s == static_cast<uint32_t>(kLumSlot) ? static_cast<uint32_t>(kLumRow) : s;
+                const bool dual = slot.dual_ch >= 0;
+                float tv[K], t2[K], wv[K];
+                float wsum = 0.0f;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const uint32_t i = lane + 32u*r;
+                    tv[r] = 0.0f; t2[r] = 0.0f; wv[r] = 0.0f;
+                    if (i < T) {
+                        tv[r] = __half2float(ws.ta[row0][i]);
+                        wv[r] = slot.pc > 1 ? slot.len2[ws.part[s - 1][i]] : slot.len2[0];
+                        if (dual) t2[r] = __half2float(ws.ta[s + 4][i]);
+                        wsum += wv[r] + (dual ? slot.len2b : 0.0f);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
+                const float inv = wsum > 0.0f ? 1.0f/wsum : 0.0f;
+#pragma unroll 1
+                for (int L = 0; L < kDataLevels; ++L) {
+                    const float nm1 = static_cast<float>(kWqN[L] - 1), inm1 = 1.0f/nm1;
+                    float e = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < K; ++r) {
+                        const float d = tv[r] - rintf(tv[r]*nm1)*inm1;
+                        e += wv[r]*d*d;
+                        if (dual) { const float d2 = t2[r] - rintf(t2[r]*nm1)*inm1; e += slot.len2b*d2*d2; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+                    if (lane == 0) ws.u.est.qn[s][L] = e*inv*(1.0f - 0.75f*inm1);
+                }
+            }
+        }
         PHASE_SYNC();
         // ---- phase 1c: estimate every (slot, mode); each lane keeps its three best
         float be0 = 3.0e38f, be1 = 3.0e38f, be2 = 3.0e38f;
         uint32_t bc0 = 0, bc1 = 0, bc2 = 0;
         if (active) {
             const float tn = static_cast<float>(T*(has_alpha ? 4u : 3u));
+            const float inv_t = 1.0f/static_cast<float>(T);
             const float* ksum = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_ksum);
-            for (uint32_t s = 0; s < kSlots; ++s) {
+            for (uint32_t s = 0; s < kSlots3; ++s) {
                 const Slot3& slot = ws.slots[s];
                 if (!slot.valid) continue;
-                const uint32_t type = slot_type(s);
+                const uint32_t type = s == static_cast<uint32_t>(kLumSlot) ? 4u : slot_type(s);
+                const uint32_t drow = s == static_cast<uint32_t>(kLumSlot) ? static_cast<uint32_t>(kLumRow) : s;
                 const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
                 const float base = kLine*slot.e_line;
@@ -869,11 +951,20 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 for (uint32_t e = lane; e < count; e += 32) {
                     const uint4 q = __ldg(list + e);
                     const uint32_t g = (q.z >> 16) & 0xFFu, mi = q.z & 0xFFFFu;
-                    float dsum = ws.u.est.D[s][g], ssum;
+                    float dsum = ws.u.est.D[drow][g], ssum;
                     if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
-                    else if (type == 0) ssum = l2sum*__ldg(ksum + g);
+                    else if (type == 0 || type == 4) ssum = l2sum*__ldg(ksum + g);
                     else ssum = ws.u.est.Sm[s - 1][g];
-                    const float est = base + kDec*dsum + kQuant*ssum*__uint_as_float(q.x) + kColor*tn*__uint_as_float(q.y);
+                    // the measured loss holds where the texel weights themselves are quantised (full-resolution grid);
+                    // decimated grid weights are blends of them, closer to the uniform model
+                    const uint32_t lvl = q.w & 0xFFu;
+                    float qv = __uint_as_float(q.x);
+                    if (lvl < static_cast<uint32_t>(kDataLevels) && !(tb.flags & 2u)) {
+                        // (footprints above 64 texels have no full-resolution grid: the measured loss is used as it is)
+                        const float a = NT > 8 ? 1.0f : static_cast<float>(q.w >> 8)*inv_t;
+                        qv = a*ws.u.est.qn[s][lvl] + (1.0f - a)*qv;
+                    }
+                    const float est = base + kDec*dsum + kQuant*ssum*qv + kColor*tn*__uint_as_float(q.y);
                     const uint32_t code = (s << 16) | mi;
                     if (est < be2) {
                         if (est < be1) {
@@ -914,8 +1005,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 if (done) refining = true;
                 else {
                     const uint32_t s = code >> 16;
-                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 4u : 0u) + slot_type(s))*tb.t3.n_modes + (code & 0xFFFFu));
-                    row0 = static_cast<int>(s); row1 = ws.slots[s].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
+                    const uint32_t type = s == static_cast<uint32_t>(kLumSlot) ? 4u : slot_type(s);
+                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 5u : 0u) + type)*tb.t3.n_modes + (code & 0xFFFFu));
+                    row0 = s == static_cast<uint32_t>(kLumSlot) ? kLumRow : static_cast<int>(s);
+                    row1 = ws.slots[s].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
                 }
             }
             if (refining) {
@@ -938,12 +1031,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                         const float a0 = static_cast<float>(e[c4]), d = static_cast<float>(e[4 + c4]) - a0;
                         if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
                     }
-                    ws.ta[13][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
-                    ws.ta[14][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
+                    ws.ta[14][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
+                    ws.ta[15][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
                 }
                 __syncwarp();
                 load_a<KS>(ws, a, lane);             // the candidates' rows are not needed any more
-                row0 = 13; row1 = dc >= 0 ? 14 : -1;
+                row0 = 14; row1 = dc >= 0 ? 15 : -1;
             }
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
@@ -970,7 +1063,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     (static_cast<uint32_t>(e[7]) << 24);
             }
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
-            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk);
+            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, bs == static_cast<uint32_t>(kLumSlot));
         }
     }
 }
@@ -1006,6 +1099,8 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
 #endif
     // above 64 texels the working set and the register file only allow 8 warps per SM
     if constexpr (NT > 8) return launch_cfg<NT, KS, 8, 1, true>(p, tb, n_exact, refine, stream);
+    // 56- and 64-texel footprints: 10 warps per CTA so that two CTAs still fit an SM's shared memory
+    else if constexpr (NT >= 7) return launch_cfg<NT, KS, 10, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
     else return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
 }
 
@@ -1019,6 +1114,8 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     const uint32_t n_exact = kExact[p.quality < 5 ? p.quality : 2];
     const uint32_t refine = p.quality >= 3 ? 3u : 2u;
     Tab3 tb; tb.ctx = ctx; tb.t3 = t3;
+    static const uint32_t dev_flags = getenv("CFX_ASTC3_FLAGS") ? static_cast<uint32_t>(atoi(getenv("CFX_ASTC3_FLAGS"))) : 0u;
+    tb.flags = dev_flags;
     const uint32_t NT = t3.NT, KS = t3.KS;
     if (NT == 2 && KS == 1) return launch_one<2, 1>(p, tb, n_exact, refine, stream);
     if (NT == 3 && KS == 2) return launch_one<3, 2>(p, tb, n_exact, refine, stream);

@@ -52,8 +52,36 @@ def _lcg_noise(n_values, seed=12345, skip=0):
     return (out >> np.uint32(24)).astype(np.float32) / np.float32(255.0)
 
 
+def ui_image(n, seed=5):
+    """Not part of generator G: a screenshot-like quality probe (gray gradient background, dark text-like strokes,
+    soft-edged coloured discs, one smooth colourful quadrant) on which encoders that lack luminance end points or
+    good partition choices fall behind the reference.  float32 [n,n,4], 8-bit snapped, alpha 1."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((n, n, 4), np.float32)
+    img[..., 3] = 1
+    yy, xx = np.mgrid[0:n, 0:n].astype(np.float32)
+    img[..., :3] = (0.85 - 0.25 * yy / n)[..., None]
+    for _ in range(max(1, n * n // 520)):
+        x0, y0 = rng.integers(0, n - 20), rng.integers(0, n - 4)
+        w_, h_ = rng.integers(3, 18), rng.integers(1, 3)
+        img[y0:y0 + h_, x0:x0 + w_, :3] = 0.15 + 0.1 * rng.random()
+    for _ in range(max(1, n * n // 3500)):
+        cx, cy, r = rng.integers(10, n - 10), rng.integers(10, n - 10), rng.integers(5, 14)
+        a = np.clip((r - np.sqrt((xx - cx) ** 2 + (yy - cy) ** 2)) / 1.5, 0, 1)[..., None]
+        img[..., :3] = img[..., :3] * (1 - a) + rng.random(3).astype(np.float32) * a
+    q = n // 2
+    f = np.stack([0.5 + 0.5 * np.sin(xx[:q, :q] / 9.0), 0.5 + 0.5 * np.sin(yy[:q, :q] / 13.0 + 1),
+                  0.5 + 0.5 * np.sin((xx[:q, :q] + yy[:q, :q]) / 17.0)], -1)
+    img[q:, q:, :3] = f + 0.03 * rng.standard_normal((q, q, 3)).astype(np.float32)
+    img = np.clip(img, 0, 1)
+    return (np.floor(img * 255 + 0.5) / 255).astype(np.float32)
+
+
 def gen_image(kind, width, height, seed=12345, rows=None):
     """Generator G. Returns float32 [H,W,4] (or rows y0..y1 of it), row 0 = top, alpha 1."""
+    if kind == "ui":
+        assert width == height and rows is None
+        return ui_image(int(width))
     w, h = int(width), int(height)
     y0, y1 = (0, h) if rows is None else (int(rows[0]), int(rows[1]))
     n = y1 - y0

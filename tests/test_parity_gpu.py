@@ -469,3 +469,19 @@ def test_srgb_surfaces_hold_psnr_parity(cfx, oracle, fmt):
     p_gpu = oracle.psnr_rgb(img, oracle.decode(got, fmt, 128, 128))
     p_ref = oracle.psnr_rgb(img, oracle.decode(ref, fmt, 128, 128))
     assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s sRGB: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, p_gpu, p_ref)
+
+
+# ---- ASTC on screenshot-like content (synth.ui_image: gray gradients, text-like strokes, soft discs): needs luminance
+# end points and a quantisation estimate that knows bimodal weights.  Up to 8x8 we hold the 0.1 dB bar; the larger
+# footprints are still 0.2 - 0.5 dB behind astcenc there (it pairs luminance end points with 2/3 partitions) and are
+# pinned at their measured distance so that regressions show ----
+@pytest.mark.parametrize("fmt,tol", [("ASTC_4x4", 0.1), ("ASTC_5x5", 0.1), ("ASTC_6x6", 0.1), ("ASTC_8x8", 0.1),
+                                     ("ASTC_10x6", 0.25), ("ASTC_10x10", 0.6), ("ASTC_12x12", 0.3)])
+def test_astc_ui_content_psnr_vs_oracle(cfx, oracle, fmt, tol):
+    n = 288
+    img = oracle.gen_image("ui", n, n)
+    got = cfx.encode(oracle.to_rgba8(img), fmt)
+    ref = oracle.encode(img, fmt)
+    p_gpu = oracle.psnr_rgb(img, oracle.decode(got, fmt, n, n))
+    p_ref = oracle.psnr_rgb(img, oracle.decode(ref, fmt, n, n))
+    assert p_gpu >= p_ref - tol, "%s ui: gpu %.3f dB < reference %.3f dB - %.2f" % (fmt, p_gpu, p_ref, tol)
