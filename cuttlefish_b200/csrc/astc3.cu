@@ -47,8 +47,14 @@ struct Slot3 {
     uint32_t pc, seed, valid;
     int32_t dual_ch;
 };
-constexpr int kSlots3 = kSlots + 1;     // slot 9: one subset with LUMINANCE end points (CEM 0), opaque blocks only
+// Slots 0..8 as in astc_core.cuh (RGB(A) end points); 9: one subset with LUMINANCE end points (CEM 0); 10, 11: the two
+// two-subset partitionings of slots 1, 2 with luminance end points.  Luminance slots: opaque blocks only.
+constexpr int kSlots3 = kSlots + 3;
 constexpr int kLumSlot = 9, kLumRow = 13;
+__device__ __forceinline__ bool slot_is_lum(uint32_t s) { return s >= static_cast<uint32_t>(kLumSlot); }
+__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : 5u); }   // est list / colour level class
+__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : s + 4u; }                           // A operand row of its first plane
+__device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 10u ? s - 10u : (s - 1u) & 3u; }          // index into Warp3T::part
 constexpr int kDataLevels = 6;          // weight levels 2,3,4,5,6,8: their quantisation loss is MEASURED on the slot's ideal
                                         // weights (text and edges are bimodal: the uniform model is far off there)
 
@@ -69,12 +75,12 @@ struct Warp3T {
     Slot3 slots[kSlots3];
     uint8_t part[4][TP];                    // subset of every texel for slots 1..4
     __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
-                                            // 9..12 second planes of slots 5..8, 13 luminance slot,
-                                            // 14/15 refinement scratch)
+                                            // 9..12 second planes of slots 5..8, 13..15 luminance slots 9..11;
+                                            // refinement re-uses rows 0/1 once the candidates are done)
     struct Est {
         float qn[kSlots3][kDataLevels];     // measured quantisation loss of the slot's ideal weights at the coarse levels
-        float D[14][GP];                    // decimation loss per slot plane and grid
-        float Sm[4][GP];                    // sum_i len2_i kappa_gi for the multi-subset slots 1..4
+        float D[16][GP];                    // decimation loss per slot plane and grid
+        float Sm[6][GP];                    // sum_i len2_i kappa_gi for the multi-subset slots 1..4 and 10, 11
     };
     struct Setup {
         LineFit lines[15];                  // slot 0, dual-plane slots 5..8, then the 10 subsets of slots 1..4
@@ -152,7 +158,7 @@ template <int K, typename WS>
 __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
     uint32_t lane)
 {
-    const bool lum = s == static_cast<uint32_t>(kLumSlot);
+    const bool lum = slot_is_lum(s);
     const uint32_t T = c.tab.texels;
     const Slot3& slot = ws.slots[s];
     const uint32_t pc = slot.pc;
@@ -173,7 +179,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     uint32_t part[K];
     bool live[K];
     const uint32_t inf_off = c.tab.off_infill + static_cast<uint32_t>(m.grid)*T*8u;
-    const uint8_t* parts = ws.part[(s - 1u) & 3u];
+    const uint8_t* parts = ws.part[slot_part(s)];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t i = lane + 32u*k;
@@ -627,6 +633,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             Slot3& sl = ws.slots[lane];
             sl.pc = 1; sl.seed = 0; sl.dual_ch = (lane >= 5 && lane < 9) ? static_cast<int32_t>(lane - 5) : -1;
             sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u)) ? 1u : 0u;
+            // (slots 10, 11 are validated in setup 8, after the two-subset partitionings are known)
         }
         // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
         TexelMask<MW> km0, km1, km2;
@@ -824,6 +831,37 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 sl.len2[0] = 3.0f*(l1 - l0)*(l1 - l0); sl.len2b = 0.0f;
                 sl.e_line = chroma*ifx*ifx;
             }
+            // the same with the two best two-subset partitionings: a gray range per subset
+            for (uint32_t k = 0; k < 2; ++k) {
+                Slot3& sl = ws.slots[10 + k];
+                const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u);
+                if (lane == 0) { sl.valid = ok ? 1u : 0u; sl.pc = 2; sl.seed = ws.slots[1 + k].seed; sl.dual_ch = -1; }
+                if (!ok) continue;
+                int mn0 = 1 << 30, mx0 = -(1 << 30), mn1 = 1 << 30, mx1 = -(1 << 30);
+                for (uint32_t i = lane; i < T; i += 32) {
+                    const int4 x = ws.v[i];
+                    const int l3 = x.x + x.y + x.z;
+                    if (ws.part[k][i]) { mn1 = min(mn1, l3); mx1 = max(mx1, l3); } else { mn0 = min(mn0, l3); mx0 = max(mx0, l3); }
+                }
+                mn0 = __reduce_min_sync(0xFFFFFFFFu, mn0); mx0 = __reduce_max_sync(0xFFFFFFFFu, mx0);
+                mn1 = __reduce_min_sync(0xFFFFFFFFu, mn1); mx1 = __reduce_max_sync(0xFFFFFFFFu, mx1);
+                const float ir0 = mx0 > mn0 ? 1.0f/static_cast<float>(mx0 - mn0) : 0.0f, ir1 = mx1 > mn1 ? 1.0f/static_cast<float>(mx1 - mn1) : 0.0f;
+                for (uint32_t i = lane; i < T; i += 32) {
+                    const int4 x = ws.v[i];
+                    const int l3 = x.x + x.y + x.z;
+                    ws.ta[14 + k][i] = __float2half_rn(ws.part[k][i] ? static_cast<float>(l3 - mn1)*ir1 : static_cast<float>(l3 - mn0)*ir0);
+                }
+                if (lane == 0) {
+                    const float a0 = static_cast<float>(mn0)*(ifx/3.0f), b0 = static_cast<float>(max(mx0, mn0))*(ifx/3.0f);
+                    const float a1 = static_cast<float>(mn1)*(ifx/3.0f), b1 = static_cast<float>(max(mx1, mn1))*(ifx/3.0f);
+                    sl.e0[0] = make_float4(a0, a0, a0, 255.0f); sl.e1[0] = make_float4(b0, b0, b0, 255.0f);
+                    sl.e0[1] = make_float4(a1, a1, a1, 255.0f); sl.e1[1] = make_float4(b1, b1, b1, 255.0f);
+                    sl.len2[0] = 3.0f*(b0 - a0)*(b0 - a0); sl.len2[1] = 3.0f*(b1 - a1)*(b1 - a1); sl.len2b = 0.0f;
+                    sl.e_line = chroma*ifx*ifx;
+                }
+            }
+        } else if (active && lane < 2) {
+            ws.slots[10 + lane].valid = 0;
         }
         PHASE_SYNC();
 
@@ -842,11 +880,14 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     lw[nt][e] = wgt;
                 }
             const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
-            const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 0.0f));
+            // rows 14, 15 (two-subset luminance slots) are weighted with the mean of their two line lengths: good enough
+            // for the ranking, and it keeps the per-texel weights to the lower fragment half
+            const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] :
+                0.5f*(ws.slots[gq + 4].len2[0] + ws.slots[gq + 4].len2[1])));
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
                 if (__ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx) + g) == 0u)
-                    for (uint32_t r = 0; r < 14; ++r) ws.u.est.D[r][g] = 0.0f;
+                    for (uint32_t r = 0; r < 16; ++r) ws.u.est.D[r][g] = 0.0f;
             // the decimated grids' R fragments are one contiguous stream: walk it with a one-tile prefetch
             const uint2* frag = reinterpret_cast<const uint2*>(ctx.blob + tb.t3.off_rstream) + lane;
             const uint8_t* dec = ctx.blob + tb.t3.off_dec_list;
@@ -875,20 +916,23 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 1); acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 2);
                 if (tq == 0) {
                     ws.u.est.D[gq][g] = acc0*scale0;
-                    if (gq + 8 < 14) ws.u.est.D[gq + 8][g] = acc1*scale1;
+                    ws.u.est.D[gq + 8][g] = acc1*scale1;
                 }
             }
         }
         // ---- phase 1b: S of the multi-subset slots (lane = grid)
         for (uint32_t g = lane; active && g < G; g += 32) {
             const float* kap = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_kappa) + g*kMaxTexels3;
-            float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, s4 = 0.0f;
+            float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, s4 = 0.0f, s5 = 0.0f, s6 = 0.0f;
             for (uint32_t i = 0; i < T; ++i) {
                 const float k = __ldg(kap + i);
-                s1 += k*ws.slots[1].len2[ws.part[0][i]]; s2 += k*ws.slots[2].len2[ws.part[1][i]];
+                const uint32_t p0 = ws.part[0][i], p1 = ws.part[1][i];
+                s1 += k*ws.slots[1].len2[p0]; s2 += k*ws.slots[2].len2[p1];
                 s3 += k*ws.slots[3].len2[ws.part[2][i]]; s4 += k*ws.slots[4].len2[ws.part[3][i]];
+                s5 += k*ws.slots[10].len2[p0]; s6 += k*ws.slots[11].len2[p1];
             }
             ws.u.est.Sm[0][g] = s1; ws.u.est.Sm[1][g] = s2; ws.u.est.Sm[2][g] = s3; ws.u.est.Sm[3][g] = s4;
+            ws.u.est.Sm[4][g] = s5; ws.u.est.Sm[5][g] = s6;
         }
         // ---- phase 1b': measured weight-quantisation loss of every slot at the coarse levels (lane = texel):
         //      qn[s][L] = sum_i len2_i (t_i - Q_L(t_i))^2 / sum_i len2_i, with the end point refit gain folded in
@@ -896,7 +940,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             for (uint32_t s = 0; s < kSlots3; ++s) {
                 const Slot3& slot = ws.slots[s];
                 if (!slot.valid) continue;
-                const uint32_t row0 = s == static_cast<uint32_t>(kLumSlot) ? static_cast<uint32_t>(kLumRow) : s;
+                const uint32_t row0 = slot_row(s);
                 const bool dual = slot.dual_ch >= 0;
                 float tv[K], t2[K], wv[K];
                 float wsum = 0.0f;
@@ -906,7 +950,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     tv[r] = 0.0f; t2[r] = 0.0f; wv[r] = 0.0f;
                     if (i < T) {
                         tv[r] = __half2float(ws.ta[row0][i]);
-                        wv[r] = slot.pc > 1 ? slot.len2[ws.part[s - 1][i]] : slot.len2[0];
+                        wv[r] = slot.pc > 1 ? slot.len2[ws.part[slot_part(s)][i]] : slot.len2[0];
                         if (dual) t2[r] = __half2float(ws.ta[s + 4][i]);
                         wsum += wv[r] + (dual ? slot.len2b : 0.0f);
                     }
@@ -941,8 +985,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             for (uint32_t s = 0; s < kSlots3; ++s) {
                 const Slot3& slot = ws.slots[s];
                 if (!slot.valid) continue;
-                const uint32_t type = s == static_cast<uint32_t>(kLumSlot) ? 4u : slot_type(s);
-                const uint32_t drow = s == static_cast<uint32_t>(kLumSlot) ? static_cast<uint32_t>(kLumRow) : s;
+                const uint32_t type = slot_kind(s);
+                const uint32_t drow = slot_row(s);
                 const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
                 const float base = kLine*slot.e_line;
@@ -954,7 +998,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     float dsum = ws.u.est.D[drow][g], ssum;
                     if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
                     else if (type == 0 || type == 4) ssum = l2sum*__ldg(ksum + g);
-                    else ssum = ws.u.est.Sm[s - 1][g];
+                    else ssum = ws.u.est.Sm[type == 5 ? s - 6 : s - 1][g];
                     // the measured loss holds where the texel weights themselves are quantised (full-resolution grid);
                     // decimated grid weights are blends of them, closer to the uniform model
                     const uint32_t lvl = q.w & 0xFFu;
@@ -1005,9 +1049,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 if (done) refining = true;
                 else {
                     const uint32_t s = code >> 16;
-                    const uint32_t type = s == static_cast<uint32_t>(kLumSlot) ? 4u : slot_type(s);
-                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 5u : 0u) + type)*tb.t3.n_modes + (code & 0xFFFFu));
-                    row0 = s == static_cast<uint32_t>(kLumSlot) ? kLumRow : static_cast<int>(s);
+                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 6u : 0u) + slot_kind(s))*tb.t3.n_modes + (code & 0xFFFFu));
+                    row0 = static_cast<int>(slot_row(s));
                     row1 = ws.slots[s].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
                 }
             }
@@ -1018,7 +1061,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const uint32_t bs = code >> 16;
                 const Slot3& bslot = ws.slots[bs];
                 const int dc = bslot.dual_ch;
-                const uint8_t* parts = ws.part[(bs - 1u) & 3u];
+                const uint8_t* parts = ws.part[slot_part(bs)];
                 for (uint32_t i = lane; i < T; i += 32) {
                     const int* e = ws.best_ep + (bslot.pc > 1 ? parts[i] : 0u)*8u;
                     const int4 xi = ws.v[i];
@@ -1031,12 +1074,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                         const float a0 = static_cast<float>(e[c4]), d = static_cast<float>(e[4 + c4]) - a0;
                         if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
                     }
-                    ws.ta[14][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
-                    ws.ta[15][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
+                    ws.ta[0][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
+                    ws.ta[1][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
                 }
                 __syncwarp();
                 load_a<KS>(ws, a, lane);             // the candidates' rows are not needed any more
-                row0 = 14; row1 = dc >= 0 ? 15 : -1;
+                row0 = 0; row1 = dc >= 0 ? 1 : -1;
             }
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
@@ -1063,7 +1106,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     (static_cast<uint32_t>(e[7]) << 24);
             }
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
-            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, bs == static_cast<uint32_t>(kLumSlot));
+            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs));
         }
     }
 }
