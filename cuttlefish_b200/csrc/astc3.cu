@@ -942,35 +942,36 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 if (!slot.valid) continue;
                 const uint32_t row0 = slot_row(s);
                 const bool dual = slot.dual_ch >= 0;
-                float tv[K], t2[K], wv[K];
+                const float l2b = dual ? slot.len2b : 0.0f;
+                float e[kDataLevels];
+#pragma unroll
+                for (int L = 0; L < kDataLevels; ++L) e[L] = 0.0f;
                 float wsum = 0.0f;
 #pragma unroll
                 for (int r = 0; r < K; ++r) {
                     const uint32_t i = lane + 32u*r;
-                    tv[r] = 0.0f; t2[r] = 0.0f; wv[r] = 0.0f;
-                    if (i < T) {
-                        tv[r] = __half2float(ws.ta[row0][i]);
-                        wv[r] = slot.pc > 1 ? slot.len2[ws.part[slot_part(s)][i]] : slot.len2[0];
-                        if (dual) t2[r] = __half2float(ws.ta[s + 4][i]);
-                        wsum += wv[r] + (dual ? slot.len2b : 0.0f);
+                    if (i >= T) continue;
+                    const float t = __half2float(ws.ta[row0][i]);
+                    const float w = slot.pc > 1 ? slot.len2[ws.part[slot_part(s)][i]] : slot.len2[0];
+                    const float t2 = dual ? __half2float(ws.ta[s + 4][i]) : 0.0f;
+                    wsum += w + l2b;
+#pragma unroll
+                    for (int L = 0; L < kDataLevels; ++L) {
+                        constexpr int kLv[kDataLevels] = {2, 3, 4, 5, 6, 8};
+                        const float nm1 = static_cast<float>(kLv[L] - 1), inm1 = 1.0f/nm1;   // compile-time constants
+                        const float d = fmaf(-rintf(t*nm1), inm1, t), d2 = fmaf(-rintf(t2*nm1), inm1, t2);
+                        e[L] += w*d*d + l2b*d2*d2;
                     }
                 }
+                // one integer reduction per level (the sums are scaled into 2^26)
+                const float wtot = static_cast<float>(redux_add(__float2int_rn(wsum*64.0f)))*(1.0f/64.0f);
+                const float sc = wtot > 0.0f ? 67108864.0f/wtot : 0.0f;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
-                const float inv = wsum > 0.0f ? 1.0f/wsum : 0.0f;
-#pragma unroll 1
                 for (int L = 0; L < kDataLevels; ++L) {
-                    const float nm1 = static_cast<float>(kWqN[L] - 1), inm1 = 1.0f/nm1;
-                    float e = 0.0f;
-#pragma unroll
-                    for (int r = 0; r < K; ++r) {
-                        const float d = tv[r] - rintf(tv[r]*nm1)*inm1;
-                        e += wv[r]*d*d;
-                        if (dual) { const float d2 = t2[r] - rintf(t2[r]*nm1)*inm1; e += slot.len2b*d2*d2; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
-                    if (lane == 0) ws.u.est.qn[s][L] = e*inv*(1.0f - 0.75f*inm1);
+                    constexpr int kLv[kDataLevels] = {2, 3, 4, 5, 6, 8};
+                    const float inm1 = 1.0f/static_cast<float>(kLv[L] - 1);
+                    const int tot = redux_add(__float2int_rn(e[L]*sc));
+                    if (lane == static_cast<uint32_t>(L)) ws.u.est.qn[s][L] = static_cast<float>(tot)*(1.0f/67108864.0f)*(1.0f - 0.75f*inm1);
                 }
             }
         }
@@ -979,9 +980,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         float be0 = 3.0e38f, be1 = 3.0e38f, be2 = 3.0e38f;
         uint32_t bc0 = 0, bc1 = 0, bc2 = 0;
         if (active) {
-            const float tn = static_cast<float>(T*(has_alpha ? 4u : 3u));
-            const float inv_t = 1.0f/static_cast<float>(T);
+            const float tn = kColor*static_cast<float>(T*(has_alpha ? 4u : 3u));
             const float* ksum = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_ksum);
+            float* gb = &ws.g[0][0];           // per grid: floor + decimation loss   (phase 2 scratch, free until then)
+            float* gs = &ws.g[1][0];           // per grid: weight-quantisation scale
             for (uint32_t s = 0; s < kSlots3; ++s) {
                 const Slot3& slot = ws.slots[s];
                 if (!slot.valid) continue;
@@ -991,25 +993,25 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
                 const float base = kLine*slot.e_line;
                 const float l2sum = slot.len2[0] + slot.len2b;
-#pragma unroll 2
-                for (uint32_t e = lane; e < count; e += 32) {
-                    const uint4 q = __ldg(list + e);
-                    const uint32_t g = (q.z >> 16) & 0xFFu, mi = q.z & 0xFFFFu;
+                // per-grid terms of this slot (lane = grid)
+                __syncwarp();
+                for (uint32_t g = lane; g < G; g += 32) {
                     float dsum = ws.u.est.D[drow][g], ssum;
                     if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
                     else if (type == 0 || type == 4) ssum = l2sum*__ldg(ksum + g);
                     else ssum = ws.u.est.Sm[type == 5 ? s - 6 : s - 1][g];
-                    // the measured loss holds where the texel weights themselves are quantised (full-resolution grid);
-                    // decimated grid weights are blends of them, closer to the uniform model
-                    const uint32_t lvl = q.w & 0xFFu;
-                    float qv = __uint_as_float(q.x);
-                    if (lvl < static_cast<uint32_t>(kDataLevels) && !(tb.flags & 2u)) {
-                        // (footprints above 64 texels have no full-resolution grid: the measured loss is used as it is)
-                        const float a = NT > 8 ? 1.0f : static_cast<float>(q.w >> 8)*inv_t;
-                        qv = a*ws.u.est.qn[s][lvl] + (1.0f - a)*qv;
-                    }
-                    const float est = base + kDec*dsum + kQuant*ssum*qv + kColor*tn*__uint_as_float(q.y);
-                    const uint32_t code = (s << 16) | mi;
+                    gb[g] = base + kDec*dsum; gs[g] = kQuant*ssum;
+                }
+                __syncwarp();
+                const float* qn = ws.u.est.qn[s];
+#pragma unroll 2
+                for (uint32_t e = lane; e < count; e += 32) {
+                    const uint4 q = __ldg(list + e);
+                    const uint32_t g = (q.z >> 16) & 0xFFu;
+                    const float a = (tb.flags & 2u) ? 0.0f : __half2float(__ushort_as_half(static_cast<unsigned short>(q.w >> 16)));
+                    const float qv = fmaf(a, qn[q.w & 0xFFu], __uint_as_float(q.x));
+                    const float est = fmaf(gs[g], qv, fmaf(tn, __uint_as_float(q.y), gb[g]));
+                    const uint32_t code = (s << 16) | (q.z & 0xFFFFu);
                     if (est < be2) {
                         if (est < be1) {
                             be2 = be1; bc2 = bc1;
@@ -1156,6 +1158,7 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     static const uint32_t kExact[5] = {2, 4, 8, 12, 16};
     const uint32_t n_exact = kExact[p.quality < 5 ? p.quality : 2];
     const uint32_t refine = p.quality >= 3 ? 3u : 2u;
+    if (ctx.tab.n_grids > t3.NT*8u) return -2;          // phase 1c keeps two per-grid arrays in the texel-sized scratch
     Tab3 tb; tb.ctx = ctx; tb.t3 = t3;
     static const uint32_t dev_flags = getenv("CFX_ASTC3_FLAGS") ? static_cast<uint32_t>(atoi(getenv("CFX_ASTC3_FLAGS"))) : 0u;
     tb.flags = dev_flags;

@@ -40,7 +40,7 @@ struct Astc3Tab {
     uint32_t off_part2w;            // [1024][MW] uint64 texel mask of subset 1 (all zero = unusable seed)
     uint32_t off_part3w;            // [1024][2][MW] uint64 masks of subsets 1 and 2
     uint32_t off_est[2][6];         // [alpha][slot type] -> uint4 list of the modes that fit:
-    uint32_t n_est[2][6];           //   {f32 kq = qvar(level), f32 kc = cvar(colour level), mode | grid << 16 | cl << 24, weight level | grid weights << 8}
+    uint32_t n_est[2][6];           //   {f32 rest, f32 kc = cvar(colour level), mode | grid << 16 | cl << 24, min(level, 5) | f16 a << 16}: see below
 };
 
 inline uint16_t f32_to_f16_bits(float f)
@@ -261,10 +261,17 @@ inline Astc3Tab build_tables3(Built& b)
                 const float kq = (1.0f/(n1*n1))*(1.0f/12.0f)*(1.0f - 0.75f/n1);
                 const float step = 255.0f/static_cast<float>(kColorQuant[cl].n - 1);
                 const float kc = step*step*(1.0f/18.0f);
+                // weight-quantisation term = a*measured(level) + rest: coarse levels blend the loss measured on the slot's
+                // ideal weights (weight a = grid weights / texels: it holds where the texel weights themselves are
+                // quantised, decimated grid weights are blends of them; footprints above 64 texels have no
+                // full-resolution grid and take it as it is) with the uniform model kq; fine levels are model only
+                float a = 0.0f;
+                if (m.level < 6) a = T > 64 ? 1.0f : static_cast<float>(m.nw)/static_cast<float>(T);
+                const float rest = (1.0f - a)*kq;
                 uint32_t w[4];
-                std::memcpy(&w[0], &kq, 4); std::memcpy(&w[1], &kc, 4);
+                std::memcpy(&w[0], &rest, 4); std::memcpy(&w[1], &kc, 4);
                 w[2] = mi | (static_cast<uint32_t>(m.grid) << 16) | (static_cast<uint32_t>(cl) << 24);
-                w[3] = m.level | (static_cast<uint32_t>(m.nw) << 8);
+                w[3] = (m.level < 6 ? m.level : 5u) | (static_cast<uint32_t>(f32_to_f16_bits(a)) << 16);
                 ent.insert(ent.end(), w, w + 4);
             }
             t3.n_est[alpha][type] = static_cast<uint32_t>(ent.size()/4);
