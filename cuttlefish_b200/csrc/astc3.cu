@@ -84,7 +84,7 @@ struct Warp3T {
     };
     struct Setup {
         LineFit lines[15];                  // slot 0, dual-plane slots 5..8, then the 10 subsets of slots 1..4
-        Mom moms[10];                       // moments of those 10 subsets
+        Mom moms[11];                       // moments of those 10 subsets; [10] = the whole block
     };
     union { Est est; Setup setup; } u;      // the setup scratch is dead before phase 1 writes D
     float g[2][TP];                         // decimated ideal grid weights of the current candidate, per plane
@@ -308,10 +308,10 @@ __device__ __forceinline__ float warp_max_f(float f)
 }
 
 // Principal line of a texel set from its moments; zero_ch (>= 0) is left out (it gets its own weight plane).
-__device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, LineFit& out)
+__device__ __forceinline__ float line_core(const Mom& mo, int zero_ch, int iters, float (&m)[4], float (&v)[4])
 {
     const float inv = mo.n > 0.0f ? 1.0f/mo.n : 0.0f;
-    float m[4] = {mo.s[0]*inv, mo.s[1]*inv, mo.s[2]*inv, mo.s[3]*inv};
+    m[0] = mo.s[0]*inv; m[1] = mo.s[1]*inv; m[2] = mo.s[2]*inv; m[3] = mo.s[3]*inv;
     float cv[10];
     cv[0] = mo.p[0] - mo.s[0]*m[0]; cv[1] = mo.p[1] - mo.s[0]*m[1]; cv[2] = mo.p[2] - mo.s[0]*m[2]; cv[3] = mo.p[3] - mo.s[0]*m[3];
     cv[4] = mo.p[4] - mo.s[1]*m[1]; cv[5] = mo.p[5] - mo.s[1]*m[2]; cv[6] = mo.p[6] - mo.s[1]*m[3];
@@ -320,7 +320,7 @@ __device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, 
     if (zero_ch == 1) { cv[1] = cv[4] = cv[5] = cv[6] = 0.0f; }
     if (zero_ch == 2) { cv[2] = cv[5] = cv[7] = cv[8] = 0.0f; }
     if (zero_ch == 3) { cv[3] = cv[6] = cv[8] = cv[9] = 0.0f; }
-    float v[4] = {cv[0], cv[1], cv[2], cv[3]};
+    v[0] = cv[0]; v[1] = cv[1]; v[2] = cv[2]; v[3] = cv[3];
     float best = cv[0];
     if (cv[4] > best) { best = cv[4]; v[0] = cv[1]; v[1] = cv[4]; v[2] = cv[5]; v[3] = cv[6]; }
     if (cv[7] > best) { best = cv[7]; v[0] = cv[2]; v[1] = cv[5]; v[2] = cv[7]; v[3] = cv[8]; }
@@ -341,10 +341,33 @@ __device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, 
     v[0] *= s2; v[1] *= s2; v[2] *= s2; v[3] *= s2;
     if (n2 <= 1e-20f) { v[0] = v[1] = v[2] = 0.57735f; v[3] = 0.0f; }
     if (v[0] + v[1] + v[2] < 0.0f) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; v[3] = -v[3]; }
+    return fmaxf(cv[0] + cv[4] + cv[7] + cv[9] - lam, 0.0f);
+}
+
+// Full line fit; mo and out live in SHARED memory (no local-memory traffic).
+__device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, LineFit& out)
+{
+    float m[4], v[4];
+    const float resid = line_core(mo, zero_ch, iters, m, v);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { out.m[k] = m[k]; out.v[k] = v[k]; }
-    out.resid = fmaxf(cv[0] + cv[4] + cv[7] + cv[9] - lam, 0.0f);
+    out.resid = resid;
 }
+
+// Residual only, moments passed in registers (integer sums about the block centre).
+__device__ __noinline__ float subset_resid(int n, int s0, int s1, int s2, int s3, int p0, int p1, int p2, int p3, int p4, int p5,
+    int p6, int p7, int p8, int p9)
+{
+    Mom mo;
+    mo.n = static_cast<float>(n);
+    mo.s[0] = static_cast<float>(s0); mo.s[1] = static_cast<float>(s1); mo.s[2] = static_cast<float>(s2); mo.s[3] = static_cast<float>(s3);
+    mo.p[0] = static_cast<float>(p0); mo.p[1] = static_cast<float>(p1); mo.p[2] = static_cast<float>(p2); mo.p[3] = static_cast<float>(p3);
+    mo.p[4] = static_cast<float>(p4); mo.p[5] = static_cast<float>(p5); mo.p[6] = static_cast<float>(p6); mo.p[7] = static_cast<float>(p7);
+    mo.p[8] = static_cast<float>(p8); mo.p[9] = static_cast<float>(p9);
+    float m[4], v[4];
+    return line_core(mo, -1, 4, m, v);
+}
+#define CFX_RESID15(a) subset_resid(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14])
 
 // A set of texels: one bit per texel, MW 64-bit words (footprints above 64 texels need 2 or 3).
 template <int MW> struct TexelMask { uint64_t w[MW]; };
@@ -408,9 +431,8 @@ __device__ __forceinline__ uint32_t mask_mismatch3(const TexelMask<MW>& k1, cons
 
 // Lane-local masked moments: texels whose bit is set in `mask`, about `ctr`.
 template <int MW>
-__device__ __noinline__ void masked_moments(const int4* v, uint32_t T, int4 ctr, TexelMask<MW> mask, int (&acc)[15])
+__device__ __forceinline__ void masked_moments(const int4* v, uint32_t T, int4 ctr, TexelMask<MW> mask, int (&acc)[15])
 {
-    // accumulate in registers (the caller's array lives in local memory: this function is not inlined)
     int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0, a9 = 0, a10 = 0, a11 = 0, a12 = 0, a13 = 0, a14 = 0;
 #pragma unroll
     for (int wd = 0; wd < MW; ++wd) {
@@ -624,10 +646,11 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             for (int k = 0; k < 15; ++k) tot[k] = redux_add(acc[k]);
         }
         // ---- setup 2: lines of the single-subset slot (lane 0) and of the four dual-plane slots (lanes 1..4)
-        if (active && lane < 5) {
-            Mom mo;
-            mom_from(tot, mo);
-            subset_line(mo, static_cast<int>(lane) - 1, 6, lines[lane]);
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 15; ++k) if (lane == static_cast<uint32_t>(k)) (&moms[10].n)[k] = static_cast<float>(tot[k]);
+            __syncwarp();
+            if (lane < 5) subset_line(moms[10], static_cast<int>(lane) - 1, 6, lines[lane]);
         }
         if (active && lane < kSlots3) {
             Slot3& sl = ws.slots[lane];
@@ -663,19 +686,18 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             }
         }
         PHASE_SYNC();
-        // ---- setup 4: exact line-fit residual of every lane's two-subset seed; the two best become slots 1, 2
+        // ---- setup 4: exact line-fit residual of every lane's two-subset seed; the two best become slots 1, 2.
+        //      (Moments stay in registers; only the residual survives: the winners' moments are re-derived in setup 6.)
         if (active) {
             float sc = 3.0e38f;
-            int a1[15], a0[15];
             if (b2 != 0xFFFFFFFFu) {
+                int a1[15];
                 masked_moments<MW>(ws.v, T, ctr, load_mask<MW>(ctx, tb.t3.off_part2w + (b2 & 1023u)*(8u*MW)), a1);
+                if (a1[0] >= 1 && tot[0] - a1[0] >= 1) {
+                    const float r1 = CFX_RESID15(a1);
 #pragma unroll
-                for (int k = 0; k < 15; ++k) a0[k] = tot[k] - a1[k];
-                if (a0[0] >= 1 && a1[0] >= 1) {
-                    Mom m0, m1; LineFit l0, l1;
-                    mom_from(a0, m0); mom_from(a1, m1);
-                    subset_line(m0, -1, 4, l0); subset_line(m1, -1, 4, l1);
-                    sc = l0.resid + l1.resid;
+                    for (int k = 0; k < 15; ++k) a1[k] = tot[k] - a1[k];
+                    sc = r1 + CFX_RESID15(a1);
                 }
             }
             for (uint32_t rank = 0; rank < 2; ++rank) {
@@ -683,10 +705,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const uint32_t wl = kmin & 31u;
                 const bool ok = __shfl_sync(0xFFFFFFFFu, sc, wl) < 3.0e38f;
                 const uint32_t seed = __shfl_sync(0xFFFFFFFFu, b2, wl) & 1023u;
-                if (lane == wl) {
-                    if (ok) { mom_from(a0, moms[rank*2]); mom_from(a1, moms[rank*2 + 1]); }
-                    sc = 3.0e38f;
-                }
+                if (lane == wl) sc = 3.0e38f;
                 if (lane == 0) { Slot3& sl = ws.slots[1 + rank]; sl.pc = 2; sl.seed = seed; sl.dual_ch = -1; sl.valid = ok ? 1u : 0u; }
                 const TexelMask<MW> m1 = load_mask<MW>(ctx, tb.t3.off_part2w + seed*(8u*MW));
                 for (uint32_t i = lane; i < TP; i += 32) ws.part[rank][i] = static_cast<uint8_t>(mask_bit<MW>(m1, i));
@@ -696,29 +715,23 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         // ---- setup 5: same for the three-subset seeds -> slots 3, 4
         if (active) {
             float sc = 3.0e38f;
-            int a1[15], a2[15], a0[15];
             if (b3 != 0xFFFFFFFFu) {
                 const uint32_t seed = b3 & 1023u;
+                int a1[15], a2[15];
                 masked_moments<MW>(ws.v, T, ctr, load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW)), a1);
+                const float r1 = a1[0] >= 1 ? CFX_RESID15(a1) : 3.0e38f;
                 masked_moments<MW>(ws.v, T, ctr, load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW) + 8u*MW), a2);
+                const float r2 = a2[0] >= 1 ? CFX_RESID15(a2) : 3.0e38f;
 #pragma unroll
-                for (int k = 0; k < 15; ++k) a0[k] = tot[k] - a1[k] - a2[k];
-                if (a0[0] >= 1 && a1[0] >= 1 && a2[0] >= 1) {
-                    Mom m0, m1, m2; LineFit l0, l1, l2;
-                    mom_from(a0, m0); mom_from(a1, m1); mom_from(a2, m2);
-                    subset_line(m0, -1, 4, l0); subset_line(m1, -1, 4, l1); subset_line(m2, -1, 4, l2);
-                    sc = l0.resid + l1.resid + l2.resid;
-                }
+                for (int k = 0; k < 15; ++k) a1[k] = tot[k] - a1[k] - a2[k];
+                if (a1[0] >= 1 && r1 < 3.0e38f && r2 < 3.0e38f) sc = r1 + r2 + CFX_RESID15(a1);
             }
             for (uint32_t rank = 0; rank < 2; ++rank) {
                 const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(sc) & ~31u) | lane);
                 const uint32_t wl = kmin & 31u;
                 const bool ok = __shfl_sync(0xFFFFFFFFu, sc, wl) < 3.0e38f;
                 const uint32_t seed = __shfl_sync(0xFFFFFFFFu, b3, wl) & 1023u;
-                if (lane == wl) {
-                    if (ok) { mom_from(a0, moms[4 + rank*3]); mom_from(a1, moms[4 + rank*3 + 1]); mom_from(a2, moms[4 + rank*3 + 2]); }
-                    sc = 3.0e38f;
-                }
+                if (lane == wl) sc = 3.0e38f;
                 if (lane == 0) { Slot3& sl = ws.slots[3 + rank]; sl.pc = 3; sl.seed = seed; sl.dual_ch = -1; sl.valid = ok ? 1u : 0u; }
                 const TexelMask<MW> m1 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW));
                 const TexelMask<MW> m2 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW) + 8u*MW);
@@ -727,10 +740,36 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             }
         }
         PHASE_SYNC();
-        // ---- setup 6: lines of the ten subsets of slots 1..4 (lane = subset)
-        if (active && lane < 10) {
-            const uint32_t sl = lane < 2 ? 1u : (lane < 4 ? 2u : (lane < 7 ? 3u : 4u));
-            if (ws.slots[sl].valid) subset_line(moms[lane], -1, 6, lines[5 + lane]);
+        // ---- setup 6: moments of the ten subsets of slots 1..4 (lane = texel, redux per field), then their lines
+        //      (lane = subset)
+        if (active) {
+#pragma unroll 1
+            for (uint32_t job = 0; job < 10; ++job) {
+                const uint32_t k = job < 2 ? 0u : (job < 4 ? 1u : (job < 7 ? 2u : 3u));          // part index = slot - 1
+                const uint32_t q = job < 4 ? (job & 1u) : (job < 7 ? job - 4u : job - 7u);       // subset
+                if (!ws.slots[1 + k].valid) continue;
+                int acc[15];
+#pragma unroll
+                for (int f = 0; f < 15; ++f) acc[f] = 0;
+                for (uint32_t i = lane; i < T; i += 32) {
+                    if (ws.part[k][i] != q) continue;
+                    const int4 x = ws.v[i];
+                    const int x0 = x.x - ctr.x, x1 = x.y - ctr.y, x2 = x.z - ctr.z, x3 = x.w - ctr.w;
+                    acc[0] += 1; acc[1] += x0; acc[2] += x1; acc[3] += x2; acc[4] += x3;
+                    acc[5] += x0*x0; acc[6] += x0*x1; acc[7] += x0*x2; acc[8] += x0*x3; acc[9] += x1*x1;
+                    acc[10] += x1*x2; acc[11] += x1*x3; acc[12] += x2*x2; acc[13] += x2*x3; acc[14] += x3*x3;
+                }
+#pragma unroll
+                for (int f = 0; f < 15; ++f) {
+                    const int t = redux_add(acc[f]);
+                    if (lane == static_cast<uint32_t>(f)) (&moms[job].n)[f] = static_cast<float>(t);
+                }
+            }
+            __syncwarp();
+            if (lane < 10) {
+                const uint32_t sl = lane < 2 ? 1u : (lane < 4 ? 2u : (lane < 7 ? 3u : 4u));
+                if (ws.slots[sl].valid) subset_line(moms[lane], -1, 6, lines[5 + lane]);
+            }
         }
         __syncwarp();
         // ---- setup 7: per slot, project the texels on their subset's line -> ideal weights (fp16 A operand rows),

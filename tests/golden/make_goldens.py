@@ -49,13 +49,28 @@ def cases():
     yield "BC6H_hdr_64x64", "BC6H", {"type": "UFloat"}, hdr
     hdr = oracle.gen_image("hdr", 30, 22)
     yield "BC6H_hdr_30x22", "BC6H", {"type": "UFloat"}, hdr
+    # formats added later in round 1: the rest of the ETC/EAC family, signed BC4/BC5, the other ASTC footprints
+    img = oracle.gen_image("noise+grad", 32, 32)
+    for fmt in ["EAC_R11", "EAC_R11G11", "ETC2_R8G8B8A1", "ASTC_5x4", "ASTC_5x5", "ASTC_6x5", "ASTC_8x5", "ASTC_8x6",
+                "ASTC_10x5", "ASTC_10x6", "ASTC_10x8", "ASTC_10x10", "ASTC_12x10", "ASTC_12x12"]:
+        yield "%s_noisegrad_32x32" % fmt, fmt, {}, img
+    punch = alpha_variant(img)
+    punch[..., 3] = (punch[..., 3] >= 0.5).astype(np.float32)
+    yield "ETC2_R8G8B8A1_alpha_32x32", "ETC2_R8G8B8A1", {}, punch
+    signed = (img*np.float32(2.0) - np.float32(1.0)).astype(np.float16).astype(np.float32)
+    signed[..., 3] = 1.0
+    for fmt in ["BC4", "BC5", "EAC_R11", "EAC_R11G11"]:
+        yield "%s_snorm_32x32" % fmt, fmt, {"type": "SNorm"}, signed
+    ui = oracle.gen_image("ui", 48, 48)
+    for fmt in ["ASTC_4x4", "ASTC_6x6", "ASTC_8x8", "BC7", "ETC2_R8G8B8"]:
+        yield "%s_ui_48x48" % fmt, fmt, {}, ui
 
 
 def main():
     n = 0
     for name, fmt, kw, img in cases():
         blocks = oracle.encode(img, fmt, threads=0, **kw)
-        if kw.get("type") == "UFloat":
+        if kw.get("type") in ("UFloat", "SNorm"):
             src = img.astype(np.float16).view(np.uint16)      # RNE, same as the kernels' f32->f16
         else:
             src = oracle.to_rgba8(img)

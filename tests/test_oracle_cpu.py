@@ -34,8 +34,8 @@ def test_generator_is_8bit_snapped(oracle):
     assert np.array_equal(u8.astype(np.float32) / np.float32(255.0), img)
 
 
-GLUE_FORMATS = ["BC1_RGB", "BC1_RGBA", "BC2", "BC3", "BC4", "BC5", "BC7", "ETC1", "ETC2_R8G8B8", "ETC2_R8G8B8A8",
-                "ASTC_4x4", "ASTC_6x6", "ASTC_10x6"]
+GLUE_FORMATS = ["BC1_RGB", "BC1_RGBA", "BC2", "BC3", "BC4", "BC5", "BC7", "ETC1", "ETC2_R8G8B8", "ETC2_R8G8B8A1",
+                "ETC2_R8G8B8A8", "EAC_R11", "EAC_R11G11", "ASTC_4x4", "ASTC_6x6", "ASTC_10x6", "ASTC_12x12"]
 
 
 @pytest.mark.parametrize("fmt", GLUE_FORMATS)
@@ -53,6 +53,15 @@ def test_restated_glue_matches_reference_glue(oracle, fmt):
     img = oracle.gen_image("noise+grad", 24, 24)
     assert np.array_equal(oracle.encode(img, fmt, color_mask=5), oracle.encode_glue(img, fmt, color_mask=5))
     assert np.array_equal(oracle.encode(img, fmt, srgb=True), oracle.encode_glue(img, fmt, srgb=True))
+
+
+@pytest.mark.parametrize("fmt", ["BC4", "BC5", "EAC_R11", "EAC_R11G11"])
+def test_restated_glue_matches_reference_glue_snorm(oracle, fmt):
+    if not oracle.glue_available():
+        pytest.skip("oracle/_ref/libcfglue.so not built (needs /root/reference)")
+    img = (oracle.gen_image("noise+grad", 30, 22, seed=5)*2.0 - 1.0).astype(np.float32)
+    img[..., 3] = 1.0
+    assert np.array_equal(oracle.encode(img, fmt, type="SNorm"), oracle.encode_glue(img, fmt, type="SNorm"))
 
 
 def test_restated_glue_matches_reference_glue_bc6h(oracle):

@@ -485,3 +485,31 @@ def test_astc_ui_content_psnr_vs_oracle(cfx, oracle, fmt, tol):
     p_gpu = oracle.psnr_rgb(img, oracle.decode(got, fmt, n, n))
     p_ref = oracle.psnr_rgb(img, oracle.decode(ref, fmt, n, n))
     assert p_gpu >= p_ref - tol, "%s ui: gpu %.3f dB < reference %.3f dB - %.2f" % (fmt, p_gpu, p_ref, tol)
+
+
+# ---- every committed golden case of a PSNR-parity format: our blocks against the reference's blocks on the same
+# input, decoded by the same decoder (covers the formats / types / footprints that have no dedicated test above) ----
+@pytest.mark.parametrize("name", [n for n in golden_cases() if not any(n.startswith(p + "_") for p in EXACT_FORMATS) or "snorm" in n])
+def test_golden_inputs_psnr_parity(cfx, oracle, name):
+    from util import decode_any
+    src, blocks, fmt, kw = load_golden(name)
+    h, w, _ = src.shape
+    if not cfx.format_supported(fmt, kw.get("type", "UNorm")):
+        pytest.skip("no GPU encoder for this pair")
+    got = cfx.encode(src, fmt, **kw)
+    assert got.size == blocks.size
+    img = src_as_float(src)
+    d_gpu, d_ref = decode_any(oracle, got, fmt, w, h, kw), decode_any(oracle, blocks, fmt, w, h, kw)
+    nch = {"EAC_R11": 1, "BC4": 1, "EAC_R11G11": 2, "BC5": 2}.get(fmt, 3)
+    ref_img = img
+    if kw.get("type") == "SNorm" and fmt in ("BC4", "BC5"):
+        ref_img = np.round(np.clip(img, -1, 1)*127)/127
+    peak = 64.0 if kw.get("type") == "UFloat" else (2.0 if kw.get("type") == "SNorm" else 1.0)
+    mse = lambda d: float(np.mean((d[..., :nch].astype(np.float64) - ref_img[..., :nch])**2))
+    if fmt == "ETC2_R8G8B8A1":
+        opaque = img[..., 3] >= 0.5
+        assert np.array_equal(d_gpu[..., 3] >= 0.5, opaque)
+        mse = lambda d: float(np.mean(((d[..., :3].astype(np.float64) - img[..., :3])**2)[opaque]))
+    p_gpu, p_ref = 10*np.log10(peak**2/max(mse(d_gpu), 1e-12)), 10*np.log10(peak**2/max(mse(d_ref), 1e-12))
+    # a 32x32 case is 16-64 blocks: allow the sampling noise of a few blocks on top of the 0.1 dB bar
+    assert p_gpu >= p_ref - (PSNR_TOLERANCE_DB + 0.15), "%s: gpu %.3f dB < reference %.3f dB" % (name, p_gpu, p_ref)

@@ -96,3 +96,20 @@ def decode_eac_r11(blocks, width, height, signed):
             v = np.clip(base * 8 + 4 + step, 0, 2047) / 2047.0
         out[(p % 4)::4, (p // 4)::4] = v
     return out[:height, :width]
+
+
+def decode_any(oracle, blocks, fmt, width, height, kw):
+    """Decoded float32 [H, W, C] for any golden case: the reference's decoders where the oracle has one, the spec
+    decoders above for signed BC4/BC5 and EAC R11/RG11 (the reference's own decode path asserts on those)."""
+    typ = kw.get("type", "UNorm")
+    blocks = np.asarray(blocks, np.uint8)
+    if fmt in ("EAC_R11", "EAC_R11G11") or (fmt in ("BC4", "BC5") and typ == "SNorm"):
+        nch = 1 if fmt in ("EAC_R11", "BC4") else 2
+        b = blocks.reshape(-1, 8*nch)
+        out = np.zeros((height, width, 4), np.float32)
+        out[..., 3] = 1.0
+        for c in range(nch):
+            part = np.ascontiguousarray(b[:, 8*c:8*c + 8])
+            out[..., c] = decode_eac_r11(part, width, height, typ == "SNorm") if fmt.startswith("EAC") else decode_bc4_snorm(part, width, height)
+        return out
+    return oracle.decode(blocks, fmt, width, height, **kw)
