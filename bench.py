@@ -60,6 +60,17 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic(fmt, texels):
+    """DRAM bytes of one launch from the committed ncu capture (profiles/r01_dram_traffic.json), scaled to the
+    texels of the launch timed here; None when no capture exists for the format."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as f:
+            t = json.load(f)[fmt]
+        return int((t["dram_read_bytes"] + t["dram_write_bytes"]) * (texels / t["texels"])), t["csv"]
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -278,6 +289,7 @@ def main():
         e2e_value = total_texels / (e2e_ms / a.steps * 1e-3) / 1e6
         bpt = wl["read"] + wl["write"]
         achieved = kernel_texels * bpt / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(a.format, kernel_texels) if a.quality == "Normal" else (None, None)
         out = {"metric": "Mtexels/s encode", "value": value, "unit": "Mtexels/s", "n_gpus": world,
                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -287,7 +299,8 @@ def main():
                        "d2h_bytes_per_step": int(host_out.numel()) * world},
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": how,
+                            "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                            "traffic_source": traffic_src, "algorithmic_bytes": int(kernel_texels * bpt), "peak_source": how,
                             "kernel": "%s encode kernel, %.3f ms per launch over %d texels, %.3f B/texel" %
                                       (a.format, kernel_ms, kernel_texels, bpt)},
                "clocks": clocks}
