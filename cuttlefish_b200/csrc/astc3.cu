@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     code = __shfl_sync(0xFFFFFFFFu, bc0, wl);
                     if (lane == wl) { be0 = be1; bc0 = bc1; be1 = be2; bc1 = bc2; be2 = 3.0e38f; }
                     // estimates come out sorted: stop when nothing later can win
-                    done = est >= 3.0e38f || 0.8f*est*fx2 > best_err;
+                    done = est >= 3.0e38f || (n_exact > 8u ? 0.6f : 0.8f)*est*fx2 > best_err;
                     ++n;
                 }
                 if (done) refining = true;
@@ -1194,9 +1194,13 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
 // t3 must describe tables appended to ctx.blob by build_tables3() (astc.cu owns the per-device table cache).
 int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cudaStream_t stream)
 {
-    static const uint32_t kExact[5] = {2, 4, 8, 12, 16};
-    const uint32_t n_exact = kExact[p.quality < 5 ? p.quality : 2];
-    const uint32_t refine = p.quality >= 3 ? 3u : 2u;
+    // exact evaluations / refinement rounds per Texture::Quality (AstcConverter maps the levels to astcenc's fastest,
+    // fast, medium, thorough, exhaustive presets, lib/src/AstcConverter.cpp:174-195)
+    static const uint32_t kExact[5] = {4, 6, 8, 16, 32};
+    static const uint32_t kRefine[5] = {1, 2, 2, 3, 4};
+    const uint32_t q5 = p.quality < 5 ? p.quality : 2;
+    const uint32_t n_exact = kExact[q5];
+    const uint32_t refine = kRefine[q5];
     if (ctx.tab.n_grids > t3.NT*8u) return -2;          // phase 1c keeps two per-grid arrays in the texel-sized scratch
     Tab3 tb; tb.ctx = ctx; tb.t3 = t3;
     static const uint32_t dev_flags = getenv("CFX_ASTC3_FLAGS") ? static_cast<uint32_t>(atoi(getenv("CFX_ASTC3_FLAGS"))) : 0u;
