@@ -676,13 +676,19 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const uint32_t left = T > 64u*w ? T - 64u*w : 0u;
                 full.w[w] = left >= 64u ? ~0ull : ((1ull << left) - 1ull);
             }
+            // compacted seed lists: every lane scores a usable seed in every iteration
 #pragma unroll 4
-            for (uint32_t seed = lane; seed < 1024; seed += 32) {
-                const TexelMask<MW> q = load_mask<MW>(ctx, tb.t3.off_part2w + seed*(8u*MW));
-                if (!mask_empty<MW>(q)) b2 = min(b2, (mask_mismatch2<MW>(km0, q, T) << 10) | seed);
-                const TexelMask<MW> q1 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW));
-                const TexelMask<MW> q2 = load_mask<MW>(ctx, tb.t3.off_part3w + seed*(16u*MW) + 8u*MW);
-                if (!mask_empty<MW>(q1)) b3 = min(b3, (mask_mismatch3<MW>(km1, km2, q1, q2, full, T) << 10) | seed);
+            for (uint32_t i = lane; i < tb.t3.n_seed2; i += 32) {
+                const uint32_t seed = tab_u16(ctx, tb.t3.off_seed2 + i*2u);
+                const TexelMask<MW> q = load_mask<MW>(ctx, tb.t3.off_part2c + i*(8u*MW));
+                b2 = min(b2, (mask_mismatch2<MW>(km0, q, T) << 10) | seed);
+            }
+#pragma unroll 2
+            for (uint32_t i = lane; i < tb.t3.n_seed3; i += 32) {
+                const uint32_t seed = tab_u16(ctx, tb.t3.off_seed3 + i*2u);
+                const TexelMask<MW> q1 = load_mask<MW>(ctx, tb.t3.off_part3c + i*(16u*MW));
+                const TexelMask<MW> q2 = load_mask<MW>(ctx, tb.t3.off_part3c + i*(16u*MW) + 8u*MW);
+                b3 = min(b3, (mask_mismatch3<MW>(km1, km2, q1, q2, full, T) << 10) | seed);
             }
         }
         PHASE_SYNC();

@@ -39,6 +39,10 @@ struct Astc3Tab {
     uint32_t MW;                    // 64-bit words per texel mask
     uint32_t off_part2w;            // [1024][MW] uint64 texel mask of subset 1 (all zero = unusable seed)
     uint32_t off_part3w;            // [1024][2][MW] uint64 masks of subsets 1 and 2
+    uint32_t n_seed2, n_seed3;      // usable (distinct, non-degenerate) seeds
+    uint32_t off_seed2, off_seed3;  // [n_seed] uint16 seed numbers, ascending
+    uint32_t off_part2c;            // [n_seed2][MW] the same masks, compacted in off_seed2 order
+    uint32_t off_part3c;            // [n_seed3][2][MW]
     uint32_t off_est[2][6];         // [alpha][slot type] -> uint4 list of the modes that fit:
     uint32_t n_est[2][6];           //   {f32 rest, f32 kc = cvar(colour level), mode | grid << 16 | cl << 24, min(level, 5) | f16 a << 16}: see below
 };
@@ -248,6 +252,27 @@ inline Astc3Tab build_tables3(Built& b)
                 std::memcpy(&blob[t3.off_part3w + (static_cast<size_t>(seed)*2 + 1)*MW*8], b2.data(), MW*8);
             }
         }
+    }
+    // compacted copies for the seed scan (every lane of the warp then has a usable seed in every iteration)
+    {
+        const int MW = static_cast<int>(t3.MW);
+        std::vector<uint16_t> s2, s3;
+        std::vector<uint64_t> m2, m3;
+        for (int seed = 0; seed < 1024; ++seed) {
+            const uint64_t* a = reinterpret_cast<const uint64_t*>(&blob[t3.off_part2w + static_cast<size_t>(seed)*MW*8]);
+            bool any = false;
+            for (int w = 0; w < MW; ++w) any |= a[w] != 0;
+            if (any) { s2.push_back(static_cast<uint16_t>(seed)); m2.insert(m2.end(), a, a + MW); }
+            const uint64_t* b3 = reinterpret_cast<const uint64_t*>(&blob[t3.off_part3w + static_cast<size_t>(seed)*2*MW*8]);
+            any = false;
+            for (int w = 0; w < MW; ++w) any |= b3[w] != 0;
+            if (any) { s3.push_back(static_cast<uint16_t>(seed)); m3.insert(m3.end(), b3, b3 + 2*MW); }
+        }
+        t3.n_seed2 = static_cast<uint32_t>(s2.size()); t3.n_seed3 = static_cast<uint32_t>(s3.size());
+        t3.off_seed2 = reserve(s2.size()*2 + 2, 4); t3.off_seed3 = reserve(s3.size()*2 + 2, 4);
+        t3.off_part2c = reserve(m2.size()*8 + 8, 8); t3.off_part3c = reserve(m3.size()*8 + 8, 8);
+        if (!s2.empty()) { std::memcpy(&blob[t3.off_seed2], s2.data(), s2.size()*2); std::memcpy(&blob[t3.off_part2c], m2.data(), m2.size()*8); }
+        if (!s3.empty()) { std::memcpy(&blob[t3.off_seed3], s3.data(), s3.size()*2); std::memcpy(&blob[t3.off_part3c], m3.data(), m3.size()*8); }
     }
     // estimate lists: per (alpha, slot type) the modes that fit, with their model terms
     for (int alpha = 0; alpha < 2; ++alpha)
