@@ -85,9 +85,9 @@ static Launcher find_launcher(uint32_t format, uint32_t type)
 #endif
 #ifdef CFX_HAVE_BC6H
         case CFX_FORMAT_BC6H:
-            // Type::Float (signed) is not enabled: the reference's own signed output (Compressonator) decodes to
-            // garbage with its own decoder, so there is no oracle to hold the signed code path in bc6h_core.cuh to
-            return type == CFX_TYPE_UFLOAT ? launch_bc6h : nullptr;
+            // Type::Float (signed): checked against a spec decoder (tests/util.py decode_bc6h) -- the reference's own
+            // signed output (Compressonator) is not a valid encoding of its input, see DESIGN.md
+            return (type == CFX_TYPE_UFLOAT || type == CFX_TYPE_FLOAT) ? launch_bc6h : nullptr;
 #endif
         default:
 #ifdef CFX_HAVE_ASTC

@@ -70,3 +70,20 @@ def test_restated_glue_matches_reference_glue_bc6h(oracle):
     hdr = oracle.gen_image("hdr", 30, 22)
     for q in ("Normal", "Low"):
         assert np.array_equal(oracle.encode(hdr, "BC6H", type="UFloat", quality=q), oracle.encode_glue(hdr, "BC6H", type="UFloat", quality=q))
+
+
+def test_bc6h_spec_decoder_pinned_on_reference_decoder(oracle):
+    """tests/util.py decode_bc6h (used to check the SIGNED format, where the reference has no usable decode) agrees
+    with the reference's decoder on unsigned blocks: exactly on the reference encoder's blocks, within one half ulp
+    everywhere it covers."""
+    from util import decode_bc6h
+    covered = 0
+    for name in golden_cases(["BC6H"]):
+        src, blocks, fmt, kw = load_golden(name)
+        h, w, _ = src.shape
+        mine = decode_bc6h(blocks, w, h, False)
+        ref = oracle.decode(blocks, "BC6H", w, h, **kw)[..., :3]
+        ok = np.isfinite(mine)
+        covered += int(ok.sum())
+        assert np.array_equal(mine[ok], ref[ok])
+    assert covered > 0

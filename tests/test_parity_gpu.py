@@ -515,3 +515,39 @@ def test_golden_inputs_psnr_parity(cfx, oracle, name):
     # (above 60 dB both are within a quarter of an 8-bit step of the source: our search stops at astcenc's own
     # quality target + 12 dB, the reference happens to land higher on a pure ramp)
     assert p_gpu >= p_ref - (PSNR_TOLERANCE_DB + 0.15) or p_gpu >= 60.0, "%s: gpu %.3f dB < reference %.3f dB" % (name, p_gpu, p_ref)
+
+
+# ---- BC6H signed (Texture::Type::Float).  The reference's signed output (Compressonator CompressBlockBC6 with
+# SetSignedBC6) is not a valid encoding of its input -- decoded per the D3D11 specification it is tens of dB below
+# zero -- so the check is a specification decoder (tests/util.py, pinned on the reference decoder for unsigned blocks):
+# the signed encode of data with negative texels must be as good as the unsigned encode of the same data shifted
+# positive, and of course not worse than the reference ----
+def test_bc6h_signed_vs_spec_decoder(cfx, oracle):
+    from util import decode_bc6h
+    assert cfx.format_supported("BC6H", "Float")
+    n = 96
+    rng = np.random.default_rng(7)
+    base = oracle.gen_image("hdr", n, n)
+    base[..., :3] *= (1.0 + 0.5*rng.random((n, n, 3), dtype=np.float32))
+    pos16 = base.astype(np.float16)
+    neg16 = (base - np.array([16.0, 2.0, 0.25, 0.0], np.float32)).astype(np.float16)
+    posf, negf = pos16.astype(np.float32), neg16.astype(np.float32)
+    assert (negf[..., :3] < 0).mean() > 0.1
+    psnr = lambda a, b: 10*np.log10(64.0**2/max(float(np.mean((a[..., :3] - b[..., :3])**2)), 1e-12))
+    got_u = cfx.encode(pos16, "BC6H", type="UFloat")
+    d_u = decode_bc6h(got_u, n, n, False)
+    assert np.isfinite(d_u).all()
+    # the spec decoder agrees with the reference decoder on our unsigned blocks to one half ulp
+    assert np.max(np.abs(d_u - oracle.decode(got_u, "BC6H", n, n, type="UFloat")[..., :3])) <= 0.0626
+    got_s = cfx.encode(neg16, "BC6H", type="Float")
+    d_s = decode_bc6h(got_s, n, n, True)
+    assert np.isfinite(d_s).all()
+    p_u, p_s = psnr(posf, d_u), psnr(negf, d_s)
+    # one bit less per end point, and blocks that straddle zero span a wider range: measured 2.0 dB on this image
+    assert p_s >= p_u - 3.0, "signed %.2f dB vs unsigned %.2f dB" % (p_s, p_u)
+    ref = oracle.encode(negf, "BC6H", type="Float")
+    d_r = decode_bc6h(ref, n, n, True)
+    ok = np.isfinite(d_r).all(axis=-1)
+    if ok.any():
+        p_r = 10*np.log10(64.0**2/max(float(np.mean((d_r[ok] - negf[..., :3][ok])**2)), 1e-12))
+        assert p_s >= p_r - PSNR_TOLERANCE_DB

@@ -113,3 +113,132 @@ def decode_any(oracle, blocks, fmt, width, height, kw):
             out[..., c] = decode_eac_r11(part, width, height, typ == "SNorm") if fmt.startswith("EAC") else decode_bc4_snorm(part, width, height)
         return out
     return oracle.decode(blocks, fmt, width, height, **kw)
+
+
+# ---- BC6H decoder for the block modes OUR encoder emits (1, 2, 10, 11-14), per the D3D11 BC6H specification.
+# Used to check the signed format (Texture::Type::Float): the reference's own signed pipeline (Compressonator) does
+# not survive a round trip through its own decoder, so there is no oracle decode to lean on.  The decoder is pinned on
+# UNSIGNED blocks against the reference decoder (tests/test_oracle_cpu.py), signed differs only in the sign extension
+# of the end points, the signed unquantiser and the signed half conversion the spec mandates.
+_BC6_PART2 = [0xcccc, 0x8888, 0xeeee, 0xecc8, 0xc880, 0xfeec, 0xfec8, 0xec80, 0xc800, 0xffec, 0xfe80, 0xe800, 0xffe8,
+              0xff00, 0xfff0, 0xf000, 0xf710, 0x008e, 0x7100, 0x08ce, 0x008c, 0x7310, 0x3100, 0x8cce, 0x088c, 0x3110,
+              0x6666, 0x366c, 0x17e8, 0x0ff0, 0x718e, 0x399c]
+_BC6_ANCHOR2 = [15]*16 + [15, 2, 8, 2, 2, 8, 8, 15, 2, 8, 2, 2, 8, 8, 2, 2]
+_BC6_W3 = [0, 9, 18, 27, 37, 46, 55, 64]
+_BC6_W4 = [0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64]
+
+
+def _bc6_unq(x, bits, signed):
+    if not signed:
+        if bits >= 15:
+            return x
+        if x == 0:
+            return 0
+        if x == (1 << bits) - 1:
+            return 0xFFFF
+        return ((x << 15) + 0x4000) >> (bits - 1)
+    if bits >= 16:
+        return x
+    neg, ax = x < 0, abs(x)
+    if ax == 0:
+        u = 0
+    elif ax >= (1 << (bits - 1)) - 1:
+        u = 0x7FFF
+    else:
+        u = ((ax << 15) + 0x4000) >> (bits - 1)
+    return -u if neg else u
+
+
+def _sext(v, bits):
+    v &= (1 << bits) - 1
+    return v - (1 << bits) if v & (1 << (bits - 1)) else v
+
+
+def _bc6_finish(p, signed):
+    if not signed:
+        return (p * 31) >> 6
+    return (0x8000 | (((-p) * 31) >> 5)) if p < 0 else ((p * 31) >> 5)
+
+
+def decode_bc6h_block(block, signed):
+    """16 bytes -> [16, 3] uint16 half bit patterns (texel t = y*4 + x); None for a mode this decoder does not cover."""
+    v = int.from_bytes(bytes(block), "little")
+    bits = lambda pos, n: (v >> pos) & ((1 << n) - 1)
+    bit = lambda pos: (v >> pos) & 1
+    m2 = v & 3
+    m5 = v & 31
+    out = np.zeros((16, 3), np.uint16)
+    if m2 >= 2 and m5 in (0x03, 0x07, 0x0B, 0x0F):              # one region: modes 11..14
+        k = {0x03: 0, 0x07: 1, 0x0B: 2, 0x0F: 3}[m5]
+        wb, tb = [10, 11, 12, 16][k], [10, 9, 8, 4][k]
+        e0, e1 = [], []
+        for c in range(3):
+            w = bits(5 + 10 * c, 10)
+            for b in range(10, wb):
+                w |= bit(35 + 10 * c + (9 - (b - 10))) << b
+            x = bits(35 + 10 * c, tb)
+            if k == 0:
+                a, b_ = w, x
+            else:
+                a, b_ = w, (w + _sext(x, tb)) & ((1 << wb) - 1)
+            if signed:
+                a, b_ = _sext(a, wb), _sext(b_, wb)
+            e0.append(_bc6_unq(a, wb, signed)); e1.append(_bc6_unq(b_, wb, signed))
+        for t in range(16):
+            idx = bits(65, 3) if t == 0 else bits(65 + 3 + 4 * (t - 1), 4)
+            wgt = _BC6_W4[idx]
+            for c in range(3):
+                out[t, c] = _bc6_finish((e0[c] * (64 - wgt) + e1[c] * wgt + 32) >> 6, signed)
+        return out
+    if m2 == 0 or m2 == 1 or m5 == 0x1E:                        # two regions: modes 1 (10.5.5.5), 2 (7.6.6.6), 10 (6.6.6.6)
+        if m5 == 0x1E:
+            wb, tb, direct = 6, 6, True
+            w = [bits(5, 6), bits(15, 6), bits(25, 6)]; x = [bits(35, 6), bits(45, 6), bits(55, 6)]
+            y = [bits(65, 6), bits(41, 4) | bit(24) << 4 | bit(21) << 5, bits(61, 4) | bit(14) << 4 | bit(22) << 5]
+            z = [bits(71, 6), bits(51, 4) | bit(11) << 4 | bit(31) << 5,
+                 bit(12) | bit(13) << 1 | bit(23) << 2 | bit(32) << 3 | bit(34) << 4 | bit(33) << 5]
+        elif m2 == 1:
+            wb, tb, direct = 7, 6, False
+            w = [bits(5, 7), bits(15, 7), bits(25, 7)]; x = [bits(35, 6), bits(45, 6), bits(55, 6)]
+            y = [bits(65, 6), bits(41, 4) | bit(24) << 4 | bit(2) << 5, bits(61, 4) | bit(14) << 4 | bit(22) << 5]
+            z = [bits(71, 6), bits(51, 4) | bit(3) << 4 | bit(4) << 5,
+                 bit(12) | bit(13) << 1 | bit(23) << 2 | bit(32) << 3 | bit(34) << 4 | bit(33) << 5]
+        else:
+            wb, tb, direct = 10, 5, False
+            w = [bits(5, 10), bits(15, 10), bits(25, 10)]; x = [bits(35, 5), bits(45, 5), bits(55, 5)]
+            y = [bits(65, 5), bits(41, 4) | bit(2) << 4, bits(61, 4) | bit(3) << 4]
+            z = [bits(71, 5), bits(51, 4) | bit(40) << 4, bit(50) | bit(60) << 1 | bit(70) << 2 | bit(76) << 3 | bit(4) << 4]
+        shape = bits(77, 5)
+        ep = []
+        for c in range(3):
+            vals = [w[c]]
+            for d in (x[c], y[c], z[c]):
+                vals.append(d if direct else (w[c] + _sext(d, tb)) & ((1 << wb) - 1))
+            if signed:
+                vals = [_sext(q, wb) for q in vals]
+            ep.append([_bc6_unq(q, wb, signed) for q in vals])
+        pos = 82
+        mask, anchor = _BC6_PART2[shape], _BC6_ANCHOR2[shape]
+        for t in range(16):
+            nb = 2 if (t == 0 or t == anchor) else 3
+            idx = bits(pos, nb); pos += nb
+            wgt = _BC6_W3[idx]
+            r = (mask >> t) & 1
+            for c in range(3):
+                a, b_ = ep[c][2 * r], ep[c][2 * r + 1]
+                out[t, c] = _bc6_finish((a * (64 - wgt) + b_ * wgt + 32) >> 6, signed)
+        return out
+    return None
+
+
+def decode_bc6h(blocks, width, height, signed):
+    """float32 [H, W, 3] (NaN where a block uses a mode outside 1, 2, 10..14)."""
+    bx, by = (width + 3) // 4, (height + 3) // 4
+    b = np.asarray(blocks, np.uint8).reshape(by, bx, 16)
+    out = np.full((by * 4, bx * 4, 3), np.nan, np.float32)
+    for j in range(by):
+        for i in range(bx):
+            h = decode_bc6h_block(b[j, i], signed)
+            if h is not None:
+                out[j * 4:j * 4 + 4, i * 4:i * 4 + 4] = h.reshape(4, 4, 3).view(np.float16).astype(np.float32)
+    return out[:height, :width]
