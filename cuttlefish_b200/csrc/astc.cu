@@ -171,7 +171,7 @@ int launch_astc(const EncodeParams& p, cudaStream_t stream)
     // candidate, below).
     static const int version = getenv("CFX_ASTC_V") ? atoi(getenv("CFX_ASTC_V")) : (getenv("CFX_ASTC_V1") ? 1 : 3);
     if (version >= 3) return launch_astc3(p, ctx, t3, stream);
-    if (p.block_w*p.block_h > static_cast<uint32_t>(kMaxTexels)) return -2;     // the older kernels stop at 64 texels
+    if (p.block_w*p.block_h > static_cast<uint32_t>(kMaxTexels) || p.type != 0u) return -2;     // the older kernels: LDR, <= 64 texels
     if (version == 2) return launch_astc2(p, ctx, stream);
     const Plan plan = make_plan(p.quality, ctx.tab);
     const size_t smem = kAstcWarps*kWarpBytes;

@@ -17,6 +17,7 @@
 // candidate refinement loop.  Our own search: PSNR parity with the reference, not byte parity.
 #include "astc3_tables.hpp"
 #include "astc_core.cuh"
+#include "astc_hdr.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -89,7 +90,10 @@ struct Warp3T {
     union { Est est; Setup setup; } u;      // the setup scratch is dead before phase 1 writes D
     float g[2][TP];                         // decimated ideal grid weights of the current candidate, per plane
     int ep[24];                             // quantised end points of the candidate: [subset][e0 rgba, e1 rgba]
-    int best_ep[24];
+    int best_ep[24];                        // (HDR: 12-bit values as end point mode 11 decodes them)
+    float epf[24];                          // HDR: least-squares end points before mode-11 packing, 8-bit-like units
+    int epv[18], best_epv[18];              // HDR: the six packed mode-11 values of every subset
+    uint32_t hkey[28];                      // HDR: (error, sub-mode) keys of the 9 packing candidates per subset
     uint8_t su[2*TP];                       // candidate grid weights (unquantised values 0..64), bit-stream order
     uint8_t sk[2*TP];                       // ... and their rank in the quantisation level's value table
     uint8_t best_su[2*TP];
@@ -99,7 +103,7 @@ struct Warp3T {
 // model constants (fitted on the host with tools/emu_astc3.py)
 constexpr float kLine = 1.1f, kDec = 1.0f, kQuant = 0.9f, kColor = 0.5f;
 
-struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; };   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
+struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; };   // hdr: Texture::Type::UFloat (texels searched as LNS, end point mode 11)   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
 
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t redux_addu(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -156,7 +160,7 @@ __device__ __forceinline__ void decimate_mma(const Tab3& tb, WS& ws, const uint3
 // its exact decoded error (FX^2 units) is returned.
 template <int K, typename WS>
 __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
-    uint32_t lane)
+    uint32_t lane, bool hdr)
 {
     const bool lum = slot_is_lum(s);
     const uint32_t T = c.tab.texels;
@@ -243,17 +247,49 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
                 val = (__shfl_sync(0xFFu, val, b4) + __shfl_sync(0xFFu, val, b4 + 1u) + __shfl_sync(0xFFu, val, b4 + 2u))*(1.0f/3.0f);
             }
             int q = 255;
-            if (ch < 3 || has_alpha) {
+            if (hdr) ws.epf[p*8u + lane] = val;
+            else if (ch < 3 || has_alpha) {
                 const int iv = min(max(__float2int_rn(val), 0), 255);
                 const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(iv));
                 q = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + rank));
             }
-            ws.ep[p*8u + lane] = q;
+            if (!hdr) ws.ep[p*8u + lane] = q;
         }
     }
     __syncwarp();
+    if (hdr) {
+        // end point mode 11: lane = (subset, sub-mode) packs the least-squares end points, snaps the six values to the
+        // colour level, decodes them again; the sub-mode whose decoded end points are closest wins (astc_hdr.cuh)
+        const uint32_t hp = lane/9u, hm = lane - hp*9u;
+        int vq[6], e0[3], e1[3];
+        float herr = 3.0e38f;
+        if (hp < pc) {
+            float t0[3], t1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                t0[k] = fminf(fmaxf(ws.epf[hp*8u + k]*16.0f, 0.0f), 4095.0f);
+                t1[k] = fminf(fmaxf(ws.epf[hp*8u + 4u + k]*16.0f, 0.0f), 4095.0f);
+            }
+            herr = hdr_rgb_try(c, cl, static_cast<int>(hm), t0, t1, vq, e0, e1);
+            ws.hkey[lane] = (__float_as_uint(herr) & ~15u) | hm;
+        }
+        __syncwarp();
+        if (hp < pc) {
+            uint32_t bestk = 0xFFFFFFFFu;
+#pragma unroll
+            for (uint32_t k = 0; k < 9; ++k) bestk = min(bestk, ws.hkey[hp*9u + k]);
+            if ((bestk & 15u) == hm) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { ws.ep[hp*8u + k] = e0[k]; ws.ep[hp*8u + 4u + k] = e1[k]; }
+                ws.ep[hp*8u + 3u] = 4080; ws.ep[hp*8u + 7u] = 4080;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ws.epv[hp*6u + k] = vq[k];
+            }
+        }
+        __syncwarp();
+    }
     // keep sum(e1.rgb) >= sum(e0.rgb) (otherwise the decoder would blue-contract): swap the end points
-    if (lane < pc && !lum) {
+    if (lane < pc && !lum && !hdr) {
         int* e = ws.ep + lane*8u;
         if (e[4] + e[5] + e[6] < e[0] + e[1] + e[2]) {
 #pragma unroll
@@ -262,6 +298,21 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     }
     __syncwarp();
     // exact decoded error (lane = texel)
+    if (hdr) {
+        // 12-bit end points against LNS texels (FX units are LNS/32 = half a 12-bit step); result in FX^2 units
+        uint32_t err12 = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (!live[k]) continue;
+            const int* e = ws.ep + part[k]*8u;
+            const int4 x = ws.v[lane + 32u*k];
+            const int w0 = w[k][0], w1 = w[k][1];
+            int d = ((e[0]*(64 - (dc == 0 ? w1 : w0)) + e[4]*(dc == 0 ? w1 : w0) + 32) >> 6) - 2*x.x; err12 += static_cast<uint32_t>(d*d) >> 2;
+            d = ((e[1]*(64 - (dc == 1 ? w1 : w0)) + e[5]*(dc == 1 ? w1 : w0) + 32) >> 6) - 2*x.y; err12 += static_cast<uint32_t>(d*d) >> 2;
+            d = ((e[2]*(64 - (dc == 2 ? w1 : w0)) + e[6]*(dc == 2 ? w1 : w0) + 32) >> 6) - 2*x.z; err12 += static_cast<uint32_t>(d*d) >> 2;
+        }
+        return static_cast<float>(redux_addu(err12));
+    }
     uint32_t err = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -285,6 +336,7 @@ __device__ __forceinline__ void keep_best3(WS& ws, uint32_t nw, uint32_t planes,
 {
     for (uint32_t j = lane; j < nw*planes; j += 32) { ws.best_su[j] = ws.su[j]; ws.best_sk[j] = ws.sk[j]; }
     if (lane < pc*8u) ws.best_ep[lane] = ws.ep[lane];
+    if (lane < pc*6u) ws.best_epv[lane] = ws.epv[lane];
     __syncwarp();
 }
 
@@ -590,6 +642,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     v = make_float4(fminf(fmaxf(f.x, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.y, 0.0f), 1.0f)*255.0f,
                         fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
                 }
+                if (tb.hdr) {
+                    // HDR: colour as 16-bit LNS scaled to the 8-bit-like range the search works in (LNS/256); alpha is
+                    // taken as opaque (end point mode 11 carries none)
+                    const float4 f = load_texel_f32(p, x, y);
+                    v = make_float4(lns_from_float(f.x)*(1.0f/256.0f), lns_from_float(f.y)*(1.0f/256.0f), lns_from_float(f.z)*(1.0f/256.0f), 255.0f);
+                }
                 if (!(p.color_mask & 1u)) v.x = 0.0f;
                 if (!(p.color_mask & 2u)) v.y = 0.0f;
                 if (!(p.color_mask & 4u)) v.z = 0.0f;
@@ -610,7 +668,14 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         const bool has_alpha = __any_sync(0xFFFFFFFFu, alpha);
         uint4* dst = reinterpret_cast<uint4*>(p.dst) + blk;
         if (constant) {
-            if (active && lane == 0) *dst = pack_void_extent(first);
+            if (active && lane == 0) {
+                if (tb.hdr) {
+                    const float4 f = load_texel_f32(p, min(bx*bw, p.width - 1), min(by*bh, p.height - 1));
+                    auto hb = [](float q) -> uint32_t { return __half_as_ushort(__float2half_rn(fminf(fmaxf(q, 0.0f), 65504.0f))); };
+                    *dst = pack_void_extent_hdr((p.color_mask & 1u) ? hb(f.x) : 0u, (p.color_mask & 2u) ? hb(f.y) : 0u,
+                        (p.color_mask & 4u) ? hb(f.z) : 0u, 0x3C00u);
+                } else *dst = pack_void_extent(first);
+            }
             active = false;
         }
         const uint32_t nch = has_alpha ? 4u : 3u;
@@ -655,7 +720,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         if (active && lane < kSlots3) {
             Slot3& sl = ws.slots[lane];
             sl.pc = 1; sl.seed = 0; sl.dual_ch = (lane >= 5 && lane < 9) ? static_cast<int32_t>(lane - 5) : -1;
-            sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u)) ? 1u : 0u;
+            sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u) && !tb.hdr) ? 1u : 0u;
             // (slots 10, 11 are validated in setup 8, after the two-subset partitionings are known)
         }
         // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
@@ -879,7 +944,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             // the same with the two best two-subset partitionings: a gray range per subset
             for (uint32_t k = 0; k < 2; ++k) {
                 Slot3& sl = ws.slots[10 + k];
-                const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u);
+                const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u) && !tb.hdr;
                 if (lane == 0) { sl.valid = ok ? 1u : 0u; sl.pc = 2; sl.seed = ws.slots[1 + k].seed; sl.dual_ch = -1; }
                 if (!ok) continue;
                 int mn0 = 1 << 30, mx0 = -(1 << 30), mn1 = 1 << 30, mx1 = -(1 << 30);
@@ -1108,6 +1173,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const uint32_t bs = code >> 16;
                 const Slot3& bslot = ws.slots[bs];
                 const int dc = bslot.dual_ch;
+                const float escale = tb.hdr ? 1.0f/16.0f : 1.0f;     // HDR end points are 12-bit, texels 8-bit-like
                 const uint8_t* parts = ws.part[slot_part(bs)];
                 for (uint32_t i = lane; i < T; i += 32) {
                     const int* e = ws.best_ep + (bslot.pc > 1 ? parts[i] : 0u)*8u;
@@ -1118,7 +1184,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         if (c4 == 3 && !has_alpha) continue;
-                        const float a0 = static_cast<float>(e[c4]), d = static_cast<float>(e[4 + c4]) - a0;
+                        const float a0 = static_cast<float>(e[c4])*escale, d = static_cast<float>(e[4 + c4])*escale - a0;
                         if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
                     }
                     ws.ta[0][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
@@ -1131,7 +1197,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
             decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
-            const float err = evaluate3<K>(ctx, ws, s, m, cl, has_alpha, lane);
+            const float err = evaluate3<K>(ctx, ws, s, m, cl, has_alpha, lane, tb.hdr != 0u);
             if (err < best_err) {
                 best_err = err; best_code = code; best_cl = cl;
                 keep_best3(ws, m.nw, ws.slots[s].dual_ch >= 0 ? 2u : 1u, ws.slots[s].pc, lane);
@@ -1153,7 +1219,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     (static_cast<uint32_t>(e[7]) << 24);
             }
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
-            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs));
+            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), tb.hdr ? ws.best_epv : nullptr);
         }
     }
 }
@@ -1189,8 +1255,8 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
 #endif
     // above 64 texels the working set and the register file only allow 8 warps per SM
     if constexpr (NT > 8) return launch_cfg<NT, KS, 8, 1, true>(p, tb, n_exact, refine, stream);
-    // 56- and 64-texel footprints: 10 warps per CTA so that two CTAs still fit an SM's shared memory
-    else if constexpr (NT >= 7) return launch_cfg<NT, KS, 10, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
+    // 56- and 64-texel footprints: 9 warps per CTA so that two CTAs still fit an SM's shared memory
+    else if constexpr (NT >= 7) return launch_cfg<NT, KS, 9, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
     else return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
 }
 
@@ -1211,6 +1277,7 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     Tab3 tb; tb.ctx = ctx; tb.t3 = t3;
     static const uint32_t dev_flags = getenv("CFX_ASTC3_FLAGS") ? static_cast<uint32_t>(atoi(getenv("CFX_ASTC3_FLAGS"))) : 0u;
     tb.flags = dev_flags;
+    tb.hdr = p.type == 4u ? 1u : 0u;                      // Texture::Type::UFloat
     const uint32_t NT = t3.NT, KS = t3.KS;
     if (NT == 2 && KS == 1) return launch_one<2, 1>(p, tb, n_exact, refine, stream);
     if (NT == 3 && KS == 2) return launch_one<3, 2>(p, tb, n_exact, refine, stream);

@@ -91,11 +91,11 @@ static Launcher find_launcher(uint32_t format, uint32_t type)
 #endif
         default:
 #ifdef CFX_HAVE_ASTC
-            // all 14 LDR footprints; the HDR profiles have no GPU encoder yet
+            // all 14 footprints: UNorm = LDR profile, UFloat = HDR profile (colour in end point mode 11, opaque alpha)
             if (format >= CFX_FORMAT_ASTC_4x4 && format <= CFX_FORMAT_ASTC_12x12) {
                 const uint32_t* d = kAstcDims[format - CFX_FORMAT_ASTC_4x4];
                 (void)d;
-                return type == CFX_TYPE_UNORM ? launch_astc : nullptr;
+                return (type == CFX_TYPE_UNORM || type == CFX_TYPE_UFLOAT) ? launch_astc : nullptr;
             }
 #endif
             return nullptr;

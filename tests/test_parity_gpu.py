@@ -551,3 +551,41 @@ def test_bc6h_signed_vs_spec_decoder(cfx, oracle):
     if ok.any():
         p_r = 10*np.log10(64.0**2/max(float(np.mean((d_r[ok] - negf[..., :3][ok])**2)), 1e-12))
         assert p_s >= p_r - PSNR_TOLERANCE_DB
+
+
+# ---- ASTC HDR (Texture::Type::UFloat -> astcenc's HDR profile, lib/src/AstcConverter.cpp:151-163): texels searched as
+# LNS, colour in end point mode 11, decoded by the reference's decoder ----
+@pytest.mark.parametrize("fmt", ["ASTC_4x4", "ASTC_6x6", "ASTC_8x8", "ASTC_10x10"])
+@pytest.mark.parametrize("kind", ["ramp", "ramp+noise"])
+def test_astc_hdr_psnr_vs_oracle(cfx, oracle, fmt, kind):
+    assert cfx.format_supported(fmt, "UFloat")
+    n = 120
+    img = oracle.gen_image("hdr", n, n)
+    if kind == "ramp+noise":
+        rng = np.random.default_rng(7)
+        img[..., :3] *= (1.0 + 0.5*rng.random((n, n, 3), dtype=np.float32))
+        img[n//3:n//2, :, :3] *= 4.0
+    img16 = img.astype(np.float16)
+    imgf = img16.astype(np.float32)
+    ref = oracle.encode(imgf, fmt, type="UFloat")
+    p_ref = oracle.psnr_rgb(imgf, oracle.decode(ref, fmt, n, n, type="UFloat"), 64.0)
+    for src in (img16, imgf):                      # RGBA16F and RGBA32F sources
+        got = cfx.encode(src, fmt, type="UFloat")
+        dec = oracle.decode(got, fmt, n, n, type="UFloat")
+        assert np.allclose(dec[..., 3], 1.0)
+        p_gpu = oracle.psnr_rgb(imgf, dec, 64.0)
+        assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s HDR %s: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, kind, p_gpu, p_ref)
+
+
+def test_astc_hdr_constant_and_ragged(cfx, oracle):
+    img = np.zeros((13, 9, 4), np.float32)
+    img[..., 0], img[..., 1], img[..., 2], img[..., 3] = 12.5, 0.25, 3.0, 1.0       # constant -> FP16 void-extent blocks
+    got = cfx.encode(img, "ASTC_6x6", type="UFloat")
+    dec = oracle.decode(got, "ASTC_6x6", 9, 13, type="UFloat")
+    assert np.allclose(dec[..., :3], img[..., :3], rtol=2e-3)
+    rag = oracle.gen_image("hdr", 37, 23)
+    got = cfx.encode(rag.astype(np.float16), "ASTC_8x5", type="UFloat")
+    assert got.size == cfx.encoded_size("ASTC_8x5", 37, 23)
+    ref = oracle.encode(rag.astype(np.float16).astype(np.float32), "ASTC_8x5", type="UFloat")
+    e = lambda b: float(np.mean((oracle.decode(b, "ASTC_8x5", 37, 23, type="UFloat")[..., :3] - rag[..., :3])**2))
+    assert e(got) <= e(ref)*1.25 + 1e-4
