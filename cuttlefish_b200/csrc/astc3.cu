@@ -39,6 +39,8 @@ constexpr int kDefaultCtasPerSm = 2;
 #define PHASE_SYNC() do { if (LOCK) __syncthreads(); else __syncwarp(); } while (0)
 constexpr int FX = 8;                          // texel fixed point scale
 constexpr int kMaxCand = 16;
+constexpr int kHdrAlphaShift = 3;              // HDR blocks keep alpha at 1/8 of the LDR scale (error weight 1/64): about the
+constexpr float kHdrAlphaScale = 1.0f/static_cast<float>(1 << kHdrAlphaShift);     // weight the reference's HDR-alpha metric gives it
 
 struct Slot3 {
     float4 e0[3], e1[3];       // line end points (0..255 per channel), sum(e1.rgb) >= sum(e0.rgb)
@@ -92,7 +94,7 @@ struct Warp3T {
     int ep[24];                             // quantised end points of the candidate: [subset][e0 rgba, e1 rgba]
     int best_ep[24];                        // (HDR: 12-bit values as end point mode 11 decodes them)
     float epf[24];                          // HDR: least-squares end points before mode-11 packing, 8-bit-like units
-    int epv[18], best_epv[18];              // HDR: the six packed mode-11 values of every subset
+    int epv[24], best_epv[24];              // HDR: per subset the six packed mode-11 values + two LDR alpha end points
     uint32_t hkey[28];                      // HDR: (error, sub-mode) keys of the 9 packing candidates per subset
     uint8_t su[2*TP];                       // candidate grid weights (unquantised values 0..64), bit-stream order
     uint8_t sk[2*TP];                       // ... and their rank in the quantisation level's value table
@@ -281,9 +283,16 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
             if ((bestk & 15u) == hm) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { ws.ep[hp*8u + k] = e0[k]; ws.ep[hp*8u + 4u + k] = e1[k]; }
-                ws.ep[hp*8u + 3u] = 4080; ws.ep[hp*8u + 7u] = 4080;
+                // alpha (end point mode 14: HDR RGB + LDR alpha) stays an 8-bit pair at the same colour level
+                int a0 = 255, a1 = 255;
+                if (has_alpha) {
+                    a0 = static_cast<int>(quant_color(c, cl, ws.epf[hp*8u + 3u]*(1.0f/kHdrAlphaScale)));
+                    a1 = static_cast<int>(quant_color(c, cl, ws.epf[hp*8u + 7u]*(1.0f/kHdrAlphaScale)));
+                }
+                ws.ep[hp*8u + 3u] = a0; ws.ep[hp*8u + 7u] = a1;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) ws.epv[hp*6u + k] = vq[k];
+                for (int k = 0; k < 6; ++k) ws.epv[hp*8u + k] = vq[k];
+                ws.epv[hp*8u + 6u] = a0; ws.epv[hp*8u + 7u] = a1;
             }
         }
         __syncwarp();
@@ -310,6 +319,11 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
             int d = ((e[0]*(64 - (dc == 0 ? w1 : w0)) + e[4]*(dc == 0 ? w1 : w0) + 32) >> 6) - 2*x.x; err12 += static_cast<uint32_t>(d*d) >> 2;
             d = ((e[1]*(64 - (dc == 1 ? w1 : w0)) + e[5]*(dc == 1 ? w1 : w0) + 32) >> 6) - 2*x.y; err12 += static_cast<uint32_t>(d*d) >> 2;
             d = ((e[2]*(64 - (dc == 2 ? w1 : w0)) + e[6]*(dc == 2 ? w1 : w0) + 32) >> 6) - 2*x.z; err12 += static_cast<uint32_t>(d*d) >> 2;
+            if (has_alpha) {
+                // alpha end points are real 8-bit values, the texel's alpha is scaled by kHdrAlphaScale
+                d = (((e[3]*(64 - (dc == 3 ? w1 : w0)) + e[7]*(dc == 3 ? w1 : w0))*FX + (32 << kHdrAlphaShift)) >> (6 + kHdrAlphaShift)) - x.w;
+                err12 += static_cast<uint32_t>(d*d);
+            }
         }
         return static_cast<float>(redux_addu(err12));
     }
@@ -336,7 +350,7 @@ __device__ __forceinline__ void keep_best3(WS& ws, uint32_t nw, uint32_t planes,
 {
     for (uint32_t j = lane; j < nw*planes; j += 32) { ws.best_su[j] = ws.su[j]; ws.best_sk[j] = ws.sk[j]; }
     if (lane < pc*8u) ws.best_ep[lane] = ws.ep[lane];
-    if (lane < pc*6u) ws.best_epv[lane] = ws.epv[lane];
+    if (lane < pc*8u) ws.best_epv[lane] = ws.epv[lane];
     __syncwarp();
 }
 
@@ -625,11 +639,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         const uint32_t by = blk / p.blocks_x, bx = blk - by*p.blocks_x;
         PHASE_SYNC();
         bool differs = false, alpha = false;
+        const float opaque = tb.hdr ? 255.0f*kHdrAlphaScale : 255.0f;
         float4 first = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < T; i0 += 32) {
             const uint32_t i = i0 + lane;
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 255.0f);
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, opaque);
             if (i < T) {
                 const uint32_t ty = i / bw, tx = i - ty*bw;
                 const uint32_t x = min(bx*bw + tx, p.width - 1), y = min(by*bh + ty, p.height - 1);
@@ -643,15 +658,17 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                         fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
                 }
                 if (tb.hdr) {
-                    // HDR: colour as 16-bit LNS scaled to the 8-bit-like range the search works in (LNS/256); alpha is
-                    // taken as opaque (end point mode 11 carries none)
+                    // HDR: colour as 16-bit LNS scaled to the 8-bit-like range the search works in (LNS/256); alpha stays
+                    // an LDR channel (end point mode 14 when the block is not opaque), scaled down so that its error
+                    // weighs about what the reference's HDR-alpha metric gives it
                     const float4 f = load_texel_f32(p, x, y);
-                    v = make_float4(lns_from_float(f.x)*(1.0f/256.0f), lns_from_float(f.y)*(1.0f/256.0f), lns_from_float(f.z)*(1.0f/256.0f), 255.0f);
+                    v = make_float4(lns_from_float(f.x)*(1.0f/256.0f), lns_from_float(f.y)*(1.0f/256.0f), lns_from_float(f.z)*(1.0f/256.0f),
+                        fminf(fmaxf(f.w, 0.0f), 1.0f)*(255.0f*kHdrAlphaScale));
                 }
                 if (!(p.color_mask & 1u)) v.x = 0.0f;
                 if (!(p.color_mask & 2u)) v.y = 0.0f;
                 if (!(p.color_mask & 4u)) v.z = 0.0f;
-                if (!(p.color_mask & 8u)) v.w = 0.0f; else if (alpha_off) v.w = 255.0f;
+                if (!(p.color_mask & 8u)) v.w = 0.0f; else if (alpha_off) v.w = opaque;
                 ws.v[i] = make_int4(__float2int_rn(v.x*FX), __float2int_rn(v.y*FX), __float2int_rn(v.z*FX), __float2int_rn(v.w*FX));
             }
             if (i0 == 0) {
@@ -660,7 +677,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             }
             if (i < T) {
                 differs |= v.x != first.x || v.y != first.y || v.z != first.z || v.w != first.w;
-                alpha |= v.w != 255.0f;
+                alpha |= v.w != opaque;
             }
         }
         __syncwarp();
@@ -673,7 +690,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     const float4 f = load_texel_f32(p, min(bx*bw, p.width - 1), min(by*bh, p.height - 1));
                     auto hb = [](float q) -> uint32_t { return __half_as_ushort(__float2half_rn(fminf(fmaxf(q, 0.0f), 65504.0f))); };
                     *dst = pack_void_extent_hdr((p.color_mask & 1u) ? hb(f.x) : 0u, (p.color_mask & 2u) ? hb(f.y) : 0u,
-                        (p.color_mask & 4u) ? hb(f.z) : 0u, 0x3C00u);
+                        (p.color_mask & 4u) ? hb(f.z) : 0u, !(p.color_mask & 8u) ? 0u : (alpha_off ? 0x3C00u : hb(fminf(f.w, 1.0f))));
                 } else *dst = pack_void_extent(first);
             }
             active = false;
@@ -1184,7 +1201,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         if (c4 == 3 && !has_alpha) continue;
-                        const float a0 = static_cast<float>(e[c4])*escale, d = static_cast<float>(e[4 + c4])*escale - a0;
+                        const float es = c4 < 3 ? escale : (tb.hdr ? kHdrAlphaScale : 1.0f);
+                        const float a0 = static_cast<float>(e[c4])*es, d = static_cast<float>(e[4 + c4])*es - a0;
                         if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
                     }
                     ws.ta[0][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);

@@ -589,3 +589,21 @@ def test_astc_hdr_constant_and_ragged(cfx, oracle):
     ref = oracle.encode(rag.astype(np.float16).astype(np.float32), "ASTC_8x5", type="UFloat")
     e = lambda b: float(np.mean((oracle.decode(b, "ASTC_8x5", 37, 23, type="UFloat")[..., :3] - rag[..., :3])**2))
     assert e(got) <= e(ref)*1.25 + 1e-4
+
+
+def test_astc_hdr_with_alpha(cfx, oracle):
+    """HDR colour + varying alpha: we pair end point mode 11 with an LDR alpha pair (mode 14); the reference (HDR
+    profile) stores alpha as HDR too.  Colour must hold the bar, alpha must be about as close."""
+    n = 96
+    img = oracle.gen_image("hdr", n, n)
+    yy, xx = np.mgrid[0:n, 0:n]
+    img[..., 3] = (((xx*3 + yy*5) % 256)/255.0).astype(np.float32)
+    img[:24, :24, 3] = 1.0
+    img16 = img.astype(np.float16)
+    imgf = img16.astype(np.float32)
+    for fmt in ("ASTC_4x4", "ASTC_6x6"):
+        ref = oracle.decode(oracle.encode(imgf, fmt, type="UFloat"), fmt, n, n, type="UFloat")
+        got = oracle.decode(cfx.encode(img16, fmt, type="UFloat"), fmt, n, n, type="UFloat")
+        assert oracle.psnr_rgb(imgf, got, 64.0) >= oracle.psnr_rgb(imgf, ref, 64.0) - PSNR_TOLERANCE_DB, fmt
+        a_gpu = float(np.mean((got[..., 3] - imgf[..., 3])**2)); a_ref = float(np.mean((ref[..., 3] - imgf[..., 3])**2))
+        assert a_gpu <= a_ref*1.25 + 1e-5, "%s alpha mse %.3g vs reference %.3g" % (fmt, a_gpu, a_ref)
