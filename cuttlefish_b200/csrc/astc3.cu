@@ -160,9 +160,9 @@ __device__ __forceinline__ void decimate_mma(const Tab3& tb, WS& ws, const uint3
 
 // Evaluate block mode m on slot s with the decimated weights in ws.g; on success ws.su / ws.ep hold the candidate and
 // its exact decoded error (FX^2 units) is returned.
-template <int K, typename WS>
+template <int K, bool hdr, typename WS>
 __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
-    uint32_t lane, bool hdr)
+    uint32_t lane)
 {
     const bool lum = slot_is_lum(s);
     const uint32_t T = c.tab.texels;
@@ -605,7 +605,7 @@ struct SlotView {           // what pack_block needs from a slot
 
 } // namespace
 
-template <int NT, int KS, int W, int CTAS, bool LOCK>
+template <int NT, int KS, int W, int CTAS, bool LOCK, bool HDR>
 __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p, const Tab3 tb, uint32_t n_exact, uint32_t refine)
 {
     constexpr int K = (NT*8 + 31)/32;            // texels per lane
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         const uint32_t by = blk / p.blocks_x, bx = blk - by*p.blocks_x;
         PHASE_SYNC();
         bool differs = false, alpha = false;
-        const float opaque = tb.hdr ? 255.0f*kHdrAlphaScale : 255.0f;
+        const float opaque = HDR ? 255.0f*kHdrAlphaScale : 255.0f;
         float4 first = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < T; i0 += 32) {
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     v = make_float4(fminf(fmaxf(f.x, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.y, 0.0f), 1.0f)*255.0f,
                         fminf(fmaxf(f.z, 0.0f), 1.0f)*255.0f, fminf(fmaxf(f.w, 0.0f), 1.0f)*255.0f);
                 }
-                if (tb.hdr) {
+                if (HDR) {
                     // HDR: colour as 16-bit LNS scaled to the 8-bit-like range the search works in (LNS/256); alpha stays
                     // an LDR channel (end point mode 14 when the block is not opaque), scaled down so that its error
                     // weighs about what the reference's HDR-alpha metric gives it
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         uint4* dst = reinterpret_cast<uint4*>(p.dst) + blk;
         if (constant) {
             if (active && lane == 0) {
-                if (tb.hdr) {
+                if (HDR) {
                     const float4 f = load_texel_f32(p, min(bx*bw, p.width - 1), min(by*bh, p.height - 1));
                     auto hb = [](float q) -> uint32_t { return __half_as_ushort(__float2half_rn(fminf(fmaxf(q, 0.0f), 65504.0f))); };
                     *dst = pack_void_extent_hdr((p.color_mask & 1u) ? hb(f.x) : 0u, (p.color_mask & 2u) ? hb(f.y) : 0u,
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         if (active && lane < kSlots3) {
             Slot3& sl = ws.slots[lane];
             sl.pc = 1; sl.seed = 0; sl.dual_ch = (lane >= 5 && lane < 9) ? static_cast<int32_t>(lane - 5) : -1;
-            sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u) && !tb.hdr) ? 1u : 0u;
+            sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u) && !HDR) ? 1u : 0u;
             // (slots 10, 11 are validated in setup 8, after the two-subset partitionings are known)
         }
         // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             // the same with the two best two-subset partitionings: a gray range per subset
             for (uint32_t k = 0; k < 2; ++k) {
                 Slot3& sl = ws.slots[10 + k];
-                const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u) && !tb.hdr;
+                const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u) && !HDR;
                 if (lane == 0) { sl.valid = ok ? 1u : 0u; sl.pc = 2; sl.seed = ws.slots[1 + k].seed; sl.dual_ch = -1; }
                 if (!ok) continue;
                 int mn0 = 1 << 30, mx0 = -(1 << 30), mn1 = 1 << 30, mx1 = -(1 << 30);
@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const uint32_t bs = code >> 16;
                 const Slot3& bslot = ws.slots[bs];
                 const int dc = bslot.dual_ch;
-                const float escale = tb.hdr ? 1.0f/16.0f : 1.0f;     // HDR end points are 12-bit, texels 8-bit-like
+                const float escale = HDR ? 1.0f/16.0f : 1.0f;     // HDR end points are 12-bit, texels 8-bit-like
                 const uint8_t* parts = ws.part[slot_part(bs)];
                 for (uint32_t i = lane; i < T; i += 32) {
                     const int* e = ws.best_ep + (bslot.pc > 1 ? parts[i] : 0u)*8u;
@@ -1201,7 +1201,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         if (c4 == 3 && !has_alpha) continue;
-                        const float es = c4 < 3 ? escale : (tb.hdr ? kHdrAlphaScale : 1.0f);
+                        const float es = c4 < 3 ? escale : (HDR ? kHdrAlphaScale : 1.0f);
                         const float a0 = static_cast<float>(e[c4])*es, d = static_cast<float>(e[4 + c4])*es - a0;
                         if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
                     }
@@ -1215,7 +1215,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
             decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
-            const float err = evaluate3<K>(ctx, ws, s, m, cl, has_alpha, lane, tb.hdr != 0u);
+            const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane);
             if (err < best_err) {
                 best_err = err; best_code = code; best_cl = cl;
                 keep_best3(ws, m.nw, ws.slots[s].dual_ch >= 0 ? 2u : 1u, ws.slots[s].pc, lane);
@@ -1237,7 +1237,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     (static_cast<uint32_t>(e[7]) << 24);
             }
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
-            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), tb.hdr ? ws.best_epv : nullptr);
+            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr);
         }
     }
 }
@@ -1247,7 +1247,9 @@ namespace {
 template <int NT, int KS, int W, int CTAS, bool LOCK>
 int launch_cfg(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t refine, cudaStream_t stream)
 {
-    const void* k = reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK>);
+    // the HDR variant is its own instantiation, so that the LDR kernel carries none of its code
+    const void* k = tb.hdr ? reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK, true>)
+                           : reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK, false>);
     const size_t smem = W*((sizeof(Warp3T<NT>) + 15)/16*16);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -4;
     const uint32_t ctas_needed = (p.total_blocks + W - 1)/W;
