@@ -287,14 +287,16 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality, bool sg = 
             if (sc < bs0) { bs1 = bs0; sh1 = sh0; bs0 = sc; sh0 = s; }
             else if (sc < bs1) { bs1 = sc; sh1 = s; }
         }
-        const int two_w[3] = {6, 7, 10}, two_t[3] = {6, 6, 5};
+        // two-region precisions tried: mode 10 (6.6.6.6 direct), 2 (7.6.6.6), 1 (10.5.5.5), 6 (9.5.5.5): the last one
+        // catches the noisy blocks whose deltas overflow 5 bits at 10-bit precision
+        const int two_w[4] = {6, 7, 10, 9}, two_t[4] = {6, 6, 5, 5};
         const uint32_t nshapes = quality >= 2 ? 2u : 1u;
 #pragma unroll 1
         for (uint32_t si = 0; si < nshapes; ++si) {
             const uint32_t shape = si ? sh1 : sh0;
             const uint32_t m1 = kBc7Part2[shape], m0 = ~m1 & 0xFFFFu;
 #pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 SubsetFit f0, f1;
                 fit_subset(xs, lane, m0, two_w[k], 3, f0, sg);
                 fit_subset(xs, lane, m1, two_w[k], 3, f1, sg);
@@ -348,12 +350,12 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality, bool sg = 
             for (int c = 0; c < 3; ++c) { const int tmp = bf1.q0[c]; bf1.q0[c] = bf1.q1[c]; bf1.q1[c] = tmp; }
             bf1.idx = 0x7777777777777777ull - bf1.idx;
         }
-        const int tb = k == 0 ? 6 : (k == 1 ? 6 : 5);
+        const int tb = k <= 1 ? 6 : 5;
         const uint32_t tm = (1u << tb) - 1u;
         uint32_t w[3], x[3], y[3], z[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            w[c] = static_cast<uint32_t>(bf0.q0[c]) & ((1u << (k == 0 ? 6 : (k == 1 ? 7 : 10))) - 1u);
+            w[c] = static_cast<uint32_t>(bf0.q0[c]) & ((1u << (k == 0 ? 6 : (k == 1 ? 7 : (k == 2 ? 10 : 9)))) - 1u);
             if (k == 0) { x[c] = static_cast<uint32_t>(bf0.q1[c]) & 63u; y[c] = static_cast<uint32_t>(bf1.q0[c]) & 63u; z[c] = static_cast<uint32_t>(bf1.q1[c]) & 63u; }
             else {
                 x[c] = static_cast<uint32_t>(bf0.q1[c] - bf0.q0[c]) & tm;
@@ -382,6 +384,16 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality, bool sg = 
             b.put(61, y[2] & 15u, 4); b.put(14, bit(y[2], 4), 1); b.put(22, bit(y[2], 5), 1);
             b.put(12, bit(z[2], 0), 1); b.put(13, bit(z[2], 1), 1); b.put(23, bit(z[2], 2), 1);
             b.put(32, bit(z[2], 3), 1); b.put(34, bit(z[2], 4), 1); b.put(33, bit(z[2], 5), 1);
+        } else if (k == 3) {    // mode 6: 9.5.5.5
+            b.put(0, 0x0E, 5);
+            b.put(5, w[0], 9); b.put(15, w[1], 9); b.put(25, w[2], 9);
+            b.put(35, x[0], 5); b.put(45, x[1], 5); b.put(55, x[2], 5);
+            b.put(65, y[0], 5); b.put(71, z[0], 5);
+            b.put(41, y[1] & 15u, 4); b.put(24, bit(y[1], 4), 1);
+            b.put(51, z[1] & 15u, 4); b.put(40, bit(z[1], 4), 1);
+            b.put(61, y[2] & 15u, 4); b.put(14, bit(y[2], 4), 1);
+            b.put(50, bit(z[2], 0), 1); b.put(60, bit(z[2], 1), 1); b.put(70, bit(z[2], 2), 1);
+            b.put(76, bit(z[2], 3), 1); b.put(34, bit(z[2], 4), 1);
         } else {                // mode 1: 10.5.5.5
             b.put(0, 0x00, 2);
             b.put(5, w[0], 10); b.put(15, w[1], 10); b.put(25, w[2], 10);

@@ -607,3 +607,20 @@ def test_astc_hdr_with_alpha(cfx, oracle):
         assert oracle.psnr_rgb(imgf, got, 64.0) >= oracle.psnr_rgb(imgf, ref, 64.0) - PSNR_TOLERANCE_DB, fmt
         a_gpu = float(np.mean((got[..., 3] - imgf[..., 3])**2)); a_ref = float(np.mean((ref[..., 3] - imgf[..., 3])**2))
         assert a_gpu <= a_ref*1.25 + 1e-5, "%s alpha mse %.3g vs reference %.3g" % (fmt, a_gpu, a_ref)
+
+
+def test_bc6h_noisy_hdr_psnr_vs_oracle(cfx, oracle):
+    """Noisy HDR content (the ramp times per-channel noise, one band four times brighter): this is where the
+    10.5.5.5 deltas overflow and the 9.5.5.5 mode earns its place."""
+    n = 128
+    rng = np.random.default_rng(7)
+    img = oracle.gen_image("hdr", n, n)
+    img[..., :3] *= (1.0 + 0.5*rng.random((n, n, 3), dtype=np.float32))
+    img[n//3:n//2, :, :3] *= 4.0
+    img16 = img.astype(np.float16)
+    imgf = img16.astype(np.float32)
+    ref = oracle.encode(imgf, "BC6H", type="UFloat")
+    got = cfx.encode(img16, "BC6H", type="UFloat")
+    p_ref = oracle.psnr_rgb(imgf, oracle.decode(ref, "BC6H", n, n, type="UFloat"), 64.0)
+    p_gpu = oracle.psnr_rgb(imgf, oracle.decode(got, "BC6H", n, n, type="UFloat"), 64.0)
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "BC6H noisy HDR: gpu %.3f dB < reference %.3f dB - 0.1" % (p_gpu, p_ref)

@@ -190,13 +190,18 @@ def decode_bc6h_block(block, signed):
             for c in range(3):
                 out[t, c] = _bc6_finish((e0[c] * (64 - wgt) + e1[c] * wgt + 32) >> 6, signed)
         return out
-    if m2 == 0 or m2 == 1 or m5 == 0x1E:                        # two regions: modes 1 (10.5.5.5), 2 (7.6.6.6), 10 (6.6.6.6)
+    if m2 == 0 or m2 == 1 or m5 in (0x1E, 0x0E):                # two regions: modes 1 (10.5.5.5), 2 (7.6.6.6), 6 (9.5.5.5), 10 (6.6.6.6)
         if m5 == 0x1E:
             wb, tb, direct = 6, 6, True
             w = [bits(5, 6), bits(15, 6), bits(25, 6)]; x = [bits(35, 6), bits(45, 6), bits(55, 6)]
             y = [bits(65, 6), bits(41, 4) | bit(24) << 4 | bit(21) << 5, bits(61, 4) | bit(14) << 4 | bit(22) << 5]
             z = [bits(71, 6), bits(51, 4) | bit(11) << 4 | bit(31) << 5,
                  bit(12) | bit(13) << 1 | bit(23) << 2 | bit(32) << 3 | bit(34) << 4 | bit(33) << 5]
+        elif m5 == 0x0E:
+            wb, tb, direct = 9, 5, False
+            w = [bits(5, 9), bits(15, 9), bits(25, 9)]; x = [bits(35, 5), bits(45, 5), bits(55, 5)]
+            y = [bits(65, 5), bits(41, 4) | bit(24) << 4, bits(61, 4) | bit(14) << 4]
+            z = [bits(71, 5), bits(51, 4) | bit(40) << 4, bit(50) | bit(60) << 1 | bit(70) << 2 | bit(76) << 3 | bit(34) << 4]
         elif m2 == 1:
             wb, tb, direct = 7, 6, False
             w = [bits(5, 7), bits(15, 7), bits(25, 7)]; x = [bits(35, 6), bits(45, 6), bits(55, 6)]
