@@ -299,7 +299,40 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
 
 // ---- ETC2 T and H modes --------------------------------------------------------------------------
 // Two 444 colours from a 2-means split of the block along its principal axis.
-CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out)
+// Error and selectors of one T / H configuration: kind 0: T with A single, B +-d; kind 1: T with B single, A +-d;
+// kind 2: H.  qA, qB: the two RGB444 colours; di: distance index.  Stops early once `limit` is exceeded.
+CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const int* qA, const int* qB, float limit, uint32_t& sel_out)
+{
+    const int d = kDist[di];
+    int pal[4][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int eA = expand4(qA[c]), eB = expand4(qB[c]);
+        const int s = kind == 1 ? eB : eA, o = kind == 1 ? eA : eB;
+        if (kind < 2) { pal[0][c] = s; pal[1][c] = clamp255(o + d); pal[2][c] = o; pal[3][c] = clamp255(o - d); }
+        else { pal[0][c] = clamp255(eA + d); pal[1][c] = clamp255(eA - d); pal[2][c] = clamp255(eB + d); pal[3][c] = clamp255(eB - d); }
+    }
+    float err = 0.0f;
+    uint32_t sel = 0;
+    for (uint32_t t = 0; t < 16 && err < limit; ++t) {
+        float be = 3.0e38f;
+        uint32_t bk = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            const float d0 = static_cast<float>(pal[k][0]) - px(xs, lane, t, 0), d1 = static_cast<float>(pal[k][1]) - px(xs, lane, t, 1),
+                d2 = static_cast<float>(pal[k][2]) - px(xs, lane, t, 2);
+            const float e = d0*d0 + d1*d1 + d2*d2;
+            if (e < be) { be = e; bk = k; }
+        }
+        err += be; sel |= bk << (2*t);
+    }
+    sel_out = sel;
+    return err;
+}
+
+// rounds > 0 (Quality::High and up): +-1 descent on the six RGB444 components of the winner, distance index +-1
+// (etc2comp widens its T / H search the same way in its later iterations, EtcBlock4x4Encoding_RGB8.cpp:370-...).
+CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
     float m[3] = {0, 0, 0};
@@ -346,43 +379,45 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out)
             if (dB < dA) side |= 1u << t;
         }
     }
-    int qA[3], qB[3], eA[3], eB[3];
+    int qA[3], qB[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         qA[c] = min(max(__float2int_rn(cA[c]*(15.0f/255.0f)), 0), 15); qB[c] = min(max(__float2int_rn(cB[c]*(15.0f/255.0f)), 0), 15);
-        eA[c] = expand4(qA[c]); eB[c] = expand4(qB[c]);
     }
-    // kind 0: T with A single, B +-d; kind 1: T with B single, A +-d; kind 2: H
     float best = 3.0e38f;
     uint32_t best_kind = 0, best_d = 0, best_sel = 0;
 #pragma unroll 1
     for (uint32_t kind = 0; kind < 3; ++kind) {
 #pragma unroll 1
         for (uint32_t di = 0; di < 8; ++di) {
-            const int d = kDist[di];
-            int pal[4][3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int s = kind == 1 ? eB[c] : eA[c], o = kind == 1 ? eA[c] : eB[c];
-                if (kind < 2) { pal[0][c] = s; pal[1][c] = clamp255(o + d); pal[2][c] = o; pal[3][c] = clamp255(o - d); }
-                else { pal[0][c] = clamp255(eA[c] + d); pal[1][c] = clamp255(eA[c] - d); pal[2][c] = clamp255(eB[c] + d); pal[3][c] = clamp255(eB[c] - d); }
-            }
-            float err = 0.0f;
-            uint32_t sel = 0;
-            for (uint32_t t = 0; t < 16 && err < best; ++t) {
-                float be = 3.0e38f;
-                uint32_t bk = 0;
-#pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) {
-                    const float d0 = static_cast<float>(pal[k][0]) - px(xs, lane, t, 0), d1 = static_cast<float>(pal[k][1]) - px(xs, lane, t, 1),
-                        d2 = static_cast<float>(pal[k][2]) - px(xs, lane, t, 2);
-                    const float e = d0*d0 + d1*d1 + d2*d2;
-                    if (e < be) { be = e; bk = k; }
-                }
-                err += be; sel |= bk << (2*t);
-            }
+            uint32_t sel;
+            const float err = th_eval(xs, lane, kind, di, qA, qB, best, sel);
             if (err < best) { best = err; best_kind = kind; best_d = di; best_sel = sel; }
         }
+    }
+    for (int round = 0; round < rounds && best > 0.0f && best < 3.0e38f; ++round) {
+        bool improved = false;
+#pragma unroll 1
+        for (int k = 0; k < 12; ++k) {
+            int tA[3] = {qA[0], qA[1], qA[2]}, tB[3] = {qB[0], qB[1], qB[2]};
+            int* tgt = k < 6 ? tA : tB;
+            const int c = (k % 6) >> 1, d = (k & 1) ? 1 : -1;
+            if (tgt[c] + d < 0 || tgt[c] + d > 15) continue;
+            tgt[c] += d;
+#pragma unroll 1
+            for (int dd = -1; dd <= 1; ++dd) {
+                const int di = static_cast<int>(best_d) + dd;
+                if (di < 0 || di > 7) continue;
+                uint32_t sel;
+                const float err = th_eval(xs, lane, best_kind, static_cast<uint32_t>(di), tA, tB, best, sel);
+                if (err < best) {
+                    best = err; best_d = static_cast<uint32_t>(di); best_sel = sel; improved = true;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { qA[q] = tA[q]; qB[q] = tB[q]; }
+                }
+            }
+        }
+        if (!improved) break;
     }
     if (best >= 3.0e38f) return;
     out.err = best;
@@ -511,7 +546,7 @@ CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds)
         encode_planar(xs, lane, rounds, r);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r);
+            encode_th(xs, lane, r, rounds >= 2 ? rounds : 0);
             if (r.err < best.err) best = r;
         }
     }
@@ -593,7 +628,7 @@ CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds)
         encode_planar(xs, lane, rounds, r);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r);
+            encode_th(xs, lane, r, rounds >= 2 ? rounds : 0);
             if (r.err < best.err) best = r;
         }
     }
