@@ -996,7 +996,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         uint32_t a[KS][4];
         load_a<KS>(ws, a, lane);
         if (active) {
-            float lw[NT][2];
+            float lw[NT][2], lw2[NT][2];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -1005,12 +1005,13 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     float wgt = i < T ? 1.0f : 0.0f;
                     if (gq >= 1 && gq <= 4 && i < T) wgt = ws.slots[gq].len2[ws.part[gq - 1][i]];
                     lw[nt][e] = wgt;
+                    // upper fragment half: rows 14, 15 are the two-subset luminance slots 10, 11 (partitionings 0, 1)
+                    float wgt2 = i < T ? 1.0f : 0.0f;
+                    if (gq >= 6 && i < T) wgt2 = ws.slots[gq + 4].len2[ws.part[gq - 6][i]];
+                    lw2[nt][e] = wgt2;
                 }
             const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
-            // rows 14, 15 (two-subset luminance slots) are weighted with the mean of their two line lengths: good enough
-            // for the ranking, and it keeps the per-texel weights to the lower fragment half
-            const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] :
-                0.5f*(ws.slots[gq + 4].len2[0] + ws.slots[gq + 4].len2[1])));
+            const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 1.0f));
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
                 if (__ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx) + g) == 0u)
@@ -1035,7 +1036,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], bcur[ks]);
                     acc0 += lw[nt][0]*c[0]*c[0] + lw[nt][1]*c[1]*c[1];
-                    acc1 += c[2]*c[2] + c[3]*c[3];
+                    acc1 += lw2[nt][0]*c[2]*c[2] + lw2[nt][1]*c[3]*c[3];
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) bcur[ks] = bnext[ks];
                 }
