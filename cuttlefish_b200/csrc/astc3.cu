@@ -50,14 +50,16 @@ struct Slot3 {
     uint32_t pc, seed, valid;
     int32_t dual_ch;
 };
-// Slots 0..8 as in astc_core.cuh (RGB(A) end points); 9: one subset with LUMINANCE end points (CEM 0); 10, 11: the two
-// two-subset partitionings of slots 1, 2 with luminance end points.  Luminance slots: opaque blocks only.
-constexpr int kSlots3 = kSlots + 3;
+// Slots 0..8 as in astc_core.cuh (RGB(A) end points); 9: one subset with LUMINANCE end points (CEM 0); 10, 11 / 12, 13:
+// the two-subset / three-subset partitionings of slots 1, 2 / 3, 4 with luminance end points.  Luminance slots are
+// for opaque blocks only, which is why 12, 13 can live in the A operand rows of the alpha dual-plane slot (8, 12).
+constexpr int kSlots3 = kSlots + 5;
 constexpr int kLumSlot = 9, kLumRow = 13;
 __device__ __forceinline__ bool slot_is_lum(uint32_t s) { return s >= static_cast<uint32_t>(kLumSlot); }
-__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : 5u); }   // est list / colour level class
-__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : s + 4u; }                           // A operand row of its first plane
+__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : (s < 12u ? 5u : 6u)); }   // est list / colour level class
+__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : (s < 12u ? s + 4u : (s == 12u ? 8u : 12u)); }        // A operand row of its first plane
 __device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 10u ? s - 10u : (s - 1u) & 3u; }          // index into Warp3T::part
+constexpr float kMismatchWeight = 0.05f; // partition ranking: cost of one texel off the clustering, in mean squared spreads
 constexpr int kDataLevels = 6;          // weight levels 2,3,4,5,6,8: their quantisation loss is MEASURED on the slot's ideal
                                         // weights (text and edges are bimodal: the uniform model is far off there)
 
@@ -83,7 +85,7 @@ struct Warp3T {
     struct Est {
         float qn[kSlots3][kDataLevels];     // measured quantisation loss of the slot's ideal weights at the coarse levels
         float D[16][GP];                    // decimation loss per slot plane and grid
-        float Sm[6][GP];                    // sum_i len2_i kappa_gi for the multi-subset slots 1..4 and 10, 11
+        float Sm[8][GP];                    // sum_i len2_i kappa_gi for the multi-subset slots 1..4 and 10..13
     };
     struct Setup {
         LineFit lines[15];                  // slot 0, dual-plane slots 5..8, then the 10 subsets of slots 1..4
@@ -105,7 +107,7 @@ struct Warp3T {
 // model constants (fitted on the host with tools/emu_astc3.py)
 constexpr float kLine = 1.1f, kDec = 1.0f, kQuant = 0.9f, kColor = 0.5f;
 
-struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; };   // hdr: Texture::Type::UFloat (texels searched as LNS, end point mode 11)   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
+struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; float mis_w; };   // hdr: Texture::Type::UFloat (texels searched as LNS, end point mode 11)   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
 
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t redux_addu(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -774,6 +776,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             }
         }
         PHASE_SYNC();
+        // A texel the seed assigns differently from the clustering costs a fraction of the block's mean squared spread:
+        // on gray (one-dimensional) content every partitioning has a zero line-fit residual and only this term tells
+        // the seed that follows the clusters from an arbitrary one.
+        const float mis_unit = tb.mis_w*static_cast<float>(tot[5] + tot[9] + tot[12] + tot[14])/static_cast<float>(T);
         // ---- setup 4: exact line-fit residual of every lane's two-subset seed; the two best become slots 1, 2.
         //      (Moments stay in registers; only the residual survives: the winners' moments are re-derived in setup 6.)
         if (active) {
@@ -785,7 +791,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     const float r1 = CFX_RESID15(a1);
 #pragma unroll
                     for (int k = 0; k < 15; ++k) a1[k] = tot[k] - a1[k];
-                    sc = r1 + CFX_RESID15(a1);
+                    sc = r1 + CFX_RESID15(a1) + mis_unit*static_cast<float>(b2 >> 10);
                 }
             }
             for (uint32_t rank = 0; rank < 2; ++rank) {
@@ -812,7 +818,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const float r2 = a2[0] >= 1 ? CFX_RESID15(a2) : 3.0e38f;
 #pragma unroll
                 for (int k = 0; k < 15; ++k) a1[k] = tot[k] - a1[k] - a2[k];
-                if (a1[0] >= 1 && r1 < 3.0e38f && r2 < 3.0e38f) sc = r1 + r2 + CFX_RESID15(a1);
+                if (a1[0] >= 1 && r1 < 3.0e38f && r2 < 3.0e38f) sc = r1 + r2 + CFX_RESID15(a1) + mis_unit*static_cast<float>(b3 >> 10);
             }
             for (uint32_t rank = 0; rank < 2; ++rank) {
                 const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(sc) & ~31u) | lane);
@@ -958,36 +964,46 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 sl.len2[0] = 3.0f*(l1 - l0)*(l1 - l0); sl.len2b = 0.0f;
                 sl.e_line = chroma*ifx*ifx;
             }
-            // the same with the two best two-subset partitionings: a gray range per subset
-            for (uint32_t k = 0; k < 2; ++k) {
+            // the same with the two-subset (k = 0, 1) and three-subset (k = 2, 3) partitionings: a gray range per subset
+            for (uint32_t k = 0; k < 4; ++k) {
                 Slot3& sl = ws.slots[10 + k];
+                const uint32_t npc = k < 2 ? 2u : 3u;
                 const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u) && !HDR;
-                if (lane == 0) { sl.valid = ok ? 1u : 0u; sl.pc = 2; sl.seed = ws.slots[1 + k].seed; sl.dual_ch = -1; }
+                if (lane == 0) { sl.valid = ok ? 1u : 0u; sl.pc = npc; sl.seed = ws.slots[1 + k].seed; sl.dual_ch = -1; }
                 if (!ok) continue;
-                int mn0 = 1 << 30, mx0 = -(1 << 30), mn1 = 1 << 30, mx1 = -(1 << 30);
+                int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
                 for (uint32_t i = lane; i < T; i += 32) {
                     const int4 x = ws.v[i];
                     const int l3 = x.x + x.y + x.z;
-                    if (ws.part[k][i]) { mn1 = min(mn1, l3); mx1 = max(mx1, l3); } else { mn0 = min(mn0, l3); mx0 = max(mx0, l3); }
+                    const uint32_t q = ws.part[k][i];
+#pragma unroll
+                    for (int qq = 0; qq < 3; ++qq) if (q == static_cast<uint32_t>(qq)) { mn[qq] = min(mn[qq], l3); mx[qq] = max(mx[qq], l3); }
                 }
-                mn0 = __reduce_min_sync(0xFFFFFFFFu, mn0); mx0 = __reduce_max_sync(0xFFFFFFFFu, mx0);
-                mn1 = __reduce_min_sync(0xFFFFFFFFu, mn1); mx1 = __reduce_max_sync(0xFFFFFFFFu, mx1);
-                const float ir0 = mx0 > mn0 ? 1.0f/static_cast<float>(mx0 - mn0) : 0.0f, ir1 = mx1 > mn1 ? 1.0f/static_cast<float>(mx1 - mn1) : 0.0f;
+                float ir[3];
+#pragma unroll
+                for (int qq = 0; qq < 3; ++qq) {
+                    mn[qq] = __reduce_min_sync(0xFFFFFFFFu, mn[qq]); mx[qq] = __reduce_max_sync(0xFFFFFFFFu, mx[qq]);
+                    if (mx[qq] < mn[qq]) { mn[qq] = 0; mx[qq] = 0; }           // empty subset
+                    ir[qq] = mx[qq] > mn[qq] ? 1.0f/static_cast<float>(mx[qq] - mn[qq]) : 0.0f;
+                }
+                const uint32_t row = slot_row(10 + k);
                 for (uint32_t i = lane; i < T; i += 32) {
                     const int4 x = ws.v[i];
                     const int l3 = x.x + x.y + x.z;
-                    ws.ta[14 + k][i] = __float2half_rn(ws.part[k][i] ? static_cast<float>(l3 - mn1)*ir1 : static_cast<float>(l3 - mn0)*ir0);
+                    const uint32_t q = ws.part[k][i];
+                    const int lo = q == 0 ? mn[0] : (q == 1 ? mn[1] : mn[2]);
+                    const float r = q == 0 ? ir[0] : (q == 1 ? ir[1] : ir[2]);
+                    ws.ta[row][i] = __float2half_rn(static_cast<float>(l3 - lo)*r);
                 }
-                if (lane == 0) {
-                    const float a0 = static_cast<float>(mn0)*(ifx/3.0f), b0 = static_cast<float>(max(mx0, mn0))*(ifx/3.0f);
-                    const float a1 = static_cast<float>(mn1)*(ifx/3.0f), b1 = static_cast<float>(max(mx1, mn1))*(ifx/3.0f);
-                    sl.e0[0] = make_float4(a0, a0, a0, 255.0f); sl.e1[0] = make_float4(b0, b0, b0, 255.0f);
-                    sl.e0[1] = make_float4(a1, a1, a1, 255.0f); sl.e1[1] = make_float4(b1, b1, b1, 255.0f);
-                    sl.len2[0] = 3.0f*(b0 - a0)*(b0 - a0); sl.len2[1] = 3.0f*(b1 - a1)*(b1 - a1); sl.len2b = 0.0f;
-                    sl.e_line = chroma*ifx*ifx;
+                if (lane < npc) {
+                    const float a0 = static_cast<float>(lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]))*(ifx/3.0f);
+                    const float b0 = static_cast<float>(lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]))*(ifx/3.0f);
+                    sl.e0[lane] = make_float4(a0, a0, a0, 255.0f); sl.e1[lane] = make_float4(b0, b0, b0, 255.0f);
+                    sl.len2[lane] = 3.0f*(b0 - a0)*(b0 - a0);
                 }
+                if (lane == 0) { sl.len2b = 0.0f; sl.e_line = chroma*ifx*ifx; }
             }
-        } else if (active && lane < 2) {
+        } else if (active && lane < 4) {
             ws.slots[10 + lane].valid = 0;
         }
         PHASE_SYNC();
@@ -1008,10 +1024,15 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     // upper fragment half: rows 14, 15 are the two-subset luminance slots 10, 11 (partitionings 0, 1)
                     float wgt2 = i < T ? 1.0f : 0.0f;
                     if (gq >= 6 && i < T) wgt2 = ws.slots[gq + 4].len2[ws.part[gq - 6][i]];
+                    // rows 8 / 12 belong to the three-subset luminance slots 12 / 13 when the block is opaque
+                    if (gq == 0 && i < T && ws.slots[12].valid) wgt2 = ws.slots[12].len2[ws.part[2][i]];
+                    if (gq == 4 && i < T && ws.slots[13].valid) wgt2 = ws.slots[13].len2[ws.part[3][i]];
                     lw2[nt][e] = wgt2;
                 }
             const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
-            const float scale1 = gq == 0 ? ws.slots[8].len2[0] : (gq <= 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 1.0f));
+            const float scale1 = gq == 0 ? (ws.slots[12].valid ? 1.0f : ws.slots[8].len2[0]) :
+                (gq == 4 ? (ws.slots[13].valid ? 1.0f : ws.slots[8].len2b) :
+                (gq < 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 1.0f)));
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
                 if (__ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx) + g) == 0u)
@@ -1051,16 +1072,17 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         // ---- phase 1b: S of the multi-subset slots (lane = grid)
         for (uint32_t g = lane; active && g < G; g += 32) {
             const float* kap = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_kappa) + g*kMaxTexels3;
-            float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, s4 = 0.0f, s5 = 0.0f, s6 = 0.0f;
+            float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, s4 = 0.0f, s5 = 0.0f, s6 = 0.0f, s7 = 0.0f, s8 = 0.0f;
             for (uint32_t i = 0; i < T; ++i) {
                 const float k = __ldg(kap + i);
-                const uint32_t p0 = ws.part[0][i], p1 = ws.part[1][i];
+                const uint32_t p0 = ws.part[0][i], p1 = ws.part[1][i], p2 = ws.part[2][i], p3 = ws.part[3][i];
                 s1 += k*ws.slots[1].len2[p0]; s2 += k*ws.slots[2].len2[p1];
-                s3 += k*ws.slots[3].len2[ws.part[2][i]]; s4 += k*ws.slots[4].len2[ws.part[3][i]];
+                s3 += k*ws.slots[3].len2[p2]; s4 += k*ws.slots[4].len2[p3];
                 s5 += k*ws.slots[10].len2[p0]; s6 += k*ws.slots[11].len2[p1];
+                s7 += k*ws.slots[12].len2[p2]; s8 += k*ws.slots[13].len2[p3];
             }
             ws.u.est.Sm[0][g] = s1; ws.u.est.Sm[1][g] = s2; ws.u.est.Sm[2][g] = s3; ws.u.est.Sm[3][g] = s4;
-            ws.u.est.Sm[4][g] = s5; ws.u.est.Sm[5][g] = s6;
+            ws.u.est.Sm[4][g] = s5; ws.u.est.Sm[5][g] = s6; ws.u.est.Sm[6][g] = s7; ws.u.est.Sm[7][g] = s8;
         }
         // ---- phase 1b': measured weight-quantisation loss of every slot at the coarse levels (lane = texel):
         //      qn[s][L] = sum_i len2_i (t_i - Q_L(t_i))^2 / sum_i len2_i, with the end point refit gain folded in
@@ -1127,7 +1149,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     float dsum = ws.u.est.D[drow][g], ssum;
                     if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
                     else if (type == 0 || type == 4) ssum = l2sum*__ldg(ksum + g);
-                    else ssum = ws.u.est.Sm[type == 5 ? s - 6 : s - 1][g];
+                    else ssum = ws.u.est.Sm[type >= 5 ? s - 6 : s - 1][g];
                     gb[g] = base + kDec*dsum; gs[g] = kQuant*ssum;
                 }
                 __syncwarp();
@@ -1179,7 +1201,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 if (done) refining = true;
                 else {
                     const uint32_t s = code >> 16;
-                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 6u : 0u) + slot_kind(s))*tb.t3.n_modes + (code & 0xFFFFu));
+                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 7u : 0u) + slot_kind(s))*tb.t3.n_modes + (code & 0xFFFFu));
                     row0 = static_cast<int>(slot_row(s));
                     row1 = ws.slots[s].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
                 }
@@ -1298,6 +1320,8 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     Tab3 tb; tb.ctx = ctx; tb.t3 = t3;
     static const uint32_t dev_flags = getenv("CFX_ASTC3_FLAGS") ? static_cast<uint32_t>(atoi(getenv("CFX_ASTC3_FLAGS"))) : 0u;
     tb.flags = dev_flags;
+    static const float mis_w = getenv("CFX_ASTC3_MISW") ? static_cast<float>(atof(getenv("CFX_ASTC3_MISW"))) : kMismatchWeight;   // developer knob
+    tb.mis_w = mis_w;
     tb.hdr = p.type == 4u ? 1u : 0u;                      // Texture::Type::UFloat
     const uint32_t NT = t3.NT, KS = t3.KS;
     if (NT == 2 && KS == 1) return launch_one<2, 1>(p, tb, n_exact, refine, stream);
