@@ -1300,6 +1300,7 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
     if constexpr (NT > 8) return launch_cfg<NT, KS, 8, 1, true>(p, tb, n_exact, refine, stream);
     // 56- and 64-texel footprints: 9 warps per CTA so that two CTAs still fit an SM's shared memory
     else if constexpr (NT >= 7) return launch_cfg<NT, KS, 9, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
+    else if constexpr (NT == 6) return launch_cfg<NT, KS, 11, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);   // 48 texels: same reason
     else return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
 }
 
