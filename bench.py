@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=2048, help="CPU baseline crop is SxS texels")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mips", action="store_true",
+                    help="encode the full mip chain of the image (BASELINE config 5 shape): every rank encodes one "
+                         "texture, level by level, through cfx_encode_device / cfx_encode_batch")
     return ap.parse_args()
 
 
@@ -190,6 +193,9 @@ def main():
     import cuttlefish_b200 as cfx
     from cuttlefish_b200 import synth
 
+    if a.mips:
+        return bench_mips(a, wl, size, rank, world, local, config)
+
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -307,6 +313,102 @@ def main():
         if world == 1 and not a.no_cpu:
             out["cpu_baseline"], _ = cpu_reference(a, wl, size, 1, 1)
         print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_mips(a, wl, size, rank, world, local, config):
+    """BASELINE config 5 shape: one texture WITH its full mip chain per rank (box-filtered levels of generator G --
+    the reference builds them on the host with FreeImage, outside this path), level by level through the encoder."""
+    import torch
+    import torch.distributed as dist
+    import cuttlefish_b200 as cfx
+    from cuttlefish_b200 import synth
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfx.init(local)
+    kw = dict(type=wl["type"], quality=a.quality)
+    img = synth.gen_image(wl["kind"], size, size, seed=12345 + rank)
+    levels = []
+    while True:
+        levels.append(np.ascontiguousarray(synth.to_rgba8(img) if wl["src"] == "RGBA8" else img.astype(np.float16)))
+        if img.shape[0] == 1 and img.shape[1] == 1:
+            break
+        h2, w2 = max(img.shape[0]//2, 1), max(img.shape[1]//2, 1)
+        img = img[:h2*2, :w2*2].reshape(h2, img.shape[0]//h2, w2, img.shape[1]//w2, 4).mean(axis=(1, 3)).astype(np.float32)
+    host = [torch.from_numpy(l).pin_memory() for l in levels]
+    d_src = [h.to(dev) for h in host]
+    d_out = [torch.empty(cfx.encoded_size(a.format, l.shape[1], l.shape[0]), dtype=torch.uint8, device=dev) for l in levels]
+    texels = sum(l.shape[0]*l.shape[1] for l in levels)
+    out_bytes = sum(int(o.numel()) for o in d_out)
+    gathered = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def device_step():
+        for s_, o_ in zip(d_src, d_out):
+            cfx.encode_device(s_, a.format, out=o_, **kw)
+        if world > 1:
+            dist.gather(torch.cat(d_out), gathered, dst=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        device_step()
+    barrier()
+    l0 = cfx.kernel_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = cfx.kernel_launches() - l0
+    hlevels = [h.numpy() for h in host]
+    for _ in range(max(a.warmup, 3)):
+        cfx.encode_batch(hlevels, a.format, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cfx.encode_batch(hlevels, a.format, **kw)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0)*1e3
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt)
+    if rank == 0:
+        dev_ms, e2e_ms = [float(x) for x in t.tolist()]
+        peak, how = peaks()
+        ms = dev_ms/a.steps
+        config = dict(config, mip_levels=len(levels), layers=world, workload=config["workload"] + " + full mip chain (%d levels, box filter)" % len(levels),
+                      sharding="one texture with its chain per rank",
+                      l2="base level (%d MiB) larger than L2; the tail levels are launch bound" % (levels[0].nbytes >> 20))
+        bpt = wl["read"] + wl["write"]
+        print(json.dumps({"metric": "Mtexels/s encode", "value": world*texels/(ms*1e-3)/1e6, "unit": "Mtexels/s", "n_gpus": world,
+                          "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8" if wl["src"] == "RGBA8" else "f16", "data": "synthetic", "config": config,
+                          "e2e": {"value": world*texels/(e2e_ms/a.steps*1e-3)/1e6, "unit": "Mtexels/s",
+                                  "h2d_bytes_per_step": int(sum(l.nbytes for l in levels))*world, "d2h_bytes_per_step": out_bytes*world},
+                          "gpu_launches": int(lt.item()),
+                          "roofline": {"bound": "hbm", "achieved": texels*bpt/(ms*1e-3)/1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": texels*bpt/(ms*1e-3)/1e9/peak, "traffic": None, "peak_source": how,
+                                       "kernel": "%s encode kernels of one mip chain (%d launches, step time)" % (a.format, len(levels))},
+                          "clocks": clocks}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
