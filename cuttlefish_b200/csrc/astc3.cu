@@ -160,6 +160,50 @@ __device__ __forceinline__ void decimate_mma(const Tab3& tb, WS& ws, const uint3
     __syncwarp();
 }
 
+// Multi-subset slots: M_g is the UNWEIGHTED least-squares decimation, but a grid weight shared by texels of two
+// subsets should follow the subset whose line is long -- a texel of a nearly constant subset does not care what its
+// weight is (astcenc weights its ideal-weight decimation the same way, compute_ideal_weights_for_decimation,
+// lib/astc-encoder/Source/astcenc_ideal_endpoints_and_weights.cpp:845).  Two damped Jacobi steps of the weighted
+// problem, starting from M_g t: residual per texel through the infill table (lane = texel), update per grid weight
+// through the transposed table (lane = grid weight).  Single plane only (multi-subset slots have no second plane).
+template <typename WS>
+__device__ __forceinline__ void reweight_decimation(const Ctx& c, WS& ws, uint32_t s, uint32_t grid, uint32_t nw, uint32_t row, uint32_t lane)
+{
+    const uint32_t T = c.tab.texels;
+    const Slot3& slot = ws.slots[s];
+    const uint8_t* parts = ws.part[slot_part(s)];
+    const float wmax = fmaxf(fmaxf(slot.len2[0], slot.len2[1]), slot.pc > 2 ? slot.len2[2] : 0.0f);
+    if (!(wmax > 0.0f)) return;
+    const float iw = 1.0f/wmax;
+    const uint32_t inf_off = c.tab.off_infill + grid*T*8u;
+    const uint32_t start_off = c.tab.off_csr_start + grid*(kMaxTexels + 2)*2u;
+    const uint32_t ent_off = c.tab.off_csr_ent + grid*4u*T*2u;
+    float* res = ws.g[1];                                  // scratch: weighted residual per texel
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+        for (uint32_t i = lane; i < T; i += 32) {
+            const uint2 inf = tab_u32x2(c, inf_off + i*8u);
+            float r = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r += static_cast<float>((inf.y >> (8*k)) & 0xFFu)*ws.g[0][(inf.x >> (8*k)) & 0xFFu];
+            res[i] = (__half2float(ws.ta[row][i]) - r*(1.0f/16.0f))*(slot.len2[parts[i]]*iw + 1e-3f);
+        }
+        __syncwarp();
+        for (uint32_t j = lane; j < nw; j += 32) {
+            const uint32_t e0 = tab_u16(c, start_off + j*2u), e1 = tab_u16(c, start_off + (j + 1u)*2u);
+            float num = 0.0f, den = 0.0f;
+            for (uint32_t e = e0; e < e1; ++e) {
+                const uint32_t ent = tab_u16(c, ent_off + e*2u);
+                const uint32_t i = ent & 0xFFu;
+                const float f = static_cast<float>(ent >> 8);
+                num += f*res[i]; den += f*f*(slot.len2[parts[i]]*iw + 1e-3f);
+            }
+            if (den > 0.0f) ws.g[0][j] = fminf(fmaxf(ws.g[0][j] + 12.0f*num/den, 0.0f), 1.0f);
+        }
+        __syncwarp();
+    }
+}
+
 // Evaluate block mode m on slot s with the decimated weights in ws.g; on success ws.su / ws.ep hold the candidate and
 // its exact decoded error (FX^2 units) is returned.
 template <int K, bool hdr, typename WS>
@@ -889,6 +933,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 }
             }
             float eline = 0.0f;
+            float rg0 = 0.0f, rg1 = 0.0f, rg2 = 0.0f, dom_rg = -1.0f, dom_mn = 0.0f;
+            uint32_t qd = 0;
             for (uint32_t q = 0; q < pc; ++q) {
                 float mn = 3.0e38f, mx = -3.0e38f;
 #pragma unroll
@@ -899,6 +945,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const float ir = range > 1e-6f*FX ? 1.0f/range : 0.0f;
 #pragma unroll
                 for (int r = 0; r < K; ++r) if (ql[r] == q) tl[r] = (tl[r] - mn)*ir;
+                if (q == 0) rg0 = range; else if (q == 1) rg1 = range; else rg2 = range;
+                if (range > dom_rg) { dom_rg = range; dom_mn = mn; qd = q; }
                 const LineFit& lf = lines[base + q];
                 eline += lf.resid;
                 if (lane == 0) {
@@ -907,6 +955,24 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     slot.e0[q] = make_float4((c0 + mn*lf.v[0])*ifx, (c1 + mn*lf.v[1])*ifx, (c2 + mn*lf.v[2])*ifx, (c3 + mn*lf.v[3])*ifx);
                     slot.e1[q] = make_float4((c0 + mx*lf.v[0])*ifx, (c1 + mx*lf.v[1])*ifx, (c2 + mx*lf.v[2])*ifx, (c3 + mx*lf.v[3])*ifx);
                     slot.len2[q] = range*range*ifx*ifx;
+                }
+            }
+            if (pc > 1 && dom_rg > 1e-6f*FX && !(tb.flags & 64u)) {
+                // a subset whose line is negligible next to the longest one cannot lose much whatever its weights
+                // are: its texels take the weights the longest line would give them, so a shared (decimated) weight
+                // grid is not pulled about by the rounding noise of a flat background
+                const LineFit& ld = lines[base + qd];
+                const float dir = 1.0f/dom_rg;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const uint32_t i = lane + 32u*r;
+                    const float rq = ql[r] == 0 ? rg0 : (ql[r] == 1 ? rg1 : rg2);
+                    if (i < T && ql[r] != qd && rq*8.0f < dom_rg) {
+                        const int4 x = ws.v[i];
+                        const float t = (static_cast<float>(x.x - ctr.x) - ld.m[0])*ld.v[0] + (static_cast<float>(x.y - ctr.y) - ld.m[1])*ld.v[1] +
+                            (static_cast<float>(x.z - ctr.z) - ld.m[2])*ld.v[2] + (static_cast<float>(x.w - ctr.w) - ld.m[3])*ld.v[3];
+                        tl[r] = fminf(fmaxf((t - dom_mn)*dir, 0.0f), 1.0f);
+                    }
                 }
             }
 #pragma unroll
@@ -986,6 +1052,15 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     if (mx[qq] < mn[qq]) { mn[qq] = 0; mx[qq] = 0; }           // empty subset
                     ir[qq] = mx[qq] > mn[qq] ? 1.0f/static_cast<float>(mx[qq] - mn[qq]) : 0.0f;
                 }
+                // a subset whose range is negligible next to the widest one cannot lose much whatever its weights are:
+                // give its texels the weights the widest subset's range would, so that a shared (decimated) weight
+                // grid is not pulled about by the rounding noise of a flat background
+                int rg[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+                const int qd = rg[0] >= rg[1] && rg[0] >= rg[2] ? 0 : (rg[1] >= rg[2] ? 1 : 2);
+                const int dom_lo = qd == 0 ? mn[0] : (qd == 1 ? mn[1] : mn[2]);
+                const int dom_rg = qd == 0 ? rg[0] : (qd == 1 ? rg[1] : rg[2]);
+                const float dom_ir = qd == 0 ? ir[0] : (qd == 1 ? ir[1] : ir[2]);
+                const bool borrow = !(tb.flags & 64u);
                 const uint32_t row = slot_row(10 + k);
                 for (uint32_t i = lane; i < T; i += 32) {
                     const int4 x = ws.v[i];
@@ -993,7 +1068,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     const uint32_t q = ws.part[k][i];
                     const int lo = q == 0 ? mn[0] : (q == 1 ? mn[1] : mn[2]);
                     const float r = q == 0 ? ir[0] : (q == 1 ? ir[1] : ir[2]);
-                    ws.ta[row][i] = __float2half_rn(static_cast<float>(l3 - lo)*r);
+                    const int rq = q == 0 ? rg[0] : (q == 1 ? rg[1] : rg[2]);
+                    float t = static_cast<float>(l3 - lo)*r;
+                    if (borrow && rq*8 < dom_rg) t = fminf(fmaxf(static_cast<float>(l3 - dom_lo)*dom_ir, 0.0f), 1.0f);
+                    ws.ta[row][i] = __float2half_rn(t);
                 }
                 if (lane < npc) {
                     const float a0 = static_cast<float>(lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]))*(ifx/3.0f);
@@ -1238,6 +1316,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
             decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
+            if (NT > 8 && ws.slots[s].pc > 1 && m.nw < T && !(tb.flags & 32u)) reweight_decimation(ctx, ws, s, m.grid, m.nw, static_cast<uint32_t>(row0), lane);
             const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane);
             if (err < best_err) {
                 best_err = err; best_code = code; best_cl = cl;
