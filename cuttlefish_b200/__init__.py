@@ -8,6 +8,6 @@ Host-side mirror (Python) of the reference's convert surface over the C-ABI in i
 plus array-level helpers `encode()` (host buffers) and `encode_device()` (torch CUDA tensors).
 All encoding happens in hand-written sm_100a kernels inside lib/libcfx.so; there is no CPU path.
 """
-from .api import (ALPHA, FORMATS, QUALITY, SRC_FORMATS, TYPES, CfxError, ColorMask, Texture,  # noqa: F401
-                  block_info, encode, encode_batch, encode_device, encoded_size, format_is_exact, format_supported, init,
+from .api import (ALPHA, FILTERS, FORMATS, QUALITY, SRC_FORMATS, TYPES, CfxError, ColorMask, Texture,  # noqa: F401
+                  block_info, encode, encode_batch, encode_device, encode_mip_chain, mip_levels, resize, encoded_size, format_is_exact, format_supported, init,
                   kernel_launches, last_error, shard_block_rows, version)

@@ -30,6 +30,12 @@ SYMBOLS = [
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     ("cfx_encode_device", ctypes.c_int, [ctypes.POINTER(SurfaceDesc), ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_size_t, ctypes.c_void_p]),
+    ("cfx_resize", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_void_p,
+                                  ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32]),
+    ("cfx_mip_levels", ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]),
+    ("cfx_encode_mip_chain", ctypes.c_int, [ctypes.POINTER(SurfaceDesc), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                            ctypes.POINTER(ctypes.c_void_p)]),
     ("cfx_host_alloc", ctypes.c_void_p, [ctypes.c_size_t]),
     ("cfx_host_free", None, [ctypes.c_void_p]),
     ("cfx_kernel_launches", ctypes.c_uint64, []),

@@ -19,6 +19,8 @@ TYPES = {"UNorm": 0, "SNorm": 1, "UInt": 2, "Int": 3, "UFloat": 4, "Float": 5}
 QUALITY = {"Lowest": 0, "Low": 1, "Normal": 2, "High": 3, "Highest": 4}
 ALPHA = {"None": 0, "Standard": 1, "PreMultiplied": 2, "Encoded": 3}
 SRC_FORMATS = {"RGBA8": 0, "RGBA16F": 1, "RGBA32F": 2}
+# cuttlefish::Image::ResizeFilter (lib/include/cuttlefish/Image.h:79-86)
+FILTERS = {"Box": 0, "Linear": 1, "Cubic": 2, "CatmullRom": 3, "BSpline": 4}
 
 CFX_ERR_UNSUPPORTED = -2
 
@@ -195,6 +197,50 @@ def shard_block_rows(height, block_h, rank, world):
     return r0, r1, r0 * block_h, min(int(height), r1 * block_h)
 
 
+def resize(img, width, height, filter="CatmullRom", srgb=False):
+    """Image::resize() (lib/src/Image.cpp:1324-1379) for a HOST float32 [H,W,4] image on the GPU: FreeImage's
+    separable filter, bit-identical for linear images. Returns a float32 [height,width,4] array."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    if img.ndim != 3 or img.shape[2] != 4:
+        raise ValueError("expected [H,W,4] RGBA texels")
+    out = np.empty((int(height), int(width), 4), np.float32)
+    _check(load().cfx_resize(img.ctypes.data, img.shape[1], img.shape[0], img.shape[1] * 16, out.ctypes.data,
+                             int(width), int(height), int(width) * 16, _enum(FILTERS, filter), 1 if srgb else 0))
+    return out
+
+
+def mip_levels(width, height):
+    """Texture::maxMipmapLevels() for a 2D texture (lib/src/Texture.cpp:514-527)."""
+    return int(load().cfx_mip_levels(int(width), int(height)))
+
+
+def encode_mip_chain(img, fmt, filter="CatmullRom", levels=None, return_images=False, **kw):
+    """Texture::generateMipmaps(filter, levels) + Texture::convert() for one HOST float32 [H,W,4] surface with one
+    cfx_encode_mip_chain call: level 0 is uploaded once, the mips are made and encoded on the GPU.
+    Returns a list of uint8 block arrays (and, with return_images, the list of float32 mip images)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    if img.ndim != 3 or img.shape[2] != 4:
+        raise ValueError("expected [H,W,4] RGBA texels")
+    h, w, _ = img.shape
+    n = mip_levels(w, h)
+    n = n if levels is None else max(1, min(int(levels), n))
+    d = make_desc(fmt, w, h, "RGBA32F", w * 16, **kw)
+    outs, images = [], [img]
+    for k in range(n):
+        dk = make_desc(fmt, max(1, w >> k), max(1, h >> k), "RGBA32F", 16, **kw)
+        size = int(load().cfx_encoded_size(ctypes.byref(dk)))
+        if size == 0:
+            raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
+        outs.append(np.empty(size, np.uint8))
+        if return_images and k:
+            images.append(np.empty((max(1, h >> k), max(1, w >> k), 4), np.float32))
+    dst = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+    sizes = (ctypes.c_size_t * n)(*[o.size for o in outs])
+    mips = (ctypes.c_void_p * n)(*([None] + [m.ctypes.data for m in images[1:]])) if return_images else None
+    _check(load().cfx_encode_mip_chain(ctypes.byref(d), img.ctypes.data, _enum(FILTERS, filter), n, dst, sizes, mips))
+    return (outs, images) if return_images else outs
+
+
 class Texture:
     """The slice of cuttlefish::Texture the convert path uses (lib/include/cuttlefish/Texture.h).
 
@@ -220,6 +266,24 @@ class Texture:
         if image.shape != (h, w, 4):
             return False
         self._images[mip][depth] = image
+        return True
+
+    def generateMipmaps(self, filter="CatmullRom", mipLevels=None):
+        """Texture::generateMipmaps (lib/src/Texture.cpp:1320-1514) for a 2D texture without custom mips: every level is
+        resized on the GPU from the level above. Level 0 must be set; returns False otherwise."""
+        if self._images is None or any(im is None for im in self._images[0]):
+            return False
+        n = mip_levels(self.width, self.height)
+        n = n if mipLevels is None else max(1, min(int(mipLevels), n))
+        images = [list(self._images[0])] + [[None] * self.depth for _ in range(n - 1)]
+        for d in range(self.depth):
+            for mip in range(1, n):
+                w, h = self.mip_size(mip)
+                above = images[mip - 1][d]
+                if above.dtype == np.uint8:         # Image::convert(RGBAF) of an 8-bit image
+                    above = above.astype(np.float32) / np.float32(255.0)
+                images[mip][d] = resize(above, w, h, filter, self.srgb)
+        self._images, self.mip_levels = images, n
         return True
 
     def imagesComplete(self):

@@ -23,6 +23,7 @@ NVCC_FLAGS = [
 # (source, extra flags, macro that advertises it to cfx.cu)
 UNITS = [
     ("cfx.cu", [], None),
+    ("resize.cu", ["-fmad=false", "-Xcompiler", "-ffp-contract=off"], None),
     ("bc4_bc5.cu", [], None),
     ("bc7.cu", [], "CFX_HAVE_BC7"),
     ("bc1_bc3.cu", ["-fmad=false"], "CFX_HAVE_BC1"),

@@ -119,6 +119,7 @@ struct Context {
     cudaStream_t streams[kStreams] = {};
     uint8_t* d_src = nullptr; size_t d_src_cap = 0;
     uint8_t* d_dst = nullptr; size_t d_dst_cap = 0;
+    uint8_t* d_mip = nullptr; size_t d_mip_cap = 0;       // resized surfaces + the resize scratch
 };
 static Context g_ctx;
 
@@ -153,7 +154,8 @@ static int ensure_init(int device)
         for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
         if (g_ctx.d_src) cudaFree(g_ctx.d_src);
         if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
-        g_ctx.d_src = g_ctx.d_dst = nullptr; g_ctx.d_src_cap = g_ctx.d_dst_cap = 0;
+        if (g_ctx.d_mip) cudaFree(g_ctx.d_mip);
+        g_ctx.d_src = g_ctx.d_dst = g_ctx.d_mip = nullptr; g_ctx.d_src_cap = g_ctx.d_dst_cap = g_ctx.d_mip_cap = 0;
         g_ctx.ready = false;
     }
     cudaDeviceProp prop;
@@ -275,6 +277,114 @@ static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst,
     return CFX_OK;
 }
 
+// resize.cu
+size_t resize_scratch_bytes(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh);
+int resize_device(const uint8_t* src, size_t src_pitch, uint32_t sw, uint32_t sh, uint8_t* dst, size_t dst_pitch,
+    uint32_t dw, uint32_t dh, uint32_t filter, bool srgb, uint8_t* scratch, size_t scratch_cap, cudaStream_t stream);
+
+static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+static int resize_host(const void* src, uint32_t sw, uint32_t sh, size_t src_pitch, void* dst, uint32_t dw, uint32_t dh,
+    size_t dst_pitch, uint32_t filter, uint32_t color_space)
+{
+    if (!src || !dst) return fail(CFX_ERR_INVALID, "null buffer");
+    if (!sw || !sh || !dw || !dh) return fail(CFX_ERR_INVALID, "empty surface");
+    if (filter > CFX_FILTER_BSPLINE) return fail(CFX_ERR_INVALID, "filter %u out of range", filter);
+    if (src_pitch < static_cast<size_t>(sw)*16u || dst_pitch < static_cast<size_t>(dw)*16u || (src_pitch & 3) || (dst_pitch & 3))
+        return fail(CFX_ERR_INVALID, "row pitch too small or not a multiple of 4");
+    int rc = ensure_init(-1);
+    if (rc != CFX_OK) return rc;
+    const size_t sp = align256(static_cast<size_t>(sw)*16u), dp = align256(static_cast<size_t>(dw)*16u);
+    const size_t scratch = resize_scratch_bytes(sw, sh, dw, dh);
+    rc = reserve(g_ctx.d_src, g_ctx.d_src_cap, sp*sh);
+    if (rc != CFX_OK) return rc;
+    rc = reserve(g_ctx.d_mip, g_ctx.d_mip_cap, dp*dh + 256 + scratch);
+    if (rc != CFX_OK) return rc;
+    cudaStream_t s = g_ctx.streams[0];
+    CFX_CUDA(cudaMemcpy2DAsync(g_ctx.d_src, sp, src, src_pitch, static_cast<size_t>(sw)*16u, sh, cudaMemcpyHostToDevice, s));
+    uint8_t* d_out = g_ctx.d_mip;
+    int n = resize_device(g_ctx.d_src, sp, sw, sh, d_out, dp, dw, dh, filter, color_space != 0, d_out + align256(dp*dh),
+        scratch, s);
+    if (n < 0) return fail(n, "resize failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches += static_cast<uint64_t>(n);
+    CFX_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, d_out, dp, static_cast<size_t>(dw)*16u, dh, cudaMemcpyDeviceToHost, s));
+    CFX_CUDA(cudaStreamSynchronize(s));
+    return CFX_OK;
+}
+
+static uint32_t mip_levels(uint32_t w, uint32_t h)
+{
+    uint32_t m = w > h ? w : h, n = 0;
+    while (m) { ++n; m >>= 1; }
+    return n;
+}
+
+static int encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels,
+    void* const* dsts, const size_t* dst_sizes, void* const* mip_images)
+{
+    EncodeParams p0; Launcher launcher;
+    int rc = validate(level0, p0, launcher);
+    if (rc != CFX_OK) return rc;
+    if (level0->src_format != CFX_SRC_RGBA32F)
+        return fail(CFX_ERR_INVALID, "the mip chain is generated from an RGBA32F level 0 (Image::Format::RGBAF)");
+    if (filter > CFX_FILTER_BSPLINE) return fail(CFX_ERR_INVALID, "filter %u out of range", filter);
+    if (!src || !dsts || !dst_sizes) return fail(CFX_ERR_INVALID, "null buffer");
+    if (levels < 1) levels = 1;                                  // Texture.cpp:1341: clamped to [1, max]
+    const uint32_t max_levels = mip_levels(level0->width, level0->height);
+    if (levels > max_levels) levels = max_levels;
+    // every level's descriptor and output size, checked before any work is queued
+    std::vector<cfx_surface_desc> descs(levels, *level0);
+    std::vector<size_t> out_off(levels + 1, 0);
+    for (uint32_t k = 0; k < levels; ++k) {
+        descs[k].width = level0->width >> k ? level0->width >> k : 1u;
+        descs[k].height = level0->height >> k ? level0->height >> k : 1u;
+        if (k) descs[k].src_row_pitch = align256(static_cast<size_t>(descs[k].width)*16u);
+        const size_t bytes = cfx_encoded_size(&descs[k]);
+        if (!dsts[k] || dst_sizes[k] < bytes) return fail(CFX_ERR_INVALID, "level %u: dst_size %zu < %zu", k, dst_sizes[k], bytes);
+        out_off[k + 1] = out_off[k] + (k ? align256(bytes) : 0);
+    }
+    // level 0: the chunked upload + encode of cfx_encode(); it leaves the whole RGBA32F surface in d_src
+    rc = encode_host(level0, src, dsts[0], dst_sizes[0]);
+    if (rc != CFX_OK || levels == 1) return rc;
+
+    const size_t pitch0 = align256(static_cast<size_t>(level0->width)*16u);
+    const size_t lvl1 = descs[1].src_row_pitch*descs[1].height;
+    const size_t lvl2 = levels > 2 ? descs[2].src_row_pitch*descs[2].height : 0;
+    const size_t scratch = resize_scratch_bytes(level0->width, level0->height, descs[1].width, descs[1].height);
+    rc = reserve(g_ctx.d_mip, g_ctx.d_mip_cap, align256(lvl1) + align256(lvl2) + scratch + 512);
+    if (rc != CFX_OK) return rc;
+    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, out_off[levels]);
+    if (rc != CFX_OK) return rc;
+    // odd levels live in the first region, even levels in the second: a level only needs the one above it
+    uint8_t* region[2] = {g_ctx.d_mip, g_ctx.d_mip + align256(lvl1)};
+    uint8_t* d_scratch = g_ctx.d_mip + align256(lvl1) + align256(lvl2);
+    cudaStream_t s = g_ctx.streams[0];
+    const uint8_t* prev = g_ctx.d_src;
+    size_t prev_pitch = pitch0;
+    for (uint32_t k = 1; k < levels; ++k) {
+        uint8_t* cur = region[(k - 1) & 1];
+        const cfx_surface_desc& d = descs[k];
+        int n = resize_device(prev, prev_pitch, descs[k - 1].width, descs[k - 1].height, cur, d.src_row_pitch, d.width, d.height,
+            filter, level0->color_space != 0, d_scratch, scratch, s);
+        if (n < 0) return fail(n, "level %u: resize failed", k);
+        g_launches += static_cast<uint64_t>(n);
+        EncodeParams p; Launcher l;
+        rc = validate(&d, p, l);
+        if (rc != CFX_OK) return rc;
+        p.src = cur;
+        p.dst = g_ctx.d_dst + out_off[k];
+        rc = launch(l, p, s);
+        if (rc != CFX_OK) return rc;
+        CFX_CUDA(cudaMemcpyAsync(dsts[k], p.dst, static_cast<size_t>(p.total_blocks)*p.block_bytes, cudaMemcpyDeviceToHost, s));
+        if (mip_images && mip_images[k])
+            CFX_CUDA(cudaMemcpy2DAsync(mip_images[k], static_cast<size_t>(d.width)*16u, cur, d.src_row_pitch,
+                static_cast<size_t>(d.width)*16u, d.height, cudaMemcpyDeviceToHost, s));
+        prev = cur; prev_pitch = d.src_row_pitch;
+    }
+    CFX_CUDA(cudaStreamSynchronize(s));
+    return CFX_OK;
+}
+
 } // namespace cfx
 
 using namespace cfx;
@@ -297,7 +407,8 @@ void cfx_shutdown(void)
     for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
     if (g_ctx.d_src) cudaFree(g_ctx.d_src);
     if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
-    g_ctx.d_src = g_ctx.d_dst = nullptr; g_ctx.d_src_cap = g_ctx.d_dst_cap = 0;
+    if (g_ctx.d_mip) cudaFree(g_ctx.d_mip);
+    g_ctx.d_src = g_ctx.d_dst = g_ctx.d_mip = nullptr; g_ctx.d_src_cap = g_ctx.d_dst_cap = g_ctx.d_mip_cap = 0;
     g_ctx.ready = false;
 }
 
@@ -380,6 +491,24 @@ int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_d
     p.dst = static_cast<uint8_t*>(d_dst);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);   // NULL = the CUDA default stream
     return launch(launcher, p, s);
+}
+
+int cfx_resize(const void* src, uint32_t src_width, uint32_t src_height, size_t src_row_pitch, void* dst, uint32_t dst_width,
+    uint32_t dst_height, size_t dst_row_pitch, uint32_t filter, uint32_t color_space)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    t_error[0] = 0;
+    return resize_host(src, src_width, src_height, src_row_pitch, dst, dst_width, dst_height, dst_row_pitch, filter, color_space);
+}
+
+uint32_t cfx_mip_levels(uint32_t width, uint32_t height) { return mip_levels(width, height); }
+
+int cfx_encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels, void* const* dsts,
+    const size_t* dst_sizes, void* const* mip_images)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    t_error[0] = 0;
+    return encode_mip_chain(level0, src, filter, levels, dsts, dst_sizes, mip_images);
 }
 
 void* cfx_host_alloc(size_t bytes)

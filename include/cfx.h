@@ -19,6 +19,13 @@
  *                            lib/src/EtcConverter.cpp:120-152, lib/src/AstcConverter.cpp:208-230)
  *   cfx_encode_batch      <- the mip/depth/face loop around it, lib/src/Converter.cpp:521-527
  *   cfx_encode_device     <- same as cfx_encode for callers that already hold the surface in HBM
+ *   cfx_resize            <- Image::resize() on an RGBAF image, lib/src/Image.cpp:1324-1379 (FreeImage_Rescale,
+ *                            lib/FreeImage/Source/FreeImageToolkit/Resize.cpp:140-218, :232-506, :1236-1273,
+ *                            :2070-2112): bit-identical for linear images
+ *   cfx_mip_levels        <- Texture::maxMipmapLevels() for a 2D texture, lib/src/Texture.cpp:514-527
+ *   cfx_encode_mip_chain  <- Texture::generateMipmaps() (2D: each level resized from the one above,
+ *                            lib/src/Texture.cpp:1457-1511) followed by Texture::convert(): level 0 is
+ *                            uploaded once, the chain never leaves the GPU
  *   cfx_init/cfx_shutdown <- the one-time encoder table inits (rgbcx::init, bc7enc_compress_block_init,
  *                            astcenc context alloc), lib/src/S3tcConverter.cpp:54-64,158-168
  */
@@ -54,6 +61,10 @@ enum { CFX_QUALITY_LOWEST = 0, CFX_QUALITY_LOW = 1, CFX_QUALITY_NORMAL = 2, CFX_
  * Converter holds (Image::Format::RGBAF, lib/src/Converter.h:52-56); the kernels do the
  * float->u8 / float->half step of lib/src/S3tcConverter.cpp:97-129 themselves. */
 enum { CFX_SRC_RGBA8 = 0, CFX_SRC_RGBA16F = 1, CFX_SRC_RGBA32F = 2 };
+
+/* cuttlefish::Image::ResizeFilter, lib/include/cuttlefish/Image.h:79-86 (same numeric values). */
+enum { CFX_FILTER_BOX = 0, CFX_FILTER_LINEAR = 1, CFX_FILTER_CUBIC = 2, CFX_FILTER_CATMULL_ROM = 3,
+       CFX_FILTER_BSPLINE = 4 };
 
 enum {
     CFX_OK = 0,
@@ -109,6 +120,23 @@ int cfx_encode_batch(int n, const cfx_surface_desc* descs, const void* const* sr
  * 16-byte aligned with a 16-byte-multiple pitch for the fast path; otherwise a slower path runs. */
 int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_dst, size_t dst_size,
                       void* cuda_stream);
+
+/* Resize one RGBA32F surface (host memory in, host memory out; rows top-down, pitches in bytes) the way
+ * Image::resize() does: FreeImage's separable filter with double-precision weights and accumulation, the pass
+ * along x first unless the width grows; color_space 1 (sRGB) filters in linear space. Linear results are
+ * bit-identical to the reference's; sRGB ones differ only where pow() rounds differently. */
+int cfx_resize(const void* src, uint32_t src_width, uint32_t src_height, size_t src_row_pitch,
+               void* dst, uint32_t dst_width, uint32_t dst_height, size_t dst_row_pitch,
+               uint32_t filter, uint32_t color_space);
+/* floor(log2(max(width, height))) + 1: the length of a full 2D mip chain. */
+uint32_t cfx_mip_levels(uint32_t width, uint32_t height);
+/* generateMipmaps(filter, levels) + convert() for one 2D surface. level0 describes the RGBA32F level-0 image
+ * (src); level k has size max(1, w >> k) x max(1, h >> k), is resized on the GPU from level k-1 and encoded
+ * with level0's format/type/quality/...; dsts[k] / dst_sizes[k] receive its blocks (k = 0 .. levels-1).
+ * mip_images, if not NULL, is an array of `levels` host pointers (entries may be NULL; entry 0 is ignored)
+ * that receive the generated RGBA32F levels, tightly packed rows, top-down. */
+int cfx_encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels,
+                         void* const* dsts, const size_t* dst_sizes, void* const* mip_images);
 
 /* Pinned host memory helpers for callers that want zero-copy staging. */
 void* cfx_host_alloc(size_t bytes);
