@@ -5,7 +5,7 @@ Two things live here:
     oracle/_ref/libfiresize.so by oracle/Makefile (see oracle/fi_resize.cpp);
   * resize_np(): a numpy restatement of the same algorithm (float64 weights and accumulation in window order,
     each pass rounded to float32), which travels without the compiled library. tests/test_resize_cpu.py pins it
-    bit-for-bit to resize_ref() and to the committed vectors in tests/golden/resize_*.npz.
+    bit-for-bit to resize_ref() and to the committed vectors in tests/golden/resize/cases.npz.
 File:line references are to /root/reference/lib.
 """
 import ctypes

@@ -1,4 +1,4 @@
-"""Generates tests/golden/resize_cases.npz from the REFERENCE's Image::resize(): the real FreeImage_Rescale compiled
+"""Generates tests/golden/resize/cases.npz from the REFERENCE's Image::resize(): the real FreeImage_Rescale compiled
 from /root/reference by oracle/Makefile (oracle/_ref/libfiresize.so, see oracle/fi_resize.cpp). Run in the build
 container (needs /root/reference): python tests/golden/make_resize_goldens.py"""
 import os
@@ -36,7 +36,7 @@ def main():
     out["chain/src"] = img
     for k, level in enumerate(R.mip_chain(img, "CatmullRom", fn=R.resize_ref)[1:], 1):
         out["chain/%d" % k] = level
-    path = os.path.join(ROOT, "tests", "golden", "resize_cases.npz")
+    path = os.path.join(ROOT, "tests", "golden", "resize", "cases.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
 

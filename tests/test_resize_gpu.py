@@ -12,7 +12,7 @@ from oracle import resize as R
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_cases.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize", "cases.npz")
 CASES = {"down_odd": (18, 11, False), "mixed": (40, 9, False), "y_only": (9, 16, False), "up": (20, 20, False),
          "to_1x1": (1, 1, False), "half": (16, 12, False)}
 
