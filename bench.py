@@ -60,6 +60,10 @@ def parse():
     ap.add_argument("--mips", action="store_true",
                     help="encode the full mip chain of the image (BASELINE config 5 shape): every rank encodes one "
                          "texture, level by level, through cfx_encode_device / cfx_encode_batch")
+    ap.add_argument("--mipgen", action="store_true",
+                    help="with --mips: build the chain on the GPU too (Texture::generateMipmaps, Catmull-Rom) from a float32 "
+                         "level 0 through cfx_encode_mip_chain(_device); the reference arm then times FreeImage's chain + "
+                         "Converter::convert")
     return ap.parse_args()
 
 
@@ -161,6 +165,42 @@ def cpu_reference(a, wl, size, steps, warmup):
                       (s, s, size, size, wl["kind"], a.format, a.quality, threads, dt)}, dt
 
 
+def cpu_reference_mips(a, wl, size, steps, warmup):
+    """Times the reference's Texture::generateMipmaps + convert on a bounded level 0: the real FreeImage_Rescale chain
+    (oracle/_ref/libfiresize.so; single-threaded, as in the reference) and the real Converter::convert per level."""
+    import oracle
+    from oracle import resize as oresize
+    from cuttlefish_b200 import synth
+    s = min(a.cpu_sample // 2, size)
+    img = synth.gen_image(wl["kind"], size, size, rows=(0, s))[:, :s].copy().astype(np.float32)
+    threads = oracle.hardware_threads()
+    kw = dict(type=wl["type"], quality=a.quality)
+    enc = oracle.encode_glue if oracle.glue_available() else oracle.encode
+
+    def chain():
+        levels = oresize.mip_chain(img, "CatmullRom", fn=oresize.resize_ref)
+        t_mid = time.perf_counter()
+        for l in levels:
+            enc(l, a.format, threads=0, **kw)
+        return levels, t_mid
+
+    for _ in range(warmup):
+        enc(img[:64], a.format, threads=0, **kw)
+    times, resize_times = [], []
+    for _ in range(steps):
+        t = time.perf_counter()
+        levels, t_mid = chain()
+        times.append(time.perf_counter() - t)
+        resize_times.append(t_mid - t)
+    dt = float(np.mean(times))
+    texels = sum(l.shape[0] * l.shape[1] for l in levels)
+    return {"value": texels / dt / 1e6, "unit": "Mtexels/s", "cores": threads, "kind": "reference",
+            "sample": "%dx%d top-left crop of the %dx%d %s image as level 0, %d-level Catmull-Rom chain by the reference's "
+                      "FreeImage_Rescale (1 thread, %.2f s) + %s quality=%s Converter::convert per level (%d threads), "
+                      "%.2f s/step" % (s, s, size, size, wl["kind"], len(levels), float(np.mean(resize_times)), a.format,
+                                       a.quality, threads, dt)}, dt
+
+
 def main():
     a = parse()
     wl = dict(WORKLOADS[a.format])
@@ -178,7 +218,11 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        base, dt = cpu_reference(a, wl, size, a.steps, min(a.warmup, 1))
+        if a.mips and a.mipgen:
+            base, dt = cpu_reference_mips(a, wl, size, a.steps, min(a.warmup, 1))
+            config = dict(config, workload=config["workload"] + " + generateMipmaps(CatmullRom) + full mip chain")
+        else:
+            base, dt = cpu_reference(a, wl, size, a.steps, min(a.warmup, 1))
         print(json.dumps({"impl": "reference", "metric": "Mtexels/s encode", "value": base["value"],
                           "unit": "Mtexels/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -334,6 +378,8 @@ def bench_mips(a, wl, size, rank, world, local, config):
     cfx.init(local)
     kw = dict(type=wl["type"], quality=a.quality)
     img = synth.gen_image(wl["kind"], size, size, seed=12345 + rank)
+    if a.mipgen:
+        return bench_mipgen(a, wl, size, rank, world, local, config, img, kw)
     levels = []
     while True:
         levels.append(np.ascontiguousarray(synth.to_rgba8(img) if wl["src"] == "RGBA8" else img.astype(np.float16)))
@@ -409,6 +455,100 @@ def bench_mips(a, wl, size, rank, world, local, config):
                                        "frac": texels*bpt/(ms*1e-3)/1e9/peak, "traffic": None, "peak_source": how,
                                        "kernel": "%s encode kernels of one mip chain (%d launches, step time)" % (a.format, len(levels))},
                           "clocks": clocks}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_mipgen(a, wl, size, rank, world, local, config, img, kw):
+    """Texture::generateMipmaps(CatmullRom) + convert per rank, the chain generated on the GPU: `value` with the float32
+    level 0 resident (cfx_encode_mip_chain_device), `e2e` from a host level 0 (cfx_encode_mip_chain, 16 B/texel H2D)."""
+    import torch
+    import torch.distributed as dist
+    import cuttlefish_b200 as cfx
+    dev = torch.device("cuda", local)
+    img = np.ascontiguousarray(img, np.float32)
+    host = torch.from_numpy(img).pin_memory()
+    d_src = host.to(dev)
+    sizes = [(max(1, size >> k), max(1, size >> k)) for k in range(cfx.mip_levels(size, size))]
+    d_out = [torch.empty(cfx.encoded_size(a.format, w, h), dtype=torch.uint8, device=dev) for (w, h) in sizes]
+    texels = sum(w*h for (w, h) in sizes)
+    out_bytes = sum(int(o.numel()) for o in d_out)
+    gathered = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def device_step():
+        cfx.encode_mip_chain_device(d_src, a.format, "CatmullRom", outs=d_out, **kw)
+        if world > 1:
+            dist.gather(torch.cat(d_out), gathered, dst=0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        device_step()
+    barrier()
+    l0 = cfx.kernel_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = cfx.kernel_launches() - l0
+    himg = host.numpy()
+    for _ in range(max(a.warmup, 3)):
+        cfx.encode_mip_chain(himg, a.format, "CatmullRom", **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cfx.encode_mip_chain(himg, a.format, "CatmullRom", **kw)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0)*1e3
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt)
+    if rank == 0:
+        dev_ms, e2e_ms = [float(x) for x in t.tolist()]
+        peak, how = peaks()
+        ms = dev_ms/a.steps
+        # algorithmic bytes of one chain: every level read once by its encoder (16 B/texel) and written as blocks; every
+        # resize reads the level above, writes and re-reads the x-filtered intermediate, and writes the level (16 B each)
+        alg = 0.0
+        for k, (w, h) in enumerate(sizes):
+            alg += w*h*(16.0 + wl["write"])
+            if k:
+                pw, ph = sizes[k - 1]
+                alg += 16.0*(pw*ph + 2*w*ph + w*h)
+        config = dict(config, mip_levels=len(sizes), layers=world,
+                      workload=config["workload"].replace(wl["src"], "RGBA32F") + " + generateMipmaps(CatmullRom) on the GPU + full mip chain (%d levels)" % len(sizes),
+                      sharding="one texture with its chain per rank",
+                      l2="level 0 (%d MiB) larger than L2; the tail levels are launch bound" % (img.nbytes >> 20))
+        out = {"metric": "Mtexels/s encode", "value": world*texels/(ms*1e-3)/1e6, "unit": "Mtexels/s", "n_gpus": world,
+               "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64 filter / u8 encode", "data": "synthetic", "config": config,
+               "e2e": {"value": world*texels/(e2e_ms/a.steps*1e-3)/1e6, "unit": "Mtexels/s",
+                       "h2d_bytes_per_step": int(img.nbytes)*world, "d2h_bytes_per_step": out_bytes*world},
+               "gpu_launches": int(lt.item()),
+               "roofline": {"bound": "hbm", "achieved": alg/(ms*1e-3)/1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg/(ms*1e-3)/1e9/peak, "traffic": None, "peak_source": how, "algorithmic_bytes": alg,
+                            "kernel": "resize passes + %s encode kernels of one mip chain (%d launches, step time)" %
+                                      (a.format, int(lt.item())//max(a.steps, 1)//max(world, 1))},
+               "clocks": clocks}
+        if not a.no_cpu and world == 1:
+            out["cpu_baseline"], _ = cpu_reference_mips(a, wl, size, 1, 1)
+        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -187,6 +187,35 @@ def encode_device(src, fmt, out=None, stream=None, **kw):
     return out[:n]
 
 
+def encode_mip_chain_device(src, fmt, filter="CatmullRom", levels=None, outs=None, stream=None, **kw):
+    """generateMipmaps + convert for a float32 torch CUDA tensor [H,W,4]: the chain is made and encoded on the GPU,
+    asynchronously on `stream`. Returns one CUDA uint8 tensor per level. Goes through cfx_encode_mip_chain_device."""
+    import torch
+    if not src.is_cuda or src.dtype != torch.float32:
+        raise ValueError("encode_mip_chain_device needs a float32 CUDA tensor")
+    if src.dim() != 3 or src.shape[2] != 4 or src.stride(2) != 1 or src.stride(1) != 4:
+        raise ValueError("expected [H,W,4] texels with contiguous rows")
+    h, w, _ = src.shape
+    n = mip_levels(w, h)
+    n = n if levels is None else max(1, min(int(levels), n))
+    d = make_desc(fmt, w, h, "RGBA32F", src.stride(0) * 4, **kw)
+    sizes = [encoded_size(fmt, max(1, w >> k), max(1, h >> k)) for k in range(n)]
+    if sizes[0] == 0:
+        raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
+    if outs is None:
+        outs = [torch.empty(sz, dtype=torch.uint8, device=src.device) for sz in sizes]
+    assert len(outs) >= n and all(o.is_cuda and o.dtype == torch.uint8 and o.numel() >= sz for o, sz in zip(outs, sizes))
+    dst = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs[:n]])
+    csizes = (ctypes.c_size_t * n)(*[o.numel() for o in outs[:n]])
+    with torch.cuda.device(src.device):
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        _check(load().cfx_init(src.device.index))
+        _check(load().cfx_encode_mip_chain_device(ctypes.byref(d), src.data_ptr(), _enum(FILTERS, filter), n, dst, csizes,
+                                                  ctypes.c_void_p(stream.cuda_stream)))
+    return [o[:sz] for o, sz in zip(outs, sizes)]
+
+
 def shard_block_rows(height, block_h, rank, world):
     """Contiguous block-row range [r0, r1) owned by `rank` out of `world`, and the source rows
     [y0, y1) it needs. Slabs end on block-row boundaries, so each rank encodes its slab as an

@@ -110,6 +110,7 @@ static uint32_t src_texel_bytes(uint32_t src_format)
 // ---- device context ---------------------------------------------------------------------------
 
 constexpr int kStreams = 3;
+constexpr int kMaxMipLevels = 32;
 
 struct Context {
     std::mutex mutex;
@@ -120,6 +121,8 @@ struct Context {
     uint8_t* d_src = nullptr; size_t d_src_cap = 0;
     uint8_t* d_dst = nullptr; size_t d_dst_cap = 0;
     uint8_t* d_mip = nullptr; size_t d_mip_cap = 0;       // resized surfaces + the resize scratch
+    cudaEvent_t fork[kMaxMipLevels] = {};                 // "level k is filtered" / "stream i has encoded its levels"
+    cudaEvent_t join[kStreams] = {};
 };
 static Context g_ctx;
 
@@ -152,6 +155,8 @@ static int ensure_init(int device)
         // switching device: drop the old context's resources
         cudaSetDevice(g_ctx.device);
         for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
+        for (auto& e : g_ctx.fork) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : g_ctx.join) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (g_ctx.d_src) cudaFree(g_ctx.d_src);
         if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
         if (g_ctx.d_mip) cudaFree(g_ctx.d_mip);
@@ -165,6 +170,8 @@ static int ensure_init(int device)
             device, prop.major, prop.minor);
     CFX_CUDA(cudaSetDevice(device));
     for (auto& s : g_ctx.streams) CFX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : g_ctx.fork) CFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : g_ctx.join) CFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.ready = true;
@@ -319,8 +326,10 @@ static uint32_t mip_levels(uint32_t w, uint32_t h)
     return n;
 }
 
-static int encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels,
-    void* const* dsts, const size_t* dst_sizes, void* const* mip_images)
+// Validates a chain request and fills one descriptor per level (Texture::width/height(mip); levels clamped to
+// [1, maxMipmapLevels] like Texture.cpp:1341).
+static int mip_chain_descs(const cfx_surface_desc* level0, uint32_t filter, uint32_t levels, const size_t* dst_sizes,
+    std::vector<cfx_surface_desc>& descs)
 {
     EncodeParams p0; Launcher launcher;
     int rc = validate(level0, p0, launcher);
@@ -328,61 +337,124 @@ static int encode_mip_chain(const cfx_surface_desc* level0, const void* src, uin
     if (level0->src_format != CFX_SRC_RGBA32F)
         return fail(CFX_ERR_INVALID, "the mip chain is generated from an RGBA32F level 0 (Image::Format::RGBAF)");
     if (filter > CFX_FILTER_BSPLINE) return fail(CFX_ERR_INVALID, "filter %u out of range", filter);
-    if (!src || !dsts || !dst_sizes) return fail(CFX_ERR_INVALID, "null buffer");
-    if (levels < 1) levels = 1;                                  // Texture.cpp:1341: clamped to [1, max]
+    if (!dst_sizes) return fail(CFX_ERR_INVALID, "null buffer");
+    if (levels < 1) levels = 1;
     const uint32_t max_levels = mip_levels(level0->width, level0->height);
     if (levels > max_levels) levels = max_levels;
-    // every level's descriptor and output size, checked before any work is queued
-    std::vector<cfx_surface_desc> descs(levels, *level0);
-    std::vector<size_t> out_off(levels + 1, 0);
+    descs.assign(levels, *level0);
     for (uint32_t k = 0; k < levels; ++k) {
         descs[k].width = level0->width >> k ? level0->width >> k : 1u;
         descs[k].height = level0->height >> k ? level0->height >> k : 1u;
         if (k) descs[k].src_row_pitch = align256(static_cast<size_t>(descs[k].width)*16u);
         const size_t bytes = cfx_encoded_size(&descs[k]);
-        if (!dsts[k] || dst_sizes[k] < bytes) return fail(CFX_ERR_INVALID, "level %u: dst_size %zu < %zu", k, dst_sizes[k], bytes);
-        out_off[k + 1] = out_off[k] + (k ? align256(bytes) : 0);
+        if (dst_sizes[k] < bytes) return fail(CFX_ERR_INVALID, "level %u: dst_size %zu < %zu", k, dst_sizes[k], bytes);
     }
-    // level 0: the chunked upload + encode of cfx_encode(); it leaves the whole RGBA32F surface in d_src
-    rc = encode_host(level0, src, dsts[0], dst_sizes[0]);
-    if (rc != CFX_OK || levels == 1) return rc;
+    return CFX_OK;
+}
 
-    const size_t pitch0 = align256(static_cast<size_t>(level0->width)*16u);
-    const size_t lvl1 = descs[1].src_row_pitch*descs[1].height;
-    const size_t lvl2 = levels > 2 ? descs[2].src_row_pitch*descs[2].height : 0;
-    const size_t scratch = resize_scratch_bytes(level0->width, level0->height, descs[1].width, descs[1].height);
-    rc = reserve(g_ctx.d_mip, g_ctx.d_mip_cap, align256(lvl1) + align256(lvl2) + scratch + 512);
+// Levels of a chain whose RGBA32F level 0 is resident at d_level0. The filter chain runs on stream s: each level is
+// resized from the level above into the library's mip storage (every level keeps its own region until the next chain
+// call). The encoders only depend on their own level, so they fork onto the context's other streams as soon as that
+// level is filtered -- the launch-latency-bound tail levels then overlap each other and the big levels -- and join s at
+// the end. Level 0 is encoded too when d_outs[0] is set. level_ptr[k] receives where level k's image lives.
+static int run_mip_levels(const std::vector<cfx_surface_desc>& descs, const uint8_t* d_level0, size_t pitch0, uint32_t filter,
+    uint8_t* const* d_outs, std::vector<const uint8_t*>& level_ptr, cudaStream_t s)
+{
+    const uint32_t levels = static_cast<uint32_t>(descs.size());
+    level_ptr.assign(levels, nullptr);
+    level_ptr[0] = d_level0;
+    std::vector<size_t> off(levels + 1, 0);
+    for (uint32_t k = 1; k < levels; ++k) off[k + 1] = off[k] + align256(descs[k].src_row_pitch*descs[k].height);
+    const size_t scratch = levels > 1 ? resize_scratch_bytes(descs[0].width, descs[0].height, descs[1].width, descs[1].height) : 0;
+    int rc = reserve(g_ctx.d_mip, g_ctx.d_mip_cap, off[levels] + scratch + 256);
     if (rc != CFX_OK) return rc;
-    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, out_off[levels]);
-    if (rc != CFX_OK) return rc;
-    // odd levels live in the first region, even levels in the second: a level only needs the one above it
-    uint8_t* region[2] = {g_ctx.d_mip, g_ctx.d_mip + align256(lvl1)};
-    uint8_t* d_scratch = g_ctx.d_mip + align256(lvl1) + align256(lvl2);
-    cudaStream_t s = g_ctx.streams[0];
-    const uint8_t* prev = g_ctx.d_src;
+    uint8_t* d_scratch = g_ctx.d_mip + off[levels];
     size_t prev_pitch = pitch0;
-    for (uint32_t k = 1; k < levels; ++k) {
-        uint8_t* cur = region[(k - 1) & 1];
+    bool used[kStreams] = {};
+    for (uint32_t k = 0; k < levels; ++k) {
         const cfx_surface_desc& d = descs[k];
-        int n = resize_device(prev, prev_pitch, descs[k - 1].width, descs[k - 1].height, cur, d.src_row_pitch, d.width, d.height,
-            filter, level0->color_space != 0, d_scratch, scratch, s);
-        if (n < 0) return fail(n, "level %u: resize failed", k);
-        g_launches += static_cast<uint64_t>(n);
+        if (k) {
+            uint8_t* cur = g_ctx.d_mip + off[k];
+            int n = resize_device(level_ptr[k - 1], prev_pitch, descs[k - 1].width, descs[k - 1].height, cur, d.src_row_pitch,
+                d.width, d.height, filter, descs[0].color_space != 0, d_scratch, scratch, s);
+            if (n < 0) return fail(n, "level %u: resize failed", k);
+            g_launches += static_cast<uint64_t>(n);
+            level_ptr[k] = cur;
+            prev_pitch = d.src_row_pitch;
+        }
+        if (!d_outs[k]) continue;
         EncodeParams p; Launcher l;
         rc = validate(&d, p, l);
         if (rc != CFX_OK) return rc;
-        p.src = cur;
-        p.dst = g_ctx.d_dst + out_off[k];
-        rc = launch(l, p, s);
+        p.src = level_ptr[k];
+        p.pitch = k ? d.src_row_pitch : pitch0;
+        p.dst = d_outs[k];
+        // fork: one of the context's streams that is not s
+        int a = static_cast<int>(k % kStreams);
+        if (g_ctx.streams[a] == s) a = (a + 1) % kStreams;
+        CFX_CUDA(cudaEventRecord(g_ctx.fork[k % kMaxMipLevels], s));
+        CFX_CUDA(cudaStreamWaitEvent(g_ctx.streams[a], g_ctx.fork[k % kMaxMipLevels], 0));
+        rc = launch(l, p, g_ctx.streams[a]);
         if (rc != CFX_OK) return rc;
-        CFX_CUDA(cudaMemcpyAsync(dsts[k], p.dst, static_cast<size_t>(p.total_blocks)*p.block_bytes, cudaMemcpyDeviceToHost, s));
+        used[a] = true;
+    }
+    for (int a = 0; a < kStreams; ++a) {
+        if (!used[a]) continue;
+        CFX_CUDA(cudaEventRecord(g_ctx.join[a], g_ctx.streams[a]));
+        CFX_CUDA(cudaStreamWaitEvent(s, g_ctx.join[a], 0));
+    }
+    return CFX_OK;
+}
+
+static int encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels,
+    void* const* dsts, const size_t* dst_sizes, void* const* mip_images)
+{
+    std::vector<cfx_surface_desc> descs;
+    int rc = mip_chain_descs(level0, filter, levels, dst_sizes, descs);
+    if (rc != CFX_OK) return rc;
+    levels = static_cast<uint32_t>(descs.size());
+    if (!src || !dsts) return fail(CFX_ERR_INVALID, "null buffer");
+    for (uint32_t k = 0; k < levels; ++k) if (!dsts[k]) return fail(CFX_ERR_INVALID, "level %u: null buffer", k);
+    // level 0: the chunked upload + encode of cfx_encode(); it leaves the whole RGBA32F surface in d_src
+    rc = encode_host(level0, src, dsts[0], dst_sizes[0]);
+    if (rc != CFX_OK || levels == 1) return rc;
+    std::vector<size_t> bytes(levels, 0), off(levels + 1, 0);
+    for (uint32_t k = 1; k < levels; ++k) { bytes[k] = cfx_encoded_size(&descs[k]); off[k + 1] = off[k] + align256(bytes[k]); }
+    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, off[levels]);
+    if (rc != CFX_OK) return rc;
+    std::vector<uint8_t*> d_outs(levels, nullptr);
+    for (uint32_t k = 1; k < levels; ++k) d_outs[k] = g_ctx.d_dst + off[k];
+    std::vector<const uint8_t*> level_ptr;
+    cudaStream_t s = g_ctx.streams[0];
+    rc = run_mip_levels(descs, g_ctx.d_src, align256(static_cast<size_t>(level0->width)*16u), filter, d_outs.data(), level_ptr, s);
+    if (rc != CFX_OK) return rc;
+    for (uint32_t k = 1; k < levels; ++k) {
+        CFX_CUDA(cudaMemcpyAsync(dsts[k], d_outs[k], bytes[k], cudaMemcpyDeviceToHost, s));
         if (mip_images && mip_images[k])
-            CFX_CUDA(cudaMemcpy2DAsync(mip_images[k], static_cast<size_t>(d.width)*16u, cur, d.src_row_pitch,
-                static_cast<size_t>(d.width)*16u, d.height, cudaMemcpyDeviceToHost, s));
-        prev = cur; prev_pitch = d.src_row_pitch;
+            CFX_CUDA(cudaMemcpy2DAsync(mip_images[k], static_cast<size_t>(descs[k].width)*16u, level_ptr[k], descs[k].src_row_pitch,
+                static_cast<size_t>(descs[k].width)*16u, descs[k].height, cudaMemcpyDeviceToHost, s));
     }
     CFX_CUDA(cudaStreamSynchronize(s));
     return CFX_OK;
+}
+
+static int encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_src, uint32_t filter, uint32_t levels,
+    void* const* d_dsts, const size_t* dst_sizes, cudaStream_t s)
+{
+    std::vector<cfx_surface_desc> descs;
+    int rc = mip_chain_descs(level0, filter, levels, dst_sizes, descs);
+    if (rc != CFX_OK) return rc;
+    levels = static_cast<uint32_t>(descs.size());
+    if (!d_src || !d_dsts) return fail(CFX_ERR_INVALID, "null buffer");
+    for (uint32_t k = 0; k < levels; ++k) if (!d_dsts[k]) return fail(CFX_ERR_INVALID, "level %u: null buffer", k);
+    if ((reinterpret_cast<uintptr_t>(d_src) | level0->src_row_pitch) & 15)
+        return fail(CFX_ERR_INVALID, "a device-resident level 0 must be 16-byte aligned with a 16-byte-multiple pitch");
+    rc = ensure_init(-1);
+    if (rc != CFX_OK) return rc;
+    std::vector<uint8_t*> d_outs(levels, nullptr);
+    for (uint32_t k = 0; k < levels; ++k) d_outs[k] = static_cast<uint8_t*>(d_dsts[k]);
+    std::vector<const uint8_t*> level_ptr;
+    return run_mip_levels(descs, static_cast<const uint8_t*>(d_src), level0->src_row_pitch, filter, d_outs.data(), level_ptr, s);
 }
 
 } // namespace cfx
@@ -405,6 +477,8 @@ void cfx_shutdown(void)
     cudaSetDevice(g_ctx.device);
     cudaDeviceSynchronize();
     for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
+    for (auto& e : g_ctx.fork) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : g_ctx.join) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (g_ctx.d_src) cudaFree(g_ctx.d_src);
     if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
     if (g_ctx.d_mip) cudaFree(g_ctx.d_mip);
@@ -509,6 +583,14 @@ int cfx_encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32
     std::lock_guard<std::mutex> lock(g_ctx.mutex);
     t_error[0] = 0;
     return encode_mip_chain(level0, src, filter, levels, dsts, dst_sizes, mip_images);
+}
+
+int cfx_encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_src, uint32_t filter, uint32_t levels,
+    void* const* d_dsts, const size_t* dst_sizes, void* cuda_stream)
+{
+    std::lock_guard<std::mutex> lock(g_ctx.mutex);
+    t_error[0] = 0;
+    return encode_mip_chain_device(level0, d_src, filter, levels, d_dsts, dst_sizes, static_cast<cudaStream_t>(cuda_stream));
 }
 
 void* cfx_host_alloc(size_t bytes)

@@ -26,6 +26,7 @@
  *   cfx_encode_mip_chain  <- Texture::generateMipmaps() (2D: each level resized from the one above,
  *                            lib/src/Texture.cpp:1457-1511) followed by Texture::convert(): level 0 is
  *                            uploaded once, the chain never leaves the GPU
+ *   cfx_encode_mip_chain_device <- the same for callers that already hold level 0 in HBM
  *   cfx_init/cfx_shutdown <- the one-time encoder table inits (rgbcx::init, bc7enc_compress_block_init,
  *                            astcenc context alloc), lib/src/S3tcConverter.cpp:54-64,158-168
  */
@@ -137,6 +138,12 @@ uint32_t cfx_mip_levels(uint32_t width, uint32_t height);
  * that receive the generated RGBA32F levels, tightly packed rows, top-down. */
 int cfx_encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels,
                          void* const* dsts, const size_t* dst_sizes, void* const* mip_images);
+
+/* The same for a level 0 already resident in DEVICE memory (16-byte aligned, pitch a multiple of 16), blocks written
+ * to DEVICE buffers d_dsts[k], everything queued on cuda_stream. The generated levels live in library-owned memory
+ * that the next chain call reuses: one chain in flight per context. */
+int cfx_encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_src, uint32_t filter, uint32_t levels,
+                                void* const* d_dsts, const size_t* dst_sizes, void* cuda_stream);
 
 /* Pinned host memory helpers for callers that want zero-copy staging. */
 void* cfx_host_alloc(size_t bytes);

@@ -82,6 +82,18 @@ def test_mip_chain_blocks_equal_per_level_encode(fmt):
         assert np.array_equal(b, cfx.encode(want, fmt)), (fmt, k)
 
 
+def test_mip_chain_device_equals_host_chain():
+    import torch
+    rng = np.random.default_rng(31)
+    img = rng.random((200, 333, 4), dtype=np.float32)
+    want = cfx.encode_mip_chain(img, "BC7", "Cubic")
+    got = cfx.encode_mip_chain_device(torch.from_numpy(img).cuda(), "BC7", "Cubic")
+    torch.cuda.synchronize()
+    assert len(got) == len(want) == 9
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g.cpu().numpy(), w), k
+
+
 def test_mip_chain_level_limit_and_errors():
     img = np.random.default_rng(5).random((16, 16, 4), dtype=np.float32)
     assert len(cfx.encode_mip_chain(img, "BC1_RGB", levels=3)) == 3
