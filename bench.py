@@ -468,7 +468,10 @@ def bench_mipgen(a, wl, size, rank, world, local, config, img, kw):
     import torch.distributed as dist
     import cuttlefish_b200 as cfx
     dev = torch.device("cuda", local)
-    img = np.ascontiguousarray(img, np.float32)
+    from cuttlefish_b200 import synth
+    # an 8-bit workload goes up as 8-bit texels: the library takes them as v/255, Image::convert(RGBAF) of an 8-bit image
+    img = np.ascontiguousarray(synth.to_rgba8(img) if wl["src"] == "RGBA8" else img.astype(np.float32))
+    texel0 = float(img.dtype.itemsize*4)
     host = torch.from_numpy(img).pin_memory()
     d_src = host.to(dev)
     sizes = [(max(1, size >> k), max(1, size >> k)) for k in range(cfx.mip_levels(size, size))]
@@ -527,12 +530,12 @@ def bench_mipgen(a, wl, size, rank, world, local, config, img, kw):
         # resize reads the level above, writes and re-reads the x-filtered intermediate, and writes the level (16 B each)
         alg = 0.0
         for k, (w, h) in enumerate(sizes):
-            alg += w*h*(16.0 + wl["write"])
+            alg += w*h*((16.0 if k else texel0) + wl["write"])
             if k:
                 pw, ph = sizes[k - 1]
-                alg += 16.0*(pw*ph + 2*w*ph + w*h)
+                alg += (16.0 if k > 1 else texel0)*pw*ph + 16.0*(2*w*ph + w*h)
         config = dict(config, mip_levels=len(sizes), layers=world,
-                      workload=config["workload"].replace(wl["src"], "RGBA32F") + " + generateMipmaps(CatmullRom) on the GPU + full mip chain (%d levels)" % len(sizes),
+                      workload=config["workload"] + " + generateMipmaps(CatmullRom) on the GPU + full mip chain (%d levels)" % len(sizes),
                       sharding="one texture with its chain per rank",
                       l2="level 0 (%d MiB) larger than L2; the tail levels are launch bound" % (img.nbytes >> 20))
         out = {"metric": "Mtexels/s encode", "value": world*texels/(ms*1e-3)/1e6, "unit": "Mtexels/s", "n_gpus": world,

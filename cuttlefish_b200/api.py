@@ -191,14 +191,14 @@ def encode_mip_chain_device(src, fmt, filter="CatmullRom", levels=None, outs=Non
     """generateMipmaps + convert for a float32 torch CUDA tensor [H,W,4]: the chain is made and encoded on the GPU,
     asynchronously on `stream`. Returns one CUDA uint8 tensor per level. Goes through cfx_encode_mip_chain_device."""
     import torch
-    if not src.is_cuda or src.dtype != torch.float32:
-        raise ValueError("encode_mip_chain_device needs a float32 CUDA tensor")
+    if not src.is_cuda or src.dtype not in (torch.float32, torch.uint8):
+        raise ValueError("encode_mip_chain_device needs a float32 or uint8 CUDA tensor")
     if src.dim() != 3 or src.shape[2] != 4 or src.stride(2) != 1 or src.stride(1) != 4:
         raise ValueError("expected [H,W,4] texels with contiguous rows")
     h, w, _ = src.shape
     n = mip_levels(w, h)
     n = n if levels is None else max(1, min(int(levels), n))
-    d = make_desc(fmt, w, h, "RGBA32F", src.stride(0) * 4, **kw)
+    d = make_desc(fmt, w, h, "RGBA32F" if src.dtype == torch.float32 else "RGBA8", src.stride(0) * src.element_size(), **kw)
     sizes = [encoded_size(fmt, max(1, w >> k), max(1, h >> k)) for k in range(n)]
     if sizes[0] == 0:
         raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
@@ -244,16 +244,20 @@ def mip_levels(width, height):
 
 
 def encode_mip_chain(img, fmt, filter="CatmullRom", levels=None, return_images=False, **kw):
-    """Texture::generateMipmaps(filter, levels) + Texture::convert() for one HOST float32 [H,W,4] surface with one
-    cfx_encode_mip_chain call: level 0 is uploaded once, the mips are made and encoded on the GPU.
-    Returns a list of uint8 block arrays (and, with return_images, the list of float32 mip images)."""
-    img = np.ascontiguousarray(img, dtype=np.float32)
+    """Texture::generateMipmaps(filter, levels) + Texture::convert() for one HOST [H,W,4] surface (float32, or uint8 taken
+    as v/255 like Image::convert(RGBAF)) with one cfx_encode_mip_chain call: level 0 is uploaded once, the mips are made
+    and encoded on the GPU. Returns a list of uint8 block arrays (and, with return_images, the list of mip images)."""
+    img = np.asarray(img)
+    if img.dtype != np.uint8:
+        img = img.astype(np.float32, copy=False)
+    img = np.ascontiguousarray(img)
     if img.ndim != 3 or img.shape[2] != 4:
         raise ValueError("expected [H,W,4] RGBA texels")
     h, w, _ = img.shape
+    src_format, texel = _src_format_of(img.dtype)
     n = mip_levels(w, h)
     n = n if levels is None else max(1, min(int(levels), n))
-    d = make_desc(fmt, w, h, "RGBA32F", w * 16, **kw)
+    d = make_desc(fmt, w, h, src_format, w * texel, **kw)
     outs, images = [], [img]
     for k in range(n):
         dk = make_desc(fmt, max(1, w >> k), max(1, h >> k), "RGBA32F", 16, **kw)

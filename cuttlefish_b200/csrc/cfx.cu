@@ -286,7 +286,7 @@ static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst,
 
 // resize.cu
 size_t resize_scratch_bytes(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh);
-int resize_device(const uint8_t* src, size_t src_pitch, uint32_t sw, uint32_t sh, uint8_t* dst, size_t dst_pitch,
+int resize_device(const uint8_t* src, size_t src_pitch, bool src_u8, uint32_t sw, uint32_t sh, uint8_t* dst, size_t dst_pitch,
     uint32_t dw, uint32_t dh, uint32_t filter, bool srgb, uint8_t* scratch, size_t scratch_cap, cudaStream_t stream);
 
 static size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -310,7 +310,7 @@ static int resize_host(const void* src, uint32_t sw, uint32_t sh, size_t src_pit
     cudaStream_t s = g_ctx.streams[0];
     CFX_CUDA(cudaMemcpy2DAsync(g_ctx.d_src, sp, src, src_pitch, static_cast<size_t>(sw)*16u, sh, cudaMemcpyHostToDevice, s));
     uint8_t* d_out = g_ctx.d_mip;
-    int n = resize_device(g_ctx.d_src, sp, sw, sh, d_out, dp, dw, dh, filter, color_space != 0, d_out + align256(dp*dh),
+    int n = resize_device(g_ctx.d_src, sp, false, sw, sh, d_out, dp, dw, dh, filter, color_space != 0, d_out + align256(dp*dh),
         scratch, s);
     if (n < 0) return fail(n, "resize failed: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches += static_cast<uint64_t>(n);
@@ -334,8 +334,9 @@ static int mip_chain_descs(const cfx_surface_desc* level0, uint32_t filter, uint
     EncodeParams p0; Launcher launcher;
     int rc = validate(level0, p0, launcher);
     if (rc != CFX_OK) return rc;
-    if (level0->src_format != CFX_SRC_RGBA32F)
-        return fail(CFX_ERR_INVALID, "the mip chain is generated from an RGBA32F level 0 (Image::Format::RGBAF)");
+    if (level0->src_format != CFX_SRC_RGBA32F && level0->src_format != CFX_SRC_RGBA8)
+        return fail(CFX_ERR_INVALID, "the mip chain is generated from an RGBA32F level 0 (Image::Format::RGBAF) or an RGBA8 one "
+            "(taken as v/255, Image::convert(RGBAF) of an 8-bit image)");
     if (filter > CFX_FILTER_BSPLINE) return fail(CFX_ERR_INVALID, "filter %u out of range", filter);
     if (!dst_sizes) return fail(CFX_ERR_INVALID, "null buffer");
     if (levels < 1) levels = 1;
@@ -345,7 +346,7 @@ static int mip_chain_descs(const cfx_surface_desc* level0, uint32_t filter, uint
     for (uint32_t k = 0; k < levels; ++k) {
         descs[k].width = level0->width >> k ? level0->width >> k : 1u;
         descs[k].height = level0->height >> k ? level0->height >> k : 1u;
-        if (k) descs[k].src_row_pitch = align256(static_cast<size_t>(descs[k].width)*16u);
+        if (k) { descs[k].src_format = CFX_SRC_RGBA32F; descs[k].src_row_pitch = align256(static_cast<size_t>(descs[k].width)*16u); }
         const size_t bytes = cfx_encoded_size(&descs[k]);
         if (dst_sizes[k] < bytes) return fail(CFX_ERR_INVALID, "level %u: dst_size %zu < %zu", k, dst_sizes[k], bytes);
     }
@@ -375,7 +376,8 @@ static int run_mip_levels(const std::vector<cfx_surface_desc>& descs, const uint
         const cfx_surface_desc& d = descs[k];
         if (k) {
             uint8_t* cur = g_ctx.d_mip + off[k];
-            int n = resize_device(level_ptr[k - 1], prev_pitch, descs[k - 1].width, descs[k - 1].height, cur, d.src_row_pitch,
+            int n = resize_device(level_ptr[k - 1], prev_pitch, descs[k - 1].src_format == CFX_SRC_RGBA8, descs[k - 1].width,
+                descs[k - 1].height, cur, d.src_row_pitch,
                 d.width, d.height, filter, descs[0].color_space != 0, d_scratch, scratch, s);
             if (n < 0) return fail(n, "level %u: resize failed", k);
             g_launches += static_cast<uint64_t>(n);
@@ -426,7 +428,8 @@ static int encode_mip_chain(const cfx_surface_desc* level0, const void* src, uin
     for (uint32_t k = 1; k < levels; ++k) d_outs[k] = g_ctx.d_dst + off[k];
     std::vector<const uint8_t*> level_ptr;
     cudaStream_t s = g_ctx.streams[0];
-    rc = run_mip_levels(descs, g_ctx.d_src, align256(static_cast<size_t>(level0->width)*16u), filter, d_outs.data(), level_ptr, s);
+    rc = run_mip_levels(descs, g_ctx.d_src, align256(static_cast<size_t>(level0->width)*src_texel_bytes(level0->src_format)), filter,
+        d_outs.data(), level_ptr, s);
     if (rc != CFX_OK) return rc;
     for (uint32_t k = 1; k < levels; ++k) {
         CFX_CUDA(cudaMemcpyAsync(dsts[k], d_outs[k], bytes[k], cudaMemcpyDeviceToHost, s));
@@ -447,8 +450,8 @@ static int encode_mip_chain_device(const cfx_surface_desc* level0, const void* d
     levels = static_cast<uint32_t>(descs.size());
     if (!d_src || !d_dsts) return fail(CFX_ERR_INVALID, "null buffer");
     for (uint32_t k = 0; k < levels; ++k) if (!d_dsts[k]) return fail(CFX_ERR_INVALID, "level %u: null buffer", k);
-    if ((reinterpret_cast<uintptr_t>(d_src) | level0->src_row_pitch) & 15)
-        return fail(CFX_ERR_INVALID, "a device-resident level 0 must be 16-byte aligned with a 16-byte-multiple pitch");
+    if ((reinterpret_cast<uintptr_t>(d_src) | level0->src_row_pitch) & (level0->src_format == CFX_SRC_RGBA8 ? 3 : 15))
+        return fail(CFX_ERR_INVALID, "a device-resident level 0 must be texel aligned (16 bytes for RGBA32F, 4 for RGBA8)");
     rc = ensure_init(-1);
     if (rc != CFX_OK) return rc;
     std::vector<uint8_t*> d_outs(levels, nullptr);

@@ -116,11 +116,22 @@ __device__ __forceinline__ double linear_to_srgb(double c)      // Color.h:236-2
 // One pass. ALONG_X: dst(x, y) = sum_k w[x][k] * src(left[x] + k, y). Else along y with the tables indexed by the
 // bottom-up row number: dst row y is table entry dh-1-y, and its k-th tap is source row sh-1-(left+k).
 // SRGB_IN converts each tap to linear on the fly (first pass), SRGB_OUT the result back (last pass).
-template <bool ALONG_X, bool SRGB_IN, bool SRGB_OUT>
-__global__ void __launch_bounds__(256) resize_pass_kernel(const float4* __restrict__ src, size_t src_pitch4, uint32_t src_h,
+// SRC_U8: the source is an RGBA8 surface read as (float)v/255.0F, FreeImage_ConvertToRGBAF's conversion
+// (lib/FreeImage/Source/FreeImage/ConversionRGBAF.cpp:116-119) -- what Image::convert(RGBAF) stores for an 8-bit image.
+// The 256 possible values are tabulated once per CTA, already widened to double (and taken to linear for sRGB), so a
+// tap costs four shared-memory loads instead of four divisions and four conversions.
+template <bool ALONG_X, bool SRGB_IN, bool SRGB_OUT, bool SRC_U8>
+__global__ void __launch_bounds__(256) resize_pass_kernel(const uint8_t* __restrict__ src, size_t src_pitch, uint32_t src_h,
     float4* __restrict__ dst, size_t dst_pitch4, uint32_t dw, uint32_t dh,
     const int2* __restrict__ span, const double* __restrict__ weight, int window)
 {
+    __shared__ double lut[SRC_U8 ? 512 : 1];           // [0..255] colour channels, [256..511] alpha (never sRGB)
+    if (SRC_U8) {
+        const float f = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);
+        lut[threadIdx.x] = SRGB_IN ? static_cast<double>(static_cast<float>(srgb_to_linear(f))) : static_cast<double>(f);
+        lut[256 + threadIdx.x] = static_cast<double>(f);
+        __syncthreads();
+    }
     const uint32_t x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= dw || y >= dh) return;
     const uint32_t u = ALONG_X ? x : dh - 1u - y;
@@ -128,18 +139,27 @@ __global__ void __launch_bounds__(256) resize_pass_kernel(const float4* __restri
     const double* w = weight + static_cast<size_t>(u)*window;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (int k = 0; k < sp.y; ++k) {
-        const float4 v = ALONG_X ? src[y*src_pitch4 + static_cast<uint32_t>(sp.x + k)]
-                                 : src[static_cast<size_t>(src_h - 1u - static_cast<uint32_t>(sp.x + k))*src_pitch4 + x];
+        const uint32_t i = static_cast<uint32_t>(sp.x + k);
+        const uint32_t tx = ALONG_X ? i : x, ty = ALONG_X ? y : src_h - 1u - i;
         const double wk = w[k];
-        double c0 = v.x, c1 = v.y, c2 = v.z;
-        if (SRGB_IN) {
-            c0 = static_cast<float>(srgb_to_linear(c0)); c1 = static_cast<float>(srgb_to_linear(c1));
-            c2 = static_cast<float>(srgb_to_linear(c2));
+        double c0, c1, c2, c3;
+        if (SRC_U8) {
+            const uchar4 v = *reinterpret_cast<const uchar4*>(src + ty*src_pitch + static_cast<size_t>(tx)*4u);
+            c0 = lut[v.x]; c1 = lut[v.y]; c2 = lut[v.z]; c3 = lut[256 + v.w];
+        } else {
+            const float4 v = *reinterpret_cast<const float4*>(src + ty*src_pitch + static_cast<size_t>(tx)*16u);
+            if (SRGB_IN) {
+                c0 = static_cast<float>(srgb_to_linear(v.x)); c1 = static_cast<float>(srgb_to_linear(v.y));
+                c2 = static_cast<float>(srgb_to_linear(v.z));
+            } else {
+                c0 = v.x; c1 = v.y; c2 = v.z;
+            }
+            c3 = v.w;
         }
         a0 = __dadd_rn(a0, __dmul_rn(wk, c0));
         a1 = __dadd_rn(a1, __dmul_rn(wk, c1));
         a2 = __dadd_rn(a2, __dmul_rn(wk, c2));
-        a3 = __dadd_rn(a3, __dmul_rn(wk, static_cast<double>(v.w)));
+        a3 = __dadd_rn(a3, __dmul_rn(wk, c3));
     }
     float4 o = make_float4(static_cast<float>(a0), static_cast<float>(a1), static_cast<float>(a2), static_cast<float>(a3));
     if (SRGB_OUT) {
@@ -170,19 +190,39 @@ int upload_table(const WindowTable& t, uint8_t* scratch, size_t& used, size_t ca
     return CFX_OK;
 }
 
-template <bool ALONG_X>
-void launch_pass(bool srgb_in, bool srgb_out, const float4* src, size_t sp4, uint32_t sh, float4* dst, size_t dp4,
+template <bool ALONG_X, bool SRC_U8>
+void launch_pass(bool srgb_in, bool srgb_out, const uint8_t* src, size_t sp, uint32_t sh, float4* dst, size_t dp4,
     uint32_t dw, uint32_t dh, const DeviceTable& t, cudaStream_t s)
 {
     const dim3 grid((dw + 255)/256, dh), block(256);
     if (srgb_in && srgb_out)
-        resize_pass_kernel<ALONG_X, true, true><<<grid, block, 0, s>>>(src, sp4, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
+        resize_pass_kernel<ALONG_X, true, true, SRC_U8><<<grid, block, 0, s>>>(src, sp, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
     else if (srgb_in)
-        resize_pass_kernel<ALONG_X, true, false><<<grid, block, 0, s>>>(src, sp4, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
+        resize_pass_kernel<ALONG_X, true, false, SRC_U8><<<grid, block, 0, s>>>(src, sp, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
     else if (srgb_out)
-        resize_pass_kernel<ALONG_X, false, true><<<grid, block, 0, s>>>(src, sp4, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
+        resize_pass_kernel<ALONG_X, false, true, SRC_U8><<<grid, block, 0, s>>>(src, sp, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
     else
-        resize_pass_kernel<ALONG_X, false, false><<<grid, block, 0, s>>>(src, sp4, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
+        resize_pass_kernel<ALONG_X, false, false, SRC_U8><<<grid, block, 0, s>>>(src, sp, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
+}
+
+template <bool ALONG_X>
+void launch_pass(bool src_u8, bool srgb_in, bool srgb_out, const uint8_t* src, size_t sp, uint32_t sh, float4* dst, size_t dp4,
+    uint32_t dw, uint32_t dh, const DeviceTable& t, cudaStream_t s)
+{
+    if (src_u8) launch_pass<ALONG_X, true>(srgb_in, srgb_out, src, sp, sh, dst, dp4, dw, dh, t, s);
+    else launch_pass<ALONG_X, false>(srgb_in, srgb_out, src, sp, sh, dst, dp4, dw, dh, t, s);
+}
+
+// a same-size "resize" of an RGBA8 source: only the conversion
+__global__ void __launch_bounds__(256) widen_u8_kernel(const uint8_t* __restrict__ src, size_t src_pitch, float4* __restrict__ dst,
+    size_t dst_pitch4, uint32_t w, uint32_t h)
+{
+    const uint32_t x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < w && y < h) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(src + y*src_pitch + static_cast<size_t>(x)*4u);
+        dst[y*dst_pitch4 + x] = make_float4(__fdiv_rn(static_cast<float>(v.x), 255.0f), __fdiv_rn(static_cast<float>(v.y), 255.0f),
+            __fdiv_rn(static_cast<float>(v.z), 255.0f), __fdiv_rn(static_cast<float>(v.w), 255.0f));
+    }
 }
 
 } // namespace
@@ -199,15 +239,19 @@ size_t resize_scratch_bytes(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh)
     return ((tmp + 255) & ~static_cast<size_t>(255)) + table(dw, sw) + table(dh, sh);
 }
 
-// Resize one RGBA32F surface resident in device memory (pitches in bytes, multiples of 16) on `stream`.
-// `scratch` must hold resize_scratch_bytes(). Returns the number of kernels launched, or a negative CFX error.
-int resize_device(const uint8_t* src, size_t src_pitch, uint32_t sw, uint32_t sh, uint8_t* dst, size_t dst_pitch,
+// Resize one surface resident in device memory (RGBA32F, or RGBA8 when src_u8; pitches in bytes; the RGBA32F result
+// has a 16-byte-multiple pitch) on `stream`. `scratch` must hold resize_scratch_bytes(). Returns the number of kernels
+// launched, or a negative CFX error.
+int resize_device(const uint8_t* src, size_t src_pitch, bool src_u8, uint32_t sw, uint32_t sh, uint8_t* dst, size_t dst_pitch,
     uint32_t dw, uint32_t dh, uint32_t filter, bool srgb, uint8_t* scratch, size_t scratch_cap, cudaStream_t stream)
 {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
-    const size_t sp4 = src_pitch/16, dp4 = dst_pitch/16;
+    const size_t dp4 = dst_pitch/16;
     if (sw == dw && sh == dh) {                     // Image.cpp:1330-1334: a plain copy
+        if (src_u8) {
+            widen_u8_kernel<<<dim3((dw + 255)/256, dh), 256, 0, stream>>>(src, src_pitch, d4, dp4, dw, dh);
+            return cudaGetLastError() == cudaSuccess ? 1 : CFX_ERR_CUDA;
+        }
         if (cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, static_cast<size_t>(dw)*16u, dh, cudaMemcpyDeviceToDevice,
                 stream) != cudaSuccess)
             return CFX_ERR_CUDA;
@@ -219,7 +263,8 @@ int resize_device(const uint8_t* src, size_t src_pitch, uint32_t sw, uint32_t sh
     size_t used = (static_cast<size_t>(tw)*th*16u + 255) & ~static_cast<size_t>(255);
     if (used > scratch_cap) return CFX_ERR_INVALID;
     float4* tmp = reinterpret_cast<float4*>(scratch);
-    const size_t tp4 = tw;
+    const uint8_t* tmp8 = scratch;
+    const size_t tp = static_cast<size_t>(tw)*16u;
     DeviceTable tx, ty;
     WindowTable hx, hy;
     if (need_x) {
@@ -235,18 +280,18 @@ int resize_device(const uint8_t* src, size_t src_pitch, uint32_t sw, uint32_t sh
     int launches = 0;
     if (need_x && need_y) {
         if (x_first) {
-            launch_pass<true>(srgb, false, s4, sp4, sh, tmp, tp4, dw, sh, tx, stream);
-            launch_pass<false>(false, srgb, tmp, tp4, sh, d4, dp4, dw, dh, ty, stream);
+            launch_pass<true>(src_u8, srgb, false, src, src_pitch, sh, tmp, tw, dw, sh, tx, stream);
+            launch_pass<false>(false, false, srgb, tmp8, tp, sh, d4, dp4, dw, dh, ty, stream);
         } else {
-            launch_pass<false>(srgb, false, s4, sp4, sh, tmp, tp4, sw, dh, ty, stream);
-            launch_pass<true>(false, srgb, tmp, tp4, dh, d4, dp4, dw, dh, tx, stream);
+            launch_pass<false>(src_u8, srgb, false, src, src_pitch, sh, tmp, tw, sw, dh, ty, stream);
+            launch_pass<true>(false, false, srgb, tmp8, tp, dh, d4, dp4, dw, dh, tx, stream);
         }
         launches = 2;
     } else if (need_x) {
-        launch_pass<true>(srgb, srgb, s4, sp4, sh, d4, dp4, dw, dh, tx, stream);
+        launch_pass<true>(src_u8, srgb, srgb, src, src_pitch, sh, d4, dp4, dw, dh, tx, stream);
         launches = 1;
     } else {
-        launch_pass<false>(srgb, srgb, s4, sp4, sh, d4, dp4, dw, dh, ty, stream);
+        launch_pass<false>(src_u8, srgb, srgb, src, src_pitch, sh, d4, dp4, dw, dh, ty, stream);
         launches = 1;
     }
     // the host tables are pageable: the copies above have been staged by the time cudaMemcpyAsync returned

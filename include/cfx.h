@@ -131,15 +131,16 @@ int cfx_resize(const void* src, uint32_t src_width, uint32_t src_height, size_t 
                uint32_t filter, uint32_t color_space);
 /* floor(log2(max(width, height))) + 1: the length of a full 2D mip chain. */
 uint32_t cfx_mip_levels(uint32_t width, uint32_t height);
-/* generateMipmaps(filter, levels) + convert() for one 2D surface. level0 describes the RGBA32F level-0 image
- * (src); level k has size max(1, w >> k) x max(1, h >> k), is resized on the GPU from level k-1 and encoded
+/* generateMipmaps(filter, levels) + convert() for one 2D surface. level0 describes the level-0 image (src): RGBA32F,
+ * or RGBA8 taken as (float)v/255 -- what Image::convert(RGBAF) makes of an 8-bit image (FreeImage_ConvertToRGBAF), so
+ * an 8-bit source need not be widened on the host; level k has size max(1, w >> k) x max(1, h >> k), is resized on the GPU from level k-1 and encoded
  * with level0's format/type/quality/...; dsts[k] / dst_sizes[k] receive its blocks (k = 0 .. levels-1).
  * mip_images, if not NULL, is an array of `levels` host pointers (entries may be NULL; entry 0 is ignored)
  * that receive the generated RGBA32F levels, tightly packed rows, top-down. */
 int cfx_encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels,
                          void* const* dsts, const size_t* dst_sizes, void* const* mip_images);
 
-/* The same for a level 0 already resident in DEVICE memory (16-byte aligned, pitch a multiple of 16), blocks written
+/* The same for a level 0 already resident in DEVICE memory (texel aligned: 16 bytes for RGBA32F, 4 for RGBA8), blocks written
  * to DEVICE buffers d_dsts[k], everything queued on cuda_stream. The generated levels live in library-owned memory
  * that the next chain call reuses: one chain in flight per context. */
 int cfx_encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_src, uint32_t filter, uint32_t levels,

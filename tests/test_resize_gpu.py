@@ -94,6 +94,36 @@ def test_mip_chain_device_equals_host_chain():
         assert np.array_equal(g.cpu().numpy(), w), k
 
 
+def test_mip_chain_from_8bit_level0_equals_widened_float_chain():
+    """An RGBA8 level 0 is taken as (float)v/255, FreeImage_ConvertToRGBAF's conversion (ConversionRGBAF.cpp:116-119)."""
+    import torch
+    rng = np.random.default_rng(41)
+    img8 = rng.integers(0, 256, (77, 130, 4), dtype=np.uint8)
+    imgf = img8.astype(np.float32) / np.float32(255.0)
+    want_blocks, want_images = cfx.encode_mip_chain(imgf, "BC3", "CatmullRom", return_images=True)
+    got_blocks, got_images = cfx.encode_mip_chain(img8, "BC3", "CatmullRom", return_images=True)
+    dev_blocks = cfx.encode_mip_chain_device(torch.from_numpy(img8).cuda(), "BC3", "CatmullRom")
+    torch.cuda.synchronize()
+    assert len(got_blocks) == len(want_blocks) == 8
+    for k in range(8):
+        if k:
+            assert np.array_equal(got_images[k], want_images[k]), k
+            assert np.array_equal(got_images[k], R.mip_chain(imgf, "CatmullRom")[k]), k
+        assert np.array_equal(got_blocks[k], want_blocks[k]), k
+        assert np.array_equal(dev_blocks[k].cpu().numpy(), want_blocks[k]), k
+    # sRGB: the tabulated 8-bit path must agree with the float path (same transfer function, same rounding)
+    _, a = cfx.encode_mip_chain(img8, "BC1_RGB", "Cubic", return_images=True, srgb=True)
+    _, b = cfx.encode_mip_chain(imgf, "BC1_RGB", "Cubic", return_images=True, srgb=True)
+    for k in range(1, 8):
+        assert np.array_equal(a[k], b[k]), k
+    # a 1-texel-wide image only has the pass along y: the conversion must happen there too
+    col8 = rng.integers(0, 256, (33, 1, 4), dtype=np.uint8)
+    _, images = cfx.encode_mip_chain(col8, "BC1_RGB", "Box", return_images=True)
+    want = R.mip_chain(col8.astype(np.float32) / np.float32(255.0), "Box")
+    for k in range(1, len(want)):
+        assert np.array_equal(images[k], want[k]), k
+
+
 def test_mip_chain_level_limit_and_errors():
     img = np.random.default_rng(5).random((16, 16, 4), dtype=np.float32)
     assert len(cfx.encode_mip_chain(img, "BC1_RGB", levels=3)) == 3
