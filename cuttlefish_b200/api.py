@@ -243,7 +243,7 @@ def mip_levels(width, height):
     return int(load().cfx_mip_levels(int(width), int(height)))
 
 
-def encode_mip_chain(img, fmt, filter="CatmullRom", levels=None, return_images=False, **kw):
+def encode_mip_chain(img, fmt, filter="CatmullRom", levels=None, return_images=False, outs=None, **kw):
     """Texture::generateMipmaps(filter, levels) + Texture::convert() for one HOST [H,W,4] surface (float32, or uint8 taken
     as v/255 like Image::convert(RGBAF)) with one cfx_encode_mip_chain call: level 0 is uploaded once, the mips are made
     and encoded on the GPU. Returns a list of uint8 block arrays (and, with return_images, the list of mip images)."""
@@ -258,13 +258,17 @@ def encode_mip_chain(img, fmt, filter="CatmullRom", levels=None, return_images=F
     n = mip_levels(w, h)
     n = n if levels is None else max(1, min(int(levels), n))
     d = make_desc(fmt, w, h, src_format, w * texel, **kw)
-    outs, images = [], [img]
+    given, outs, images = outs, [], [img]
     for k in range(n):
         dk = make_desc(fmt, max(1, w >> k), max(1, h >> k), "RGBA32F", 16, **kw)
         size = int(load().cfx_encoded_size(ctypes.byref(dk)))
         if size == 0:
             raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
-        outs.append(np.empty(size, np.uint8))
+        if given is None:
+            outs.append(np.empty(size, np.uint8))
+        else:                                   # caller-owned (e.g. pinned) output buffers, one per level
+            assert given[k].dtype == np.uint8 and given[k].size >= size and given[k].flags["C_CONTIGUOUS"]
+            outs.append(given[k][:size])
         if return_images and k:
             images.append(np.empty((max(1, h >> k), max(1, w >> k), 4), np.float32))
     dst = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
