@@ -44,10 +44,23 @@ CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, f
     out.err = 3.0e38f; out.table = 0; out.sel = 0;
 #pragma unroll 1
     for (uint32_t tb = 0; tb < 8; ++tb) {
+        // The table's four colours p_k (clamped), kept as -2 p_k and |p_k|^2: the error of texel x to colour k is
+        // |x|^2 + (|p_k|^2 - 2 p_k.x), three multiply-adds per candidate. For 8-bit sources every term is an integer
+        // below 2^24, so this is exactly the sum of squared differences.
+        float n0[4], n1[4], n2[4], cc[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            int m = (k & 2u) ? -static_cast<int>(kMod[tb][k & 1u]) : static_cast<int>(kMod[tb][k & 1u]);
+            if (tmask && k == 0u) m = 0;
+            const float p0 = static_cast<float>(clamp255(base[0] + m)), p1 = static_cast<float>(clamp255(base[1] + m)),
+                p2 = static_cast<float>(clamp255(base[2] + m));
+            n0[k] = -2.0f*p0; n1[k] = -2.0f*p1; n2[k] = -2.0f*p2;
+            cc[k] = p0*p0 + p1*p1 + p2*p2;
+        }
         float err = 0.0f;
         uint32_t sel = 0;
-        for (uint32_t t = 0; t < 16; ++t) {
-            if (!((mask >> t) & 1u)) continue;
+        for (uint32_t left = mask; left; left &= left - 1u) {
+            const uint32_t t = static_cast<uint32_t>(__ffs(left)) - 1u;
             if ((tmask >> t) & 1u) { sel |= 2u << (2*t); continue; }
             const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
             float be = 3.0e38f;
@@ -55,14 +68,10 @@ CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, f
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k) {
                 if (tmask && k == 2u) continue;
-                int m = (k & 2u) ? -static_cast<int>(kMod[tb][k & 1u]) : static_cast<int>(kMod[tb][k & 1u]);
-                if (tmask && k == 0u) m = 0;
-                const float d0 = static_cast<float>(clamp255(base[0] + m)) - x0, d1 = static_cast<float>(clamp255(base[1] + m)) - x1,
-                    d2 = static_cast<float>(clamp255(base[2] + m)) - x2;
-                const float e = d0*d0 + d1*d1 + d2*d2;
+                const float e = cc[k] + n0[k]*x0 + n1[k]*x1 + n2[k]*x2;
                 if (e < be) { be = e; bk = k; }
             }
-            err += be;
+            err += fmaxf(be + (x0*x0 + x1*x1 + x2*x2), 0.0f);
             sel |= bk << (2*t);
             if (err >= out.err || err >= limit) break;
         }
