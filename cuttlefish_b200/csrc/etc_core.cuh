@@ -34,16 +34,21 @@ CFX_HD int expand4(int v) { return (v << 4) | v; }
 CFX_HD int expand6(int v) { return (v << 2) | (v >> 4); }
 CFX_HD int expand7(int v) { return (v << 1) | (v >> 6); }
 
+#ifndef CFX_ETC_NARROW
+#define CFX_ETC_NARROW 1
+#endif
 struct HalfFit { float err; uint32_t table; uint32_t sel; };   // sel: 2 bits per texel t (only the half's texels)
 
 // Best modifier table and selectors of one half (texel mask) for an 8-bit base colour.
 // tmask != 0: punch-through block (ETC2 RGB8A1 with the opaque bit clear): texels of tmask take selector 2
 // (transparent) at no cost, the others choose among {+0, +big, -big} (selectors 0, 1, 3).
-CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask = 0)
+// Only the tables tb0 .. tb1 are tried.
+CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask = 0,
+    uint32_t tb0 = 0, uint32_t tb1 = 7)
 {
     out.err = 3.0e38f; out.table = 0; out.sel = 0;
 #pragma unroll 1
-    for (uint32_t tb = 0; tb < 8; ++tb) {
+    for (uint32_t tb = tb0; tb <= tb1; ++tb) {
         // The table's four colours p_k (clamped), kept as -2 p_k and |p_k|^2: the error of texel x to colour k is
         // |x|^2 + (|p_k|^2 - 2 p_k.x), three multiply-adds per candidate. For 8-bit sources every term is an integer
         // below 2^24, so this is exactly the sum of squared differences.
@@ -99,7 +104,11 @@ CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* 
 #pragma unroll
             for (int c = 0; c < 3; ++c) base[c] = bits == 5 ? expand5(t[c]) : expand4(t[c]);
             HalfFit f;
-            half_fit(xs, lane, mask, base, best.err, f, tmask);
+            // a one-step move of the base colour rarely changes the best table by more than one: the short descents
+            // (up to Quality::Normal) only look at the incumbent's neighbours, the long ones at all eight
+            const bool narrow = CFX_ETC_NARROW && rounds <= 1;
+            half_fit(xs, lane, mask, base, best.err, f, tmask, narrow ? (best.table ? best.table - 1u : 0u) : 0u,
+                narrow ? min(best.table + 1u, 7u) : 7u);
             if (f.err < best.err) { best = f; q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; improved = true; }
         }
         if (!improved) break;
