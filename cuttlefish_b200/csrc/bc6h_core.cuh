@@ -124,7 +124,7 @@ CFX_HD float assign_indices(float* xs, uint32_t lane, uint32_t mask, const int* 
 }
 
 // Full fit of one subset: PCA -> quantise -> indices -> 2 x least squares.
-CFX_HD void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbits, int ibits, SubsetFit& f, bool sg)
+CFX_HD_NOINLINE void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbits, int ibits, SubsetFit& f, bool sg)
 {
     float n = 0.0f, m[3] = {0, 0, 0};
     for (uint32_t t = 0; t < 16; ++t) {
