@@ -43,7 +43,7 @@ CFX_HD int unquantize(int x, int bits, bool sg)
     return ((x << 15) + 0x4000) >> (bits - 1);
 }
 
-CFX_HD int quantize(float u, int bits, bool sg)
+CFX_HD_NOINLINE int quantize(float u, int bits, bool sg)
 {
     if (sg) {
         const int maxq = (1 << (bits - 1)) - 1;
@@ -79,7 +79,7 @@ struct SubsetFit {
 };
 
 // Exact index search for the texels of `mask` against the palette of (q0, q1); returns the error.
-CFX_HD float assign_indices(float* xs, uint32_t lane, uint32_t mask, const int* q0, const int* q1, int wbits, int ibits,
+CFX_HD_NOINLINE float assign_indices(float* xs, uint32_t lane, uint32_t mask, const int* q0, const int* q1, int wbits, int ibits,
     uint64_t& idx_out, bool sg)
 {
     const int n = 1 << ibits;
