@@ -37,51 +37,76 @@ CFX_HD int expand7(int v) { return (v << 1) | (v >> 6); }
 #ifndef CFX_ETC_NARROW
 #define CFX_ETC_NARROW 1
 #endif
-struct HalfFit { float err; uint32_t table; uint32_t sel; };   // sel: 2 bits per texel t (only the half's texels)
+struct HalfFit { float err; uint32_t table; };
 
-// Best modifier table and selectors of one half (texel mask) for an 8-bit base colour.
+// The four colours of modifier table tb around an 8-bit base colour (clamped), kept as -2 p_k and |p_k|^2: the error of
+// texel x to colour k is |x|^2 + (|p_k|^2 - 2 p_k.x), three multiply-adds per candidate. For 8-bit sources every term is
+// an integer below 2^24, so this is exactly the sum of squared differences.
 // tmask != 0: punch-through block (ETC2 RGB8A1 with the opaque bit clear): texels of tmask take selector 2
 // (transparent) at no cost, the others choose among {+0, +big, -big} (selectors 0, 1, 3).
-// Only the tables tb0 .. tb1 are tried.
+struct TableColours { float n0[4], n1[4], n2[4], cc[4]; };
+
+CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours& p)
+{
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+        int m = (k & 2u) ? -static_cast<int>(kMod[tb][k & 1u]) : static_cast<int>(kMod[tb][k & 1u]);
+        if (punch && k == 0u) m = 0;
+        const float p0 = static_cast<float>(clamp255(base[0] + m)), p1 = static_cast<float>(clamp255(base[1] + m)),
+            p2 = static_cast<float>(clamp255(base[2] + m));
+        p.n0[k] = -2.0f*p0; p.n1[k] = -2.0f*p1; p.n2[k] = -2.0f*p2;
+        p.cc[k] = p0*p0 + p1*p1 + p2*p2;
+    }
+}
+
+// Best modifier table (of tb0 .. tb1) of one half (texel mask) for an 8-bit base colour, and its error. The selectors are
+// not kept: most fits lose, half_selectors() recomputes them for the one that ends up in the block.
 CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask = 0,
     uint32_t tb0 = 0, uint32_t tb1 = 7)
 {
-    out.err = 3.0e38f; out.table = 0; out.sel = 0;
+    out.err = 3.0e38f; out.table = 0;
 #pragma unroll 1
     for (uint32_t tb = tb0; tb <= tb1; ++tb) {
-        // The table's four colours p_k (clamped), kept as -2 p_k and |p_k|^2: the error of texel x to colour k is
-        // |x|^2 + (|p_k|^2 - 2 p_k.x), three multiply-adds per candidate. For 8-bit sources every term is an integer
-        // below 2^24, so this is exactly the sum of squared differences.
-        float n0[4], n1[4], n2[4], cc[4];
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
-            int m = (k & 2u) ? -static_cast<int>(kMod[tb][k & 1u]) : static_cast<int>(kMod[tb][k & 1u]);
-            if (tmask && k == 0u) m = 0;
-            const float p0 = static_cast<float>(clamp255(base[0] + m)), p1 = static_cast<float>(clamp255(base[1] + m)),
-                p2 = static_cast<float>(clamp255(base[2] + m));
-            n0[k] = -2.0f*p0; n1[k] = -2.0f*p1; n2[k] = -2.0f*p2;
-            cc[k] = p0*p0 + p1*p1 + p2*p2;
-        }
+        TableColours p;
+        table_colours(base, tb, tmask != 0, p);
         float err = 0.0f;
-        uint32_t sel = 0;
-        for (uint32_t left = mask; left; left &= left - 1u) {
+        for (uint32_t left = mask & ~tmask; left; left &= left - 1u) {
             const uint32_t t = static_cast<uint32_t>(__ffs(left)) - 1u;
-            if ((tmask >> t) & 1u) { sel |= 2u << (2*t); continue; }
             const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
-            float be = 3.0e38f;
-            uint32_t bk = 0;
+            float be = p.cc[0] + p.n0[0]*x0 + p.n1[0]*x1 + p.n2[0]*x2;
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
+            for (uint32_t k = 1; k < 4; ++k) {
                 if (tmask && k == 2u) continue;
-                const float e = cc[k] + n0[k]*x0 + n1[k]*x1 + n2[k]*x2;
-                if (e < be) { be = e; bk = k; }
+                be = fminf(be, p.cc[k] + p.n0[k]*x0 + p.n1[k]*x1 + p.n2[k]*x2);
             }
             err += fmaxf(be + (x0*x0 + x1*x1 + x2*x2), 0.0f);
-            sel |= bk << (2*t);
             if (err >= out.err || err >= limit) break;
         }
-        if (err < out.err) { out.err = err; out.table = tb; out.sel = sel; }
+        if (err < out.err) { out.err = err; out.table = tb; }
     }
+}
+
+// Selectors (2 bits per texel t, only the half's texels) of a base colour and table: the first minimum over k.
+CFX_HD uint32_t half_selectors(float* xs, uint32_t lane, uint32_t mask, const int* base, uint32_t tb, uint32_t tmask = 0)
+{
+    TableColours p;
+    table_colours(base, tb, tmask != 0, p);
+    uint32_t sel = 0;
+    for (uint32_t left = mask; left; left &= left - 1u) {
+        const uint32_t t = static_cast<uint32_t>(__ffs(left)) - 1u;
+        if ((tmask >> t) & 1u) { sel |= 2u << (2*t); continue; }
+        const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
+        float be = 3.0e38f;
+        uint32_t bk = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            if (tmask && k == 2u) continue;
+            const float e = p.cc[k] + p.n0[k]*x0 + p.n1[k]*x1 + p.n2[k]*x2;
+            if (e < be) { be = e; bk = k; }
+        }
+        sel |= bk << (2*t);
+    }
+    return sel;
 }
 
 // Descent of one half's quantised base colour (bits = 4 or 5) within [lo, hi] per channel.
@@ -214,7 +239,10 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
                 put_be(h, l, 36, fB.table, 3);
                 put_be(h, l, 33, tmask ? 0u : static_cast<uint32_t>(diff), 1);      // RGB8A1: this bit is the opaque flag
                 put_be(h, l, 32, flip, 1);
-                l = pixel_bits((fA.sel & (maskA*0 + 0xFFFFFFFFu)) | fB.sel);
+                int bA[3], bB[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { bA[c] = diff ? expand5(qA[c]) : expand4(qA[c]); bB[c] = diff ? expand5(qB[c]) : expand4(qB[c]); }
+                l = pixel_bits(half_selectors(xs, lane, maskA, bA, fA.table, tmask) | half_selectors(xs, lane, maskB, bB, fB.table, tmask));
                 out.err = err; out.hi = h; out.lo = l;
             }
         }
