@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
             const float4* bxf = s_pxf + b*kPxfStride;
 
             // block-level facts
-            uint32_t amin = 255;
+            uint32_t amin = 255, amax = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) amin = min(amin, bx[i] >> 24);
+            for (int i = 0; i < 16; ++i) { amin = min(amin, bx[i] >> 24); amax = max(amax, bx[i] >> 24); }
             const bool has_alpha = amin < 255 && (p.color_mask & 8u);
+            const bool flat_alpha = amin == amax;        // alpha adds nothing to any scatter matrix
 
             // ---- phase 1: score 64/G two-subset shapes per lane
             float sT[4] = {0, 0, 0, 0};
@@ -120,11 +121,13 @@ __global__ void __launch_bounds__(kThreads) bc7_kernel(const EncodeParams p)
                 cT[4] += x.y*x.y; cT[5] += x.y*x.z; cT[6] += x.y*x.w;
                 cT[7] += x.z*x.z; cT[8] += x.z*x.w; cT[9] += x.w*x.w;
             }
+            const float sT3[3] = {sT[0], sT[1], sT[2]};
+            const float cT6[6] = {cT[0], cT[1], cT[2], cT[4], cT[5], cT[7]};
             uint32_t keys[kShapes];
 #pragma unroll 1
             for (int j = 0; j < kShapes; ++j) {
                 const uint32_t shape = sub*kShapes + j;
-                const uint32_t key = score_shape(bxf, sT, cT, shape);
+                const uint32_t key = flat_alpha ? score_shape_rgb(bxf, sT3, cT6, shape) : score_shape(bxf, sT, cT, shape);
 #pragma unroll
                 for (int jj = 0; jj < kShapes; ++jj) if (jj == j) keys[jj] = key;
             }

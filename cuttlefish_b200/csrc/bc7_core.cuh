@@ -122,6 +122,62 @@ CFX_HD uint32_t score_shape(const float4* bxf, const float* sT, const float* cT,
     return (__float_as_uint(score) & ~63u) | shape;
 }
 
+// The same for a block whose alpha is constant: the alpha row and column of every scatter matrix are zero, so the
+// products, the totals and the power iteration shrink from 4 to 3 dimensions (6 products instead of 10).
+// c: xx xy xz yy yz zz.
+CFX_HD float lambda_max3(const float* c)
+{
+    float v0 = c[0], v1 = c[1], v2 = c[2], best = c[0];
+    if (c[3] > best) { best = c[3]; v0 = c[1]; v1 = c[3]; v2 = c[4]; }
+    if (c[5] > best) { best = c[5]; v0 = c[2]; v1 = c[4]; v2 = c[5]; }
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const float n2 = v0*v0 + v1*v1 + v2*v2;
+        const float inv = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+        v0 *= inv; v1 *= inv; v2 *= inv;
+        const float r0 = c[0]*v0 + c[1]*v1 + c[2]*v2, r1 = c[1]*v0 + c[3]*v1 + c[4]*v2, r2 = c[2]*v0 + c[4]*v1 + c[5]*v2;
+        v0 = r0; v1 = r1; v2 = r2;
+    }
+    const float n2 = v0*v0 + v1*v1 + v2*v2;
+    const float inv = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+    v0 *= inv; v1 *= inv; v2 *= inv;
+    const float r0 = c[0]*v0 + c[1]*v1 + c[2]*v2, r1 = c[1]*v0 + c[3]*v1 + c[4]*v2, r2 = c[2]*v0 + c[4]*v1 + c[5]*v2;
+    return v0*r0 + v1*r1 + v2*r2;
+}
+
+// sT: block totals of x, y, z; cT: of the 6 products.
+CFX_HD uint32_t score_shape_rgb(const float4* bxf, const float* sT, const float* cT, uint32_t shape)
+{
+    const uint32_t m1 = kBc7Part2[shape];
+    float n1 = 0, s1[3] = {0, 0, 0}, c1[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        if ((m1 >> i) & 1u) {
+            const float4 x = bxf[i];
+            n1 += 1.0f;
+            s1[0] += x.x; s1[1] += x.y; s1[2] += x.z;
+            c1[0] += x.x*x.x; c1[1] += x.x*x.y; c1[2] += x.x*x.z;
+            c1[3] += x.y*x.y; c1[4] += x.y*x.z; c1[5] += x.z*x.z;
+        }
+    }
+    float score = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const float nn = s ? n1 : 16.0f - n1;
+        float sm[3], cc[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sm[k] = s ? s1[k] : sT[k] - s1[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cc[k] = s ? c1[k] : cT[k] - c1[k];
+        const float inv = 1.0f/nn;
+        cc[0] -= sm[0]*sm[0]*inv; cc[1] -= sm[0]*sm[1]*inv; cc[2] -= sm[0]*sm[2]*inv;
+        cc[3] -= sm[1]*sm[1]*inv; cc[4] -= sm[1]*sm[2]*inv; cc[5] -= sm[2]*sm[2]*inv;
+        score += (cc[0] + cc[3] + cc[5]) - lambda_max3(cc);
+    }
+    score = fmaxf(score, 0.0f);
+    return (__float_as_uint(score) & ~63u) | shape;
+}
+
 // Candidate descriptor of a lane: mode | rank << 4 | variant << 8 | LS rounds << 12, where rank is
 // the position of the lane's partition shape in the phase-1 ranking (ignored for mode 6), variant 1
 // = "extrapolating" first LS round, and rounds = number of least-squares refinement rounds.
