@@ -27,7 +27,8 @@ __device__ __forceinline__ float half_bits_to_domain(uint32_t h, bool sg)
 }
 } // namespace
 
-__global__ void __launch_bounds__(kBc6Warps*32) bc6h_kernel(const EncodeParams p)
+// 5 CTAs per SM (96 registers): measured 2.85 GTexel/s against 2.29 at 4 (111 registers) and 2.70 at 6 (80, spills)
+__global__ void __launch_bounds__(kBc6Warps*32, 5) bc6h_kernel(const EncodeParams p)
 {
     const bool sg = p.type == 5;                  // Texture::Type::Float -> BC6H SF16
     __shared__ float s_x[kBc6Warps][16*3*32];
