@@ -88,3 +88,35 @@ def test_no_cpu_fallback_without_gpu():
         cfx.encode(np.zeros((8, 8, 4), np.uint8), "BC4")
     assert e.value.code in (-3, -4)
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_mip_levels_follow_the_reference():
+    # Texture::maxMipmapLevels for 2D textures (lib/src/Texture.cpp:514-527): 32 - clz(max(w, h))
+    assert cfx.mip_levels(4096, 4096) == 13
+    assert cfx.mip_levels(5, 3) == 3
+    assert cfx.mip_levels(1, 1) == 1
+    assert cfx.mip_levels(1, 1024) == 11
+
+
+def test_resize_and_mip_chain_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    img = np.zeros((8, 8, 4), np.float32)
+    with pytest.raises(cfx.CfxError) as e:
+        cfx.resize(img, 4, 4)
+    assert e.value.code in (-3, -4)
+    with pytest.raises(cfx.CfxError) as e:
+        cfx.encode_mip_chain(img, "BC1_RGB")
+    assert e.value.code in (-3, -4)
+    # argument errors are reported before any device work
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    assert lib.cfx_resize(buf, 0, 4, 64, buf, 2, 2, 32, 3, 0) == -1
+    assert lib.cfx_resize(buf, 4, 4, 64, buf, 2, 2, 32, 9, 0) == -1          # no such filter
+    assert lib.cfx_resize(buf, 4, 4, 8, buf, 2, 2, 32, 3, 0) == -1           # pitch smaller than a row
+    d = cfx.api.make_desc("BC1_RGB", 8, 8, "RGBA16F", 64)
+    sizes = (ctypes.c_size_t * 4)(32, 8, 8, 8)
+    dst = (ctypes.c_void_p * 4)(*[ctypes.addressof(buf)] * 4)
+    assert lib.cfx_encode_mip_chain(ctypes.byref(d), buf, 3, 4, dst, sizes, None) == -1    # level 0 must be RGBA32F or RGBA8
+    assert b"RGBA32F" in lib.cfx_last_error()
