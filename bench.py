@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--quality", default="Normal")
     ap.add_argument("--size", type=int, default=0, help="override the square image size")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=2048, help="CPU baseline crop is SxS texels")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="CPU baseline crop is SxS texels (4096: 10-30 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--mips", action="store_true",
                     help="encode the full mip chain of the image (BASELINE config 5 shape): every rank encodes one "
