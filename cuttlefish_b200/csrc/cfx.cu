@@ -232,7 +232,10 @@ static int launch(Launcher launcher, EncodeParams& p, cudaStream_t stream)
     return CFX_OK;
 }
 
-static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst, size_t dst_size)
+// src_off / dst_off: where this surface lives in the context's device buffers (a batch lays its surfaces out back to
+// back and reserves once); sync = false leaves the copies and kernels queued on the context's streams.
+static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst, size_t dst_size, size_t src_off = 0,
+    size_t dst_off = 0, bool reserve_and_sync = true, int first_stream = 0)
 {
     EncodeParams p; Launcher launcher;
     int rc = validate(desc, p, launcher);
@@ -245,10 +248,14 @@ static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst,
 
     const size_t row_bytes = static_cast<size_t>(p.width)*src_texel_bytes(p.src_format);
     const size_t d_pitch = (row_bytes + 255) & ~static_cast<size_t>(255);
-    rc = reserve(g_ctx.d_src, g_ctx.d_src_cap, d_pitch*p.height);
-    if (rc != CFX_OK) return rc;
-    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, out_bytes);
-    if (rc != CFX_OK) return rc;
+    if (reserve_and_sync) {
+        rc = reserve(g_ctx.d_src, g_ctx.d_src_cap, src_off + d_pitch*p.height);
+        if (rc != CFX_OK) return rc;
+        rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, dst_off + out_bytes);
+        if (rc != CFX_OK) return rc;
+    }
+    uint8_t* const d_src = g_ctx.d_src + src_off;
+    uint8_t* const d_dst = g_ctx.d_dst + dst_off;
 
     // Chunk by block rows so that copy-in, encode and copy-out of neighbouring chunks overlap
     // on the three streams. ~8 M texels per chunk keeps every kernel a few full waves.
@@ -259,28 +266,29 @@ static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst,
         if (want < 1) want = 1;
         if (want < rows_per_chunk) rows_per_chunk = static_cast<uint32_t>(want);
     }
-    int k = 0;
+    int k = first_stream;
     for (uint32_t r0 = 0; r0 < p.blocks_y; r0 += rows_per_chunk, ++k) {
         uint32_t r1 = min(p.blocks_y, r0 + rows_per_chunk);
         uint32_t y0 = r0*p.block_h, y1 = min(p.height, r1*p.block_h);
         cudaStream_t s = g_ctx.streams[k % kStreams];
-        CFX_CUDA(cudaMemcpy2DAsync(g_ctx.d_src + static_cast<size_t>(y0)*d_pitch, d_pitch,
+        CFX_CUDA(cudaMemcpy2DAsync(d_src + static_cast<size_t>(y0)*d_pitch, d_pitch,
             static_cast<const uint8_t*>(src) + static_cast<size_t>(y0)*desc->src_row_pitch,
             desc->src_row_pitch, row_bytes, y1 - y0, cudaMemcpyHostToDevice, s));
         EncodeParams c = p;
-        c.src = g_ctx.d_src + static_cast<size_t>(y0)*d_pitch;
+        c.src = d_src + static_cast<size_t>(y0)*d_pitch;
         c.pitch = d_pitch;
         c.height = y1 - y0;   // interior chunks end on a block-row boundary, so the clamp is unchanged
         c.blocks_y = r1 - r0;
         c.total_blocks = c.blocks_x*c.blocks_y;
         size_t off = static_cast<size_t>(r0)*p.blocks_x*p.block_bytes;
-        c.dst = g_ctx.d_dst + off;
+        c.dst = d_dst + off;
         rc = launch(launcher, c, s);
         if (rc != CFX_OK) return rc;
         CFX_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, c.dst,
             static_cast<size_t>(c.total_blocks)*p.block_bytes, cudaMemcpyDeviceToHost, s));
     }
-    for (auto& s : g_ctx.streams) CFX_CUDA(cudaStreamSynchronize(s));
+    if (reserve_and_sync)
+        for (auto& s : g_ctx.streams) CFX_CUDA(cudaStreamSynchronize(s));
     return CFX_OK;
 }
 
@@ -544,11 +552,30 @@ int cfx_encode_batch(int n, const cfx_surface_desc* descs, const void* const* sr
         int rc = validate(&descs[i], p, l);
         if (rc != CFX_OK) return rc;
     }
+    // The surfaces of a batch (a mip chain, array layers) live back to back in the device buffers, their copies and
+    // kernels are queued round-robin on the context's streams and awaited once: the small levels of a chain, which are
+    // launch- and latency-bound, overlap each other and the tail of the big ones.
+    std::vector<size_t> src_off(n + 1, 0), dst_off(n + 1, 0);
     for (int i = 0; i < n; ++i) {
-        int rc = encode_host(&descs[i], srcs[i], dsts[i], dst_sizes[i]);
-        if (rc != CFX_OK) return rc;
+        const size_t pitch = align256(static_cast<size_t>(descs[i].width)*src_texel_bytes(descs[i].src_format));
+        src_off[i + 1] = src_off[i] + align256(pitch*descs[i].height);
+        dst_off[i + 1] = dst_off[i] + align256(cfx_encoded_size(&descs[i]));
     }
-    return CFX_OK;
+    int rc = ensure_init(-1);
+    if (rc != CFX_OK) return rc;
+    rc = reserve(g_ctx.d_src, g_ctx.d_src_cap, src_off[n]);
+    if (rc != CFX_OK) return rc;
+    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, dst_off[n]);
+    if (rc != CFX_OK) return rc;
+    for (int i = 0; i < n; ++i) {
+        rc = encode_host(&descs[i], srcs[i], dsts[i], dst_sizes[i], src_off[i], dst_off[i], false, i);
+        if (rc != CFX_OK) break;
+    }
+    for (auto& s : g_ctx.streams) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess && rc == CFX_OK) rc = fail(CFX_ERR_CUDA, "%s", cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_dst, size_t dst_size,
