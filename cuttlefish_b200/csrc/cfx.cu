@@ -123,6 +123,7 @@ struct Context {
     uint8_t* d_mip = nullptr; size_t d_mip_cap = 0;       // resized surfaces + the resize scratch
     cudaEvent_t fork[kMaxMipLevels] = {};                 // "level k is filtered" / "stream i has encoded its levels"
     cudaEvent_t join[kStreams] = {};
+    cudaEvent_t uploaded[kStreams] = {};                  // "this stream's share of a surface is in HBM"
 };
 static Context g_ctx;
 
@@ -157,6 +158,7 @@ static int ensure_init(int device)
         for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
         for (auto& e : g_ctx.fork) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto& e : g_ctx.join) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : g_ctx.uploaded) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (g_ctx.d_src) cudaFree(g_ctx.d_src);
         if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
         if (g_ctx.d_mip) cudaFree(g_ctx.d_mip);
@@ -172,6 +174,7 @@ static int ensure_init(int device)
     for (auto& s : g_ctx.streams) CFX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto& e : g_ctx.fork) CFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : g_ctx.join) CFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : g_ctx.uploaded) CFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.ready = true;
@@ -234,8 +237,10 @@ static int launch(Launcher launcher, EncodeParams& p, cudaStream_t stream)
 
 // src_off / dst_off: where this surface lives in the context's device buffers (a batch lays its surfaces out back to
 // back and reserves once); sync = false leaves the copies and kernels queued on the context's streams.
+// uploaded: if set, receives a bit per stream that carried a piece of the surface; g_ctx.uploaded[i] of those streams
+// fires once that stream's last piece is in HBM (before its encode kernel).
 static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst, size_t dst_size, size_t src_off = 0,
-    size_t dst_off = 0, bool reserve_and_sync = true, int first_stream = 0)
+    size_t dst_off = 0, bool reserve_and_sync = true, int first_stream = 0, uint32_t* uploaded = nullptr)
 {
     EncodeParams p; Launcher launcher;
     int rc = validate(desc, p, launcher);
@@ -274,6 +279,10 @@ static int encode_host(const cfx_surface_desc* desc, const void* src, void* dst,
         CFX_CUDA(cudaMemcpy2DAsync(d_src + static_cast<size_t>(y0)*d_pitch, d_pitch,
             static_cast<const uint8_t*>(src) + static_cast<size_t>(y0)*desc->src_row_pitch,
             desc->src_row_pitch, row_bytes, y1 - y0, cudaMemcpyHostToDevice, s));
+        if (uploaded) {
+            CFX_CUDA(cudaEventRecord(g_ctx.uploaded[k % kStreams], s));
+            *uploaded |= 1u << (k % kStreams);
+        }
         EncodeParams c = p;
         c.src = d_src + static_cast<size_t>(y0)*d_pitch;
         c.pitch = d_pitch;
@@ -425,28 +434,45 @@ static int encode_mip_chain(const cfx_surface_desc* level0, const void* src, uin
     levels = static_cast<uint32_t>(descs.size());
     if (!src || !dsts) return fail(CFX_ERR_INVALID, "null buffer");
     for (uint32_t k = 0; k < levels; ++k) if (!dsts[k]) return fail(CFX_ERR_INVALID, "level %u: null buffer", k);
-    // level 0: the chunked upload + encode of cfx_encode(); it leaves the whole RGBA32F surface in d_src
-    rc = encode_host(level0, src, dsts[0], dst_sizes[0]);
-    if (rc != CFX_OK || levels == 1) return rc;
+    // Level 0 goes through the chunked upload + encode of cfx_encode(), which leaves the whole surface in d_src, but is
+    // not awaited: the filter chain only needs the upload, so it starts on the least busy stream as soon as every piece
+    // of level 0 is in HBM and runs beside level 0's encoders. One wait at the end.
     std::vector<size_t> bytes(levels, 0), off(levels + 1, 0);
+    const size_t out0 = align256(cfx_encoded_size(&descs[0]));
     for (uint32_t k = 1; k < levels; ++k) { bytes[k] = cfx_encoded_size(&descs[k]); off[k + 1] = off[k] + align256(bytes[k]); }
-    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, off[levels]);
+    rc = ensure_init(-1);
     if (rc != CFX_OK) return rc;
-    std::vector<uint8_t*> d_outs(levels, nullptr);
-    for (uint32_t k = 1; k < levels; ++k) d_outs[k] = g_ctx.d_dst + off[k];
-    std::vector<const uint8_t*> level_ptr;
-    cudaStream_t s = g_ctx.streams[0];
-    rc = run_mip_levels(descs, g_ctx.d_src, align256(static_cast<size_t>(level0->width)*src_texel_bytes(level0->src_format)), filter,
-        d_outs.data(), level_ptr, s);
+    const size_t pitch0 = align256(static_cast<size_t>(level0->width)*src_texel_bytes(level0->src_format));
+    rc = reserve(g_ctx.d_src, g_ctx.d_src_cap, pitch0*level0->height);
     if (rc != CFX_OK) return rc;
-    for (uint32_t k = 1; k < levels; ++k) {
-        CFX_CUDA(cudaMemcpyAsync(dsts[k], d_outs[k], bytes[k], cudaMemcpyDeviceToHost, s));
-        if (mip_images && mip_images[k])
-            CFX_CUDA(cudaMemcpy2DAsync(mip_images[k], static_cast<size_t>(descs[k].width)*16u, level_ptr[k], descs[k].src_row_pitch,
-                static_cast<size_t>(descs[k].width)*16u, descs[k].height, cudaMemcpyDeviceToHost, s));
+    rc = reserve(g_ctx.d_dst, g_ctx.d_dst_cap, out0 + off[levels]);
+    if (rc != CFX_OK) return rc;
+    uint32_t carriers = 0;
+    rc = encode_host(level0, src, dsts[0], dst_sizes[0], 0, 0, false, 0, &carriers);
+    if (rc == CFX_OK && levels > 1) {
+        int pieces = 0;
+        for (int i = 0; i < kStreams; ++i) pieces += (carriers >> i) & 1u;
+        cudaStream_t s = g_ctx.streams[pieces % kStreams];          // the stream the next piece would have taken
+        for (int i = 0; i < kStreams; ++i)
+            if ((carriers >> i) & 1u) CFX_CUDA(cudaStreamWaitEvent(s, g_ctx.uploaded[i], 0));
+        std::vector<uint8_t*> d_outs(levels, nullptr);
+        for (uint32_t k = 1; k < levels; ++k) d_outs[k] = g_ctx.d_dst + out0 + off[k];
+        std::vector<const uint8_t*> level_ptr;
+        rc = run_mip_levels(descs, g_ctx.d_src, pitch0, filter, d_outs.data(), level_ptr, s);
+        for (uint32_t k = 1; rc == CFX_OK && k < levels; ++k) {
+            if (cudaMemcpyAsync(dsts[k], d_outs[k], bytes[k], cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = CFX_ERR_CUDA;
+            if (rc == CFX_OK && mip_images && mip_images[k] &&
+                cudaMemcpy2DAsync(mip_images[k], static_cast<size_t>(descs[k].width)*16u, level_ptr[k], descs[k].src_row_pitch,
+                    static_cast<size_t>(descs[k].width)*16u, descs[k].height, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+                rc = CFX_ERR_CUDA;
+        }
     }
-    CFX_CUDA(cudaStreamSynchronize(s));
-    return CFX_OK;
+    for (auto& st : g_ctx.streams) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess && rc == CFX_OK) rc = fail(CFX_ERR_CUDA, "%s", cudaGetErrorString(e));
+    }
+    if (rc == CFX_ERR_CUDA && !t_error[0]) fail(CFX_ERR_CUDA, "%s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
 }
 
 static int encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_src, uint32_t filter, uint32_t levels,
@@ -490,6 +516,7 @@ void cfx_shutdown(void)
     for (auto& s : g_ctx.streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
     for (auto& e : g_ctx.fork) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : g_ctx.join) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : g_ctx.uploaded) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (g_ctx.d_src) cudaFree(g_ctx.d_src);
     if (g_ctx.d_dst) cudaFree(g_ctx.d_dst);
     if (g_ctx.d_mip) cudaFree(g_ctx.d_mip);
