@@ -34,6 +34,15 @@ CFX_HD int expand4(int v) { return (v << 4) | v; }
 CFX_HD int expand6(int v) { return (v << 2) | (v >> 4); }
 CFX_HD int expand7(int v) { return (v << 1) | (v >> 6); }
 
+// T/H colour descent at the short search levels (up to Quality::Normal): off by default. Measured with it on
+// (-DCFX_ETC_TH_AT_NORMAL=1, gate 1.1): ETC2 Normal +0.11 dB over etc2comp on noise+grad instead of -0.06, +1.12 instead
+// of +1.04 on the screenshot probe, at 2.38 instead of 2.80 GTexel/s.
+#ifndef CFX_ETC_TH_AT_NORMAL
+#define CFX_ETC_TH_AT_NORMAL 0
+#endif
+#ifndef CFX_ETC_TH_GATE
+#define CFX_ETC_TH_GATE 1.1f
+#endif
 #ifndef CFX_ETC_NARROW
 #define CFX_ETC_NARROW 1
 #endif
@@ -378,7 +387,9 @@ CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const
 
 // rounds > 0 (Quality::High and up): +-1 descent on the six RGB444 components of the winner, distance index +-1
 // (etc2comp widens its T / H search the same way in its later iterations, EtcBlock4x4Encoding_RGB8.cpp:370-...).
-CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0)
+// rounds: +-1 descent rounds over the two colours; the descent only runs while the T/H error is below `gate` (the short
+// searches pass a small multiple of the incumbent's error: a T/H block that far behind will not win).
+CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0, float gate = 3.0e38f)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
     float m[3] = {0, 0, 0};
@@ -441,7 +452,7 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
             if (err < best) { best = err; best_kind = kind; best_d = di; best_sel = sel; }
         }
     }
-    for (int round = 0; round < rounds && best > 0.0f && best < 3.0e38f; ++round) {
+    for (int round = 0; round < rounds && best > 0.0f && best < gate; ++round) {
         bool improved = false;
 #pragma unroll 1
         for (int k = 0; k < 12; ++k) {
@@ -592,7 +603,7 @@ CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds)
         encode_planar(xs, lane, rounds, r);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= 2 ? rounds : 0);
+            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE);
             if (r.err < best.err) best = r;
         }
     }
@@ -674,7 +685,7 @@ CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds)
         encode_planar(xs, lane, rounds, r);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= 2 ? rounds : 0);
+            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE);
             if (r.err < best.err) best = r;
         }
     }
