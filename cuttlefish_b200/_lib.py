@@ -12,13 +12,16 @@ class SurfaceDesc(ctypes.Structure):
     _fields_ = [("format", ctypes.c_uint32), ("type", ctypes.c_uint32), ("quality", ctypes.c_uint32),
                 ("alpha_type", ctypes.c_uint32), ("color_mask", ctypes.c_uint32),
                 ("color_space", ctypes.c_uint32), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
-                ("src_format", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("src_format", ctypes.c_uint32), ("flags", ctypes.c_uint32),
                 ("src_row_pitch", ctypes.c_uint64)]
 
 
 # every symbol include/cfx.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("cfx_init", ctypes.c_int, [ctypes.c_int]),
+    ("cfx_init_devices", ctypes.c_int, [ctypes.c_int]),
+    ("cfx_set_devices", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    ("cfx_device_count", ctypes.c_int, []),
     ("cfx_shutdown", None, []),
     ("cfx_format_supported", ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32]),
     ("cfx_format_is_exact", ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),

@@ -55,7 +55,28 @@ def _check(rc):
 
 
 def init(device=-1):
+    """cfx_init: the device pool of host-buffer calls becomes {device} (device < 0: keep it / the current CUDA device)."""
     _check(load().cfx_init(int(device)))
+
+
+def init_devices(count=0):
+    """cfx_init_devices: host-buffer calls shard every surface by block row over the first `count` sm_100 devices
+    (0 = all visible) -- the multi-GPU form of Converter::convert's threadCount."""
+    _check(load().cfx_init_devices(int(count)))
+
+
+def set_devices(devices):
+    """cfx_set_devices: explicit pool, in order (a device listed twice gets two independent contexts)."""
+    ids = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+    _check(load().cfx_set_devices(len(devices), ids))
+
+
+def device_count():
+    return int(load().cfx_device_count())
+
+
+def shutdown():
+    load().cfx_shutdown()
 
 
 def version():
@@ -87,11 +108,14 @@ def block_info(fmt):
     return bw.value, bh.value, nb.value
 
 
+FLAG_BOTTOM_UP = 1
+
+
 def make_desc(fmt, width, height, src_format, row_pitch, type="UNorm", quality="Normal", alpha="Standard",
-              color_mask=15, srgb=False):
+              color_mask=15, srgb=False, bottom_up=False):
     return SurfaceDesc(_enum(FORMATS, fmt), _enum(TYPES, type), _enum(QUALITY, quality), _enum(ALPHA, alpha),
                        _mask_bits(color_mask), 1 if srgb else 0, int(width), int(height),
-                       _enum(SRC_FORMATS, src_format), 0, int(row_pitch))
+                       _enum(SRC_FORMATS, src_format), FLAG_BOTTOM_UP if bottom_up else 0, int(row_pitch))
 
 
 def encoded_size(fmt, width, height):
@@ -111,9 +135,10 @@ def _src_format_of(dtype):
 
 
 def encode(img, fmt, out=None, **kw):
-    """Encode a HOST image [H,W,4] (uint8 / float16 / float32, row 0 = top) -> uint8 block bytes.
+    """Encode a HOST image [H,W,4] (uint8 / float16 / float32, row 0 = top; bottom_up=True: row 0 = bottom, the way
+    cuttlefish::Image stores it) -> uint8 block bytes.
 
-    Goes through cfx_encode: host->device copy, kernels, device->host copy."""
+    Goes through cfx_encode: host->device copy, kernels, device->host copy, on every device of the pool."""
     img = np.asarray(img)
     if img.ndim != 3 or img.shape[2] != 4:
         raise ValueError("expected [H,W,4] RGBA texels")
@@ -181,7 +206,6 @@ def encode_device(src, fmt, out=None, stream=None, **kw):
     with torch.cuda.device(src.device):
         if stream is None:
             stream = torch.cuda.current_stream()
-        _check(load().cfx_init(src.device.index))
         _check(load().cfx_encode_device(ctypes.byref(d), src.data_ptr(), out.data_ptr(), out.numel(),
                                         ctypes.c_void_p(stream.cuda_stream)))
     return out[:n]
@@ -210,7 +234,6 @@ def encode_mip_chain_device(src, fmt, filter="CatmullRom", levels=None, outs=Non
     with torch.cuda.device(src.device):
         if stream is None:
             stream = torch.cuda.current_stream()
-        _check(load().cfx_init(src.device.index))
         _check(load().cfx_encode_mip_chain_device(ctypes.byref(d), src.data_ptr(), _enum(FILTERS, filter), n, dst, csizes,
                                                   ctypes.c_void_p(stream.cuda_stream)))
     return [o[:sz] for o, sz in zip(outs, sizes)]

@@ -23,14 +23,14 @@ NVCC_FLAGS = [
 # (source, extra flags, macro that advertises it to cfx.cu)
 UNITS = [
     ("cfx.cu", [], None),
+    ("host_stage.cpp", [], None),
     ("resize.cu", ["-fmad=false", "-Xcompiler", "-ffp-contract=off"], None),
     ("bc4_bc5.cu", [], None),
     ("bc7.cu", [], "CFX_HAVE_BC7"),
     ("bc1_bc3.cu", ["-fmad=false"], "CFX_HAVE_BC1"),
     ("etc.cu", ["-fmad=false"], "CFX_HAVE_ETC"),
     ("bc6h.cu", [], "CFX_HAVE_BC6H"),
-    ("astc.cu", [], "CFX_HAVE_ASTC"),
-    ("astc2.cu", [], None),
+    ("astc_host.cu", [], "CFX_HAVE_ASTC"),
     ("astc3.cu", ["-DCFX_ASTC3_TUNE=1"] if os.environ.get("CFX_ASTC3_TUNE") else [], None),
 ]
 

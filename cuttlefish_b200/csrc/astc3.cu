@@ -1386,7 +1386,7 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
 
 } // namespace
 
-// t3 must describe tables appended to ctx.blob by build_tables3() (astc.cu owns the per-device table cache).
+// t3 must describe tables appended to ctx.blob by build_tables3() (astc_host.cu owns the per-device table cache).
 int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cudaStream_t stream)
 {
     // exact evaluations / refinement rounds per Texture::Quality (AstcConverter maps the levels to astcenc's fastest,
@@ -1398,10 +1398,16 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     const uint32_t refine = kRefine[q5];
     if (ctx.tab.n_grids > t3.NT*8u) return -2;          // phase 1c keeps two per-grid arrays in the texel-sized scratch
     Tab3 tb; tb.ctx = ctx; tb.t3 = t3;
+#ifdef CFX_ASTC3_TUNE
+    // developer knobs, only in builds made with CFX_ASTC3_TUNE=1 (tools/astc_quality.py); never in the shipped library
     static const uint32_t dev_flags = getenv("CFX_ASTC3_FLAGS") ? static_cast<uint32_t>(atoi(getenv("CFX_ASTC3_FLAGS"))) : 0u;
+    static const float mis_w = getenv("CFX_ASTC3_MISW") ? static_cast<float>(atof(getenv("CFX_ASTC3_MISW"))) : kMismatchWeight;
     tb.flags = dev_flags;
-    static const float mis_w = getenv("CFX_ASTC3_MISW") ? static_cast<float>(atof(getenv("CFX_ASTC3_MISW"))) : kMismatchWeight;   // developer knob
     tb.mis_w = mis_w;
+#else
+    tb.flags = 0u;
+    tb.mis_w = kMismatchWeight;
+#endif
     tb.hdr = p.type == 4u ? 1u : 0u;                      // Texture::Type::UFloat
     const uint32_t NT = t3.NT, KS = t3.KS;
     if (NT == 2 && KS == 1) return launch_one<2, 1>(p, tb, n_exact, refine, stream);

@@ -158,8 +158,7 @@ bool make_tile_map(const EncodeParams& p, CUtensorMap& map)
 
 bool bc45_uses_tma(const EncodeParams& p)
 {
-    static const bool off = getenv("CFX_NO_TMA") != nullptr;
-    return !off && p.type == 0 && p.src_format == SRC_RGBA8 && p.aligned16 && p.width % 4 == 0 && p.height % 4 == 0 &&
+    return p.type == 0 && (p.pitch >> 40) == 0 && p.src_format == SRC_RGBA8 && p.aligned16 && p.width % 4 == 0 && p.height % 4 == 0 &&
         p.blocks_x % kTile == 0 && p.total_blocks >= static_cast<uint32_t>(kTile);
 }
 

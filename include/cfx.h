@@ -29,6 +29,10 @@
  *   cfx_encode_mip_chain_device <- the same for callers that already hold level 0 in HBM
  *   cfx_init/cfx_shutdown <- the one-time encoder table inits (rgbcx::init, bc7enc_compress_block_init,
  *                            astcenc context alloc), lib/src/S3tcConverter.cpp:54-64,158-168
+ *   cfx_init_devices /
+ *   cfx_set_devices       <- the `threadCount` argument of Converter::convert(), lib/src/Converter.cpp:508-509,
+ *                            :548-583: how wide one convert() call fans out -- here over the GPUs of one box
+ *                            (contiguous block-row ranges per GPU) instead of over std::threads
  */
 #ifndef CFX_H
 #define CFX_H
@@ -85,16 +89,34 @@ typedef struct cfx_surface_desc {
     uint32_t color_space;   /* 0 linear, 1 sRGB (image().colorSpace())                */
     uint32_t width, height; /* texels                                                 */
     uint32_t src_format;    /* CFX_SRC_*                                              */
-    uint32_t reserved;      /* must be 0                                              */
-    uint64_t src_row_pitch; /* bytes between rows; rows are top-down (row 0 = top).
-                               Cuttlefish images are stored bottom-up: pass scanline(y)
-                               order, i.e. point at the last stored row and use the
-                               library's helper in INTEGRATION.md, or flip on upload.  */
+    uint32_t flags;         /* CFX_FLAG_* bits, 0 by default                          */
+    uint64_t src_row_pitch; /* bytes between stored rows (> 0). Stored row 0 is the top
+                               row of the image, unless CFX_FLAG_BOTTOM_UP is set.     */
 } cfx_surface_desc;
 
-/* Select the CUDA device this thread's context encodes on and create its streams/buffers.
- * device < 0 keeps the current device. Idempotent. Returns CFX_OK or an error. */
+/* The surface is stored BOTTOM-UP: src points at the first stored row, which is the image's bottom row, and image row y
+ * (0 = top) lives at src + (height-1-y)*src_row_pitch. This is how cuttlefish::Image keeps its pixels (FreeImage,
+ * lib/src/Image.cpp:340-343, scanline(y) at :1092-1098), so the adapter hands the image over as it lies, without a
+ * flipped host copy. Accepted by cfx_encode / cfx_encode_batch / cfx_encode_device (not by the mip-chain calls). */
+#define CFX_FLAG_BOTTOM_UP 1u
+
+/* The device pool: the GPUs that ONE host-buffer call (cfx_encode, cfx_encode_batch) spreads its work over. A surface
+ * is cut into contiguous block-row ranges, range k of P going to pool device k (rows [k*R/P, (k+1)*R/P)); every device
+ * uploads only its rows, encodes them and writes its packed blocks straight into the caller's dst at the range's byte
+ * offset, so the result is the concatenation and no collective is needed. Surfaces too small to be worth cutting go
+ * whole to the least loaded device. The pool is process-wide; one library call runs at a time.
+ *
+ *   cfx_init(device)        pool := {device}; device < 0 keeps the pool, or makes it {current CUDA device} when unset.
+ *   cfx_init_devices(n)     pool := the first n sm_100 devices visible to the process; n = 0 means all of them.
+ *   cfx_set_devices(n, ids) pool := ids[0..n), in this order. A device listed twice gets two independent contexts.
+ *   cfx_device_count()      number of pool entries (0 before the first init).
+ * All are idempotent, create streams/buffers on first use, return CFX_OK or an error, and leave the caller's current
+ * CUDA device unchanged. Host-buffer calls without any init behave like cfx_init(-1). Device-pointer calls
+ * (cfx_encode_device, cfx_encode_mip_chain_device) ignore the pool: they run on the device that owns d_src. */
 int cfx_init(int device);
+int cfx_init_devices(int device_count);
+int cfx_set_devices(int n, const int* devices);
+int cfx_device_count(void);
 void cfx_shutdown(void);
 
 /* 1 if the (format,type) pair has a GPU encoder, else 0. */
@@ -110,15 +132,20 @@ int cfx_block_info(uint32_t format, uint32_t* block_w, uint32_t* block_h, uint32
 /* ceil(w/bw)*ceil(h/bh)*block_bytes, 0 if the format is unknown. */
 size_t cfx_encoded_size(const cfx_surface_desc* desc);
 
-/* Encode one surface held in HOST memory into HOST memory (blocks row-major, y*blocksX+x).
- * Does H2D, kernels, D2H; returns when dst is complete. */
+/* Encode one surface held in HOST memory into HOST memory (blocks row-major, y*blocksX+x), on every device of the
+ * pool. Does H2D, kernels, D2H in overlapping chunks of block rows; returns when dst is complete. Pinned buffers
+ * (cfx_host_alloc, cudaHostAlloc, cudaHostRegister) are DMA'd in place; a pageable src passes through the library's
+ * pinned staging slots on a few host threads, and on that pass an RGBA32F source is narrowed to what the encoder's load
+ * stage would make of it anyway (RGBA8 for BC1-5/BC7 UNorm, RGBA16F for BC6H: 4 or 8 instead of 16 bytes per texel over
+ * PCIe, identical blocks). */
 int cfx_encode(const cfx_surface_desc* desc, const void* src, void* dst, size_t dst_size);
 /* Encode n surfaces (a mip chain / array layers); same semantics per surface. */
 int cfx_encode_batch(int n, const cfx_surface_desc* descs, const void* const* srcs,
                      void* const* dsts, const size_t* dst_sizes);
 /* Encode one surface already resident in DEVICE memory into DEVICE memory, asynchronously on
- * cuda_stream (a cudaStream_t cast to void*; NULL = the CUDA default stream). src must be
- * 16-byte aligned with a 16-byte-multiple pitch for the fast path; otherwise a slower path runs. */
+ * cuda_stream (a cudaStream_t cast to void*; NULL = the CUDA default stream), on the device that owns d_src.
+ * d_src and the pitch must be multiples of the texel size (4 / 8 / 16 bytes; CFX_ERR_INVALID otherwise); a 16-byte
+ * aligned pointer and pitch take the vectorised load path. */
 int cfx_encode_device(const cfx_surface_desc* desc, const void* d_src, void* d_dst, size_t dst_size,
                       void* cuda_stream);
 

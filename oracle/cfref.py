@@ -98,7 +98,7 @@ def glue_available():
     return os.path.exists(_GLUE_PATH)
 
 
-def encode_glue(img, fmt, threads=0, **kw):
+def encode_glue(img, fmt, threads=0, out_bytes=None, **kw):
     """Same as encode(), but through the reference's REAL converter glue (lib/src/Converter.cpp and the
     *Converter.cpp files compiled from /root/reference over oracle/glue_stub.cpp) instead of our
     restatement in cfref.cpp.  Used only to pin the restatement."""
@@ -111,12 +111,51 @@ def encode_glue(img, fmt, threads=0, **kw):
     img = np.ascontiguousarray(img, dtype=np.float32)
     h, w, _ = img.shape
     d = make_desc(fmt, w, h, **kw)
-    n = lib().cfref_encoded_size(ctypes.byref(d))
+    n = out_bytes if out_bytes is not None else lib().cfref_encoded_size(ctypes.byref(d))   # out_bytes: non-block formats
     out = np.empty(n, dtype=np.uint8)
     rc = _glue.cfglue_encode(ctypes.byref(d), img.ctypes.data, w * 4, out.ctypes.data, n, threads)
     if rc != n:
         raise RuntimeError("cfglue_encode failed: %d" % rc)
     return out
+
+
+_GLUE_CUDA_PATH = os.path.join(_HERE, "_ref", "libcfglue_cuda.so")
+_glue_cuda = None
+
+
+def glue_cuda_available():
+    return os.path.exists(_GLUE_CUDA_PATH)
+
+
+def encode_glue_cuda(img, fmt, threads=0, bottom_up=False, out_bytes=None, **kw):
+    """The reference's REAL Converter::convert() with adapter/CudaConverter.cpp hooked into its createConverter()
+    (oracle/_ref/libcfglue_cuda.so): supported pairs are encoded by libcfx.so through the drop-in boundary, the rest by
+    the reference's CPU converters. bottom_up makes the stand-in Image store its rows the way cuttlefish::Image does.
+    Returns (blocks, seconds spent in Converter::convert, surfaces the adapter sent to the GPU during this call)."""
+    global _glue_cuda
+    if _glue_cuda is None:
+        _glue_cuda = ctypes.CDLL(_GLUE_CUDA_PATH)
+        _glue_cuda.cfglue_encode_timed.restype = ctypes.c_int
+        _glue_cuda.cfglue_encode_timed.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                                   ctypes.c_size_t, ctypes.c_uint, ctypes.POINTER(ctypes.c_double)]
+        _glue_cuda.cfglue_set_bottom_up.argtypes = [ctypes.c_int]
+        _glue_cuda.cfx_adapter_surfaces_encoded.restype = ctypes.c_uint
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w, _ = img.shape
+    d = make_desc(fmt, w, h, **kw)
+    n = out_bytes if out_bytes is not None else lib().cfref_encoded_size(ctypes.byref(d))
+    out = np.empty(n, dtype=np.uint8)
+    secs = ctypes.c_double(0.0)
+    before = _glue_cuda.cfx_adapter_surfaces_encoded()
+    _glue_cuda.cfglue_set_bottom_up(1 if bottom_up else 0)
+    try:
+        rc = _glue_cuda.cfglue_encode_timed(ctypes.byref(d), img.ctypes.data, w * 4, out.ctypes.data, n, threads,
+                                            ctypes.byref(secs))
+    finally:
+        _glue_cuda.cfglue_set_bottom_up(0)
+    if rc != n:
+        raise RuntimeError("cfglue_encode failed: %d" % rc)
+    return out, secs.value, _glue_cuda.cfx_adapter_surfaces_encoded() - before
 
 
 def decode(blocks, fmt, width, height, **kw):

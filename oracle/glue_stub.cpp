@@ -10,9 +10,14 @@
 
 #include "Converter.h"
 
+#include <chrono>
 #include <cstring>
 #include <thread>
 #include <vector>
+
+// cuttlefish::Image stores its rows bottom-up (FreeImage, lib/src/Image.cpp:340-343); cfglue_set_bottom_up(1) makes this
+// stand-in do the same, so that the adapter's CFX_FLAG_BOTTOM_UP path is exercised the way the real Image would.
+static bool g_bottom_up = false;
 
 namespace cuttlefish
 {
@@ -39,8 +44,8 @@ Image::Format Image::format() const {return m_impl->format;}
 ColorSpace Image::colorSpace() const {return m_impl->colorSpace;}
 unsigned int Image::width() const {return m_impl->width;}
 unsigned int Image::height() const {return m_impl->height;}
-void* Image::scanline(unsigned int y) {return m_impl->data.data() + std::size_t(y)*m_impl->width*4;}
-const void* Image::scanline(unsigned int y) const {return m_impl->data.data() + std::size_t(y)*m_impl->width*4;}
+void* Image::scanline(unsigned int y) {return m_impl->data.data() + std::size_t(g_bottom_up ? m_impl->height - 1 - y : y)*m_impl->width*4;}
+const void* Image::scanline(unsigned int y) const {return m_impl->data.data() + std::size_t(g_bottom_up ? m_impl->height - 1 - y : y)*m_impl->width*4;}
 void Image::reset() {m_impl.reset();}
 
 struct Texture::Impl
@@ -83,7 +88,12 @@ using namespace cuttlefish;
 
 struct cfglue_desc { uint32_t format, type, quality, alpha_type, color_mask, color_space, width, height; };
 
-extern "C" int cfglue_encode(const cfglue_desc* d, const float* src, size_t pitch_floats, uint8_t* dst, size_t dst_size, unsigned threads)
+extern "C" void cfglue_set_bottom_up(int on) {g_bottom_up = on != 0;}
+
+// convert_seconds (may be null) receives the wall time of the Converter::convert() call alone -- what Texture::convert()
+// costs once the RGBAF image exists -- without the set-up copy this stand-in makes.
+extern "C" int cfglue_encode_timed(const cfglue_desc* d, const float* src, size_t pitch_floats, uint8_t* dst, size_t dst_size,
+	unsigned threads, double* convert_seconds)
 {
 	Texture texture;
 	texture.convert(static_cast<Texture::Format>(d->format), static_cast<Texture::Type>(d->type),
@@ -98,10 +108,19 @@ extern "C" int cfglue_encode(const cfglue_desc* d, const float* src, size_t pitc
 	texture.setImage(img);
 	Converter::MipTextureList out;
 	if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
-	if (!Converter::convert(texture, images, out, static_cast<Texture::Quality>(d->quality), threads))
+	const auto t0 = std::chrono::steady_clock::now();
+	const bool ok = Converter::convert(texture, images, out, static_cast<Texture::Quality>(d->quality), threads);
+	if (convert_seconds)
+		*convert_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (!ok)
 		return -2;
 	const std::vector<uint8_t>& data = out[0][0][0];
 	if (data.size() > dst_size) return -1;
 	std::memcpy(dst, data.data(), data.size());
 	return static_cast<int>(data.size());
+}
+
+extern "C" int cfglue_encode(const cfglue_desc* d, const float* src, size_t pitch_floats, uint8_t* dst, size_t dst_size, unsigned threads)
+{
+	return cfglue_encode_timed(d, src, pitch_floats, dst, dst_size, threads, nullptr);
 }
