@@ -157,12 +157,12 @@ def encode(img, fmt, out=None, **kw):
     return out[:n]
 
 
-def encode_batch(images, fmt, **kw):
-    """Encode several HOST surfaces (a mip chain / array layers) with one cfx_encode_batch call.
-    Returns a list of uint8 arrays, one per surface."""
+def encode_batch(images, fmt, outs=None, **kw):
+    """Encode several HOST surfaces (a mip chain / array layers) with one cfx_encode_batch call, on every device of
+    the pool. Returns a list of uint8 arrays, one per surface (`outs`: caller-owned, e.g. pinned, output arrays)."""
     lib = load()
-    imgs, descs, outs = [], [], []
-    for img in images:
+    given, imgs, descs, outs = outs, [], [], []
+    for i, img in enumerate(images):
         img = np.ascontiguousarray(np.asarray(img))
         if img.ndim != 3 or img.shape[2] != 4:
             raise ValueError("expected [H,W,4] RGBA texels")
@@ -172,7 +172,13 @@ def encode_batch(images, fmt, **kw):
         n = int(lib.cfx_encoded_size(ctypes.byref(d)))
         if n == 0:
             raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
-        imgs.append(img); descs.append(d); outs.append(np.empty(n, dtype=np.uint8))
+        if given is None:
+            out = np.empty(n, dtype=np.uint8)
+        else:
+            out = given[i]
+            assert out.dtype == np.uint8 and out.size >= n and out.flags["C_CONTIGUOUS"]
+            out = out[:n]
+        imgs.append(img); descs.append(d); outs.append(out)
     n = len(imgs)
     c_descs = (SurfaceDesc * n)(*descs)
     c_srcs = (ctypes.c_void_p * n)(*[im.ctypes.data for im in imgs])
