@@ -13,8 +13,10 @@ Per workload:
   value     device-timed (CUDA events, max over ranks), inputs resident in HBM. At N ranks the batch
             is an N-layer array texture (Converter::convert's depth/face loop,
             lib/src/Converter.cpp:521-527); every layer is sharded by block row across the ranks
-            (SURVEY.md 8e), so per-GPU work is fixed ("weak"); each layer's packed blocks are gathered
-            on rank 0 with one NCCL gather that overlaps the next layer's kernels.
+            (SURVEY.md 8e), so per-GPU work is fixed ("weak"); the assembled output lives in rank 0's HBM
+            and every rank's encode kernel stores its packed blocks straight into it over NVLink (peer
+            memory, include/cfx.h cfx_ipc_*): the gather is fused into the kernel. --gather nccl uses one
+            NCCL gather per layer instead, overlapped with the next layer's kernels.
   scaling_strong   ONE image of the same size over the N ranks (BASELINE config 3's shape), same gather.
   e2e       the same batch through ONE cfx_encode_batch() call with HOST buffers (pinned), issued by
             rank 0 alone with libcfx's device pool set to the N GPUs: the library shards every layer by
@@ -72,6 +74,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="override the side of the CPU baseline crop")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the packed blocks reach rank 0 (peer: stored by the encode kernels over NVLink; nccl: "
+                         "one NCCL gather per layer)")
     ap.add_argument("--mips", action="store_true",
                     help="with --format: encode the image WITH its full mip chain generated on the GPU "
                          "(Texture::generateMipmaps(CatmullRom) + convert, BASELINE config 5's shape), one texture per rank")
@@ -405,36 +410,84 @@ def run_encode(a, env, fmt, steps, warmup, want_cpu):
     del host
     blocks_x = (size + bw - 1) // bw
     slab_bytes = (r1 - r0) * blocks_x * bbytes
-    d_out = torch.empty((layers, slab_bytes), dtype=torch.uint8, device=dev)
-    # rank 0 receives every rank's slab of every layer (slab sizes differ by at most one block row: pad to the largest)
+    layer_bytes = ((size + bh - 1) // bh) * blocks_x * bbytes
+    my_off = r0 * blocks_x * bbytes
+    # The assembled output (every layer, every rank's slab at its byte offset) lives in rank 0's HBM. Default gather:
+    # rank 0 exports the buffer, the other ranks map it (cfx_ipc_open) and their encode kernels store their packed
+    # blocks STRAIGHT into it over NVLink -- the gather is fused into the kernel; one tiny all-reduce per step is the
+    # stream-ordered "every slab has landed" signal. --gather nccl: blocks go to a local buffer and one NCCL gather per
+    # layer (overlapping the next layer's kernels) moves them.
+    whole = torch.empty((layers, layer_bytes), dtype=torch.uint8, device=dev) if rank == 0 else None
+    d_out = torch.empty((layers, slab_bytes), dtype=torch.uint8, device=dev) if (world == 1 or a.gather == "nccl") else None
+    base_ptr, handle, flag = None, None, None
     max_rows = max(cfx.shard_block_rows(size, bh, r, world)[1] - cfx.shard_block_rows(size, bh, r, world)[0] for r in range(world))
     pad_bytes = max_rows * blocks_x * bbytes
-    d_send = torch.empty((layers, pad_bytes), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def nccl_gather_layer0():
+        """Layer 0 through a local buffer + NCCL gather (slab sizes differ by at most one block row: pad to the largest)."""
+        send = torch.zeros(pad_bytes, dtype=torch.uint8, device=dev)
+        cfx.encode_device(d_src[0], fmt, out=send[:slab_bytes], **kw)
+        parts = [torch.empty(pad_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(send, parts, dst=0)
+        if rank != 0:
+            return None
+        sizes = [(cfx.shard_block_rows(size, bh, r, world)[1] - cfx.shard_block_rows(size, bh, r, world)[0]) * blocks_x * bbytes
+                 for r in range(world)]
+        return torch.cat([p_[:n_] for p_, n_ in zip(parts, sizes)])
+
+    if world > 1 and a.gather == "peer":
+        handles = [cfx.ipc_export(whole) if rank == 0 else None]
+        dist.broadcast_object_list(handles, src=0)
+        handle = handles[0]
+        base_ptr = whole.data_ptr() if rank == 0 else cfx.ipc_open(handle, env.local)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_send = torch.empty((layers, pad_bytes), dtype=torch.uint8, device=dev) if (world > 1 and a.gather == "nccl") else None
     gathered = [[torch.empty(pad_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] for _ in range(layers)] \
-        if (world > 1 and rank == 0) else None
+        if (world > 1 and a.gather == "nccl" and rank == 0) else None
 
     def device_step(n_layers, kev):
         works = []
         for l in range(n_layers):
-            out = d_send[l][:slab_bytes] if world > 1 else d_out[l]
             if kev is not None:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            cfx.encode_device(d_src[l], fmt, out=out, **kw)
+            if world == 1:
+                cfx.encode_device(d_src[l], fmt, out=d_out[l], **kw)
+            elif a.gather == "peer":
+                cfx.encode_device(d_src[l], fmt, out_ptr=base_ptr + l * layer_bytes + my_off, out_bytes=slab_bytes, **kw)
+            else:
+                cfx.encode_device(d_src[l], fmt, out=d_send[l][:slab_bytes], **kw)
             if kev is not None:
                 e1.record()
                 kev.append((e0, e1))
-            if world > 1:
+            if world > 1 and a.gather == "nccl":
                 # layer l's gather runs on NCCL's stream beside layer l+1's kernels
                 works.append(dist.gather(d_send[l], gathered[l] if rank == 0 else None, dst=0, async_op=True))
         for w in works:
             w.wait()
+        if world > 1 and a.gather == "peer":
+            dist.all_reduce(flag)          # stream-ordered after this rank's kernels: done everywhere = all slabs landed
+
+    gather_checked = None
+    if world > 1 and a.gather == "peer":
+        # once, before timing: the fused peer-store gather must give the bytes of the NCCL gather
+        device_step(1, None)
+        env.barrier()
+        want = nccl_gather_layer0()
+        env.barrier()
+        if rank == 0:
+            gather_checked = bool(torch.equal(whole[0], want))
+            assert gather_checked, "peer-store gather differs from the NCCL gather"
+        del want
 
     launches0 = cfx.kernel_launches()
     weak_ms, kernel_ms = time_device(env, lambda kev: device_step(layers, kev), steps, max(warmup, 3))
     launches = env.sum_over_ranks(cfx.kernel_launches() - launches0) * steps // (steps + max(warmup, 3))
     strong_ms, _ = time_device(env, lambda kev: device_step(1, None), steps, max(warmup, 3)) if world > 1 else (weak_ms, 0.0)
-    del gathered, d_send
+    if world > 1 and a.gather == "peer" and rank != 0:
+        cfx.ipc_close(base_ptr, handle)
+    env.barrier()
+    del gathered, d_send, whole
     torch.cuda.empty_cache()
 
     # ---- end to end: ONE host-buffer call from rank 0, the library's device pool = all N GPUs
@@ -484,8 +537,12 @@ def run_encode(a, env, fmt, steps, warmup, want_cpu):
            "dtype": "u8" if wl["src"] == "RGBA8" else "f16", "data": "synthetic",
            "config": {"workload": workload_name(a, fmt, wl, size), "format": fmt, "quality": a.quality, "width": size,
                       "height": size, "layers": layers,
-                      "sharding": "block-row slabs of every layer across %d rank(s); one NCCL gather per layer, overlapped "
-                                  "with the next layer's kernels" % world,
+                      "sharding": "block-row slabs of every layer across %d rank(s)" % world,
+                      "gather": "none (one rank)" if world == 1 else
+                                ("fused into the encode kernel: every rank's kernel stores its packed blocks straight into rank "
+                                 "0's HBM over NVLink (cfx_ipc_open peer memory), one tiny all-reduce per step as the completion "
+                                 "signal; checked once against the NCCL gather: %s" % gather_checked) if a.gather == "peer" else
+                                "one NCCL gather per layer, overlapped with the next layer's kernels",
                       "l2": "inputs (%d MiB per rank) larger than L2; no flush needed" % (int(d_src.numel() * d_src.element_size()) >> 20)},
            "e2e": {"value": total_texels / (e2e_ms / steps * 1e-3) / 1e6, "unit": "Mtexels/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,

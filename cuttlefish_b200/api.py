@@ -188,9 +188,31 @@ def encode_batch(images, fmt, outs=None, **kw):
     return outs
 
 
-def encode_device(src, fmt, out=None, stream=None, **kw):
+IPC_HANDLE_BYTES = 96
+
+
+def ipc_export(tensor):
+    """cfx_ipc_export: a handle (bytes) other processes can open to write into this CUDA tensor's memory."""
+    buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+    _check(load().cfx_ipc_export(ctypes.c_void_p(tensor.data_ptr()), buf))
+    return buf.raw
+
+
+def ipc_open(handle, device):
+    """cfx_ipc_open: maps an exported buffer for kernels running on `device`; returns the device pointer (int)."""
+    ptr = ctypes.c_void_p()
+    _check(load().cfx_ipc_open(handle, int(device), ctypes.byref(ptr)))
+    return int(ptr.value)
+
+
+def ipc_close(ptr, handle):
+    _check(load().cfx_ipc_close(ctypes.c_void_p(ptr), handle))
+
+
+def encode_device(src, fmt, out=None, stream=None, out_ptr=None, out_bytes=0, **kw):
     """Encode a torch CUDA tensor [H,W,4] (uint8/float16/float32) into a CUDA uint8 tensor,
-    asynchronously on `stream` (default: torch's current stream). Goes through cfx_encode_device."""
+    asynchronously on `stream` (default: torch's current stream). Goes through cfx_encode_device.
+    out_ptr / out_bytes: a raw device pointer instead of `out`, e.g. peer memory opened with ipc_open()."""
     import torch
     if not src.is_cuda:
         raise ValueError("encode_device needs a CUDA tensor; use encode() for host arrays")
@@ -206,15 +228,20 @@ def encode_device(src, fmt, out=None, stream=None, **kw):
     n = int(load().cfx_encoded_size(ctypes.byref(d)))
     if n == 0:
         raise CfxError(CFX_ERR_UNSUPPORTED, "format %r is not block compressed" % (fmt,))
-    if out is None:
-        out = torch.empty(n, dtype=torch.uint8, device=src.device)
-    assert out.is_cuda and out.dtype == torch.uint8 and out.numel() >= n and out.is_contiguous()
+    if out_ptr is not None:
+        assert out_bytes >= n
+        dst, cap = int(out_ptr), int(out_bytes)
+    else:
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=src.device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.numel() >= n and out.is_contiguous()
+        dst, cap = out.data_ptr(), out.numel()
     with torch.cuda.device(src.device):
         if stream is None:
             stream = torch.cuda.current_stream()
-        _check(load().cfx_encode_device(ctypes.byref(d), src.data_ptr(), out.data_ptr(), out.numel(),
+        _check(load().cfx_encode_device(ctypes.byref(d), src.data_ptr(), ctypes.c_void_p(dst), cap,
                                         ctypes.c_void_p(stream.cuda_stream)))
-    return out[:n]
+    return None if out_ptr is not None else out[:n]
 
 
 def encode_mip_chain_device(src, fmt, filter="CatmullRom", levels=None, outs=None, stream=None, **kw):

@@ -1042,6 +1042,84 @@ int cfx_encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_sr
     return encode_mip_chain_device(level0, d_src, filter, levels, d_dsts, dst_sizes, static_cast<cudaStream_t>(cuda_stream));
 }
 
+// ---- cross-process peer memory ------------------------------------------------------------------
+
+struct IpcBlob {                       // what cfx_ipc_export() writes into the caller's CFX_IPC_HANDLE_BYTES
+    cudaIpcMemHandle_t handle;         // names the whole allocation d_ptr lives in
+    uint64_t offset;                   // d_ptr - allocation base
+    uint64_t magic;
+};
+static_assert(sizeof(IpcBlob) <= CFX_IPC_HANDLE_BYTES, "CFX_IPC_HANDLE_BYTES too small");
+constexpr uint64_t kIpcMagic = 0x4346584950433031ull;    // "CFXIPC01"
+
+typedef int (*MemGetAddressRangeFn)(unsigned long long*, size_t*, unsigned long long);
+
+int cfx_ipc_export(const void* d_ptr, void* handle)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceGuard guard;
+    t_error[0] = 0;
+    if (!d_ptr || !handle) return fail(CFX_ERR_INVALID, "null argument");
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, d_ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return fail(CFX_ERR_INVALID, "d_ptr is not a device pointer");
+    }
+    CFX_CUDA(cudaSetDevice(attr.device));
+    // the handle names the whole allocation (a torch tensor is a slice of a caching-allocator segment): find its base
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult res;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &res) != cudaSuccess ||
+        res != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return fail(CFX_ERR_CUDA, "cuMemGetAddressRange is not available");
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<MemGetAddressRangeFn>(fn)(&base, &size, reinterpret_cast<unsigned long long>(d_ptr)) != 0)
+        return fail(CFX_ERR_CUDA, "cuMemGetAddressRange failed");
+    IpcBlob blob;
+    memset(&blob, 0, sizeof(blob));
+    CFX_CUDA(cudaIpcGetMemHandle(&blob.handle, reinterpret_cast<void*>(base)));
+    blob.offset = reinterpret_cast<unsigned long long>(d_ptr) - base;
+    blob.magic = kIpcMagic;
+    memset(handle, 0, CFX_IPC_HANDLE_BYTES);
+    memcpy(handle, &blob, sizeof(blob));
+    return CFX_OK;
+}
+
+int cfx_ipc_open(const void* handle, int device, void** d_ptr)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceGuard guard;
+    t_error[0] = 0;
+    if (!handle || !d_ptr) return fail(CFX_ERR_INVALID, "null argument");
+    IpcBlob blob;
+    memcpy(&blob, handle, sizeof(blob));
+    if (blob.magic != kIpcMagic) return fail(CFX_ERR_INVALID, "not a handle made by cfx_ipc_export");
+    Context* c = nullptr;
+    int rc = context_for_device(device, c);
+    if (rc != CFX_OK) return rc;
+    CFX_CUDA(cudaSetDevice(device));
+    void* base = nullptr;
+    // peer access between `device` and the exporting device is switched on by the driver as part of the mapping
+    CFX_CUDA(cudaIpcOpenMemHandle(&base, blob.handle, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = static_cast<uint8_t*>(base) + blob.offset;
+    return CFX_OK;
+}
+
+int cfx_ipc_close(void* d_ptr, const void* handle)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    t_error[0] = 0;
+    if (!d_ptr || !handle) return fail(CFX_ERR_INVALID, "null argument");
+    IpcBlob blob;
+    memcpy(&blob, handle, sizeof(blob));
+    if (blob.magic != kIpcMagic) return fail(CFX_ERR_INVALID, "not a handle made by cfx_ipc_export");
+    CFX_CUDA(cudaIpcCloseMemHandle(static_cast<uint8_t*>(d_ptr) - blob.offset));
+    return CFX_OK;
+}
+
 void* cfx_host_alloc(size_t bytes)
 {
     void* p = nullptr;

@@ -173,6 +173,22 @@ int cfx_encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32
 int cfx_encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_src, uint32_t filter, uint32_t levels,
                                 void* const* d_dsts, const size_t* dst_sizes, void* cuda_stream);
 
+/* Cross-process peer memory, for hosts that run one PROCESS per GPU (bench.py under torchrun): the process
+ * that is to own the assembled output exports the device buffer, the others open it and pass the mapped pointer plus
+ * their slab's byte offset as d_dst of cfx_encode_device(). The encode kernel then stores its packed blocks straight
+ * into the owner's HBM over NVLink: the gather of Converter::convert()'s `textureData[mip][d][f] = data()`
+ * (lib/src/Converter.cpp:587) is fused into the kernel -- no collective, no extra launch, no staging copy.
+ *   cfx_ipc_export(d_ptr, handle)        handle: CFX_IPC_HANDLE_BYTES bytes, to be sent to the other processes.
+ *   cfx_ipc_open(handle, device, &ptr)   maps the buffer for kernels of `device` (peer access is enabled on the way).
+ *   cfx_ipc_close(ptr, handle)           unmaps it.
+ * The owner learns that a slab is complete the way it would for any peer write: a stream-ordered signal after the
+ * kernel (an interprocess event, or the tiny collective bench.py uses). Same-process multi-GPU hosts need none of this:
+ * cfx_encode() already writes every device's blocks into the one caller-owned buffer. */
+#define CFX_IPC_HANDLE_BYTES 96
+int cfx_ipc_export(const void* d_ptr, void* handle);
+int cfx_ipc_open(const void* handle, int device, void** d_ptr);
+int cfx_ipc_close(void* d_ptr, const void* handle);
+
 /* Pinned host memory helpers for callers that want zero-copy staging. */
 void* cfx_host_alloc(size_t bytes);
 void cfx_host_free(void* p);
