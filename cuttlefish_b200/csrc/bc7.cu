@@ -47,8 +47,8 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v)
 // Candidate sets per lanes-per-block G (index 0: G=4, 1: G=8, 2: G=16, 3: G=32) and per opaque / alpha.
 #define C CFX_BC7_CAND
 __device__ __constant__ uint16_t kBc7Cand[4][2][32] = {
-    {{C(6,0,0,2), C(1,0,0,2), C(3,0,0,2), C(6,0,1,2)},
-     {C(6,0,0,2), C(7,0,0,2), C(7,1,0,2), C(6,0,1,2)}},
+    {{C(6,0,0,2), C(1,0,0,2), C(3,0,0,2), C(1,1,0,2)},
+     {C(6,0,0,2), C(7,0,0,2), C(7,1,0,2), C(7,2,0,2)}},
     {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2)},
      {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(7,1,1,2), C(7,2,0,2), C(7,2,1,2)}},
     {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2),
@@ -66,7 +66,7 @@ __device__ __constant__ uint16_t kBc7Cand[4][2][32] = {
 };
 #undef C
 // number of ranked shapes each set needs (opaque, alpha)
-__device__ __constant__ uint8_t kBc7Ranks[4][2] = {{1, 2}, {2, 3}, {4, 7}, {8, 15}};
+__device__ __constant__ uint8_t kBc7Ranks[4][2] = {{2, 3}, {2, 3}, {4, 7}, {8, 15}};
 
 #ifndef CFX_BC7_MIN_CTAS
 #define CFX_BC7_MIN_CTAS 2      // 3 (80 registers, 236 B of spills) was measured: 3.08 vs 3.16 GTexel/s
@@ -179,10 +179,9 @@ int launch_bc7(const EncodeParams& p, cudaStream_t stream)
     // lanes per block by quality: more lanes = more (mode, shape) candidates refined per block
     const void* k;
     switch (p.quality) {
-        case 0: case 1: k = reinterpret_cast<const void*>(&bc7_kernel<4>); break;
-        case 2: k = reinterpret_cast<const void*>(&bc7_kernel<8>); break;
-        case 3: k = reinterpret_cast<const void*>(&bc7_kernel<16>); break;
-        default: k = reinterpret_cast<const void*>(&bc7_kernel<32>); break;
+        case 0: case 1: case 2: k = reinterpret_cast<const void*>(&bc7_kernel<4>); break;
+        case 3: k = reinterpret_cast<const void*>(&bc7_kernel<8>); break;
+        default: k = reinterpret_cast<const void*>(&bc7_kernel<16>); break;
     }
     uint32_t grid = min(tiles, persistent_ctas(k, kThreads));
     void* args[] = {const_cast<EncodeParams*>(&p)};

@@ -85,6 +85,14 @@ CFX_HD float lambda_max(const float* c)
     return v.x*r.x + v.y*r.y + v.z*r.z + v.w*r.w;
 }
 
+// What a subset's spread ALONG its line costs after index quantisation, as a fraction of that spread: texels spread
+// evenly over the end point interval and rounded to one of N levels keep 1/(N-1)^2 of their variance as error (N = 8 for
+// mode 1). Without this term every shape of a block whose texels are collinear (black-on-white text) scores zero and the
+// ranking is arbitrary, although cutting the line into two short pieces is exactly what such blocks gain from.
+#ifndef CFX_BC7_LINE_KEEP
+#define CFX_BC7_LINE_KEEP (1.0f - 1.0f/49.0f)
+#endif
+
 // Phase-1 score of one two-subset shape: sum over subsets of (trace - lambda_max) of the subset's
 // scatter matrix = squared distance of its texels from their best-fit line.  Returned as a sortable
 // key with the shape number in the low 6 bits.  sT / cT: block totals of x and of the 10 products.
@@ -116,7 +124,7 @@ CFX_HD uint32_t score_shape(const float4* bxf, const float* sT, const float* cT,
         cc[0] -= sm[0]*sm[0]*inv; cc[1] -= sm[0]*sm[1]*inv; cc[2] -= sm[0]*sm[2]*inv; cc[3] -= sm[0]*sm[3]*inv;
         cc[4] -= sm[1]*sm[1]*inv; cc[5] -= sm[1]*sm[2]*inv; cc[6] -= sm[1]*sm[3]*inv;
         cc[7] -= sm[2]*sm[2]*inv; cc[8] -= sm[2]*sm[3]*inv; cc[9] -= sm[3]*sm[3]*inv;
-        score += (cc[0] + cc[4] + cc[7] + cc[9]) - lambda_max(cc);
+        score += (cc[0] + cc[4] + cc[7] + cc[9]) - CFX_BC7_LINE_KEEP*lambda_max(cc);
     }
     score = fmaxf(score, 0.0f);
     return (__float_as_uint(score) & ~63u) | shape;
@@ -172,7 +180,7 @@ CFX_HD uint32_t score_shape_rgb(const float4* bxf, const float* sT, const float*
         const float inv = 1.0f/nn;
         cc[0] -= sm[0]*sm[0]*inv; cc[1] -= sm[0]*sm[1]*inv; cc[2] -= sm[0]*sm[2]*inv;
         cc[3] -= sm[1]*sm[1]*inv; cc[4] -= sm[1]*sm[2]*inv; cc[5] -= sm[2]*sm[2]*inv;
-        score += (cc[0] + cc[3] + cc[5]) - lambda_max3(cc);
+        score += (cc[0] + cc[3] + cc[5]) - CFX_BC7_LINE_KEEP*lambda_max3(cc);
     }
     score = fmaxf(score, 0.0f);
     return (__float_as_uint(score) & ~63u) | shape;

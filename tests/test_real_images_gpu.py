@@ -1,0 +1,76 @@
+"""Real-image parity (run on the B200 box): 192x192 crops of the images the reference itself ships -- astcenc's
+Small LDR-RGB / LDR-RGBA / HDR-RGB sets and Compressonator's ruby.png -- committed under tests/golden/real/ together
+with the reference CPU encoders' blocks (tests/golden/make_real_goldens.py). Our blocks and the reference's are decoded
+by the same decoder and held to the north_star bar: byte-identical for BC1 / ETC1 at Quality::Normal, RGB PSNR >=
+reference - 0.1 dB for everything else, at every Texture::Quality level the crops were encoded at."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from util import block_mismatches, decode_any
+
+pytestmark = pytest.mark.gpu
+
+REAL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real")
+PSNR_TOLERANCE_DB = 0.1     # BASELINE.json north_star: "<= 0.1 dB vs reference"
+
+
+def _cases():
+    out = []
+    for path in sorted(glob.glob(os.path.join(REAL_DIR, "*.npz"))):
+        name = os.path.basename(path)[:-4]
+        with np.load(path) as z:
+            for key in z.files:
+                if key.startswith("blocks__"):
+                    _, fmt, quality = key.split("__")
+                    out.append((name, fmt, quality))
+    return out
+
+
+CASES = _cases()
+
+
+def _load(name, fmt, quality):
+    z = np.load(os.path.join(REAL_DIR, name + ".npz"))
+    src = z["src"]
+    if src.dtype == np.uint16:
+        src = src.view(np.float16)
+    return src, z["blocks__%s__%s" % (fmt, quality)]
+
+
+def test_real_goldens_are_present():
+    assert len(CASES) >= 100, "tests/golden/real/ is missing or incomplete (tests/golden/make_real_goldens.py)"
+
+
+@pytest.mark.parametrize("name,fmt,quality", CASES)
+def test_real_image_parity(cfx, oracle, name, fmt, quality):
+    src, ref = _load(name, fmt, quality)
+    h, w, _ = src.shape
+    hdr = src.dtype == np.float16
+    kw = dict(quality=quality)
+    if hdr:
+        kw["type"] = "UFloat"
+    got = cfx.encode(src, fmt, **kw)
+    assert got.size == ref.size
+    if cfx.format_is_exact(fmt, kw.get("type", "UNorm"), quality):
+        bad = block_mismatches(got, ref, cfx.block_info(fmt)[2])
+        assert bad.size == 0, "%s %s %s: %d of %d blocks differ from the reference's bytes" % (name, fmt, quality, bad.size, ref.size // cfx.block_info(fmt)[2])
+        return
+    img = src.astype(np.float32) if hdr else src.astype(np.float32) / np.float32(255.0)
+    dkw = {"type": "UFloat"} if hdr else {}
+    d_gpu, d_ref = decode_any(oracle, got, fmt, w, h, dkw), decode_any(oracle, ref, fmt, w, h, dkw)
+
+    def psnr(d, nch):
+        mse = float(np.mean((d[..., :nch].astype(np.float64) - img[..., :nch].astype(np.float64)) ** 2))
+        return 10 * np.log10(1.0 / max(mse, 1e-12))
+
+    p_gpu, p_ref = psnr(d_gpu, 3), psnr(d_ref, 3)
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s %s %s: RGB PSNR gpu %.3f dB < reference %.3f dB - %.1f" % (
+        name, fmt, quality, p_gpu, p_ref, PSNR_TOLERANCE_DB)
+    # formats that carry alpha, on images that have one: the alpha channel must not pay for the colour
+    if name.startswith("rgba") and fmt in ("BC3", "BC7", "ETC2_R8G8B8A8") or (name.startswith("rgba") and fmt.startswith("ASTC")):
+        a_gpu, a_ref = psnr(d_gpu, 4), psnr(d_ref, 4)
+        assert a_gpu >= a_ref - PSNR_TOLERANCE_DB, "%s %s %s: RGBA PSNR gpu %.3f dB < reference %.3f dB - %.1f" % (
+            name, fmt, quality, a_gpu, a_ref, PSNR_TOLERANCE_DB)
