@@ -50,15 +50,27 @@ struct Slot3 {
     uint32_t pc, seed, valid;
     int32_t dual_ch;
 };
-// Slots 0..8 as in astc_core.cuh (RGB(A) end points); 9: one subset with LUMINANCE end points (CEM 0); 10, 11 / 12, 13:
-// the two-subset / three-subset partitionings of slots 1, 2 / 3, 4 with luminance end points.  Luminance slots are
-// for opaque blocks only, which is why 12, 13 can live in the A operand rows of the alpha dual-plane slot (8, 12).
-constexpr int kSlots3 = kSlots + 5;
-constexpr int kLumSlot = 9, kLumRow = 13;
-__device__ __forceinline__ bool slot_is_lum(uint32_t s) { return s >= static_cast<uint32_t>(kLumSlot); }
-__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : (s < 12u ? 5u : 6u)); }   // est list / colour level class
-__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : (s < 12u ? s + 4u : (s == 12u ? 8u : 12u)); }        // A operand row of its first plane
-__device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 10u ? s - 10u : (s - 1u) & 3u; }          // index into Warp3T::part
+// Slots 0..8 as in astc_core.cuh (RGB(A) end points); 9: one subset with LUMINANCE end points (CEM 0); 10, 11 / 12:
+// the two-subset partitionings of slots 1, 2 / the three-subset one of slot 3 with luminance end points; 13: one subset
+// with RGB BASE + SCALE end points (CEM 6: e1 = (r, g, b), e0 = e1*s/256 -- a line through black, which is what shaded
+// surfaces of one material are; four stored values instead of six buy a finer weight grid or finer weights; astcenc
+// picks it for 20-50 % of the blocks of photographic content). These slots are for opaque blocks only, which is why
+// 12, 13 can live in the A operand rows of the alpha dual-plane slot (8, 12).
+// 14, 15 / 16, 17: the two- / three-subset partitionings of slots 1, 2 / 3, 4 with base + scale end points on every
+// subset (8 / 12 stored values instead of 12 / 18: what makes multi-subset encodings affordable at all on the larger
+// footprints -- the reference uses CEM 6 on at least one subset of most of its two-subset blocks). They are VIRTUAL:
+// partition, ideal weights (A operand row), line lengths and the measured quantisation loss are those of the RGB
+// sibling slot -- where a subset suits a line through black its free line nearly is one -- and only the error floor
+// (distance from the through-black lines, Warp3T::scale_eline), the colour level class and the end point solve differ.
+constexpr int kSlots3 = kSlots + 5;            // real slots (own Slot3 entry)
+constexpr int kSlotsAll = kSlots3 + 4;         // + the virtual base + scale slots 14..17
+constexpr int kLumSlot = 9, kLumRow = 13, kScaleSlot = 13;
+__device__ __forceinline__ bool slot_is_scale(uint32_t s) { return s >= static_cast<uint32_t>(kScaleSlot); }
+__device__ __forceinline__ bool slot_is_lum(uint32_t s) { return s >= static_cast<uint32_t>(kLumSlot) && s < static_cast<uint32_t>(kScaleSlot); }
+__device__ __forceinline__ uint32_t slot_base(uint32_t s) { return s < static_cast<uint32_t>(kSlots3) ? s : s - 13u; }              // the slot whose Slot3 entry describes s
+__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : (s < 12u ? 5u : (s == 12u ? 6u : (s == 13u ? 7u : (s < 16u ? 8u : 9u))))); }   // est list / colour level class
+__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : (s < 12u ? s + 4u : (s == 12u ? 8u : (s == 13u ? 12u : s - 13u))); }        // A operand row of its first plane
+__device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 14u ? s - 14u : (s >= 10u ? s - 10u : (s - 1u) & 3u); }          // index into Warp3T::part
 constexpr float kMismatchWeight = 0.05f; // partition ranking: cost of one texel off the clustering, in mean squared spreads
 constexpr int kDataLevels = 6;          // weight levels 2,3,4,5,6,8: their quantisation loss is MEASURED on the slot's ideal
                                         // weights (text and edges are bimodal: the uniform model is far off there)
@@ -78,6 +90,8 @@ struct Warp3T {
     static constexpr int TS = ta_stride(TP);
     int4 v[TP];                             // texels, FX fixed point
     Slot3 slots[kSlots3];
+    float scale_eline[4];                   // error floor of the virtual base + scale slots 14..17
+    uint32_t scale_valid[4];
     uint8_t part[4][TP];                    // subset of every texel for slots 1..4
     __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
                                             // 9..12 second planes of slots 5..8, 13..15 luminance slots 9..11;
@@ -170,7 +184,7 @@ template <typename WS>
 __device__ __forceinline__ void reweight_decimation(const Ctx& c, WS& ws, uint32_t s, uint32_t grid, uint32_t nw, uint32_t row, uint32_t lane)
 {
     const uint32_t T = c.tab.texels;
-    const Slot3& slot = ws.slots[s];
+    const Slot3& slot = ws.slots[slot_base(s)];
     const uint8_t* parts = ws.part[slot_part(s)];
     const float wmax = fmaxf(fmaxf(slot.len2[0], slot.len2[1]), slot.pc > 2 ? slot.len2[2] : 0.0f);
     if (!(wmax > 0.0f)) return;
@@ -211,8 +225,9 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     uint32_t lane)
 {
     const bool lum = slot_is_lum(s);
+    const bool scale = slot_is_scale(s);
     const uint32_t T = c.tab.texels;
-    const Slot3& slot = ws.slots[s];
+    const Slot3& slot = ws.slots[slot_base(s)];
     const uint32_t pc = slot.pc;
     const int dc = slot.dual_ch;
     const uint32_t planes = dc >= 0 ? 2u : 1u;
@@ -295,7 +310,25 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
                 val = (__shfl_sync(0xFFu, val, b4) + __shfl_sync(0xFFu, val, b4 + 1u) + __shfl_sync(0xFFu, val, b4 + 2u))*(1.0f/3.0f);
             }
             int q = 255;
-            if (hdr) ws.epf[p*8u + lane] = val;
+            if (scale) {
+                // base + scale: s = where the unconstrained e0 falls along e1, snapped to the colour level; with the scale
+                // fixed the least-squares base is closed form in the same moment sums: every texel is a_i*E with
+                // a_i = s(1 - w_i) + w_i, so E = sum a_i x_i / sum a_i^2 = (s P + Q)/(s^2 A + 2 s B + C)
+                const float e0r = __shfl_sync(0xFFu, val, 0), e0g = __shfl_sync(0xFFu, val, 1), e0b = __shfl_sync(0xFFu, val, 2);
+                const float e1r = __shfl_sync(0xFFu, val, 4), e1g = __shfl_sync(0xFFu, val, 5), e1b = __shfl_sync(0xFFu, val, 6);
+                const float dd = e1r*e1r + e1g*e1g + e1b*e1b;
+                const float sp = dd > 0.0f ? (e0r*e1r + e0g*e1g + e0b*e1b)/dd : 1.0f;
+                const int s8 = min(max(__float2int_rn(sp*256.0f), 0), 255);
+                const int sq = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(s8))));
+                const float sf = static_cast<float>(sq)*(1.0f/256.0f);
+                const float den = sf*sf*fA + 2.0f*sf*fB + fC;
+                const float E = den > 0.0f ? (sf*fP + fQ)*(64.0f/static_cast<float>(FX))/den : val;
+                const int iv = min(max(__float2int_rn(E), 0), 255);
+                const int qe = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(iv))));
+                // e0 as the decoder derives it; its (unused: opaque blocks only) alpha byte carries the scale to pack_block
+                q = ch == 3 ? (which ? 255 : sq) : (which ? qe : (qe*sq) >> 8);
+            }
+            else if (hdr) ws.epf[p*8u + lane] = val;
             else if (ch < 3 || has_alpha) {
                 const int iv = min(max(__float2int_rn(val), 0), 255);
                 const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(iv));
@@ -344,7 +377,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
         __syncwarp();
     }
     // keep sum(e1.rgb) >= sum(e0.rgb) (otherwise the decoder would blue-contract): swap the end points
-    if (lane < pc && !lum && !hdr) {
+    if (lane < pc && !lum && !hdr && !scale) {
         int* e = ws.ep + lane*8u;
         if (e[4] + e[5] + e[6] < e[0] + e[1] + e[2]) {
 #pragma unroll
@@ -464,6 +497,25 @@ __device__ __noinline__ void subset_line(const Mom& mo, int zero_ch, int iters, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) { out.m[k] = m[k]; out.v[k] = v[k]; }
     out.resid = resid;
+}
+
+// Squared distance of a texel set from the best line THROUGH BLACK (RGB only): trace - lambda_max of the uncentred second
+// moments, rebuilt from the moments about the block centre c.  mo lives in shared memory.
+__device__ __noinline__ float origin_residual(const Mom& mo, float c0, float c1, float c2)
+{
+    const float n = mo.n, s0 = mo.s[0], s1 = mo.s[1], s2 = mo.s[2];
+    const float m00 = mo.p[0] + 2.0f*c0*s0 + n*c0*c0, m01 = mo.p[1] + c0*s1 + c1*s0 + n*c0*c1, m02 = mo.p[2] + c0*s2 + c2*s0 + n*c0*c2;
+    const float m11 = mo.p[4] + 2.0f*c1*s1 + n*c1*c1, m12 = mo.p[5] + c1*s2 + c2*s1 + n*c1*c2, m22 = mo.p[7] + 2.0f*c2*s2 + n*c2*c2;
+    float v0 = s0 + n*c0, v1 = s1 + n*c1, v2 = s2 + n*c2, lam = 0.0f;      // start: the mean colour
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const float n2 = v0*v0 + v1*v1 + v2*v2;
+        const float is = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+        const float a0 = v0*is, a1 = v1*is, a2 = v2*is;
+        v0 = m00*a0 + m01*a1 + m02*a2; v1 = m01*a0 + m11*a1 + m12*a2; v2 = m02*a0 + m12*a1 + m22*a2;
+        lam = a0*v0 + a1*v1 + a2*v2;
+    }
+    return fmaxf(m00 + m11 + m22 - lam, 0.0f);
 }
 
 // Residual only, moments passed in registers (integer sums about the block centre).
@@ -784,7 +836,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             Slot3& sl = ws.slots[lane];
             sl.pc = 1; sl.seed = 0; sl.dual_ch = (lane >= 5 && lane < 9) ? static_cast<int32_t>(lane - 5) : -1;
             sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u) && !HDR) ? 1u : 0u;
-            // (slots 10, 11 are validated in setup 8, after the two-subset partitionings are known)
+            // (slots 10..13 are validated in setup 8, after the partitionings are known)
         }
         // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
         TexelMask<MW> km0, km1, km2;
@@ -906,7 +958,20 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             __syncwarp();
             if (lane < 10) {
                 const uint32_t sl = lane < 2 ? 1u : (lane < 4 ? 2u : (lane < 7 ? 3u : 4u));
-                if (ws.slots[sl].valid) subset_line(moms[lane], -1, 6, lines[5 + lane]);
+                if (ws.slots[sl].valid) {
+                    subset_line(moms[lane], -1, 6, lines[5 + lane]);
+                    // for the base + scale siblings (slots 14..17): the subset's distance from its line through black
+                    lines[5 + lane].pad[0] = has_alpha ? 0.0f :
+                        origin_residual(moms[lane], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z));
+                }
+            }
+            __syncwarp();
+            if (lane < 4) {
+                const uint32_t first = lane == 0 ? 5u : (lane == 1 ? 7u : (lane == 2 ? 9u : 12u)), cnt = lane < 2 ? 2u : 3u;
+                float e = 0.0f;
+                for (uint32_t q = 0; q < cnt; ++q) e += lines[first + q].pad[0];
+                ws.scale_eline[lane] = e*ifx*ifx;
+                ws.scale_valid[lane] = ws.slots[1 + lane].valid && !has_alpha && !HDR && !(tb.flags & 4u) ? 1u : 0u;
             }
         }
         __syncwarp();
@@ -1030,8 +1095,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 sl.len2[0] = 3.0f*(l1 - l0)*(l1 - l0); sl.len2b = 0.0f;
                 sl.e_line = chroma*ifx*ifx;
             }
-            // the same with the two-subset (k = 0, 1) and three-subset (k = 2, 3) partitionings: a gray range per subset
-            for (uint32_t k = 0; k < 4; ++k) {
+            // the same with the two-subset (k = 0, 1) and the best three-subset (k = 2) partitionings: a gray range per subset
+            for (uint32_t k = 0; k < 3; ++k) {
                 Slot3& sl = ws.slots[10 + k];
                 const uint32_t npc = k < 2 ? 2u : 3u;
                 const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u) && !HDR;
@@ -1081,6 +1146,51 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 }
                 if (lane == 0) { sl.len2b = 0.0f; sl.e_line = chroma*ifx*ifx; }
             }
+            // ---- setup 9: the base + scale slot: the line through black that fits the texels best = the principal axis
+            //      of the UNCENTRED second moments (from the moments about ctr), weights = position along it
+            {
+                Slot3& sl = ws.slots[kScaleSlot];
+                const float c0 = static_cast<float>(ctr.x), c1 = static_cast<float>(ctr.y), c2 = static_cast<float>(ctr.z);
+                const float s0 = static_cast<float>(tot[1]), s1 = static_cast<float>(tot[2]), s2 = static_cast<float>(tot[3]);
+                const float tn = static_cast<float>(T);
+                const float m00 = static_cast<float>(tot[5]) + 2.0f*c0*s0 + tn*c0*c0, m01 = static_cast<float>(tot[6]) + c0*s1 + c1*s0 + tn*c0*c1;
+                const float m02 = static_cast<float>(tot[7]) + c0*s2 + c2*s0 + tn*c0*c2, m11 = static_cast<float>(tot[9]) + 2.0f*c1*s1 + tn*c1*c1;
+                const float m12 = static_cast<float>(tot[10]) + c1*s2 + c2*s1 + tn*c1*c2, m22 = static_cast<float>(tot[12]) + 2.0f*c2*s2 + tn*c2*c2;
+                // power iteration from the mean colour (non-negative matrix: the axis has no negative component)
+                float v0 = s0 + tn*c0, v1 = s1 + tn*c1, v2 = s2 + tn*c2, lam = 0.0f;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const float n2 = v0*v0 + v1*v1 + v2*v2;
+                    const float is = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+                    const float a0 = v0*is, a1 = v1*is, a2 = v2*is;
+                    v0 = m00*a0 + m01*a1 + m02*a2; v1 = m01*a0 + m11*a1 + m12*a2; v2 = m02*a0 + m12*a1 + m22*a2;
+                    lam = a0*v0 + a1*v1 + a2*v2;
+                }
+                const float n2 = v0*v0 + v1*v1 + v2*v2;
+                const float is = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+                v0 *= is; v1 *= is; v2 *= is;
+                float tmin = 3.0e38f, tmax = -3.0e38f;
+                for (uint32_t i = lane; i < T; i += 32) {
+                    const int4 x = ws.v[i];
+                    const float t = static_cast<float>(x.x)*v0 + static_cast<float>(x.y)*v1 + static_cast<float>(x.z)*v2;
+                    tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
+                }
+                tmin = warp_min_f(tmin); tmax = warp_max_f(tmax);
+                const bool ok = !(tb.flags & 4u) && !HDR && n2 > 1e-20f && tmax > tmin && tmin >= 0.0f;
+                const float ir = ok ? 1.0f/(tmax - tmin) : 0.0f;
+                for (uint32_t i = lane; i < T; i += 32) {
+                    const int4 x = ws.v[i];
+                    const float t = static_cast<float>(x.x)*v0 + static_cast<float>(x.y)*v1 + static_cast<float>(x.z)*v2;
+                    ws.ta[slot_row(kScaleSlot)][i] = __float2half_rn((t - tmin)*ir);
+                }
+                if (lane == 0) {
+                    sl.valid = ok ? 1u : 0u; sl.pc = 1; sl.seed = 0; sl.dual_ch = -1;
+                    sl.e0[0] = make_float4(v0*tmin*ifx, v1*tmin*ifx, v2*tmin*ifx, 255.0f);
+                    sl.e1[0] = make_float4(v0*tmax*ifx, v1*tmax*ifx, v2*tmax*ifx, 255.0f);
+                    sl.len2[0] = (tmax - tmin)*(tmax - tmin)*ifx*ifx; sl.len2b = 0.0f;
+                    sl.e_line = fmaxf(m00 + m11 + m22 - lam, 0.0f)*ifx*ifx;
+                }
+            }
         } else if (active && lane < 4) {
             ws.slots[10 + lane].valid = 0;
         }
@@ -1104,12 +1214,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     if (gq >= 6 && i < T) wgt2 = ws.slots[gq + 4].len2[ws.part[gq - 6][i]];
                     // rows 8 / 12 belong to the three-subset luminance slots 12 / 13 when the block is opaque
                     if (gq == 0 && i < T && ws.slots[12].valid) wgt2 = ws.slots[12].len2[ws.part[2][i]];
-                    if (gq == 4 && i < T && ws.slots[13].valid) wgt2 = ws.slots[13].len2[ws.part[3][i]];
+                    // (row 12 = the base + scale slot 13 of an opaque block: one subset, unit texel weights)
                     lw2[nt][e] = wgt2;
                 }
             const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
             const float scale1 = gq == 0 ? (ws.slots[12].valid ? 1.0f : ws.slots[8].len2[0]) :
-                (gq == 4 ? (ws.slots[13].valid ? 1.0f : ws.slots[8].len2b) :
+                (gq == 4 ? (ws.slots[13].valid ? ws.slots[13].len2[0] : ws.slots[8].len2b) :
                 (gq < 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 1.0f)));
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
@@ -1157,7 +1267,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 s1 += k*ws.slots[1].len2[p0]; s2 += k*ws.slots[2].len2[p1];
                 s3 += k*ws.slots[3].len2[p2]; s4 += k*ws.slots[4].len2[p3];
                 s5 += k*ws.slots[10].len2[p0]; s6 += k*ws.slots[11].len2[p1];
-                s7 += k*ws.slots[12].len2[p2]; s8 += k*ws.slots[13].len2[p3];
+                s7 += k*ws.slots[12].len2[p2];
             }
             ws.u.est.Sm[0][g] = s1; ws.u.est.Sm[1][g] = s2; ws.u.est.Sm[2][g] = s3; ws.u.est.Sm[3][g] = s4;
             ws.u.est.Sm[4][g] = s5; ws.u.est.Sm[5][g] = s6; ws.u.est.Sm[6][g] = s7; ws.u.est.Sm[7][g] = s8;
@@ -1212,26 +1322,27 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             const float* ksum = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_ksum);
             float* gb = &ws.g[0][0];           // per grid: floor + decimation loss   (phase 2 scratch, free until then)
             float* gs = &ws.g[1][0];           // per grid: weight-quantisation scale
-            for (uint32_t s = 0; s < kSlots3; ++s) {
-                const Slot3& slot = ws.slots[s];
-                if (!slot.valid) continue;
+            for (uint32_t s = 0; s < kSlotsAll; ++s) {
+                const Slot3& slot = ws.slots[slot_base(s)];
+                const bool virt = s >= static_cast<uint32_t>(kSlots3);
+                if (virt ? !ws.scale_valid[s - kSlots3] : !slot.valid) continue;
                 const uint32_t type = slot_kind(s);
                 const uint32_t drow = slot_row(s);
                 const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
-                const float base = kLine*slot.e_line;
+                const float base = kLine*(virt ? ws.scale_eline[s - kSlots3] : slot.e_line);
                 const float l2sum = slot.len2[0] + slot.len2b;
                 // per-grid terms of this slot (lane = grid)
                 __syncwarp();
                 for (uint32_t g = lane; g < G; g += 32) {
                     float dsum = ws.u.est.D[drow][g], ssum;
                     if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
-                    else if (type == 0 || type == 4) ssum = l2sum*__ldg(ksum + g);
-                    else ssum = ws.u.est.Sm[type >= 5 ? s - 6 : s - 1][g];
+                    else if (type == 0 || type == 4 || type == 7) ssum = l2sum*__ldg(ksum + g);
+                    else ssum = ws.u.est.Sm[type >= 8 ? s - 14 : (type >= 5 ? s - 6 : s - 1)][g];
                     gb[g] = base + kDec*dsum; gs[g] = kQuant*ssum;
                 }
                 __syncwarp();
-                const float* qn = ws.u.est.qn[s];
+                const float* qn = ws.u.est.qn[slot_base(s)];
 #pragma unroll 2
                 for (uint32_t e = lane; e < count; e += 32) {
                     const uint4 q = __ldg(list + e);
@@ -1279,9 +1390,9 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 if (done) refining = true;
                 else {
                     const uint32_t s = code >> 16;
-                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? 7u : 0u) + slot_kind(s))*tb.t3.n_modes + (code & 0xFFFFu));
+                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? static_cast<uint32_t>(kSlotTypes3) : 0u) + slot_kind(s))*tb.t3.n_modes + (code & 0xFFFFu));
                     row0 = static_cast<int>(slot_row(s));
-                    row1 = ws.slots[s].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
+                    row1 = ws.slots[slot_base(s)].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
                 }
             }
             if (refining) {
@@ -1289,7 +1400,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 ++rounds;
                 code = best_code; cl = best_cl;
                 const uint32_t bs = code >> 16;
-                const Slot3& bslot = ws.slots[bs];
+                const Slot3& bslot = ws.slots[slot_base(bs)];
                 const int dc = bslot.dual_ch;
                 const float escale = HDR ? 1.0f/16.0f : 1.0f;     // HDR end points are 12-bit, texels 8-bit-like
                 const uint8_t* parts = ws.part[slot_part(bs)];
@@ -1316,16 +1427,16 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
             decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
-            if (NT > 8 && ws.slots[s].pc > 1 && m.nw < T && !(tb.flags & 32u)) reweight_decimation(ctx, ws, s, m.grid, m.nw, static_cast<uint32_t>(row0), lane);
+            if (NT > 8 && ws.slots[slot_base(s)].pc > 1 && m.nw < T && !(tb.flags & 32u)) reweight_decimation(ctx, ws, s, m.grid, m.nw, static_cast<uint32_t>(row0), lane);
             const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane);
             if (err < best_err) {
                 best_err = err; best_code = code; best_cl = cl;
-                keep_best3(ws, m.nw, ws.slots[s].dual_ch >= 0 ? 2u : 1u, ws.slots[s].pc, lane);
+                keep_best3(ws, m.nw, ws.slots[slot_base(s)].dual_ch >= 0 ? 2u : 1u, ws.slots[slot_base(s)].pc, lane);
             } else if (refining) break;
             __syncwarp();
         }
         const uint32_t bs = best_code >> 16;
-        const Slot3& bslot = ws.slots[bs];
+        const Slot3& bslot = ws.slots[slot_base(bs)];
         const ModeInfo bm = tab_mode(ctx, best_code & 0xFFFFu);
         PHASE_SYNC();
         if (active && lane == 0) {
@@ -1339,7 +1450,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     (static_cast<uint32_t>(e[7]) << 24);
             }
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
-            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr);
+            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr,
+                slot_is_scale(bs));
         }
     }
 }

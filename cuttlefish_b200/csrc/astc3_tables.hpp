@@ -22,6 +22,7 @@ namespace astc {
 
 constexpr int kMaxGrids3 = 96;
 constexpr int kMaxTexels3 = 144;    // up to 12x12
+constexpr int kSlotTypes3 = 10;     // colour level / estimate list classes, see Astc3Tab::off_modecl
 constexpr int kRows3 = 16;          // slot planes (A operand rows): 9 first planes, 4 second planes, 3 spare
 
 struct Astc3Tab {
@@ -30,8 +31,9 @@ struct Astc3Tab {
     uint32_t off_mfrag_idx;         // [n_grids] uint32: byte offset of grid's M fragments
     uint32_t off_kappa;             // [n_grids][kMaxTexels3] float: kappa_gi = sum_j P_ij^2
     uint32_t off_ksum;              // [n_grids] float: sum_i kappa_gi
-    uint32_t off_modecl;            // [2 alpha][7 slot type][n_modes1 + n_modes2] u8 colour level, 0xFF = does not fit
-                                    // slot types: 0..2 = 1..3 subsets, 3 = dual plane, 4 / 5 / 6 = one / two / three subsets with luminance end points
+    uint32_t off_modecl;            // [2 alpha][8 slot type][n_modes1 + n_modes2] u8 colour level, 0xFF = does not fit
+                                    // slot types: 0..2 = 1..3 subsets, 3 = dual plane, 4 / 5 / 6 = one / two / three subsets with luminance end points,
+                                    // 7 / 8 / 9 = one / two / three subsets with RGB base + scale end points (CEM 6)
     uint32_t n_modes;               // n_modes1 + n_modes2
     uint32_t off_rstream;           // R fragments of the decimated grids, contiguous in off_dec_list order (+1 pad tile)
     uint32_t off_dec_list;          // [n_dec] u8 grid index
@@ -43,8 +45,8 @@ struct Astc3Tab {
     uint32_t off_seed2, off_seed3;  // [n_seed] uint16 seed numbers, ascending
     uint32_t off_part2c;            // [n_seed2][MW] the same masks, compacted in off_seed2 order
     uint32_t off_part3c;            // [n_seed3][2][MW]
-    uint32_t off_est[2][7];         // [alpha][slot type] -> uint4 list of the modes that fit:
-    uint32_t n_est[2][7];           //   {f32 rest, f32 kc = cvar(colour level), mode | grid << 16 | cl << 24, min(level, 5) | f16 a << 16}: see below
+    uint32_t off_est[2][kSlotTypes3];         // [alpha][slot type] -> uint4 list of the modes that fit:
+    uint32_t n_est[2][kSlotTypes3];           //   {f32 rest, f32 kc = cvar(colour level), mode | grid << 16 | cl << 24, min(level, 5) | f16 a << 16}: see below
 };
 
 inline uint16_t f32_to_f16_bits(float f)
@@ -181,18 +183,19 @@ inline Astc3Tab build_tables3(Built& b)
         }
     }
     // colour level of every (alpha, slot type, mode)
-    t3.off_modecl = reserve(static_cast<size_t>(2)*7*t3.n_modes, 4);
+    t3.off_modecl = reserve(static_cast<size_t>(2)*kSlotTypes3*t3.n_modes, 4);
     for (int alpha = 0; alpha < 2; ++alpha)
-        for (int type = 0; type < 7; ++type)
+        for (int type = 0; type < kSlotTypes3; ++type)
             for (uint32_t mi = 0; mi < t3.n_modes; ++mi) {
                 const ModeInfo m = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes])[mi];
-                const int pc = (type == 1 || type == 5) ? 2 : ((type == 2 || type == 6) ? 3 : 1);
+                const int pc = (type == 1 || type == 5 || type == 8) ? 2 : ((type == 2 || type == 6 || type == 9) ? 3 : 1);
                 // luminance end points (CEM 0: L0 L1; with alpha CEM 4: L0 L1 A0 A1)
-                const int n_ints = type >= 4 ? pc*(alpha ? 4 : 2) : pc*(alpha ? 8 : 6);
+                // base + scale (CEM 6: R G B s; with alpha CEM 10: R G B s A0 A1)
+                const int n_ints = type >= 7 ? pc*(alpha ? 6 : 4) : (type >= 4 ? pc*(alpha ? 4 : 2) : pc*(alpha ? 8 : 6));
                 const int avail = 128 - static_cast<int>(m.wbits) - (pc == 1 ? 17 : 29) - (type == 3 ? 2 : 0);
                 uint8_t cl = 0xFF;
                 if ((m.dual != 0) == (type == 3) && n_ints <= 18 && avail >= 0) cl = blob[t.off_clevel + (n_ints >> 1)*128 + avail];
-                blob[t3.off_modecl + (static_cast<size_t>(alpha)*7 + type)*t3.n_modes + mi] = cl;
+                blob[t3.off_modecl + (static_cast<size_t>(alpha)*kSlotTypes3 + type)*t3.n_modes + mi] = cl;
             }
     // the decimated grids' R fragments again as one contiguous stream (phase 1a walks it with a one-tile prefetch)
     {
@@ -276,10 +279,10 @@ inline Astc3Tab build_tables3(Built& b)
     }
     // estimate lists: per (alpha, slot type) the modes that fit, with their model terms
     for (int alpha = 0; alpha < 2; ++alpha)
-        for (int type = 0; type < 7; ++type) {
+        for (int type = 0; type < kSlotTypes3; ++type) {
             std::vector<uint32_t> ent;
             for (uint32_t mi = 0; mi < t3.n_modes; ++mi) {
-                const uint8_t cl = blob[t3.off_modecl + (static_cast<size_t>(alpha)*7 + type)*t3.n_modes + mi];
+                const uint8_t cl = blob[t3.off_modecl + (static_cast<size_t>(alpha)*kSlotTypes3 + type)*t3.n_modes + mi];
                 if (cl == 0xFF) continue;
                 const ModeInfo m = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes])[mi];
                 const float n1 = static_cast<float>(kWeightQuant[m.level].n - 1);

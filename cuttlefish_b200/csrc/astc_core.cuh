@@ -659,24 +659,26 @@ CFX_HD uint64_t bitrev64(uint64_t v)
 template <typename SlotT>
 CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo& m, const Enc& e, bool has_alpha,
     const uint8_t* u_scr, uint32_t lane, bool linear = false, const uint8_t* k_lin = nullptr, bool lum = false,
-    const int* hdr_vals = nullptr)
+    const int* hdr_vals = nullptr, bool scale = false)
 {
     Bits128 b; b.lo = b.hi = 0;
     const uint32_t pc = slot.pc;
     // colour end point mode: 8 / 12 = LDR RGB / RGBA direct; 0 = LDR luminance direct (lum: one subset, opaque)
     // 11 / 14 = HDR RGB direct (+ LDR alpha); hdr_vals: per subset (stride 8) the six packed values of astc_hdr.cuh
     // followed by the two alpha end points
-    const uint32_t cem = hdr_vals ? (has_alpha ? 14u : 11u) : (lum ? 0u : (has_alpha ? 12u : 8u));
+    // scale: 6 = LDR RGB base + scale (one subset, opaque): stored R G B s, with s in the alpha byte of e.ep[0][0]
+    const uint32_t cem = hdr_vals ? (has_alpha ? 14u : 11u) : (scale ? 6u : (lum ? 0u : (has_alpha ? 12u : 8u)));
     b.put(0, m.mode_bits, 11);
     b.put(11, pc - 1, 2);
     uint32_t pos;
     if (pc == 1) { b.put(13, cem, 4); pos = 17; }
     else { b.put(13, slot.seed, 10); b.put(23, 0, 2); b.put(25, cem, 4); pos = 29; }
-    const uint32_t per = lum ? 2u : (has_alpha ? 8u : 6u);
+    const uint32_t per = scale ? 4u : (lum ? 2u : (has_alpha ? 8u : 6u));
     const uint32_t cl = e.clevel;
     ise_encode(c, b, pos, pc*per, kCqBits[cl], kCqTrits[cl] != 0, kCqQuints[cl] != 0, [&](uint32_t i) {
         const uint32_t s = i/per, k = i - s*per;          // k: r0 r1 g0 g1 b0 b1 a0 a1
-        const uint32_t val = hdr_vals ? static_cast<uint32_t>(hdr_vals[s*8u + k]) & 0xFFu : (e.ep[s][k & 1u] >> (8u*(k >> 1))) & 0xFFu;
+        const uint32_t val = hdr_vals ? static_cast<uint32_t>(hdr_vals[s*8u + k]) & 0xFFu :
+            (scale ? (k < 3u ? (e.ep[s][1] >> (8u*k)) & 0xFFu : e.ep[s][0] >> 24) : (e.ep[s][k & 1u] >> (8u*(k >> 1))) & 0xFFu);
         const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + val);
         return tab_u8(c, c.tab.off_cq_enc + cl*256u + rank);
     });
