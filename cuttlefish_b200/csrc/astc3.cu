@@ -23,6 +23,7 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace cfx {
@@ -121,7 +122,7 @@ struct Warp3T {
 // model constants (fitted on the host with tools/emu_astc3.py)
 constexpr float kLine = 1.1f, kDec = 1.0f, kQuant = 0.9f, kColor = 0.5f;
 
-struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; float mis_w; };   // hdr: Texture::Type::UFloat (texels searched as LNS, end point mode 11)   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
+struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; float mis_w; int dbg_slot, dbg_level, dbg_nw; };   // dbg_*: developer builds only (-1 = any)   // hdr: Texture::Type::UFloat (texels searched as LNS, end point mode 11)   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
 
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t redux_addu(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -220,9 +221,10 @@ __device__ __forceinline__ void reweight_decimation(const Ctx& c, WS& ws, uint32
 
 // Evaluate block mode m on slot s with the decimated weights in ws.g; on success ws.su / ws.ep hold the candidate and
 // its exact decoded error (FX^2 units) is returned.
+// quantise = false: ws.su / ws.sk already hold the candidate's quantised weights (realign_weights).
 template <int K, bool hdr, typename WS>
 __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
-    uint32_t lane)
+    uint32_t lane, bool quantise = true)
 {
     const bool lum = slot_is_lum(s);
     const bool scale = slot_is_scale(s);
@@ -234,7 +236,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     const uint32_t L = m.level, nw = m.nw;
     const float nm1 = static_cast<float>(kWqN[L] - 1);
     // quantise (lane = grid weight)
-    for (uint32_t pl = 0; pl < planes; ++pl)
+    for (uint32_t pl = 0; quantise && pl < planes; ++pl)
         for (uint32_t j = lane; j < nw; j += 32) {
             const int k = min(max(__float2int_rn(ws.g[pl][j]*nm1), 0), static_cast<int>(kWqN[L]) - 1);
             ws.su[j*planes + pl] = static_cast<uint8_t>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(k)));
@@ -422,6 +424,96 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     }
     err = redux_addu(err);
     return static_cast<float>(err);
+}
+
+// One pass of DISCRETE weight realignment on the best candidate so far (the role of astcenc's realign_weights_decimated,
+// lib/astc-encoder/Source/astcenc_compress_symbolic.cpp:188): every grid weight tries the quantisation level below
+// and above its own and keeps whichever lowers the exact decoded error of the texels it feeds, end points held fixed.
+// Rounding the least-squares grid weights one by one is far from the best joint choice at the coarse levels (2..6
+// values) that real images mostly end up with; this descent is what closes most of that gap. Lane = grid weight.
+// The weights a texel blends are a 2x2 patch of the grid, so weights of equal (x, y) parity never share a texel: the
+// four parity classes are swept one after the other, each class in parallel. LDR only. Leaves the result in
+// ws.su / ws.sk; the caller re-solves the end points and measures (evaluate3 with quantise = false).
+template <typename WS>
+__device__ __forceinline__ void realign_weights(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, bool has_alpha, uint32_t lane)
+{
+    constexpr uint32_t TP = WS::TP;
+    const uint32_t T = c.tab.texels;
+    const Slot3& slot = ws.slots[slot_base(s)];
+    const uint32_t pc = slot.pc;
+    const int dc = slot.dual_ch;
+    const uint32_t planes = dc >= 0 ? 2u : 1u;
+    const uint32_t L = m.level, nw = m.nw, grid = m.grid;
+    const int nq = static_cast<int>(kWqN[L]);
+    const uint8_t* parts = ws.part[slot_part(s)];
+    const uint32_t inf_off = c.tab.off_infill + grid*T*8u;
+    const uint32_t start_off = c.tab.off_csr_start + grid*(kMaxTexels + 2)*2u;
+    const uint32_t ent_off = c.tab.off_csr_ent + grid*4u*T*2u;
+    const uint32_t gw = tab_u8(c, c.tab.off_grids + grid*4u);           // GridInfo::w
+    int* S = reinterpret_cast<int*>(&ws.g[0][0]);                       // [plane][TP]: infill sums (16 x texel weight + 8)
+    for (uint32_t j = lane; j < nw*planes; j += 32) { ws.su[j] = ws.best_su[j]; ws.sk[j] = ws.best_sk[j]; }
+    __syncwarp();
+    for (uint32_t i = lane; i < T; i += 32) {
+        const uint2 inf = tab_u32x2(c, inf_off + i*8u);
+        for (uint32_t pl = 0; pl < planes; ++pl) {
+            uint32_t acc = 8;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc += ((inf.y >> (8*q)) & 0xFFu)*ws.su[((inf.x >> (8*q)) & 0xFFu)*planes + pl];
+            S[pl*TP + i] = static_cast<int>(acc);
+        }
+    }
+    __syncwarp();
+    const int nchan = has_alpha ? 4 : 3;
+#pragma unroll 1
+    for (uint32_t pl = 0; pl < planes; ++pl) {
+#pragma unroll 1
+        for (uint32_t colour = 0; colour < 4; ++colour) {
+            for (uint32_t j = lane; j < nw; j += 32) {
+                const uint32_t jy = j/gw, jx = j - jy*gw;
+                if (((jx & 1u) | ((jy & 1u) << 1)) != colour) continue;
+                const int k = ws.sk[j*planes + pl];
+                const int u = ws.su[j*planes + pl];
+                const int du_dn = k > 0 ? static_cast<int>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(k - 1))) - u : 0;
+                const int du_up = k + 1 < nq ? static_cast<int>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(k + 1))) - u : 0;
+                const uint32_t e0 = tab_u16(c, start_off + j*2u), e1 = tab_u16(c, start_off + (j + 1u)*2u);
+                int d_dn = 0, d_up = 0;
+                for (uint32_t e = e0; e < e1; ++e) {
+                    const uint32_t ent = tab_u16(c, ent_off + e*2u);
+                    const uint32_t i = ent & 0xFFu;
+                    const int f = static_cast<int>(ent >> 8);
+                    const int* ep = ws.best_ep + (pc > 1 ? parts[i] : 0u)*8u;
+                    const int4 x = ws.v[i];
+                    const int xs[4] = {x.x, x.y, x.z, x.w};
+                    const int sum = S[pl*TP + i];
+                    const int w0 = sum >> 4, wd = (sum + f*du_dn) >> 4, wu = (sum + f*du_up) >> 4;
+                    int c0 = 0, cd = 0, cu = 0;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        if (ch >= nchan) continue;
+                        // this plane's channels only: the dual channel rides the second plane
+                        if (dc >= 0 && (ch == dc) != (pl == 1u)) continue;
+                        const int a = ep[ch]*FX, b = ep[4 + ch]*FX, xv = xs[ch];
+                        int d = ((a*(64 - w0) + b*w0 + 32) >> 6) - xv; c0 += d*d;
+                        d = ((a*(64 - wd) + b*wd + 32) >> 6) - xv; cd += d*d;
+                        d = ((a*(64 - wu) + b*wu + 32) >> 6) - xv; cu += d*d;
+                    }
+                    d_dn += cd - c0; d_up += cu - c0;
+                }
+                int du = 0, dk = 0;
+                if (du_dn != 0 && d_dn < 0 && d_dn <= d_up) { du = du_dn; dk = -1; }
+                else if (du_up != 0 && d_up < 0) { du = du_up; dk = 1; }
+                if (dk != 0) {
+                    ws.su[j*planes + pl] = static_cast<uint8_t>(u + du);
+                    ws.sk[j*planes + pl] = static_cast<uint8_t>(k + dk);
+                    for (uint32_t e = e0; e < e1; ++e) {
+                        const uint32_t ent = tab_u16(c, ent_off + e*2u);
+                        S[pl*TP + (ent & 0xFFu)] += static_cast<int>(ent >> 8)*du;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
 }
 
 template <typename WS>
@@ -1221,6 +1313,15 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             const float scale1 = gq == 0 ? (ws.slots[12].valid ? 1.0f : ws.slots[8].len2[0]) :
                 (gq == 4 ? (ws.slots[13].valid ? ws.slots[13].len2[0] : ws.slots[8].len2b) :
                 (gq < 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 1.0f)));
+            // what one unit of clamped overshoot of a grid weight costs this row: its line length (multi-subset rows:
+            // the mean over the subsets, the grid is shared)
+            auto mean_len2 = [&](uint32_t sl) {
+                const Slot3& q = ws.slots[sl];
+                return q.pc > 2 ? (q.len2[0] + q.len2[1] + q.len2[2])*(1.0f/3.0f) : (q.len2[0] + q.len2[1])*0.5f;
+            };
+            const float pscale0 = gq >= 1 && gq <= 4 ? mean_len2(gq) : scale0;
+            const float pscale1 = gq == 0 && ws.slots[12].valid ? mean_len2(12) : (gq >= 6 ? mean_len2(gq + 4) : scale1);
+            const float* colen = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_colenergy);
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
                 if (__ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx) + g) == 0u)
@@ -1249,11 +1350,31 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) bcur[ks] = bnext[ks];
                 }
+                // + what clamping the least-squares grid weights into [0, 1] costs (see astc3_tables.hpp): M t on the
+                // tensor cores, overshoot^2 weighted by the weight's column energy
+                float pen0 = 0.0f, pen1 = 0.0f;
+                if (!(tb.flags & 16u)) {
+                    const uint32_t gnw = tab_u8(ctx, ctx.tab.off_grids + g*4u + 2u);          // GridInfo::nw
+                    const uint2* mf = reinterpret_cast<const uint2*>(ctx.blob + __ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_mfrag_idx) + g)) + lane;
+                    const uint32_t ntw = (gnw + 7u) >> 3;
+#pragma unroll 1
+                    for (uint32_t nt = 0; nt < ntw; ++nt) {
+                        float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], __ldg(mf + (nt*KS + ks)*32u));
+                        const float2 ce = __ldg(reinterpret_cast<const float2*>(colen + g*64u + nt*8u + 2u*tq));
+                        float o = c[0] - fminf(fmaxf(c[0], 0.0f), 1.0f); pen0 += ce.x*o*o;
+                        o = c[1] - fminf(fmaxf(c[1], 0.0f), 1.0f); pen0 += ce.y*o*o;
+                        o = c[2] - fminf(fmaxf(c[2], 0.0f), 1.0f); pen1 += ce.x*o*o;
+                        o = c[3] - fminf(fmaxf(c[3], 0.0f), 1.0f); pen1 += ce.y*o*o;
+                    }
+                }
+                acc0 = acc0*scale0 + pen0*pscale0; acc1 = acc1*scale1 + pen1*pscale1;
                 acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 1); acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 2);
                 acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 1); acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 2);
                 if (tq == 0) {
-                    ws.u.est.D[gq][g] = acc0*scale0;
-                    ws.u.est.D[gq + 8][g] = acc1*scale1;
+                    ws.u.est.D[gq][g] = acc0;
+                    ws.u.est.D[gq + 8][g] = acc1;
                 }
             }
         }
@@ -1347,10 +1468,22 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 for (uint32_t e = lane; e < count; e += 32) {
                     const uint4 q = __ldg(list + e);
                     const uint32_t g = (q.z >> 16) & 0xFFu;
+#ifdef CFX_ASTC3_TUNE
+                    {   // developer knobs: only the given slot / weight level / number of grid weights
+                        const ModeInfo dm = tab_mode(ctx, q.z & 0xFFFFu);
+                        if ((tb.dbg_slot >= 0 && static_cast<int>(s) != tb.dbg_slot) || (tb.dbg_level >= 0 && static_cast<int>(kWqN[dm.level]) != tb.dbg_level) ||
+                            (tb.dbg_nw >= 0 && static_cast<int>(dm.nw) != tb.dbg_nw)) continue;
+                    }
+#endif
                     const float a = (tb.flags & 2u) ? 0.0f : __half2float(__ushort_as_half(static_cast<unsigned short>(q.w >> 16)));
                     const float qv = fmaf(a, qn[q.w & 0xFFu], __uint_as_float(q.x));
                     const float est = fmaf(gs[g], qv, fmaf(tn, __uint_as_float(q.y), gb[g]));
                     const uint32_t code = (s << 16) | (q.z & 0xFFFFu);
+#ifdef CFX_ASTC3_TUNE
+                    if (tb.flags & 512u)     // developer: the terms of every estimate (floor, decimation, weight quantisation, colour)
+                        printf("EST blk %u slot %u mode %u base %.1f dec %.1f quant %.1f colour %.1f\n", blk, s, q.z & 0xFFFFu, base, gb[g] - base,
+                            gs[g]*qv, tn*__uint_as_float(q.y));
+#endif
                     if (est < be2) {
                         if (est < be1) {
                             be2 = be1; bc2 = bc1;
@@ -1370,13 +1503,20 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
         const float stop_db = fmaxf(95.0f - 35.0f*log10f(static_cast<float>(T)), 70.0f - 19.0f*log10f(static_cast<float>(T))) + 12.0f;
         const float stop_err = 65025.0f*exp10f(-0.1f*stop_db)*static_cast<float>(T*nch)*fx2;
         bool refining = false;
-        uint32_t n = 0, rounds = 0;
+        uint32_t n = 0, rounds = 0, fails = 0;
+#ifdef CFX_ASTC3_TUNE
+        float dbg_est = 0.0f;
+#endif
 #pragma unroll 1
         while (active) {
             uint32_t code = 0, cl = 0;
             int row0 = 0, row1 = -1;
+            bool realign = false;
             if (!refining) {
                 bool done = n >= n_exact || best_err <= stop_err;
+#ifdef CFX_ASTC3_TUNE
+                if (tb.flags & 256u) done = false;
+#endif
                 if (!done) {
                     const uint32_t kmin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(be0) & ~31u) | lane);
                     const uint32_t wl = kmin & 31u;
@@ -1385,6 +1525,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     if (lane == wl) { be0 = be1; bc0 = bc1; be1 = be2; bc1 = bc2; be2 = 3.0e38f; }
                     // estimates come out sorted: stop when nothing later can win
                     done = est >= 3.0e38f || (n_exact > 8u ? 0.6f : 0.8f)*est*fx2 > best_err;
+#ifdef CFX_ASTC3_TUNE
+                    if (tb.flags & 256u) done = est >= 3.0e38f;      // developer: evaluate everything that was kept
+                    dbg_est = est;
+#endif
                     ++n;
                 }
                 if (done) refining = true;
@@ -1396,15 +1540,20 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 }
             }
             if (refining) {
-                if (rounds >= refine || best_err <= 0.0f || best_err >= 3.0e38f) break;
+                // refinement alternates a continuous step (re-project on the quantised end points, re-decimate, re-solve)
+                // with a discrete one (realign_weights); it ends after `refine` pairs or two failures in a row
+                if (rounds >= 2u*refine || fails >= 2u || best_err <= 0.0f || best_err >= 3.0e38f) break;
+                realign = !HDR && (rounds & 1u) != 0u && !(tb.flags & 8u);
+                const bool skip = (rounds & 1u) != 0u && !realign;
                 ++rounds;
+                if (skip) { ++fails; continue; }
                 code = best_code; cl = best_cl;
                 const uint32_t bs = code >> 16;
                 const Slot3& bslot = ws.slots[slot_base(bs)];
                 const int dc = bslot.dual_ch;
                 const float escale = HDR ? 1.0f/16.0f : 1.0f;     // HDR end points are 12-bit, texels 8-bit-like
                 const uint8_t* parts = ws.part[slot_part(bs)];
-                for (uint32_t i = lane; i < T; i += 32) {
+                for (uint32_t i = lane; !realign && i < T; i += 32) {
                     const int* e = ws.best_ep + (bslot.pc > 1 ? parts[i] : 0u)*8u;
                     const int4 xi = ws.v[i];
                     const float xs[4] = {static_cast<float>(xi.x)*ifx, static_cast<float>(xi.y)*ifx, static_cast<float>(xi.z)*ifx,
@@ -1421,18 +1570,24 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     ws.ta[1][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
                 }
                 __syncwarp();
-                load_a<KS>(ws, a, lane);             // the candidates' rows are not needed any more
+                if (!realign) load_a<KS>(ws, a, lane);             // the candidates' rows are not needed any more
                 row0 = 0; row1 = dc >= 0 ? 1 : -1;
             }
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
-            decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
-            if (NT > 8 && ws.slots[slot_base(s)].pc > 1 && m.nw < T && !(tb.flags & 32u)) reweight_decimation(ctx, ws, s, m.grid, m.nw, static_cast<uint32_t>(row0), lane);
-            const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane);
+            if (realign) realign_weights(ctx, ws, s, m, has_alpha, lane);
+            else decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
+            if (!realign && NT > 8 && ws.slots[slot_base(s)].pc > 1 && m.nw < T && !(tb.flags & 32u)) reweight_decimation(ctx, ws, s, m.grid, m.nw, static_cast<uint32_t>(row0), lane);
+            const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane, !realign);
+#ifdef CFX_ASTC3_TUNE
+            if ((tb.flags & 256u) && lane == 0 && !refining)
+                printf("CAND blk %u slot %u mode %u nw %u level %u cl %u est %.1f exact %.1f\n", blk, s, code & 0xFFFFu, static_cast<uint32_t>(m.nw),
+                    kWqN[m.level], cl, dbg_est, err/fx2);
+#endif
             if (err < best_err) {
-                best_err = err; best_code = code; best_cl = cl;
+                best_err = err; best_code = code; best_cl = cl; fails = 0;
                 keep_best3(ws, m.nw, ws.slots[slot_base(s)].dual_ch >= 0 ? 2u : 1u, ws.slots[slot_base(s)].pc, lane);
-            } else if (refining) break;
+            } else if (refining) ++fails;
             __syncwarp();
         }
         const uint32_t bs = best_code >> 16;
@@ -1516,9 +1671,13 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     static const float mis_w = getenv("CFX_ASTC3_MISW") ? static_cast<float>(atof(getenv("CFX_ASTC3_MISW"))) : kMismatchWeight;
     tb.flags = dev_flags;
     tb.mis_w = mis_w;
+    tb.dbg_slot = getenv("CFX_ASTC3_SLOT") ? atoi(getenv("CFX_ASTC3_SLOT")) : -1;
+    tb.dbg_level = getenv("CFX_ASTC3_LEVEL") ? atoi(getenv("CFX_ASTC3_LEVEL")) : -1;
+    tb.dbg_nw = getenv("CFX_ASTC3_NW") ? atoi(getenv("CFX_ASTC3_NW")) : -1;
 #else
     tb.flags = 0u;
     tb.mis_w = kMismatchWeight;
+    tb.dbg_slot = tb.dbg_level = tb.dbg_nw = -1;
 #endif
     tb.hdr = p.type == 4u ? 1u : 0u;                      // Texture::Type::UFloat
     const uint32_t NT = t3.NT, KS = t3.KS;

@@ -3,6 +3,9 @@
 // matrix (texels x grid weights, ASTC spec "Weight Infill"):
 //   M_g = pinv(P_g)      least-squares decimation: ideal texel weights -> ideal grid weights
 //   R_g = I - P_g M_g    what decimation to grid g cannot represent
+//   ce_gj = sum_i P_ij^2 what clamping grid weight j by one unit costs: the least-squares grid weights of bimodal
+//                        content (text, hard edges) overshoot [0, 1] and are clamped; R t is orthogonal to range(P), so
+//                        the clamped fit loses exactly |R t|^2 + |P o|^2 ~ |R t|^2 + sum_j ce_gj o_j^2, o = M t - clamp(M t)
 // Both are stored as fp16 in the register layout of the B operand of mma.sync.m16n8k16, so that a warp
 // gets decimated weights / decimation residuals of all its partition hypotheses ("slot planes", the
 // A operand rows) from a handful of tensor-core instructions.
@@ -31,6 +34,7 @@ struct Astc3Tab {
     uint32_t off_mfrag_idx;         // [n_grids] uint32: byte offset of grid's M fragments
     uint32_t off_kappa;             // [n_grids][kMaxTexels3] float: kappa_gi = sum_j P_ij^2
     uint32_t off_ksum;              // [n_grids] float: sum_i kappa_gi
+    uint32_t off_colenergy;         // [n_grids][64] float: ce_gj = sum_i P_ij^2 (0 beyond the grid's weights)
     uint32_t off_modecl;            // [2 alpha][8 slot type][n_modes1 + n_modes2] u8 colour level, 0xFF = does not fit
                                     // slot types: 0..2 = 1..3 subsets, 3 = dual plane, 4 / 5 / 6 = one / two / three subsets with luminance end points,
                                     // 7 / 8 / 9 = one / two / three subsets with RGB base + scale end points (CEM 6)
@@ -125,6 +129,7 @@ inline Astc3Tab build_tables3(Built& b)
     t3.off_mfrag_idx = reserve(static_cast<size_t>(G)*4, 4);
     t3.off_kappa = reserve(static_cast<size_t>(G)*kMaxTexels3*4, 4);
     t3.off_ksum = reserve(static_cast<size_t>(G)*4, 4);
+    t3.off_colenergy = reserve(static_cast<size_t>(G)*64*4, 16);
     const int KS = static_cast<int>(t3.KS), NT = static_cast<int>(t3.NT);
     for (int g = 0; g < G; ++g) {
         const GridInfo gi = reinterpret_cast<const GridInfo*>(&blob[t.off_grids])[g];
@@ -142,6 +147,11 @@ inline Astc3Tab build_tables3(Built& b)
             ksum += kap;
         }
         reinterpret_cast<float*>(&blob[t3.off_ksum])[g] = static_cast<float>(ksum);
+        for (int j = 0; j < nw && j < 64; ++j) {
+            double ce = 0;
+            for (int i = 0; i < T; ++i) ce += P[i*nw + j]*P[i*nw + j];
+            reinterpret_cast<float*>(&blob[t3.off_colenergy])[g*64 + j] = static_cast<float>(ce);
+        }
         pinv_infill(P, T, nw, M);
         // M fragments: B[k = texel][n = grid weight] = M[n][k]
         const int NTW = (nw + 7)/8;
