@@ -51,27 +51,28 @@ struct Slot3 {
     uint32_t pc, seed, valid;
     int32_t dual_ch;
 };
-// Slots 0..8 as in astc_core.cuh (RGB(A) end points); 9: one subset with LUMINANCE end points (CEM 0); 10, 11 / 12:
-// the two-subset partitionings of slots 1, 2 / the three-subset one of slot 3 with luminance end points; 13: one subset
-// with RGB BASE + SCALE end points (CEM 6: e1 = (r, g, b), e0 = e1*s/256 -- a line through black, which is what shaded
-// surfaces of one material are; four stored values instead of six buy a finer weight grid or finer weights; astcenc
-// picks it for 20-50 % of the blocks of photographic content). These slots are for opaque blocks only, which is why
-// 12, 13 can live in the A operand rows of the alpha dual-plane slot (8, 12).
-// 14, 15 / 16, 17: the two- / three-subset partitionings of slots 1, 2 / 3, 4 with base + scale end points on every
-// subset (8 / 12 stored values instead of 12 / 18: what makes multi-subset encodings affordable at all on the larger
-// footprints -- the reference uses CEM 6 on at least one subset of most of its two-subset blocks). They are VIRTUAL:
-// partition, ideal weights (A operand row), line lengths and the measured quantisation loss are those of the RGB
-// sibling slot -- where a subset suits a line through black its free line nearly is one -- and only the error floor
-// (distance from the through-black lines, Warp3T::scale_eline), the colour level class and the end point solve differ.
+// Slots 0..8 as in astc_core.cuh (RGB(A) end points); 9: one subset with LUMINANCE end points (CEM 0); 10, 11 / 12, 13:
+// the two-subset / three-subset partitionings of slots 1, 2 / 3, 4 with luminance end points.  Luminance slots are
+// for opaque blocks only, which is why 12, 13 can live in the A operand rows of the alpha dual-plane slot (8, 12).
+// 14 / 15, 16 / 17, 18: slot 0 / the two-subset slots 1, 2 / the three-subset slots 3, 4 with RGB BASE + SCALE end
+// points on every subset (CEM 6: e1 = (r, g, b), e0 = e1*s/256 -- a line through black, which is what shaded surfaces of
+// one material are; 4 / 8 / 12 stored values instead of 6 / 12 / 18 buy a finer weight grid or finer weights, and are
+// what makes multi-subset encodings affordable at all on the larger footprints: astcenc picks CEM 6 for 20-50 % of the
+// blocks of photographic content and on at least one subset of most of its two-subset blocks). Opaque blocks only.
+// They are VIRTUAL: partition, ideal weights (A operand row), line lengths and the measured quantisation loss are those
+// of the RGB sibling slot -- where a subset suits a line through black its free line nearly is one -- and only the
+// error floor (distance from the through-black lines, Warp3T::scale_eline), the colour level class and the end point
+// solve differ.
 constexpr int kSlots3 = kSlots + 5;            // real slots (own Slot3 entry)
-constexpr int kSlotsAll = kSlots3 + 4;         // + the virtual base + scale slots 14..17
-constexpr int kLumSlot = 9, kLumRow = 13, kScaleSlot = 13;
+constexpr int kScaleSlot = kSlots3;            // first virtual slot
+constexpr int kSlotsAll = kSlots3 + 5;         // + the virtual base + scale slots 14..18
+constexpr int kLumSlot = 9, kLumRow = 13;
 __device__ __forceinline__ bool slot_is_scale(uint32_t s) { return s >= static_cast<uint32_t>(kScaleSlot); }
 __device__ __forceinline__ bool slot_is_lum(uint32_t s) { return s >= static_cast<uint32_t>(kLumSlot) && s < static_cast<uint32_t>(kScaleSlot); }
-__device__ __forceinline__ uint32_t slot_base(uint32_t s) { return s < static_cast<uint32_t>(kSlots3) ? s : s - 13u; }              // the slot whose Slot3 entry describes s
-__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : (s < 12u ? 5u : (s == 12u ? 6u : (s == 13u ? 7u : (s < 16u ? 8u : 9u))))); }   // est list / colour level class
-__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : (s < 12u ? s + 4u : (s == 12u ? 8u : (s == 13u ? 12u : s - 13u))); }        // A operand row of its first plane
-__device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 14u ? s - 14u : (s >= 10u ? s - 10u : (s - 1u) & 3u); }          // index into Warp3T::part
+__device__ __forceinline__ uint32_t slot_base(uint32_t s) { return s < static_cast<uint32_t>(kScaleSlot) ? s : s - static_cast<uint32_t>(kScaleSlot); }   // the slot whose Slot3 entry describes s
+__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : (s < 12u ? 5u : (s < 14u ? 6u : (s == 14u ? 7u : (s < 17u ? 8u : 9u))))); }   // est list / colour level class
+__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : (s < 12u ? s + 4u : (s == 12u ? 8u : (s == 13u ? 12u : s - 14u))); }        // A operand row of its first plane
+__device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 15u ? s - 15u : (s >= 10u ? s - 10u : (s - 1u) & 3u); }          // index into Warp3T::part
 constexpr float kMismatchWeight = 0.05f; // partition ranking: cost of one texel off the clustering, in mean squared spreads
 constexpr int kDataLevels = 6;          // weight levels 2,3,4,5,6,8: their quantisation loss is MEASURED on the slot's ideal
                                         // weights (text and edges are bimodal: the uniform model is far off there)
@@ -91,8 +92,8 @@ struct Warp3T {
     static constexpr int TS = ta_stride(TP);
     int4 v[TP];                             // texels, FX fixed point
     Slot3 slots[kSlots3];
-    float scale_eline[4];                   // error floor of the virtual base + scale slots 14..17
-    uint32_t scale_valid[4];
+    float scale_eline[5];                   // error floor of the virtual base + scale slots 14..18
+    uint32_t scale_valid[5];
     uint8_t part[4][TP];                    // subset of every texel for slots 1..4
     __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
                                             // 9..12 second planes of slots 5..8, 13..15 luminance slots 9..11;
@@ -467,10 +468,12 @@ __device__ __forceinline__ void realign_weights(const Ctx& c, WS& ws, uint32_t s
 #pragma unroll 1
     for (uint32_t pl = 0; pl < planes; ++pl) {
 #pragma unroll 1
-        for (uint32_t colour = 0; colour < 4; ++colour) {
+        // (a full-resolution grid has one weight per texel: nothing is shared, one sweep does them all)
+        const uint32_t ncol = nw == T ? 1u : 4u;
+        for (uint32_t colour = 0; colour < ncol; ++colour) {
             for (uint32_t j = lane; j < nw; j += 32) {
                 const uint32_t jy = j/gw, jx = j - jy*gw;
-                if (((jx & 1u) | ((jy & 1u) << 1)) != colour) continue;
+                if (ncol == 4u && ((jx & 1u) | ((jy & 1u) << 1)) != colour) continue;
                 const int k = ws.sk[j*planes + pl];
                 const int u = ws.su[j*planes + pl];
                 const int du_dn = k > 0 ? static_cast<int>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(k - 1))) - u : 0;
@@ -1062,8 +1065,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const uint32_t first = lane == 0 ? 5u : (lane == 1 ? 7u : (lane == 2 ? 9u : 12u)), cnt = lane < 2 ? 2u : 3u;
                 float e = 0.0f;
                 for (uint32_t q = 0; q < cnt; ++q) e += lines[first + q].pad[0];
-                ws.scale_eline[lane] = e*ifx*ifx;
-                ws.scale_valid[lane] = ws.slots[1 + lane].valid && !has_alpha && !HDR && !(tb.flags & 4u) ? 1u : 0u;
+                ws.scale_eline[1 + lane] = e*ifx*ifx;
+                ws.scale_valid[1 + lane] = ws.slots[1 + lane].valid && !has_alpha && !HDR && !(tb.flags & 4u) ? 1u : 0u;
+            } else if (lane == 4) {
+                ws.scale_eline[0] = has_alpha ? 0.0f :
+                    origin_residual(moms[10], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z))*ifx*ifx;
+                ws.scale_valid[0] = !has_alpha && !HDR && !(tb.flags & 4u) ? 1u : 0u;
             }
         }
         __syncwarp();
@@ -1187,8 +1194,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 sl.len2[0] = 3.0f*(l1 - l0)*(l1 - l0); sl.len2b = 0.0f;
                 sl.e_line = chroma*ifx*ifx;
             }
-            // the same with the two-subset (k = 0, 1) and the best three-subset (k = 2) partitionings: a gray range per subset
-            for (uint32_t k = 0; k < 3; ++k) {
+            // the same with the two-subset (k = 0, 1) and three-subset (k = 2, 3) partitionings: a gray range per subset
+            for (uint32_t k = 0; k < 4; ++k) {
                 Slot3& sl = ws.slots[10 + k];
                 const uint32_t npc = k < 2 ? 2u : 3u;
                 const bool ok = ws.slots[1 + k].valid != 0 && !(tb.flags & 1u) && !HDR;
@@ -1238,51 +1245,6 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 }
                 if (lane == 0) { sl.len2b = 0.0f; sl.e_line = chroma*ifx*ifx; }
             }
-            // ---- setup 9: the base + scale slot: the line through black that fits the texels best = the principal axis
-            //      of the UNCENTRED second moments (from the moments about ctr), weights = position along it
-            {
-                Slot3& sl = ws.slots[kScaleSlot];
-                const float c0 = static_cast<float>(ctr.x), c1 = static_cast<float>(ctr.y), c2 = static_cast<float>(ctr.z);
-                const float s0 = static_cast<float>(tot[1]), s1 = static_cast<float>(tot[2]), s2 = static_cast<float>(tot[3]);
-                const float tn = static_cast<float>(T);
-                const float m00 = static_cast<float>(tot[5]) + 2.0f*c0*s0 + tn*c0*c0, m01 = static_cast<float>(tot[6]) + c0*s1 + c1*s0 + tn*c0*c1;
-                const float m02 = static_cast<float>(tot[7]) + c0*s2 + c2*s0 + tn*c0*c2, m11 = static_cast<float>(tot[9]) + 2.0f*c1*s1 + tn*c1*c1;
-                const float m12 = static_cast<float>(tot[10]) + c1*s2 + c2*s1 + tn*c1*c2, m22 = static_cast<float>(tot[12]) + 2.0f*c2*s2 + tn*c2*c2;
-                // power iteration from the mean colour (non-negative matrix: the axis has no negative component)
-                float v0 = s0 + tn*c0, v1 = s1 + tn*c1, v2 = s2 + tn*c2, lam = 0.0f;
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const float n2 = v0*v0 + v1*v1 + v2*v2;
-                    const float is = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
-                    const float a0 = v0*is, a1 = v1*is, a2 = v2*is;
-                    v0 = m00*a0 + m01*a1 + m02*a2; v1 = m01*a0 + m11*a1 + m12*a2; v2 = m02*a0 + m12*a1 + m22*a2;
-                    lam = a0*v0 + a1*v1 + a2*v2;
-                }
-                const float n2 = v0*v0 + v1*v1 + v2*v2;
-                const float is = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
-                v0 *= is; v1 *= is; v2 *= is;
-                float tmin = 3.0e38f, tmax = -3.0e38f;
-                for (uint32_t i = lane; i < T; i += 32) {
-                    const int4 x = ws.v[i];
-                    const float t = static_cast<float>(x.x)*v0 + static_cast<float>(x.y)*v1 + static_cast<float>(x.z)*v2;
-                    tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
-                }
-                tmin = warp_min_f(tmin); tmax = warp_max_f(tmax);
-                const bool ok = !(tb.flags & 4u) && !HDR && n2 > 1e-20f && tmax > tmin && tmin >= 0.0f;
-                const float ir = ok ? 1.0f/(tmax - tmin) : 0.0f;
-                for (uint32_t i = lane; i < T; i += 32) {
-                    const int4 x = ws.v[i];
-                    const float t = static_cast<float>(x.x)*v0 + static_cast<float>(x.y)*v1 + static_cast<float>(x.z)*v2;
-                    ws.ta[slot_row(kScaleSlot)][i] = __float2half_rn((t - tmin)*ir);
-                }
-                if (lane == 0) {
-                    sl.valid = ok ? 1u : 0u; sl.pc = 1; sl.seed = 0; sl.dual_ch = -1;
-                    sl.e0[0] = make_float4(v0*tmin*ifx, v1*tmin*ifx, v2*tmin*ifx, 255.0f);
-                    sl.e1[0] = make_float4(v0*tmax*ifx, v1*tmax*ifx, v2*tmax*ifx, 255.0f);
-                    sl.len2[0] = (tmax - tmin)*(tmax - tmin)*ifx*ifx; sl.len2b = 0.0f;
-                    sl.e_line = fmaxf(m00 + m11 + m22 - lam, 0.0f)*ifx*ifx;
-                }
-            }
         } else if (active && lane < 4) {
             ws.slots[10 + lane].valid = 0;
         }
@@ -1306,12 +1268,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     if (gq >= 6 && i < T) wgt2 = ws.slots[gq + 4].len2[ws.part[gq - 6][i]];
                     // rows 8 / 12 belong to the three-subset luminance slots 12 / 13 when the block is opaque
                     if (gq == 0 && i < T && ws.slots[12].valid) wgt2 = ws.slots[12].len2[ws.part[2][i]];
-                    // (row 12 = the base + scale slot 13 of an opaque block: one subset, unit texel weights)
+                    if (gq == 4 && i < T && ws.slots[13].valid) wgt2 = ws.slots[13].len2[ws.part[3][i]];
                     lw2[nt][e] = wgt2;
                 }
             const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
             const float scale1 = gq == 0 ? (ws.slots[12].valid ? 1.0f : ws.slots[8].len2[0]) :
-                (gq == 4 ? (ws.slots[13].valid ? ws.slots[13].len2[0] : ws.slots[8].len2b) :
+                (gq == 4 ? (ws.slots[13].valid ? 1.0f : ws.slots[8].len2b) :
                 (gq < 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 1.0f)));
             // what one unit of clamped overshoot of a grid weight costs this row: its line length (multi-subset rows:
             // the mean over the subsets, the grid is shared)
@@ -1320,7 +1282,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 return q.pc > 2 ? (q.len2[0] + q.len2[1] + q.len2[2])*(1.0f/3.0f) : (q.len2[0] + q.len2[1])*0.5f;
             };
             const float pscale0 = gq >= 1 && gq <= 4 ? mean_len2(gq) : scale0;
-            const float pscale1 = gq == 0 && ws.slots[12].valid ? mean_len2(12) : (gq >= 6 ? mean_len2(gq + 4) : scale1);
+            const float pscale1 = gq == 0 && ws.slots[12].valid ? mean_len2(12) : (gq == 4 && ws.slots[13].valid ? mean_len2(13) :
+                (gq >= 6 ? mean_len2(gq + 4) : scale1));
             const float* colen = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_colenergy);
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
@@ -1388,7 +1351,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 s1 += k*ws.slots[1].len2[p0]; s2 += k*ws.slots[2].len2[p1];
                 s3 += k*ws.slots[3].len2[p2]; s4 += k*ws.slots[4].len2[p3];
                 s5 += k*ws.slots[10].len2[p0]; s6 += k*ws.slots[11].len2[p1];
-                s7 += k*ws.slots[12].len2[p2];
+                s7 += k*ws.slots[12].len2[p2]; s8 += k*ws.slots[13].len2[p3];
             }
             ws.u.est.Sm[0][g] = s1; ws.u.est.Sm[1][g] = s2; ws.u.est.Sm[2][g] = s3; ws.u.est.Sm[3][g] = s4;
             ws.u.est.Sm[4][g] = s5; ws.u.est.Sm[5][g] = s6; ws.u.est.Sm[6][g] = s7; ws.u.est.Sm[7][g] = s8;
@@ -1445,13 +1408,13 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
             float* gs = &ws.g[1][0];           // per grid: weight-quantisation scale
             for (uint32_t s = 0; s < kSlotsAll; ++s) {
                 const Slot3& slot = ws.slots[slot_base(s)];
-                const bool virt = s >= static_cast<uint32_t>(kSlots3);
-                if (virt ? !ws.scale_valid[s - kSlots3] : !slot.valid) continue;
+                const bool virt = slot_is_scale(s);
+                if (virt ? !(ws.scale_valid[s - kScaleSlot] && slot.valid) : !slot.valid) continue;
                 const uint32_t type = slot_kind(s);
                 const uint32_t drow = slot_row(s);
                 const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
-                const float base = kLine*(virt ? ws.scale_eline[s - kSlots3] : slot.e_line);
+                const float base = kLine*(virt ? ws.scale_eline[s - kScaleSlot] : slot.e_line);
                 const float l2sum = slot.len2[0] + slot.len2b;
                 // per-grid terms of this slot (lane = grid)
                 __syncwarp();
@@ -1459,7 +1422,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     float dsum = ws.u.est.D[drow][g], ssum;
                     if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
                     else if (type == 0 || type == 4 || type == 7) ssum = l2sum*__ldg(ksum + g);
-                    else ssum = ws.u.est.Sm[type >= 8 ? s - 14 : (type >= 5 ? s - 6 : s - 1)][g];
+                    else ssum = ws.u.est.Sm[type >= 8 ? s - 15 : (type >= 5 ? s - 6 : s - 1)][g];
                     gb[g] = base + kDec*dsum; gs[g] = kQuant*ssum;
                 }
                 __syncwarp();
