@@ -65,14 +65,19 @@ struct Slot3 {
 // solve differ.
 constexpr int kSlots3 = kSlots + 5;            // real slots (own Slot3 entry)
 constexpr int kScaleSlot = kSlots3;            // first virtual slot
-constexpr int kSlotsAll = kSlots3 + 5;         // + the virtual base + scale slots 14..18
+// 19, 20: the two-subset partitionings of slots 1, 2 with MIXED end point modes -- opaque blocks: the subset that loses
+// least by it goes through black (CEM 6), the other keeps RGB (CEM 8), 10 stored values; blocks with alpha: a subset
+// whose alpha is 255 throughout stores RGB only (CEM 8), the other RGBA (CEM 12), 14 values instead of 16 (valid when
+// exactly one subset is opaque). Which subset is the cheap one: Warp3T::mix_mask.
+constexpr int kMixSlot = kSlots3 + 5;
+constexpr int kSlotsAll = kSlots3 + 7;         // + the virtual slots 14..20
 constexpr int kLumSlot = 9, kLumRow = 13;
 __device__ __forceinline__ bool slot_is_scale(uint32_t s) { return s >= static_cast<uint32_t>(kScaleSlot); }
 __device__ __forceinline__ bool slot_is_lum(uint32_t s) { return s >= static_cast<uint32_t>(kLumSlot) && s < static_cast<uint32_t>(kScaleSlot); }
-__device__ __forceinline__ uint32_t slot_base(uint32_t s) { return s < static_cast<uint32_t>(kScaleSlot) ? s : s - static_cast<uint32_t>(kScaleSlot); }   // the slot whose Slot3 entry describes s
-__device__ __forceinline__ uint32_t slot_kind(uint32_t s) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : (s < 12u ? 5u : (s < 14u ? 6u : (s == 14u ? 7u : (s < 17u ? 8u : 9u))))); }   // est list / colour level class
-__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : (s < 12u ? s + 4u : (s == 12u ? 8u : (s == 13u ? 12u : s - 14u))); }        // A operand row of its first plane
-__device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 15u ? s - 15u : (s >= 10u ? s - 10u : (s - 1u) & 3u); }          // index into Warp3T::part
+__device__ __forceinline__ uint32_t slot_base(uint32_t s) { return s < static_cast<uint32_t>(kScaleSlot) ? s : (s < static_cast<uint32_t>(kMixSlot) ? s - static_cast<uint32_t>(kScaleSlot) : s - 18u); }   // the slot whose Slot3 entry describes s
+__device__ __forceinline__ uint32_t slot_kind(uint32_t s, bool has_alpha) { return s < 9u ? slot_type(s) : (s == 9u ? 4u : (s < 12u ? 5u : (s < 14u ? 6u : (s == 14u ? 7u : (s < 17u ? 8u : (s < 19u ? 9u : (has_alpha ? 11u : 10u))))))); }   // est list / colour level class
+__device__ __forceinline__ uint32_t slot_row(uint32_t s) { return s < 9u ? s : (s < 12u ? s + 4u : (s == 12u ? 8u : (s == 13u ? 12u : slot_base(s)))); }        // A operand row of its first plane
+__device__ __forceinline__ uint32_t slot_part(uint32_t s) { return s >= 19u ? s - 19u : (s >= 15u ? s - 15u : (s >= 10u ? s - 10u : (s - 1u) & 3u)); }          // index into Warp3T::part
 constexpr float kMismatchWeight = 0.05f; // partition ranking: cost of one texel off the clustering, in mean squared spreads
 constexpr int kDataLevels = 6;          // weight levels 2,3,4,5,6,8: their quantisation loss is MEASURED on the slot's ideal
                                         // weights (text and edges are bimodal: the uniform model is far off there)
@@ -92,8 +97,10 @@ struct Warp3T {
     static constexpr int TS = ta_stride(TP);
     int4 v[TP];                             // texels, FX fixed point
     Slot3 slots[kSlots3];
-    float scale_eline[5];                   // error floor of the virtual base + scale slots 14..18
-    uint32_t scale_valid[5];
+    float scale_eline[7];                   // error floor of the virtual slots 14..20
+    uint32_t scale_valid[7];
+    uint32_t mix_mask[2];                   // slots 19, 20: bit p = subset p takes the cheaper end point mode
+    int sc[3], best_sc[3];                  // base + scale subsets: the quantised scale
     uint8_t part[4][TP];                    // subset of every texel for slots 1..4
     __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
                                             // 9..12 second planes of slots 5..8, 13..15 luminance slots 9..11;
@@ -228,7 +235,13 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     uint32_t lane, bool quantise = true)
 {
     const bool lum = slot_is_lum(s);
-    const bool scale = slot_is_scale(s);
+    // per-subset end point mode: 0 = direct (RGB / RGBA), 1 = base + scale (+ alpha pair), 2 = RGB only in a block with alpha
+    const uint32_t mixm = s >= static_cast<uint32_t>(kMixSlot) ? ws.mix_mask[s - kMixSlot] : 0u;
+    auto sub_mode = [&](uint32_t p) -> uint32_t {
+        if (s < static_cast<uint32_t>(kScaleSlot)) return 0u;
+        if (s < static_cast<uint32_t>(kMixSlot)) return 1u;
+        return (mixm >> p) & 1u ? (has_alpha ? 2u : 1u) : 0u;
+    };
     const uint32_t T = c.tab.texels;
     const Slot3& slot = ws.slots[slot_base(s)];
     const uint32_t pc = slot.pc;
@@ -313,7 +326,8 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
                 val = (__shfl_sync(0xFFu, val, b4) + __shfl_sync(0xFFu, val, b4 + 1u) + __shfl_sync(0xFFu, val, b4 + 2u))*(1.0f/3.0f);
             }
             int q = 255;
-            if (scale) {
+            const uint32_t smode = sub_mode(p);
+            if (smode == 1u) {
                 // base + scale: s = where the unconstrained e0 falls along e1, snapped to the colour level; with the scale
                 // fixed the least-squares base is closed form in the same moment sums: every texel is a_i*E with
                 // a_i = s(1 - w_i) + w_i, so E = sum a_i x_i / sum a_i^2 = (s P + Q)/(s^2 A + 2 s B + C)
@@ -328,11 +342,18 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
                 const float E = den > 0.0f ? (sf*fP + fQ)*(64.0f/static_cast<float>(FX))/den : val;
                 const int iv = min(max(__float2int_rn(E), 0), 255);
                 const int qe = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(iv))));
-                // e0 as the decoder derives it; its (unused: opaque blocks only) alpha byte carries the scale to pack_block
-                q = ch == 3 ? (which ? 255 : sq) : (which ? qe : (qe*sq) >> 8);
+                // e0 as the decoder derives it; alpha (CEM 10, blocks with alpha) keeps its own direct pair
+                if (ch == 3) {
+                    q = 255;
+                    if (has_alpha) {
+                        const int av = min(max(__float2int_rn(val), 0), 255);
+                        q = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(av))));
+                    }
+                } else q = which ? qe : (qe*sq) >> 8;
+                if (lane == 0) ws.sc[p] = sq;
             }
             else if (hdr) ws.epf[p*8u + lane] = val;
-            else if (ch < 3 || has_alpha) {
+            else if (ch < 3 || (has_alpha && smode != 2u)) {
                 const int iv = min(max(__float2int_rn(val), 0), 255);
                 const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(iv));
                 q = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + rank));
@@ -380,7 +401,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
         __syncwarp();
     }
     // keep sum(e1.rgb) >= sum(e0.rgb) (otherwise the decoder would blue-contract): swap the end points
-    if (lane < pc && !lum && !hdr && !scale) {
+    if (lane < pc && !lum && !hdr && sub_mode(lane) != 1u) {
         int* e = ws.ep + lane*8u;
         if (e[4] + e[5] + e[6] < e[0] + e[1] + e[2]) {
 #pragma unroll
@@ -525,6 +546,7 @@ __device__ __forceinline__ void keep_best3(WS& ws, uint32_t nw, uint32_t planes,
     for (uint32_t j = lane; j < nw*planes; j += 32) { ws.best_su[j] = ws.su[j]; ws.best_sk[j] = ws.sk[j]; }
     if (lane < pc*8u) ws.best_ep[lane] = ws.ep[lane];
     if (lane < pc*8u) ws.best_epv[lane] = ws.epv[lane];
+    if (lane < 3u) ws.best_sc[lane] = ws.sc[lane];
     __syncwarp();
 }
 
@@ -611,6 +633,27 @@ __device__ __noinline__ float origin_residual(const Mom& mo, float c0, float c1,
         lam = a0*v0 + a1*v1 + a2*v2;
     }
     return fmaxf(m00 + m11 + m22 - lam, 0.0f);
+}
+
+// Squared distance of a texel set from its best FREE line in RGB alone (alpha left out): trace - lambda_max of the RGB
+// scatter about the mean.
+__device__ __noinline__ float rgb_free_residual(const Mom& mo)
+{
+    const float inv = mo.n > 0.0f ? 1.0f/mo.n : 0.0f;
+    const float c00 = mo.p[0] - mo.s[0]*mo.s[0]*inv, c01 = mo.p[1] - mo.s[0]*mo.s[1]*inv, c02 = mo.p[2] - mo.s[0]*mo.s[2]*inv;
+    const float c11 = mo.p[4] - mo.s[1]*mo.s[1]*inv, c12 = mo.p[5] - mo.s[1]*mo.s[2]*inv, c22 = mo.p[7] - mo.s[2]*mo.s[2]*inv;
+    float v0 = c00, v1 = c01, v2 = c02, best = c00, lam = 0.0f;
+    if (c11 > best) { best = c11; v0 = c01; v1 = c11; v2 = c12; }
+    if (c22 > best) { v0 = c02; v1 = c12; v2 = c22; }
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const float n2 = v0*v0 + v1*v1 + v2*v2;
+        const float is = n2 > 1e-20f ? rsqrtf(n2) : 0.0f;
+        const float a0 = v0*is, a1 = v1*is, a2 = v2*is;
+        v0 = c00*a0 + c01*a1 + c02*a2; v1 = c01*a0 + c11*a1 + c12*a2; v2 = c02*a0 + c12*a1 + c22*a2;
+        lam = a0*v0 + a1*v1 + a2*v2;
+    }
+    return fmaxf(c00 + c11 + c22 - lam, 0.0f);
 }
 
 // Residual only, moments passed in registers (integer sums about the block centre).
@@ -1051,6 +1094,19 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 }
             }
             __syncwarp();
+            uint32_t opq2[2] = {0u, 0u};
+            if (has_alpha) {
+                const int full = __float2int_rn(opaque*static_cast<float>(FX));
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k) {
+                    bool t0 = false, t1 = false;                        // "has a translucent texel"
+                    for (uint32_t i = lane; i < T; i += 32) {
+                        const bool tr = ws.v[i].w != full;
+                        if (ws.part[k][i]) t1 |= tr; else t0 |= tr;
+                    }
+                    opq2[k] = (__any_sync(0xFFFFFFFFu, t0) ? 0u : 1u) | (__any_sync(0xFFFFFFFFu, t1) ? 0u : 2u);
+                }
+            }
             if (lane < 10) {
                 const uint32_t sl = lane < 2 ? 1u : (lane < 4 ? 2u : (lane < 7 ? 3u : 4u));
                 if (ws.slots[sl].valid) {
@@ -1068,9 +1124,27 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 ws.scale_eline[1 + lane] = e*ifx*ifx;
                 ws.scale_valid[1 + lane] = ws.slots[1 + lane].valid && !has_alpha && !HDR && !(tb.flags & 4u) ? 1u : 0u;
             } else if (lane == 4) {
-                ws.scale_eline[0] = has_alpha ? 0.0f :
-                    origin_residual(moms[10], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z))*ifx*ifx;
-                ws.scale_valid[0] = !has_alpha && !HDR && !(tb.flags & 4u) ? 1u : 0u;
+                // one subset: CEM 6, or CEM 10 in a block with alpha (the alpha pair stays direct: what the RGB part
+                // loses by going through black comes on top of the RGBA line's floor)
+                const float org = origin_residual(moms[10], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z));
+                ws.scale_eline[0] = org*ifx*ifx;
+                ws.scale_valid[0] = !HDR && !(tb.flags & 4u) ? 1u : 0u;
+                if (has_alpha) ws.scale_eline[0] = fmaxf(org - rgb_free_residual(moms[10]), 0.0f)*ifx*ifx;     // + slot 0's floor, added in phase 1c
+            } else if (lane == 5 || lane == 6) {
+                // mixed modes on the two-subset partitionings (slots 19, 20)
+                const uint32_t k = lane - 5u, first = k == 0 ? 5u : 7u;
+                uint32_t ok = ws.slots[1 + k].valid && !HDR && !(tb.flags & 4u) ? 1u : 0u, mask = 0u;
+                float e = 0.0f;
+                if (!has_alpha) {
+                    const float d0 = lines[first].pad[0] - lines[first].resid, d1 = lines[first + 1].pad[0] - lines[first + 1].resid;
+                    mask = d0 <= d1 ? 1u : 2u;
+                    e = (mask == 1u ? lines[first].pad[0] + lines[first + 1].resid : lines[first].resid + lines[first + 1].pad[0])*ifx*ifx;
+                } else {
+                    mask = opq2[k];                                     // subsets whose alpha is 255 throughout
+                    if (mask != 1u && mask != 2u) ok = 0u;
+                    e = (lines[first].resid + lines[first + 1].resid)*ifx*ifx;
+                }
+                ws.scale_eline[5 + k] = e; ws.scale_valid[5 + k] = ok; ws.mix_mask[k] = mask;
             }
         }
         __syncwarp();
@@ -1410,11 +1484,11 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 const Slot3& slot = ws.slots[slot_base(s)];
                 const bool virt = slot_is_scale(s);
                 if (virt ? !(ws.scale_valid[s - kScaleSlot] && slot.valid) : !slot.valid) continue;
-                const uint32_t type = slot_kind(s);
+                const uint32_t type = slot_kind(s, has_alpha);
                 const uint32_t drow = slot_row(s);
                 const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
-                const float base = kLine*(virt ? ws.scale_eline[s - kScaleSlot] : slot.e_line);
+                const float base = kLine*(virt ? ws.scale_eline[s - kScaleSlot] + (s == static_cast<uint32_t>(kScaleSlot) && has_alpha ? slot.e_line : 0.0f) : slot.e_line);
                 const float l2sum = slot.len2[0] + slot.len2b;
                 // per-grid terms of this slot (lane = grid)
                 __syncwarp();
@@ -1422,7 +1496,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     float dsum = ws.u.est.D[drow][g], ssum;
                     if (type == 3) { dsum += ws.u.est.D[s + 4][g]; ssum = l2sum*__ldg(ksum + g); }
                     else if (type == 0 || type == 4 || type == 7) ssum = l2sum*__ldg(ksum + g);
-                    else ssum = ws.u.est.Sm[type >= 8 ? s - 15 : (type >= 5 ? s - 6 : s - 1)][g];
+                    else ssum = ws.u.est.Sm[type >= 10 ? s - 19 : (type >= 8 ? s - 15 : (type >= 5 ? s - 6 : s - 1))][g];
                     gb[g] = base + kDec*dsum; gs[g] = kQuant*ssum;
                 }
                 __syncwarp();
@@ -1497,7 +1571,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                 if (done) refining = true;
                 else {
                     const uint32_t s = code >> 16;
-                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? static_cast<uint32_t>(kSlotTypes3) : 0u) + slot_kind(s))*tb.t3.n_modes + (code & 0xFFFFu));
+                    cl = __ldg(ctx.blob + tb.t3.off_modecl + ((has_alpha ? static_cast<uint32_t>(kSlotTypes3) : 0u) + slot_kind(s, has_alpha))*tb.t3.n_modes + (code & 0xFFFFu));
                     row0 = static_cast<int>(slot_row(s));
                     row1 = ws.slots[slot_base(s)].dual_ch >= 0 ? static_cast<int>(s) + 4 : -1;
                 }
@@ -1568,8 +1642,14 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p,
                     (static_cast<uint32_t>(e[7]) << 24);
             }
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
+            uint8_t cems[4] = {0, 0, 0, 0};
+            const bool virt = slot_is_scale(bs);
+            for (uint32_t q = 0; q < bslot.pc; ++q) {
+                const bool cheap = bs >= static_cast<uint32_t>(kMixSlot) ? ((ws.mix_mask[bs - kMixSlot] >> q) & 1u) != 0u : virt;
+                cems[q] = static_cast<uint8_t>(!cheap ? (has_alpha ? 12 : 8) : (bs >= static_cast<uint32_t>(kMixSlot) && has_alpha ? 8 : (has_alpha ? 10 : 6)));
+            }
             *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr,
-                slot_is_scale(bs));
+                virt ? cems : nullptr, ws.best_sc);
         }
     }
 }

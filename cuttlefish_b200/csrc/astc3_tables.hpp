@@ -25,7 +25,7 @@ namespace astc {
 
 constexpr int kMaxGrids3 = 96;
 constexpr int kMaxTexels3 = 144;    // up to 12x12
-constexpr int kSlotTypes3 = 10;     // colour level / estimate list classes, see Astc3Tab::off_modecl
+constexpr int kSlotTypes3 = 12;     // colour level / estimate list classes, see Astc3Tab::off_modecl
 constexpr int kRows3 = 16;          // slot planes (A operand rows): 9 first planes, 4 second planes, 3 spare
 
 struct Astc3Tab {
@@ -37,7 +37,10 @@ struct Astc3Tab {
     uint32_t off_colenergy;         // [n_grids][64] float: ce_gj = sum_i P_ij^2 (0 beyond the grid's weights)
     uint32_t off_modecl;            // [2 alpha][8 slot type][n_modes1 + n_modes2] u8 colour level, 0xFF = does not fit
                                     // slot types: 0..2 = 1..3 subsets, 3 = dual plane, 4 / 5 / 6 = one / two / three subsets with luminance end points,
-                                    // 7 / 8 / 9 = one / two / three subsets with RGB base + scale end points (CEM 6)
+                                    // 7 / 8 / 9 = one / two / three subsets with RGB base + scale end points (CEM 6; one
+                                    // subset of a block with alpha: CEM 10 = base + scale + alpha pair),
+                                    // 10 = two subsets, MIXED end point modes, opaque: one subset base + scale (CEM 6), one RGB (CEM 8),
+                                    // 11 = two subsets, mixed, block with alpha: one subset RGB (CEM 8, alpha 255), one RGBA (CEM 12)
     uint32_t n_modes;               // n_modes1 + n_modes2
     uint32_t off_rstream;           // R fragments of the decimated grids, contiguous in off_dec_list order (+1 pad tile)
     uint32_t off_dec_list;          // [n_dec] u8 grid index
@@ -198,13 +201,18 @@ inline Astc3Tab build_tables3(Built& b)
         for (int type = 0; type < kSlotTypes3; ++type)
             for (uint32_t mi = 0; mi < t3.n_modes; ++mi) {
                 const ModeInfo m = reinterpret_cast<const ModeInfo*>(&blob[t.off_modes])[mi];
-                const int pc = (type == 1 || type == 5 || type == 8) ? 2 : ((type == 2 || type == 6 || type == 9) ? 3 : 1);
+                const int pc = (type == 1 || type == 5 || type == 8 || type >= 10) ? 2 : ((type == 2 || type == 6 || type == 9) ? 3 : 1);
                 // luminance end points (CEM 0: L0 L1; with alpha CEM 4: L0 L1 A0 A1)
                 // base + scale (CEM 6: R G B s; with alpha CEM 10: R G B s A0 A1)
-                const int n_ints = type >= 7 ? pc*(alpha ? 6 : 4) : (type >= 4 ? pc*(alpha ? 4 : 2) : pc*(alpha ? 8 : 6));
-                const int avail = 128 - static_cast<int>(m.wbits) - (pc == 1 ? 17 : 29) - (type == 3 ? 2 : 0);
+                int n_ints = type >= 7 ? pc*(alpha ? 6 : 4) : (type >= 4 ? pc*(alpha ? 4 : 2) : pc*(alpha ? 8 : 6));
+                if (type == 10) n_ints = 10;
+                if (type == 11) n_ints = 14;
+                // mixed modes spill 3*pc - 4 bits of their end point mode field to just below the weights
+                const int extra = type >= 10 ? 3*pc - 4 : 0;
+                const int avail = 128 - static_cast<int>(m.wbits) - (pc == 1 ? 17 : 29) - (type == 3 ? 2 : 0) - extra;
                 uint8_t cl = 0xFF;
-                if ((m.dual != 0) == (type == 3) && n_ints <= 18 && avail >= 0) cl = blob[t.off_clevel + (n_ints >> 1)*128 + avail];
+                const bool usable = !((type == 10 && alpha) || (type == 11 && !alpha) || ((type == 8 || type == 9) && alpha));
+                if (usable && (m.dual != 0) == (type == 3) && n_ints <= 18 && avail >= 0) cl = blob[t.off_clevel + (n_ints >> 1)*128 + avail];
                 blob[t3.off_modecl + (static_cast<size_t>(alpha)*kSlotTypes3 + type)*t3.n_modes + mi] = cl;
             }
     // the decimated grids' R fragments again as one contiguous stream (phase 1a walks it with a one-tile prefetch)

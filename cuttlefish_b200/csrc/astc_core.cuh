@@ -659,26 +659,58 @@ CFX_HD uint64_t bitrev64(uint64_t v)
 template <typename SlotT>
 CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo& m, const Enc& e, bool has_alpha,
     const uint8_t* u_scr, uint32_t lane, bool linear = false, const uint8_t* k_lin = nullptr, bool lum = false,
-    const int* hdr_vals = nullptr, bool scale = false)
+    const int* hdr_vals = nullptr, const uint8_t* cems = nullptr, const int* scales = nullptr)
 {
     Bits128 b; b.lo = b.hi = 0;
     const uint32_t pc = slot.pc;
-    // colour end point mode: 8 / 12 = LDR RGB / RGBA direct; 0 = LDR luminance direct (lum: one subset, opaque)
+    // colour end point mode: 8 / 12 = LDR RGB / RGBA direct; 0 = LDR luminance direct (lum: opaque)
     // 11 / 14 = HDR RGB direct (+ LDR alpha); hdr_vals: per subset (stride 8) the six packed values of astc_hdr.cuh
-    // followed by the two alpha end points
-    // scale: 6 = LDR RGB base + scale (one subset, opaque): stored R G B s, with s in the alpha byte of e.ep[0][0]
-    const uint32_t cem = hdr_vals ? (has_alpha ? 14u : 11u) : (scale ? 6u : (lum ? 0u : (has_alpha ? 12u : 8u)));
+    // followed by the two alpha end points.
+    // cems (per subset, optional): 6 = RGB base + scale (R G B s), 10 = base + scale + alpha pair, 8, 12; the scale of
+    // subset s is scales[s]. Subsets may differ (classes of adjacent numbers only: 6 with 8, 8 with 12).
+    uint32_t cem[4];
+    bool same = true;
+    for (uint32_t s = 0; s < pc; ++s) {
+        cem[s] = cems ? cems[s] : (hdr_vals ? (has_alpha ? 14u : 11u) : (lum ? 0u : (has_alpha ? 12u : 8u)));
+        same = same && cem[s] == cem[0];
+    }
     b.put(0, m.mode_bits, 11);
     b.put(11, pc - 1, 2);
     uint32_t pos;
-    if (pc == 1) { b.put(13, cem, 4); pos = 17; }
-    else { b.put(13, slot.seed, 10); b.put(23, 0, 2); b.put(25, cem, 4); pos = 29; }
-    const uint32_t per = scale ? 4u : (lum ? 2u : (has_alpha ? 8u : 6u));
+    uint32_t below = 128u - m.wbits;                  // first free bit below the weights
+    if (pc == 1) { b.put(13, cem[0], 4); pos = 17; }
+    else {
+        b.put(13, slot.seed, 10);
+        if (same) { b.put(23, 0, 2); b.put(25, cem[0], 4); }
+        else {
+            // ASTC spec, "Color Endpoint Mode" for multi-partition blocks: 2 bits = lowest class + 1, one class bit
+            // per partition, two low bits of the mode per partition; what exceeds 6 bits sits just below the weights
+            uint32_t low = 4;
+            for (uint32_t s = 0; s < pc; ++s) low = low < (cem[s] >> 2) ? low : (cem[s] >> 2);
+            if (low == 3) low = 2;
+            uint32_t enc = low + 1u, bp = 2;
+            for (uint32_t s = 0; s < pc; ++s) enc |= ((cem[s] >> 2) - low) << bp++;
+            for (uint32_t s = 0; s < pc; ++s) { enc |= (cem[s] & 3u) << bp; bp += 2; }
+            const uint32_t hi_bits = 3u*pc - 4u;
+            b.put(23, enc & 0x3Fu, 6);
+            below -= hi_bits;
+            b.put(below, enc >> 6, hi_bits);
+        }
+        pos = 29;
+    }
+    uint32_t start[5];                                  // first value of every subset
+    start[0] = 0;
+    for (uint32_t s = 0; s < pc; ++s) start[s + 1] = start[s] + ((cem[s] >> 2) + 1u)*2u;
     const uint32_t cl = e.clevel;
-    ise_encode(c, b, pos, pc*per, kCqBits[cl], kCqTrits[cl] != 0, kCqQuints[cl] != 0, [&](uint32_t i) {
-        const uint32_t s = i/per, k = i - s*per;          // k: r0 r1 g0 g1 b0 b1 a0 a1
-        const uint32_t val = hdr_vals ? static_cast<uint32_t>(hdr_vals[s*8u + k]) & 0xFFu :
-            (scale ? (k < 3u ? (e.ep[s][1] >> (8u*k)) & 0xFFu : e.ep[s][0] >> 24) : (e.ep[s][k & 1u] >> (8u*(k >> 1))) & 0xFFu);
+    ise_encode(c, b, pos, start[pc], kCqBits[cl], kCqTrits[cl] != 0, kCqQuints[cl] != 0, [&](uint32_t i) {
+        uint32_t s = 0;
+        while (s + 1u < pc && i >= start[s + 1]) ++s;
+        const uint32_t k = i - start[s];
+        uint32_t val;
+        if (hdr_vals) val = static_cast<uint32_t>(hdr_vals[s*8u + k]) & 0xFFu;
+        else if (cem[s] == 6u || cem[s] == 10u)       // R G B s (a0 a1)
+            val = k < 3u ? (e.ep[s][1] >> (8u*k)) & 0xFFu : (k == 3u ? static_cast<uint32_t>(scales[s]) & 0xFFu : e.ep[s][k & 1u] >> 24);
+        else val = (e.ep[s][k & 1u] >> (8u*(k >> 1))) & 0xFFu;       // r0 r1 g0 g1 b0 b1 a0 a1 (luminance: the r pair)
         const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + val);
         return tab_u8(c, c.tab.off_cq_enc + cl*256u + rank);
     });
@@ -686,7 +718,7 @@ CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo
     Bits128 w; w.lo = w.hi = 0;
     const uint32_t L = m.level;
     const uint32_t planes = slot.dual_ch >= 0 ? 2u : 1u;
-    if (planes == 2) b.put(128u - m.wbits - 2u, static_cast<uint32_t>(slot.dual_ch), 2);
+    if (planes == 2) b.put(below - 2u, static_cast<uint32_t>(slot.dual_ch), 2);
     ise_encode(c, w, 0, m.nw*planes, kWqBits[L], kWqTrits[L] != 0, kWqQuints[L] != 0, [&](uint32_t j) {
         if (k_lin) return tab_u8(c, c.tab.off_wq_enc + L*32u + k_lin[j]);    // the caller kept the ranks
         const uint32_t u = linear ? u_scr[j] : u_scr[scr_index(j, lane)];
