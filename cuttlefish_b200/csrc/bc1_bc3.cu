@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
     bool exact)
 {
     __shared__ __align__(16) uint32_t s_px[kBc1Warps][32*kBlkStride];
+    __shared__ __align__(16) uint32_t s_tab[FORMAT == 32 ? kBc1Warps : 1][kBc4TableWords];
     const uint32_t lane = lane_id(), warp = warp_id();
     uint32_t* sp = s_px[warp];
     const uint32_t groups = (p.total_blocks + 31)/32;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
         } else {
             uint2 mine = make_uint2(0, 0);
             for (uint32_t b = 0; b < nblk; ++b) {
-                const uint2 a = bc4_encode_warp(sp + b*kBlkStride, 3, radius, hq != 0);
+                const uint2 a = bc4_encode_warp(sp + b*kBlkStride, 3, radius, hq != 0, s_tab[FORMAT == 32 ? warp : 0]);
                 if (b == lane) mine = a;
             }
             if (lane < nblk) reinterpret_cast<uint4*>(p.dst)[first + lane] = make_uint4(mine.x, mine.y, color.x, color.y);

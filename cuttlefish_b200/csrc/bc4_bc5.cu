@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(kThreads) bc45_kernel(const EncodeParams p, ui
 {
     __shared__ __align__(16) uint32_t s_px[kTile*16];
     __shared__ __align__(16) uint32_t s_out[kTile*2*CHANNELS];
+    __shared__ __align__(16) uint32_t s_tab[kWarps][kBc4TableWords];
     const uint32_t tiles = (p.total_blocks + kTile - 1)/kTile;
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         uint32_t first = tile*kTile;
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(kThreads) bc45_kernel(const EncodeParams p, ui
         for (uint32_t b = warp_id(); b < n; b += kWarps) {
 #pragma unroll
             for (int c = 0; c < CHANNELS; ++c) {
-                uint2 r = bc4_encode_warp<SIGNED>(s_px + b*16, c, radius, hq != 0);
+                uint2 r = bc4_encode_warp<SIGNED>(s_px + b*16, c, radius, hq != 0, s_tab[warp_id()]);
                 if (lane_id() == 0) {
                     s_out[(b*CHANNELS + c)*2] = r.x;
                     s_out[(b*CHANNELS + c)*2 + 1] = r.y;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(kThreads) bc45_tma_kernel(const EncodeParams p
     __shared__ __align__(128) uint32_t s_px[2][kTile*16];          // two 256 x 4 texel boxes
     __shared__ __align__(16) uint32_t s_out[kTile*2*CHANNELS];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(16) uint32_t s_tab[kWarps][kBc4TableWords];
     const uint32_t tiles = p.total_blocks/kTile;                   // the launcher guarantees whole tiles
     const uint32_t tiles_x = p.blocks_x/kTile;
     constexpr uint32_t kBoxBytes = kTile*16*4;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) bc45_tma_kernel(const EncodeParams p
         for (uint32_t b = warp_id(); b < kTile; b += kWarps) {
 #pragma unroll
             for (int c = 0; c < CHANNELS; ++c) {
-                uint2 r = bc4_encode_warp<false>(s_px[buf] + b*4, c, radius, hq != 0, kTile*4);
+                uint2 r = bc4_encode_warp<false>(s_px[buf] + b*4, c, radius, hq != 0, s_tab[warp_id()], kTile*4);
                 if (lane_id() == 0) {
                     s_out[(b*CHANNELS + c)*2] = r.x;
                     s_out[(b*CHANNELS + c)*2 + 1] = r.y;

@@ -51,26 +51,55 @@ __device__ __forceinline__ void bc4_trial_endpoints(uint32_t t, uint32_t n, int 
     if ((mode == 0) ? alpha6 : !alpha6) { uint32_t tmp = e0; e0 = e1; e1 = tmp; }
 }
 
+// Words of shared memory bc4_encode_warp needs per warp for its threshold table (hq path).
+constexpr uint32_t kBc4TableWords = 512;
+
+// Ascending palette of a trial: q[0..7].  8-value mode: E_lo, the six sevenths, E_hi; 6-value mode: the low constant,
+// E_lo, the four fifths, E_hi, 255 (bc4_block::get_block_values, rgbcx.h:391-423, sorted).  The floor divisions by 7
+// and 5 are multiplications by ceil(2^16/7) and ceil(2^16/5) (exact for numerators <= 1785).
+template <bool SIGNED>
+__device__ __forceinline__ void bc4_sorted_palette(uint32_t mode, uint32_t elo, uint32_t ehi, uint32_t (&q)[8])
+{
+    const uint32_t diff = ehi - elo;
+    if (mode == 0) {
+        const uint32_t dm = diff*9363u, bm = elo*(7u*9363u);
+        q[0] = elo; q[7] = ehi;
+#pragma unroll
+        for (uint32_t j = 1; j <= 6; ++j) q[j] = (j*dm + bm) >> 16;
+    } else {
+        const uint32_t dm = diff*13108u, bm = elo*(5u*13108u);
+        q[0] = SIGNED ? 1u : 0u; q[1] = elo; q[6] = ehi; q[7] = 255u;
+#pragma unroll
+        for (uint32_t j = 1; j <= 4; ++j) q[1 + j] = (j*dm + bm) >> 16;
+    }
+}
+
 // s_blk: RGBA8 texels of the block in shared memory, texel (row r, column c) at s_blk[r*row_stride + c] (block-major
 // tiles: row_stride 4; row-major tiles as TMA writes them: row_stride = texels per tile row); chan: byte lane of the
-// channel.  Returns the 8 block bytes as (lo, hi) words; identical in every lane.
+// channel; s_tab: kBc4TableWords words of shared memory owned by this warp.  Returns the 8 block bytes as (lo, hi)
+// words; identical in every lane.
+//
+// hq path.  The reference evaluates every trial's SSE = sum_i min_j (pal_j - v_i)^2 texel by texel (16 x 8 distances).
+// The same integer falls out of the SORTED palette q_0 <= ... <= q_7 and two prefix functions of the block,
+// N(x) = #{v_i <= x} and D(x) = 2 sum_{v_i <= x} v_i: a texel belongs to q_c when it lies in (tau_{c-1}, tau_c] with
+// tau_c = floor((q_c + q_{c+1})/2) (ties are equidistant, so they do not change the SSE), and summing
+// n_c q_c^2 - 2 q_c S1_c over the clusters by parts gives
+//     SSE - sum v^2 = sum_{c<7} (q_c - q_{c+1}) (N(tau_c) (q_c + q_{c+1}) - D(tau_c)) + 16 q_7^2 - D(255) q_7,
+// i.e. 7 table look-ups per trial.  The table (indexed by q_c + q_{c+1}, 512 entries of D | N << 16) is built once per
+// block with 16 shared-memory atomics and a warp scan.  Trials keep the reference's order (mode, lo_delta, hi_delta)
+// and the lexicographic (SSE, trial) minimum is the serial loop's first minimum; the selectors are then computed for
+// the winner only, with the reference's first-smallest-index tie rule.
 template <bool SIGNED = false>
 __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t chan, uint32_t radius,
-    bool hq, uint32_t row_stride = 4)
+    bool hq, uint32_t* s_tab, uint32_t row_stride = 4)
 {
     auto texel = [&](uint32_t i) -> uint32_t { return s_blk[(i >> 2)*row_stride + (i & 3u)]; };
     // end point bytes as stored: SNORM blocks hold two's complement s = b - 128
     auto stored = [](uint32_t e) -> uint32_t { return SIGNED ? ((e - 128u) & 0xFFu) : e; };
     const uint32_t lane = lane_id();
     const uint32_t shift = chan*8;
-    uint32_t rep[16];
-    uint32_t mn = 255, mx = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        uint32_t v = (texel(i) >> shift) & 0xFFu;
-        mn = min(mn, v); mx = max(mx, v);
-        rep[i] = v*0x01010101u;
-    }
+    const uint32_t v = (texel(lane & 15u) >> shift) & 0xFFu;       // lanes 16..31 mirror 0..15
+    const uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, v), mx = __reduce_max_sync(0xFFFFFFFFu, v);
 
     if (!hq && !SIGNED) {
         // encode_bc4: endpoints max/min, threshold selector assignment.
@@ -79,10 +108,9 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
         int bias = 4 - static_cast<int>(mn)*14;
         uint32_t sel = 0;
         if (lane < 16) {
-            int v = static_cast<int>((texel(lane) >> shift) & 0xFFu);
-            v = v*14 + bias;
-            int cnt = (v >= delta*13) + (v >= delta*11) + (v >= delta*9) + (v >= delta*7) +
-                (v >= delta*5) + (v >= delta*3) + (v >= delta);
+            int x = static_cast<int>(v)*14 + bias;
+            int cnt = (x >= delta*13) + (x >= delta*11) + (x >= delta*9) + (x >= delta*7) +
+                (x >= delta*5) + (x >= delta*3) + (x >= delta);
             // s_tran: {1,7,6,5,4,3,2,0}
             sel = (0x02345671u >> (cnt*4)) & 7u;
         }
@@ -95,27 +123,57 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
 
     if (mx == mn) return make_uint2(stored(mn) | (stored(mn) << 8), 0u);
 
-    const uint32_t n = 2*radius + 1;
-    const uint32_t total = 2*n*n;
-    uint32_t best_err = 0xFFFFFFFFu, best_t = 0xFFFFFFFFu;
-    for (uint32_t t = lane; t < total; t += 32) {
-        uint32_t e0, e1; bool valid;
-        bc4_trial_endpoints<SIGNED>(t, n, static_cast<int>(radius), mn, mx, e0, e1, valid);
-        if (!valid) continue;
-        uint32_t lo4, hi4;
-        bc4_palette<SIGNED>(e0, e1, lo4, hi4);
-        uint32_t err = 0;
+    // ---- threshold table: T[x] = D(x) | N(x) << 16 for x = 0..255, stored twice (index q_c + q_{c+1}) ----
+    uint32_t dtot;
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_tab) + lane*2;           // histogram lives in the first 256 words
+        z[0] = make_uint4(0, 0, 0, 0); z[1] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        if (lane < 16) atomicAdd(&s_tab[v], (1u << 16) | (2u*v));
+        __syncwarp();
+        uint4 a = z[0], b = z[1];
+        a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
+        uint32_t run = b.w;                                            // inclusive scan of the lanes' totals
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            uint32_t m = __vminu4(__vabsdiffu4(lo4, rep[i]), __vabsdiffu4(hi4, rep[i]));
-            m = __vminu4(m, m >> 16);
-            m = min(m & 0xFFu, (m >> 8) & 0xFFu);
-            err += m*m;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, run, d);
+            if (lane >= static_cast<uint32_t>(d)) run += o;
         }
-        if (err < best_err) { best_err = err; best_t = t; }
+        const uint32_t base = run - b.w;
+        dtot = __shfl_sync(0xFFFFFFFFu, run, 31) & 0xFFFFu;
+        a.x += base; a.y += base; a.z += base; a.w += base; b.x += base; b.y += base; b.z += base; b.w += base;
+        __syncwarp();                                                  // every lane has read its histogram words
+        uint4* o4 = reinterpret_cast<uint4*>(s_tab) + lane*4;
+        o4[0] = make_uint4(a.x, a.x, a.y, a.y); o4[1] = make_uint4(a.z, a.z, a.w, a.w);
+        o4[2] = make_uint4(b.x, b.x, b.y, b.y); o4[3] = make_uint4(b.z, b.z, b.w, b.w);
+        __syncwarp();
     }
-    uint32_t werr = __reduce_min_sync(0xFFFFFFFFu, best_err);
-    uint32_t wt = __reduce_min_sync(0xFFFFFFFFu, best_err == werr ? best_t : 0xFFFFFFFFu);
+
+    const uint32_t n = 2*radius + 1, nn = n*n;
+    const uint32_t inv = ((1u << 20) + n - 1)/n;                       // r / n == (r*inv) >> 20 for r < n*n <= 4225
+    const int lowest = SIGNED ? 1 : 0;
+    int best_err = 0x7FFFFFFF; uint32_t best_t = 0xFFFFFFFFu;
+    for (uint32_t mode = 0; mode < 2; ++mode) {
+        for (uint32_t r = lane; r < nn; r += 32) {
+            const uint32_t lo_i = (r*inv) >> 20, hi_i = r - lo_i*n;
+            const int a = min(max(static_cast<int>(mx + hi_i) - static_cast<int>(radius), lowest), 255);
+            const int b = min(max(static_cast<int>(mn + lo_i) - static_cast<int>(radius), lowest), 255);
+            if (a == b) continue;
+            uint32_t q[8];
+            bc4_sorted_palette<SIGNED>(mode, static_cast<uint32_t>(min(a, b)), static_cast<uint32_t>(max(a, b)), q);
+            int acc = static_cast<int>(q[7]*(16u*q[7] - dtot));
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const uint32_t s = q[c] + q[c + 1];
+                const uint32_t w = s_tab[s];
+                const int inner = static_cast<int>((w >> 16)*s) - static_cast<int>(w & 0xFFFFu);
+                acc += (static_cast<int>(q[c]) - static_cast<int>(q[c + 1]))*inner;
+            }
+            if (acc < best_err) { best_err = acc; best_t = mode*nn + r; }
+        }
+    }
+    const int werr = __reduce_min_sync(0xFFFFFFFFu, best_err);
+    const uint32_t wt = __reduce_min_sync(0xFFFFFFFFu, best_err == werr ? best_t : 0xFFFFFFFFu);
 
     uint32_t e0, e1; bool valid;
     bc4_trial_endpoints<SIGNED>(wt, n, static_cast<int>(radius), mn, mx, e0, e1, valid);
@@ -123,7 +181,6 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     bc4_palette<SIGNED>(e0, e1, lo4, hi4);
     uint32_t sel = 0;
     if (lane < 16) {
-        uint32_t v = (texel(lane) >> shift) & 0xFFu;
         uint32_t bestd = 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -137,6 +194,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     if (lane >= 16) bits = 0;
     uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(bits));
     uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(bits >> 32));
+    __syncwarp();                                                      // the table is free for the next call
     return make_uint2(stored(e0) | (stored(e1) << 8) | (lo << 16), (lo >> 16) | (hi << 16));
 }
 
