@@ -31,7 +31,7 @@ __device__ __forceinline__ float half_bits_to_domain(uint32_t h, bool sg)
 __global__ void __launch_bounds__(kBc6Warps*32, 5) bc6h_kernel(const EncodeParams p)
 {
     const bool sg = p.type == 5;                  // Texture::Type::Float -> BC6H SF16
-    __shared__ float s_x[kBc6Warps][16*3*32];
+    __shared__ float s_x[kBc6Warps][bc6h::kWordsPerLane*32];
     const uint32_t lane = lane_id(), warp = warp_id();
     float* xs = s_x[warp];
     const uint32_t groups = (p.total_blocks + 31)/32;

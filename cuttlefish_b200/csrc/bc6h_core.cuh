@@ -10,6 +10,9 @@
 // error in the decoder's pre-"finish" integer domain wins.
 // Compiles for the device and, through hostdev.h, for tools/emu_bc6h.cpp.
 #pragma once
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+#endif
 #include "bc7_tables.cuh"
 #include "hostdev.h"
 
@@ -22,6 +25,58 @@ CFX_CONST uint8_t kW3[8] = {0, 9, 18, 27, 37, 46, 55, 64};
 // texel channel c of texel t of the lane's block: xs[(t*3 + c)*32 + lane], values in the decoder's
 // unquantised domain (half bits * 64 / 31, 0..65535)
 CFX_HD float& px(float* xs, uint32_t lane, uint32_t t, uint32_t c) { return xs[(t*3u + c)*32u + lane]; }
+
+// Error metric.  The search runs in the decoder's integer domain (half BITS, i.e. a piecewise-linear logarithm of the
+// value), but the reference minimises -- and the parity tests measure -- the squared error of the decoded FLOAT values
+// (Compressonator converts the block to float before it searches, bc6_encode_kernel.cpp).  So:
+//  * the index search and every error that decides between fits, shapes and modes is the EXACT squared error of the
+//    decoded values (half_value of the palette entry against half_value of the texel);
+//  * the continuous steps (moments, principal axis, least-squares end points) stay in the integer domain, where the
+//    palette is a straight line, with every texel channel weighted by its local slope^2 = 4^(e - e_max of the block),
+//    e = the half's exponent -- floored at 4^-3 so that the shadows of a block with highlights keep a say in where
+//    the line goes (their error is re-measured exactly afterwards).
+// xs[(48 + t)*32 + lane] holds texel t's three exponent distances (5 bits each) and, at bit 15, the smallest of them
+// (the texel's weight where one number per texel is needed: moments, principal axis).
+CFX_HD float half_bits_value(uint32_t h)
+{
+#ifdef __CUDA_ARCH__
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
+#else
+    const int e = static_cast<int>(h >> 10) & 31, m = static_cast<int>(h & 1023u);
+    return e ? ldexpf(static_cast<float>(1024 + m), e - 25) : ldexpf(static_cast<float>(m), -24);
+#endif
+}
+// value the decoder's "finish" step gives an integer-domain colour p (unsigned: p*31/64 as half bits; signed: sign and
+// |p|*31/32)
+CFX_HD float value_of(int p, bool sg)
+{
+    if (!sg) return half_bits_value(static_cast<uint32_t>(max(p, 0)*31) >> 6);
+    const float v = half_bits_value(static_cast<uint32_t>(abs(p)*31) >> 5);
+    return p < 0 ? -v : v;
+}
+constexpr int kMaxWeightShift = 2, kMaxWeightShiftSigned = 8;
+constexpr uint32_t kWordsPerLane = 64;     // 48 texel channels + 16 weight words
+CFX_HD uint32_t& pw(float* xs, uint32_t lane, uint32_t t) { return reinterpret_cast<uint32_t*>(xs)[(48u + t)*32u + lane]; }
+CFX_HD float w_of(uint32_t d) { return __uint_as_float((127u - 2u*(d & 31u)) << 23); }        // 4^-d
+CFX_HD void prepare_weights(float* xs, uint32_t lane, bool sg)
+{
+    const float to_half = sg ? 31.0f/32.0f : 31.0f/64.0f;
+    int emax = 1;
+    for (uint32_t t = 0; t < 16; ++t)
+#pragma unroll
+        for (uint32_t c = 0; c < 3; ++c) emax = max(emax, __float2int_rn(fabsf(px(xs, lane, t, c))*to_half) >> 10);
+    for (uint32_t t = 0; t < 16; ++t) {
+        uint32_t word = 0, dmin = 31;
+#pragma unroll
+        for (uint32_t c = 0; c < 3; ++c) {
+            const int e = max(__float2int_rn(fabsf(px(xs, lane, t, c))*to_half) >> 10, 1);
+            const uint32_t d = static_cast<uint32_t>(min(emax - e, sg ? kMaxWeightShiftSigned : kMaxWeightShift));
+            word |= d << (5u*c);
+            dmin = min(dmin, d);
+        }
+        pw(xs, lane, t) = word | (dmin << 15);
+    }
+}
 
 // sg: signed format (BC6H SF16, Texture::Type::Float -> SetSignedBC6, lib/src/S3tcConverter.cpp:566-570): end points are
 // two's complement, the unquantised domain is +-0x7FFF and texels are sign * half magnitude * 32/31.
@@ -84,34 +139,38 @@ CFX_HD_NOINLINE float assign_indices(float* xs, uint32_t lane, uint32_t mask, co
 {
     const int n = 1 << ibits;
     int a[3], d[3];
-    float len2 = 0.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         a[c] = unquantize(q0[c], wbits, sg);
         d[c] = unquantize(q1[c], wbits, sg) - a[c];
-        len2 += static_cast<float>(d[c])*static_cast<float>(d[c]);
     }
-    const float scale = len2 > 0.0f ? static_cast<float>(n - 1)/len2 : 0.0f;
     float err = 0.0f;
     uint64_t idx = idx_out;
     for (uint32_t t = 0; t < 16; ++t) {
         if (!((mask >> t) & 1u)) continue;
         const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
-        const float proj = ((x0 - static_cast<float>(a[0]))*static_cast<float>(d[0]) + (x1 - static_cast<float>(a[1]))*static_cast<float>(d[1]) +
-            (x2 - static_cast<float>(a[2]))*static_cast<float>(d[2]))*scale;
+        const uint32_t wd = pw(xs, lane, t);
+        const float w0 = w_of(wd), w1 = w_of(wd >> 5), w2 = w_of(wd >> 10);
+        const float f0 = value_of(__float2int_rn(x0), sg), f1 = value_of(__float2int_rn(x1), sg), f2 = value_of(__float2int_rn(x2), sg);
+        // weighted projection on the palette line
+        const float d0 = static_cast<float>(d[0]), d1 = static_cast<float>(d[1]), d2 = static_cast<float>(d[2]);
+        const float len2 = w0*d0*d0 + w1*d1*d1 + w2*d2*d2;
+        const float proj = len2 > 0.0f ? (w0*(x0 - static_cast<float>(a[0]))*d0 + w1*(x1 - static_cast<float>(a[1]))*d1 +
+            w2*(x2 - static_cast<float>(a[2]))*d2)*static_cast<float>(n - 1)/len2 : 0.0f;
         const int k0 = min(max(__float2int_rn(proj), 0), n - 1);
+        // the nearest index along the line and its neighbour on the side the texel lies on
+        const int k1 = min(max(proj > static_cast<float>(k0) ? k0 + 1 : k0 - 1, 0), n - 1);
         float beste = 3.0e38f;
         int bestk = k0;
 #pragma unroll
-        for (int dk = -1; dk <= 1; ++dk) {
-            const int k = k0 + dk;
-            if (k < 0 || k >= n) continue;
+        for (int dk = 0; dk < 2; ++dk) {
+            const int k = dk ? k1 : k0;
             const int w = ibits == 4 ? kW4[k] : kW3[k];
             float e = 0.0f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const int p = a[c] + ((d[c]*w + 32) >> 6);          // == (a*(64-w) + b*w + 32) >> 6
-                const float df = static_cast<float>(p) - (c == 0 ? x0 : (c == 1 ? x1 : x2));
+                const float df = value_of(p, sg) - (c == 0 ? f0 : (c == 1 ? f1 : f2));
                 e += df*df;
             }
             if (e < beste) { beste = e; bestk = k; }
@@ -129,15 +188,17 @@ CFX_HD_NOINLINE void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbi
     float n = 0.0f, m[3] = {0, 0, 0};
     for (uint32_t t = 0; t < 16; ++t) {
         if (!((mask >> t) & 1u)) continue;
-        n += 1.0f; m[0] += px(xs, lane, t, 0); m[1] += px(xs, lane, t, 1); m[2] += px(xs, lane, t, 2);
+        const float wt = w_of(pw(xs, lane, t) >> 15);
+        n += wt; m[0] += wt*px(xs, lane, t, 0); m[1] += wt*px(xs, lane, t, 1); m[2] += wt*px(xs, lane, t, 2);
     }
     const float inv = n > 0.0f ? 1.0f/n : 0.0f;
     m[0] *= inv; m[1] *= inv; m[2] *= inv;
     float cv[6] = {0, 0, 0, 0, 0, 0};
     for (uint32_t t = 0; t < 16; ++t) {
         if (!((mask >> t) & 1u)) continue;
+        const float wt = w_of(pw(xs, lane, t) >> 15);
         const float d0 = px(xs, lane, t, 0) - m[0], d1 = px(xs, lane, t, 1) - m[1], d2 = px(xs, lane, t, 2) - m[2];
-        cv[0] += d0*d0; cv[1] += d0*d1; cv[2] += d0*d2; cv[3] += d1*d1; cv[4] += d1*d2; cv[5] += d2*d2;
+        cv[0] += wt*d0*d0; cv[1] += wt*d0*d1; cv[2] += wt*d0*d2; cv[3] += wt*d1*d1; cv[4] += wt*d1*d2; cv[5] += wt*d2*d2;
     }
     float v[3] = {cv[0], cv[1], cv[2]};
     float best = cv[0];
@@ -171,17 +232,19 @@ CFX_HD_NOINLINE void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbi
     f.idx = 0;
     f.err = assign_indices(xs, lane, mask, f.q0, f.q1, wbits, ibits, f.idx, sg);
     for (int round = 0; round < 2 && f.err > 0.0f; ++round) {
+        // weighted normal equations (one weight per texel: its brightest channel's)
         float A = 0, B = 0, C = 0, P[3] = {0, 0, 0}, Q[3] = {0, 0, 0};
         for (uint32_t t = 0; t < 16; ++t) {
             if (!((mask >> t) & 1u)) continue;
             const uint32_t k = static_cast<uint32_t>(f.idx >> (4*t)) & 15u;
             const float w = static_cast<float>(ibits == 4 ? kW4[k] : kW3[k])*(1.0f/64.0f), iw = 1.0f - w;
-            A += iw*iw; B += iw*w; C += w*w;
+            const float wt = w_of(pw(xs, lane, t) >> 15), wiw = wt*iw, ww = wt*w;
+            A += wiw*iw; B += wiw*w; C += ww*w;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { const float x = px(xs, lane, t, c); P[c] += iw*x; Q[c] += w*x; }
+            for (int c = 0; c < 3; ++c) { const float x = px(xs, lane, t, c); P[c] += wiw*x; Q[c] += ww*x; }
         }
         const float det = A*C - B*B;
-        if (fabsf(det) < 1e-6f) break;
+        if (!(fabsf(det) > 1e-6f*(A + C)*(A + C))) break;      // (relative test: the weights span orders of magnitude)
         const float id = 1.0f/det;
         SubsetFit trial;
 #pragma unroll
@@ -196,11 +259,11 @@ CFX_HD_NOINLINE void fit_subset(float* xs, uint32_t lane, uint32_t mask, int wbi
 }
 
 // Line-fit residual of a two-region shape (sum over regions of trace - lambda_max).
-CFX_HD float shape_score(float* xs, uint32_t lane, uint32_t m1, const float* sT, const float* cT)
+CFX_HD float shape_score(float* xs, uint32_t lane, uint32_t m1, const float* sT, const float* cT, float wT)
 {
     float n1 = 0, s1[3] = {0, 0, 0}, c1[6] = {0, 0, 0, 0, 0, 0};
     for (uint32_t t = 0; t < 16; ++t) {
-        const float f = ((m1 >> t) & 1u) ? 1.0f : 0.0f;
+        const float f = ((m1 >> t) & 1u) ? w_of(pw(xs, lane, t) >> 15) : 0.0f;
         const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
         n1 += f; s1[0] += f*x0; s1[1] += f*x1; s1[2] += f*x2;
         c1[0] += f*x0*x0; c1[1] += f*x0*x1; c1[2] += f*x0*x2; c1[3] += f*x1*x1; c1[4] += f*x1*x2; c1[5] += f*x2*x2;
@@ -208,13 +271,13 @@ CFX_HD float shape_score(float* xs, uint32_t lane, uint32_t m1, const float* sT,
     float score = 0.0f;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        const float nn = s ? n1 : 16.0f - n1;
+        const float nn = s ? n1 : wT - n1;
         float sm[3], cc[6];
 #pragma unroll
         for (int k = 0; k < 3; ++k) sm[k] = s ? s1[k] : sT[k] - s1[k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) cc[k] = s ? c1[k] : cT[k] - c1[k];
-        const float inv = 1.0f/nn;
+        const float inv = nn > 0.0f ? 1.0f/nn : 0.0f;
         cc[0] -= sm[0]*sm[0]*inv; cc[1] -= sm[0]*sm[1]*inv; cc[2] -= sm[0]*sm[2]*inv;
         cc[3] -= sm[1]*sm[1]*inv; cc[4] -= sm[1]*sm[2]*inv; cc[5] -= sm[2]*sm[2]*inv;
         float v[3] = {cc[0], cc[1], cc[2]};
@@ -255,6 +318,7 @@ CFX_HD bool delta_fits(int d, int bits) { const int lim = (1 << (bits - 1)) - 1;
 // Encode the lane's block; returns the 16 bytes.
 CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality, bool sg = false)
 {
+    prepare_weights(xs, lane, sg);
     // ---- one-region modes: {mode bits, wBits, delta bits}
     const int one_mode[4] = {0x03, 0x07, 0x0B, 0x0F}, one_w[4] = {10, 11, 12, 16}, one_t[4] = {10, 9, 8, 4};
     float best_err = 3.0e38f;
@@ -272,18 +336,19 @@ CFX_HD uint4 encode_block(float* xs, uint32_t lane, uint32_t quality, bool sg = 
     // ---- two-region modes on the best shape
     uint32_t best_shape = 0;
     if (best_err > 0.0f && quality >= 1) {
-        float sT[3] = {0, 0, 0}, cT[6] = {0, 0, 0, 0, 0, 0};
+        float sT[3] = {0, 0, 0}, cT[6] = {0, 0, 0, 0, 0, 0}, wT = 0.0f;
         for (uint32_t t = 0; t < 16; ++t) {
             const float x0 = px(xs, lane, t, 0), x1 = px(xs, lane, t, 1), x2 = px(xs, lane, t, 2);
-            sT[0] += x0; sT[1] += x1; sT[2] += x2;
-            cT[0] += x0*x0; cT[1] += x0*x1; cT[2] += x0*x2; cT[3] += x1*x1; cT[4] += x1*x2; cT[5] += x2*x2;
+            const float wt = w_of(pw(xs, lane, t) >> 15);
+            wT += wt; sT[0] += wt*x0; sT[1] += wt*x1; sT[2] += wt*x2;
+            cT[0] += wt*x0*x0; cT[1] += wt*x0*x1; cT[2] += wt*x0*x2; cT[3] += wt*x1*x1; cT[4] += wt*x1*x2; cT[5] += wt*x2*x2;
         }
         // the two best shapes by line-fit residual
         float bs0 = 3.0e38f, bs1 = 3.0e38f;
         uint32_t sh0 = 0, sh1 = 0;
 #pragma unroll 1
         for (uint32_t s = 0; s < 32; ++s) {
-            const float sc = shape_score(xs, lane, kBc7Part2[s], sT, cT);
+            const float sc = shape_score(xs, lane, kBc7Part2[s], sT, cT, wT);
             if (sc < bs0) { bs1 = bs0; sh1 = sh0; bs0 = sc; sh0 = s; }
             else if (sc < bs1) { bs1 = sc; sh1 = s; }
         }

@@ -18,7 +18,7 @@ for fmt in fmts:
         src = z["src"]; img = src.astype(np.float32) / np.float32(255)
         pr = oracle.psnr_rgb(img, oracle.decode(z[key], fmt, 192, 192))
         line = "%s %-7s ref(medium) %.2f |" % (fmt, name, pr)
-        for q in ("Low", "Normal", "High", "Highest"):
+        for q in ("Lowest", "Low", "Normal", "High", "Highest"):
             pg = oracle.psnr_rgb(img, oracle.decode(cfx.encode(src, fmt, quality=q), fmt, 192, 192))
             line += " %s %+.2f" % (q, pg - pr)
         print(line, flush=True)

@@ -6,7 +6,7 @@ using namespace cfx;
 extern "C" int emu_bc6h_encode(const uint16_t* rgba16f, uint32_t w, uint32_t h, uint8_t* out, uint32_t quality, uint32_t is_signed)
 {
     uint32_t bxn = (w + 3)/4, byn = (h + 3)/4;
-    std::vector<float> xs(16*3*32);
+    std::vector<float> xs(bc6h::kWordsPerLane*32);
     for (uint32_t by = 0; by < byn; ++by)
         for (uint32_t bx = 0; bx < bxn; ++bx) {
             for (uint32_t t = 0; t < 16; ++t) {
