@@ -23,7 +23,7 @@ constexpr int kBlkStride = 20;     // words per block in shared memory (16 texel
 
 template <int FORMAT>   // 29 BC1_RGB, 30 BC1_RGBA, 31 BC2, 32 BC3
 __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams p, int descent, uint32_t radius, uint32_t hq,
-    bool exact)
+    bool exact, bool both)
 {
     __shared__ __align__(16) uint32_t s_px[kBc1Warps][32*kBlkStride];
     __shared__ __align__(16) uint32_t s_tab[FORMAT == 32 ? kBc1Warps : 1][kBc4TableWords];
@@ -75,6 +75,14 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
         else
 #endif
             color = bc1::encode_color_block(px, flags, descent);
+#ifdef CFX_HAVE_RGBCX_TABLES
+        // High / Highest (rgbcx levels 13 / 18 in the reference: more orderings, more refinement): two independent
+        // searches, ours with its +-1 descent and the level-9 flow, and the block keeps the better one
+        if (both && !transparent) {
+            const uint2 alt = rgbcx9::encode_bc1_level9(px, FORMAT == 29 || FORMAT == 30, FORMAT == 29);
+            if (bc1::block_sse(px, alt, FORMAT >= 31) < bc1::block_sse(px, color, FORMAT >= 31)) color = alt;
+        }
+#endif
         if (FORMAT == 29 || FORMAT == 30) {
             if (lane < nblk) reinterpret_cast<uint2*>(p.dst)[first + lane] = color;
         } else if (FORMAT == 31) {
@@ -127,8 +135,9 @@ int launch_bc123(const EncodeParams& p, cudaStream_t stream)
     }
     const uint32_t grid = min(ctas, persistent_ctas(k, kBc1Warps*32));
     bool exact = bc1_color_is_exact(p.quality);
+    bool both = p.quality >= 3;
     void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&descent), const_cast<uint32_t*>(&radius),
-        const_cast<uint32_t*>(&hq), &exact};
+        const_cast<uint32_t*>(&hq), &exact, &both};
     if (cudaLaunchKernel(k, dim3(grid), dim3(kBc1Warps*32), args, 0, stream) != cudaSuccess) return -4;
     return 1;
 }

@@ -273,5 +273,24 @@ CFX_HD uint2 encode_color_block(const uint32_t* px, uint32_t flags, int descent_
     return pack(best, four);
 }
 
+// SSE of a packed colour block against the texels (decoder of palette(): thirds and halves by integer division).
+// always4: BC2 / BC3 colour halves, which decode in four-colour mode whatever the order of c0 and c1.
+CFX_HD uint32_t block_sse(const uint32_t* px, uint2 blk, bool always4)
+{
+    const uint32_t c0 = blk.x & 0xFFFFu, c1 = blk.x >> 16;
+    uint32_t lin[4];
+    const bool four = always4 || c0 > c1;
+    palette(c0, c1, four, lin);
+    // selector order: four colours c0, c1, 2/3, 1/3; three colours c0, c1, 1/2, black
+    const uint32_t col[4] = {lin[0], four ? lin[3] : lin[2], lin[1], four ? lin[2] : 0u};
+    uint32_t sse = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t k = (blk.y >> (2*i)) & 3u;
+        sse += rgb_sse(px[i], k == 0 ? col[0] : (k == 1 ? col[1] : (k == 2 ? col[2] : col[3])));
+    }
+    return sse;
+}
+
 } // namespace bc1
 } // namespace cfx

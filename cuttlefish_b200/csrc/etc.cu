@@ -88,7 +88,7 @@ bool etc1_is_exact(uint32_t quality) { return quality <= 2; }
 
 int launch_etc(const EncodeParams& p, cudaStream_t stream)
 {
-    static const int rounds_by_quality[5] = {0, 1, 1, 2, 3};
+    static const int rounds_by_quality[5] = {0, 1, 1, 3, 5};
     static const int radius_by_quality[5] = {0, 1, 2, 3, 4};
     const int rounds = rounds_by_quality[p.quality], radius = radius_by_quality[p.quality];
     const uint32_t groups = (p.total_blocks + 31)/32;

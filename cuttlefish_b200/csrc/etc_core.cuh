@@ -129,11 +129,17 @@ CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* 
     for (int round = 0; round < rounds && best.err > 0.0f; ++round) {
         bool improved = false;
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
-            // k 0,1: all channels -1 / +1 (luma); k 2..7: one channel -1 / +1
+        const int moves = rounds >= 5 ? 20 : 8;          // Quality::Highest also moves two channels at once
+        for (int k = 0; k < moves; ++k) {
+            // k 0,1: all channels -1 / +1 (luma); k 2..7: one channel -1 / +1; k 8..19: two channels, the four sign pairs
             int t[3] = {q[0], q[1], q[2]};
             const int d = (k & 1) ? 1 : -1;
-            if (k < 2) { t[0] += d; t[1] += d; t[2] += d; } else t[(k - 2) >> 1] += d;
+            if (k < 2) { t[0] += d; t[1] += d; t[2] += d; }
+            else if (k < 8) t[(k - 2) >> 1] += d;
+            else {
+                const int pr = (k - 8) >> 2, c1 = pr == 2 ? 1 : 0, c2 = pr == 0 ? 1 : 2;
+                t[c1] += d; t[c2] += (k & 2) ? 1 : -1;
+            }
             if (t[0] < lo[0] || t[0] > hi[0] || t[1] < lo[1] || t[1] > hi[1] || t[2] < lo[2] || t[2] > hi[2]) continue;
 #pragma unroll
             for (int c = 0; c < 3; ++c) base[c] = bits == 5 ? expand5(t[c]) : expand4(t[c]);
