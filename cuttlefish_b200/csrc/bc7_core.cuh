@@ -36,6 +36,7 @@ struct Fit {
     uint32_t e0[2], e1[2];     // quantised endpoints per subset, one byte per channel (incl. p-bit)
     uint32_t err[2];           // SSE per subset
     uint32_t sel_lo, sel_hi;   // 16 x 4-bit indices
+    uint32_t sel2_lo, sel2_hi; // modes 4 / 5: the scalar channel's indices (sel_* are the colour indices)
 };
 
 CFX_HD uint32_t nibble_mask8(uint32_t m8)
@@ -191,7 +192,9 @@ CFX_HD uint32_t score_shape_rgb(const float4* bxf, const float* sT, const float*
 // = "extrapolating" first LS round, and rounds = number of least-squares refinement rounds.
 #define CFX_BC7_CAND(mode, rank, variant, rounds) ((mode) | ((rank) << 4) | ((variant) << 8) | ((rounds) << 12))
 CFX_HD uint32_t cand_mode(uint32_t d) { return d & 15u; }
-CFX_HD uint32_t cand_rank(uint32_t d) { return (d & 15u) == 6u ? 0xFFFFFFFFu : ((d >> 4) & 15u); }
+CFX_HD bool cand_is_dual(uint32_t d) { return (d & 15u) == 4u || (d & 15u) == 5u; }      // modes 4, 5: rank field = rotation, variant bit 0 = index mode
+CFX_HD uint32_t cand_rank(uint32_t d) { return (d & 15u) == 6u || cand_is_dual(d) ? 0xFFFFFFFFu : ((d >> 4) & 15u); }
+CFX_HD uint32_t cand_rotation(uint32_t d) { return (d >> 4) & 3u; }
 CFX_HD uint32_t cand_variant(uint32_t d) { return (d >> 8) & 15u; }
 CFX_HD uint32_t cand_rounds(uint32_t d) { return (d >> 12) & 15u; }
 
@@ -658,6 +661,193 @@ struct BitWriter {
         pos += bits;
     }
 };
+
+// ---- modes 4 and 5: one subset, colour and one scalar channel on SEPARATE index sets, channel rotation ----------------
+// (bc7enc uses mode 5 for blocks with alpha, lib/bc7enc_rdo/bc7enc.cpp:2039-2137; bc7e all of them,
+// lib/bc7enc_rdo/bc7e.ispc:3909-4603.)  Rotation r swaps alpha with channel r-1 after decoding, so the encoder swaps
+// them before: the "scalar" is then R, G or B and the colour triple carries alpha in its place -- what a block needs
+// when one channel runs independently of the others.  Mode 5: colour 7.7.7 + scalar 8 bits, two 2-bit index sets.
+// Mode 4: colour 5.5.5 + scalar 6 bits, a 2-bit and a 3-bit set; idx_mode says which one the colour gets.
+// No p-bits.  Fit::e0[0] / e1[0] hold the colour codes in bytes 0..2 and the scalar code in byte 3; err[0] is the colour
+// SSE, err[1] the scalar's; sel_* the colour indices, sel2_* the scalar's.
+CFX_HD uint32_t rotation_selector(uint32_t rot) { return rot == 0 ? 0x3210u : (rot == 1 ? 0x0213u : (rot == 2 ? 0x1230u : 0x2310u)); }
+
+CFX_HD uint32_t eval_colour3(const uint32_t* s_x, uint32_t psel, const SubsetEval& s, uint32_t nm1, uint32_t half, uint32_t recip,
+    uint32_t cmask, uint32_t& sel_lo, uint32_t& sel_hi)
+{
+    uint32_t err = 0;
+    uint64_t sel = 0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t x = __byte_perm(s_x[i], 0u, psel);
+        int dot = dp2a_lo_s16_u8(s.d_rg, x, 0);
+        dot = dp2a_hi_s16_u8(s.d_ba, x, dot);              // the alpha delta is zero: both end points decode to 255
+        const float t = static_cast<float>(dot - s.c0)*s.scale;
+        int k = min(max(__float2int_rn(t), 0), static_cast<int>(nm1));
+        const int kn = min(max(t > static_cast<float>(k) ? k + 1 : k - 1, 0), static_cast<int>(nm1));
+        uint32_t er = entry_error(s, x, index_weight(k, half, recip), cmask);
+        const uint32_t ern = entry_error(s, x, index_weight(kn, half, recip), cmask);
+        if (ern < er) { er = ern; k = kn; }
+        err += er;
+        sel |= static_cast<uint64_t>(k) << (4*i);
+    }
+    sel_lo = static_cast<uint32_t>(sel); sel_hi = static_cast<uint32_t>(sel >> 32);
+    return err;
+}
+
+CFX_HD uint32_t eval_scalar(const uint32_t* s_x, uint32_t psel, int lo, int hi, uint32_t nm1, uint32_t half, uint32_t recip,
+    bool enabled, uint32_t& sel_lo, uint32_t& sel_hi)
+{
+    uint32_t err = 0;
+    uint64_t sel = 0;
+    const float scale = hi != lo ? static_cast<float>(nm1)/static_cast<float>(hi - lo) : 0.0f;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int v = static_cast<int>(__byte_perm(s_x[i], 0u, psel) >> 24);
+        const float t = static_cast<float>(v - lo)*scale;
+        int k = min(max(__float2int_rn(t), 0), static_cast<int>(nm1));
+        const int kn = min(max(t > static_cast<float>(k) ? k + 1 : k - 1, 0), static_cast<int>(nm1));
+        const int w = static_cast<int>(index_weight(k, half, recip)), wn = static_cast<int>(index_weight(kn, half, recip));
+        const int d = ((lo*(64 - w) + hi*w + 32) >> 6) - v, dn = ((lo*(64 - wn) + hi*wn + 32) >> 6) - v;
+        uint32_t er = static_cast<uint32_t>(d*d);
+        if (static_cast<uint32_t>(dn*dn) < er) { er = static_cast<uint32_t>(dn*dn); k = kn; }
+        err += er;
+        sel |= static_cast<uint64_t>(k) << (4*i);
+    }
+    sel_lo = static_cast<uint32_t>(sel); sel_hi = static_cast<uint32_t>(sel >> 32);
+    return enabled ? err : 0u;
+}
+
+CFX_HD uint32_t scalar_code(float v, uint32_t bits)
+{
+    const float maxv = static_cast<float>((1u << bits) - 1u);
+    return static_cast<uint32_t>(min(max(__float2int_rn(fminf(fmaxf(v, 0.0f), 255.0f)*(maxv*(1.0f/255.0f))), 0), static_cast<int>(maxv)));
+}
+CFX_HD int scalar_value(uint32_t code, uint32_t bits) { return static_cast<int>(((code << (8u - bits)) | (code >> (2u*bits - 8u))) & 0xFFu); }
+
+CFX_HD_NOINLINE void fit_dual(const uint32_t* s_x, uint32_t mode, uint32_t rot, uint32_t idx_mode, uint32_t rounds, uint32_t chmask, Fit& best)
+{
+    const uint32_t psel = rotation_selector(rot);
+    const uint32_t cmask = __byte_perm(chmask, 0u, psel);            // the channel enables travel with their channels
+    const uint32_t cbits = mode == 5 ? 7u : 5u, abits = mode == 5 ? 8u : 6u;
+    const uint32_t cib = mode == 5 ? 2u : (idx_mode ? 3u : 2u), aib = mode == 5 ? 2u : (idx_mode ? 2u : 3u);
+    const uint32_t cn = (1u << cib) - 1u, an = (1u << aib) - 1u;
+    const uint32_t chalf = cn >> 1, ahalf = an >> 1;
+    const uint32_t crecip = cn == 3 ? 43691u : 18725u, arecip = an == 3 ? 43691u : 18725u;
+
+    // ---- colour triple: principal axis, quantise, indices, least squares
+    float sm[3] = {0, 0, 0}, cc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int amin = 255, amax = 0;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t x = __byte_perm(s_x[i], 0u, psel);
+        const float r = static_cast<float>(x & 0xFFu), g = static_cast<float>((x >> 8) & 0xFFu), b = static_cast<float>((x >> 16) & 0xFFu);
+        sm[0] += r; sm[1] += g; sm[2] += b;
+        cc[0] += r*r; cc[1] += r*g; cc[2] += r*b; cc[4] += g*g; cc[5] += g*b; cc[7] += b*b;
+        amin = min(amin, static_cast<int>(x >> 24)); amax = max(amax, static_cast<int>(x >> 24));
+    }
+    const float m[3] = {sm[0]*(1.0f/16.0f), sm[1]*(1.0f/16.0f), sm[2]*(1.0f/16.0f)};
+    cc[0] -= sm[0]*m[0]; cc[1] -= sm[0]*m[1]; cc[2] -= sm[0]*m[2]; cc[4] -= sm[1]*m[1]; cc[5] -= sm[1]*m[2]; cc[7] -= sm[2]*m[2];
+    const float4 ax = principal_axis(cc, 4);
+    float tmin = 1e30f, tmax = -1e30f;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t x = __byte_perm(s_x[i], 0u, psel);
+        const float t = (static_cast<float>(x & 0xFFu) - m[0])*ax.x + (static_cast<float>((x >> 8) & 0xFFu) - m[1])*ax.y +
+            (static_cast<float>((x >> 16) & 0xFFu) - m[2])*ax.z;
+        tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
+    }
+    float q;
+    uint32_t e0 = quantize_endpoint(make_float4(m[0] + tmin*ax.x, m[1] + tmin*ax.y, m[2] + tmin*ax.z, 255.0f), cbits, 0u, false, 0u, q);
+    uint32_t e1 = quantize_endpoint(make_float4(m[0] + tmax*ax.x, m[1] + tmax*ax.y, m[2] + tmax*ax.z, 255.0f), cbits, 0u, false, 0u, q);
+    SubsetEval ev = make_eval(e0, e1, cbits, 0u, cn);
+    uint32_t clo, chi;
+    uint32_t cerr = eval_colour3(s_x, psel, ev, cn, chalf, crecip, cmask & 0x00FFFFFFu, clo, chi);
+    uint32_t cur_lo = clo, cur_hi = chi;
+    for (uint32_t round = 0; round < rounds && cerr; ++round) {
+        float A = 0, B = 0, C = 0, P[3] = {0, 0, 0}, Q[3] = {0, 0, 0};
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t x = __byte_perm(s_x[i], 0u, psel);
+            const uint32_t k = ((i < 8 ? cur_lo : cur_hi) >> (4*(i & 7))) & 15u;
+            const float w = static_cast<float>(index_weight(k, chalf, crecip))*(1.0f/64.0f), iw = 1.0f - w;
+            A += iw*iw; B += iw*w; C += w*w;
+            const float xs[3] = {static_cast<float>(x & 0xFFu), static_cast<float>((x >> 8) & 0xFFu), static_cast<float>((x >> 16) & 0xFFu)};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) { P[ch] += iw*xs[ch]; Q[ch] += w*xs[ch]; }
+        }
+        const float det = A*C - B*B;
+        if (!(fabsf(det) > 1e-4f)) break;
+        const float id = 1.0f/det;
+        const uint32_t n0 = quantize_endpoint(make_float4((C*P[0] - B*Q[0])*id, (C*P[1] - B*Q[1])*id, (C*P[2] - B*Q[2])*id, 255.0f), cbits, 0u, false, 0u, q);
+        const uint32_t n1 = quantize_endpoint(make_float4((A*Q[0] - B*P[0])*id, (A*Q[1] - B*P[1])*id, (A*Q[2] - B*P[2])*id, 255.0f), cbits, 0u, false, 0u, q);
+        ev = make_eval(n0, n1, cbits, 0u, cn);
+        const uint32_t nerr = eval_colour3(s_x, psel, ev, cn, chalf, crecip, cmask & 0x00FFFFFFu, cur_lo, cur_hi);
+        if (nerr < cerr) { cerr = nerr; e0 = n0; e1 = n1; clo = cur_lo; chi = cur_hi; }
+    }
+
+    // ---- scalar channel: range, quantise, indices, least squares
+    const bool enabled = (cmask >> 24) != 0u;
+    uint32_t a0 = scalar_code(static_cast<float>(amin), abits), a1 = scalar_code(static_cast<float>(amax), abits);
+    uint32_t alo, ahi;
+    uint32_t aerr = eval_scalar(s_x, psel, scalar_value(a0, abits), scalar_value(a1, abits), an, ahalf, arecip, enabled, alo, ahi);
+    cur_lo = alo; cur_hi = ahi;
+    for (uint32_t round = 0; round < rounds && aerr; ++round) {
+        float A = 0, B = 0, C = 0, P = 0, Q = 0;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const float v = static_cast<float>(__byte_perm(s_x[i], 0u, psel) >> 24);
+            const uint32_t k = ((i < 8 ? cur_lo : cur_hi) >> (4*(i & 7))) & 15u;
+            const float w = static_cast<float>(index_weight(k, ahalf, arecip))*(1.0f/64.0f), iw = 1.0f - w;
+            A += iw*iw; B += iw*w; C += w*w; P += iw*v; Q += w*v;
+        }
+        const float det = A*C - B*B;
+        if (!(fabsf(det) > 1e-4f)) break;
+        const float id = 1.0f/det;
+        const uint32_t n0 = scalar_code((C*P - B*Q)*id, abits), n1 = scalar_code((A*Q - B*P)*id, abits);
+        const uint32_t nerr = eval_scalar(s_x, psel, scalar_value(n0, abits), scalar_value(n1, abits), an, ahalf, arecip, enabled, cur_lo, cur_hi);
+        if (nerr < aerr) { aerr = nerr; a0 = n0; a1 = n1; alo = cur_lo; ahi = cur_hi; }
+    }
+    best.e0[0] = (e0 & 0x00FFFFFFu) | (a0 << 24); best.e1[0] = (e1 & 0x00FFFFFFu) | (a1 << 24);
+    best.e0[1] = best.e1[1] = 0u;
+    best.err[0] = cerr; best.err[1] = aerr;
+    best.sel_lo = clo; best.sel_hi = chi; best.sel2_lo = alo; best.sel2_hi = ahi;
+}
+
+// Pack modes 4, 5.
+CFX_HD_NOINLINE uint4 pack_dual(uint32_t mode, uint32_t rot, uint32_t idx_mode, Fit f)
+{
+    const uint32_t cbits = mode == 5 ? 7u : 5u, abits = mode == 5 ? 8u : 6u;
+    const uint32_t cib = mode == 5 ? 2u : (idx_mode ? 3u : 2u), aib = mode == 5 ? 2u : (idx_mode ? 2u : 3u);
+    uint64_t csel = (static_cast<uint64_t>(f.sel_hi) << 32) | f.sel_lo, asel = (static_cast<uint64_t>(f.sel2_hi) << 32) | f.sel2_lo;
+    uint32_t c0 = f.e0[0] & 0x00FFFFFFu, c1 = f.e1[0] & 0x00FFFFFFu, a0 = f.e0[0] >> 24, a1 = f.e1[0] >> 24;
+    // the first index of each set must have a clear MSB: swap that set's end points and invert its indices
+    if ((static_cast<uint32_t>(csel) & 15u) >> (cib - 1u)) {
+        const uint32_t t = c0; c0 = c1; c1 = t;
+        csel = 0x1111111111111111ull*((1u << cib) - 1u) - csel;
+    }
+    if ((static_cast<uint32_t>(asel) & 15u) >> (aib - 1u)) {
+        const uint32_t t = a0; a0 = a1; a1 = t;
+        asel = 0x1111111111111111ull*((1u << aib) - 1u) - asel;
+    }
+    BitWriter bw; bw.init();
+    bw.put(1u << mode, mode + 1u);
+    bw.put(rot, 2);
+    if (mode == 4) bw.put(idx_mode, 1);
+#pragma unroll 1
+    for (uint32_t ch = 0; ch < 3; ++ch) { bw.put((c0 >> (8*ch)) & 0xFFu, cbits); bw.put((c1 >> (8*ch)) & 0xFFu, cbits); }
+    bw.put(a0, abits); bw.put(a1, abits);
+    // mode 5: colour indices then scalar indices; mode 4: the 2-bit set then the 3-bit set, whoever owns them
+    const bool colour_first = mode == 5 || idx_mode == 0;
+    const uint64_t first = colour_first ? csel : asel, second = colour_first ? asel : csel;
+    const uint32_t fb = colour_first ? cib : aib, sb = colour_first ? aib : cib;
+#pragma unroll 1
+    for (uint32_t i = 0; i < 16; ++i) bw.put(static_cast<uint32_t>(first >> (4*i)) & 15u, i == 0 ? fb - 1u : fb);
+#pragma unroll 1
+    for (uint32_t i = 0; i < 16; ++i) bw.put(static_cast<uint32_t>(second >> (4*i)) & 15u, i == 0 ? sb - 1u : sb);
+    return make_uint4(static_cast<uint32_t>(bw.lo), static_cast<uint32_t>(bw.lo >> 32),
+        static_cast<uint32_t>(bw.hi), static_cast<uint32_t>(bw.hi >> 32));
+}
 
 // Pack modes 1, 3, 6, 7 (one index set, p-bits).
 CFX_HD_NOINLINE uint4 pack_block(uint32_t mode, uint32_t part, uint32_t m1, Fit f)

@@ -120,6 +120,10 @@ __device__ __forceinline__ double linear_to_srgb(double c)      // Color.h:236-2
 // (lib/FreeImage/Source/FreeImage/ConversionRGBAF.cpp:116-119) -- what Image::convert(RGBAF) stores for an 8-bit image.
 // The 256 possible values are tabulated once per CTA, already widened to double (and taken to linear for sRGB), so a
 // tap costs four shared-memory loads instead of four divisions and four conversions.
+// One CTA row per image row; rows beyond the 65535 limit of gridDim.y continue in gridDim.z.
+constexpr uint32_t kMaxGridY = 65535;
+static inline dim3 rows_grid(uint32_t w, uint32_t h) { return dim3((w + 255)/256, h < kMaxGridY ? h : kMaxGridY, (h + kMaxGridY - 1)/kMaxGridY); }
+
 template <bool ALONG_X, bool SRGB_IN, bool SRGB_OUT, bool SRC_U8>
 __global__ void __launch_bounds__(256) resize_pass_kernel(const uint8_t* __restrict__ src, size_t src_pitch, uint32_t src_h,
     float4* __restrict__ dst, size_t dst_pitch4, uint32_t dw, uint32_t dh,
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(256) resize_pass_kernel(const uint8_t* __restr
         lut[256 + threadIdx.x] = static_cast<double>(f);
         __syncthreads();
     }
-    const uint32_t x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
+    const uint32_t x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.z*kMaxGridY + blockIdx.y;
     if (x >= dw || y >= dh) return;
     const uint32_t u = ALONG_X ? x : dh - 1u - y;
     const int2 sp = span[u];
@@ -194,7 +198,7 @@ template <bool ALONG_X, bool SRC_U8>
 void launch_pass(bool srgb_in, bool srgb_out, const uint8_t* src, size_t sp, uint32_t sh, float4* dst, size_t dp4,
     uint32_t dw, uint32_t dh, const DeviceTable& t, cudaStream_t s)
 {
-    const dim3 grid((dw + 255)/256, dh), block(256);
+    const dim3 grid = rows_grid(dw, dh), block(256);
     if (srgb_in && srgb_out)
         resize_pass_kernel<ALONG_X, true, true, SRC_U8><<<grid, block, 0, s>>>(src, sp, sh, dst, dp4, dw, dh, t.span, t.weight, t.window);
     else if (srgb_in)
@@ -217,7 +221,7 @@ void launch_pass(bool src_u8, bool srgb_in, bool srgb_out, const uint8_t* src, s
 __global__ void __launch_bounds__(256) widen_u8_kernel(const uint8_t* __restrict__ src, size_t src_pitch, float4* __restrict__ dst,
     size_t dst_pitch4, uint32_t w, uint32_t h)
 {
-    const uint32_t x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.y;
+    const uint32_t x = blockIdx.x*blockDim.x + threadIdx.x, y = blockIdx.z*kMaxGridY + blockIdx.y;
     if (x < w && y < h) {
         const uchar4 v = *reinterpret_cast<const uchar4*>(src + y*src_pitch + static_cast<size_t>(x)*4u);
         dst[y*dst_pitch4 + x] = make_float4(__fdiv_rn(static_cast<float>(v.x), 255.0f), __fdiv_rn(static_cast<float>(v.y), 255.0f),
@@ -249,7 +253,7 @@ int resize_device(const uint8_t* src, size_t src_pitch, bool src_u8, uint32_t sw
     const size_t dp4 = dst_pitch/16;
     if (sw == dw && sh == dh) {                     // Image.cpp:1330-1334: a plain copy
         if (src_u8) {
-            widen_u8_kernel<<<dim3((dw + 255)/256, dh), 256, 0, stream>>>(src, src_pitch, d4, dp4, dw, dh);
+            widen_u8_kernel<<<rows_grid(dw, dh), 256, 0, stream>>>(src, src_pitch, d4, dp4, dw, dh);
             return cudaGetLastError() == cudaSuccess ? 1 : CFX_ERR_CUDA;
         }
         if (cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, static_cast<size_t>(dw)*16u, dh, cudaMemcpyDeviceToDevice,

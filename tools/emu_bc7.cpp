@@ -52,12 +52,13 @@ extern "C" int emu_bc7_encode(const uint8_t* rgba, uint32_t w, uint32_t h, uint8
                 uint32_t mode = cand_mode(desc), variant = cand_variant(desc);
                 uint32_t m1 = mode == 6 ? 0u : kBc7Part2[shape];
                 Fit fit;
-                fit_candidate(pxf, px, mode, m1, variant, cand_rounds(desc), chmask, fit);
+                if (cand_is_dual(desc)) fit_dual(px, mode, cand_rotation(desc), variant & 1u, cand_rounds(desc), chmask, fit);
+                else fit_candidate(pxf, px, mode, m1, variant, cand_rounds(desc), chmask, fit);
                 uint32_t total = fit.err[0] + fit.err[1];
                 uint32_t key = (std::min(total, 0x03FFFFFFu) << 5) | sub;
                 if (key < best_key) {
                     best_key = key;
-                    best_blk = pack_block(mode, shape, m1, fit);
+                    best_blk = cand_is_dual(desc) ? pack_dual(mode, cand_rotation(desc), variant & 1u, fit) : pack_block(mode, shape, m1, fit);
                     bm = mode; bs = shape; bv = variant; be = total;
                 }
             }
