@@ -12,8 +12,8 @@
 //            subset's texels from their best-fit line (3 power iterations);
 //   phase 2  the G-1 best shapes are picked with butterfly min-reductions over
 //            (score | shape) keys;
-//   phase 3  lane 0 takes mode 6, the other lanes take mode 1 / mode 3 (opaque) or mode 7 /
-//            mode 5 (alpha) on the ranked shapes; each lane runs the whole fit for ITS candidate:
+//   phase 3  lane 0 takes mode 6, the other lanes take mode 1 / mode 3 (opaque) or mode 7 (alpha) on the ranked
+//            shapes, or modes 5 / 4 (two index sets, channel rotation: fit_dual); each lane runs the whole fit for ITS candidate:
 //            PCA endpoints -> p-bit aware quantisation -> index assignment with exact integer
 //            palette error (packed 2x16 IMAD interpolation, vabsdiff4 + dp4a SSE) -> two rounds
 //            of least-squares endpoint refinement, each subset keeping its own best;
@@ -46,27 +46,30 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v)
 
 // Candidate sets per lanes-per-block G (index 0: G=4, 1: G=8, 2: G=16, 3: G=32) and per opaque / alpha.
 #define C CFX_BC7_CAND
+// Modes 4 / 5 entries: C(mode, rotation, index mode, rounds).  Blocks with alpha give one lane to mode 5 at Normal and
+// three to modes 5 / 4 at High (an alpha channel that runs independently of the colour is what they are for); the
+// widest set also tries the rotations, on opaque blocks too (one colour channel on the scalar index set).
 __device__ __constant__ uint16_t kBc7Cand[4][2][32] = {
     {{C(6,0,0,2), C(1,0,0,2), C(3,0,0,2), C(1,1,0,2)},
-     {C(6,0,0,2), C(7,0,0,2), C(7,1,0,2), C(7,2,0,2)}},
+     {C(6,0,0,2), C(7,0,0,2), C(7,1,0,2), C(5,0,0,2)}},
     {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2)},
-     {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(7,1,1,2), C(7,2,0,2), C(7,2,1,2)}},
+     {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(5,0,0,2), C(4,0,0,2), C(4,0,1,2)}},
     {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2),
-      C(1,1,1,2), C(3,1,1,2), C(1,2,0,2), C(3,2,0,2), C(1,2,1,2), C(3,2,1,2), C(1,3,0,2), C(3,3,0,2)},
+      C(1,1,1,2), C(3,1,1,2), C(1,2,0,2), C(3,2,0,2), C(1,2,1,2), C(3,2,1,2), C(5,1,0,2), C(5,3,0,2)},
      {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(7,1,1,2), C(7,2,0,2), C(7,2,1,2),
-      C(7,3,0,2), C(7,3,1,2), C(7,4,0,2), C(7,4,1,2), C(7,5,0,2), C(7,5,1,2), C(7,6,0,2), C(7,6,1,2)}},
+      C(7,3,0,2), C(7,3,1,2), C(5,0,0,2), C(4,0,0,2), C(4,0,1,2), C(5,1,0,2), C(5,2,0,2), C(5,3,0,2)}},
     {{C(6,0,0,2), C(6,0,1,2), C(1,0,0,2), C(3,0,0,2), C(1,0,1,2), C(3,0,1,2), C(1,1,0,2), C(3,1,0,2),
       C(1,1,1,2), C(3,1,1,2), C(1,2,0,2), C(3,2,0,2), C(1,2,1,2), C(3,2,1,2), C(1,3,0,2), C(3,3,0,2),
       C(1,3,1,2), C(3,3,1,2), C(1,4,0,2), C(3,4,0,2), C(1,4,1,2), C(3,4,1,2), C(1,5,0,2), C(3,5,0,2),
-      C(1,5,1,2), C(3,5,1,2), C(1,6,0,2), C(3,6,0,2), C(1,6,1,2), C(3,6,1,2), C(1,7,0,2), C(3,7,0,2)},
+      C(1,5,1,2), C(3,5,1,2), C(1,6,0,2), C(3,6,0,2), C(5,1,0,2), C(5,2,0,2), C(5,3,0,2), C(4,1,1,2)},
      {C(6,0,0,2), C(6,0,1,2), C(7,0,0,2), C(7,0,1,2), C(7,1,0,2), C(7,1,1,2), C(7,2,0,2), C(7,2,1,2),
       C(7,3,0,2), C(7,3,1,2), C(7,4,0,2), C(7,4,1,2), C(7,5,0,2), C(7,5,1,2), C(7,6,0,2), C(7,6,1,2),
-      C(7,7,0,2), C(7,7,1,2), C(7,8,0,2), C(7,8,1,2), C(7,9,0,2), C(7,9,1,2), C(7,10,0,2), C(7,10,1,2),
-      C(7,11,0,2), C(7,11,1,2), C(7,12,0,2), C(7,12,1,2), C(7,13,0,2), C(7,13,1,2), C(7,14,0,2), C(7,14,1,2)}},
+      C(7,7,0,2), C(7,7,1,2), C(7,8,0,2), C(7,8,1,2), C(7,9,0,2), C(7,9,1,2), C(5,0,0,2), C(4,0,0,2),
+      C(4,0,1,2), C(5,1,0,2), C(5,2,0,2), C(5,3,0,2), C(4,1,0,2), C(4,1,1,2), C(4,2,0,2), C(4,3,0,2)}},
 };
 #undef C
 // number of ranked shapes each set needs (opaque, alpha)
-__device__ __constant__ uint8_t kBc7Ranks[4][2] = {{2, 3}, {2, 3}, {4, 7}, {8, 15}};
+__device__ __constant__ uint8_t kBc7Ranks[4][2] = {{2, 2}, {2, 2}, {3, 4}, {7, 10}};
 
 #ifndef CFX_BC7_MIN_CTAS
 #define CFX_BC7_MIN_CTAS 2      // 3 (80 registers, 236 B of spills) was measured: 3.08 vs 3.16 GTexel/s
@@ -154,17 +157,19 @@ __global__ void __launch_bounds__(kThreads, CFX_BC7_MIN_CTAS) bc7_kernel(const E
                 if (my_rank == r) my_shape = win & 63u;
             }
             const uint32_t mode = cand_mode(desc);
-            const uint32_t m1 = mode == 6 ? 0u : kBc7Part2[my_shape];
+            const uint32_t m1 = (mode == 6 || cand_is_dual(desc)) ? 0u : kBc7Part2[my_shape];
 
             Fit fit;
-            fit_candidate(bxf, bx, mode, m1, cand_variant(desc), cand_rounds(desc), chmask, fit);
+            const bool dual = cand_is_dual(desc);           // modes 4 / 5: their own fit (divergent lanes of the group)
+            if (dual) fit_dual(bx, mode, cand_rotation(desc), cand_variant(desc) & 1u, cand_rounds(desc), chmask, fit);
+            else fit_candidate(bxf, bx, mode, m1, cand_variant(desc), cand_rounds(desc), chmask, fit);
 
             // ---- phase 4: winner
             uint32_t total = fit.err[0] + fit.err[1];
             uint32_t key = (min(total, 0x03FFFFFFu) << 5) | sub;
             uint32_t win = group_min<G>(key);
             if (key == win && b0 + grp < n) {
-                uint4 blk = pack_block(mode, my_shape, m1, fit);
+                uint4 blk = dual ? pack_dual(mode, cand_rotation(desc), cand_variant(desc) & 1u, fit) : pack_block(mode, my_shape, m1, fit);
                 *reinterpret_cast<uint4*>(s_out + b*4) = blk;
             }
         }

@@ -73,6 +73,58 @@ def test_bc7_alpha_psnr_vs_oracle(cfx, oracle):
     assert 10*np.log10(1/mse(d_gpu)) >= 10*np.log10(1/mse(d_ref)) - PSNR_TOLERANCE_DB
 
 
+def _bc7_modes(blocks):
+    """BC7 mode of every block: position of the lowest set bit of byte 0."""
+    b0 = blocks.reshape(-1, 16)[:, 0].astype(np.uint32)
+    return np.array([(int(v) & -int(v)).bit_length() - 1 if v else 8 for v in b0])
+
+
+@pytest.mark.parametrize("quality", ["Normal", "High", "Highest"])
+def test_bc7_alpha_uncorrelated_with_colour(cfx, oracle, quality):
+    # alpha that runs independently of the colour is what modes 4 / 5 (separate index sets, channel rotation) exist
+    # for (bc7enc's alpha path uses mode 5, lib/bc7enc_rdo/bc7enc.cpp:2039-2137): RGB and RGBA error vs the reference,
+    # and the dual-index modes must actually be chosen
+    n = 128
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:n, 0:n].astype(np.float32)
+    img = np.empty((n, n, 4), np.float32)
+    img[..., 0] = (xx % 16)/15.0
+    img[..., 1] = 0.2 + 0.6*(xx % 16)/15.0
+    img[..., 2] = 1.0 - 0.8*(xx % 16)/15.0
+    img[..., :3] += 0.02*rng.standard_normal((n, n, 3)).astype(np.float32)
+    img[..., 3] = 0.1 + 0.8*(yy % 8)/7.0 + 0.02*rng.standard_normal((n, n)).astype(np.float32)
+    img = np.clip(img, 0, 1)
+    src = oracle.to_rgba8(img)
+    img = src.astype(np.float32)/np.float32(255)
+    got = cfx.encode(src, "BC7", quality=quality)
+    ref = oracle.encode(img, "BC7", quality=quality)
+    d_gpu, d_ref = oracle.decode(got, "BC7", n, n), oracle.decode(ref, "BC7", n, n)
+    for nch in (3, 4):
+        mse = lambda d: float(np.mean((d[..., :nch].astype(np.float64) - img[..., :nch])**2))
+        assert 10*np.log10(1/mse(d_gpu)) >= 10*np.log10(1/mse(d_ref)) - PSNR_TOLERANCE_DB, "%d channels" % nch
+    modes = _bc7_modes(got)
+    assert np.isin(modes, [4, 5]).mean() > 0.2, "modes chosen: %s" % np.bincount(modes, minlength=8)
+
+
+def test_bc7_rotation_on_opaque_blocks(cfx, oracle):
+    # Highest: blue ramps down the rows while red and green ramp along the columns -- no single line through RGB, but a
+    # line through (R, G) plus a scalar B: mode 5 with a rotation
+    n = 64
+    yy, xx = np.mgrid[0:n, 0:n].astype(np.float32)
+    img = np.ones((n, n, 4), np.float32)
+    img[..., 0] = (xx % 16)/15.0
+    img[..., 1] = 1.0 - (xx % 16)/15.0*0.7
+    img[..., 2] = (yy % 8)/7.0
+    src = oracle.to_rgba8(img)
+    img = src.astype(np.float32)/np.float32(255)
+    got = cfx.encode(src, "BC7", quality="Highest")
+    ref = oracle.encode(img, "BC7", quality="Highest")
+    p_gpu, p_ref = oracle.psnr_rgb(img, oracle.decode(got, "BC7", n, n)), oracle.psnr_rgb(img, oracle.decode(ref, "BC7", n, n))
+    assert p_gpu >= p_ref - PSNR_TOLERANCE_DB
+    modes = _bc7_modes(got)
+    assert np.isin(modes, [4, 5]).mean() > 0.1, "modes chosen: %s" % np.bincount(modes, minlength=8)
+
+
 def test_bc7_solid_blocks_exact(cfx, oracle):
     # flat colours must decode to within the reference's error (usually exactly)
     img = np.zeros((16, 16, 4), np.float32)
