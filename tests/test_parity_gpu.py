@@ -524,6 +524,33 @@ def test_srgb_surfaces_hold_psnr_parity(cfx, oracle, fmt):
     assert p_gpu >= p_ref - PSNR_TOLERANCE_DB, "%s sRGB: gpu %.3f dB < reference %.3f dB - 0.1" % (fmt, p_gpu, p_ref)
 
 
+# ---- Texture::Alpha: None makes AstcConverter swizzle alpha to 1 (AstcConverter.cpp:145); Standard / PreMultiplied
+# turn on astcenc's alpha weighting (:164-170) and libsquish's in the BC1A path (S3tcConverter.cpp:236); the other
+# converters ignore it.  Same descriptor on both sides, RGB and RGBA error against the reference's output ----
+@pytest.mark.parametrize("alpha", ["None", "PreMultiplied", "Encoded"])
+@pytest.mark.parametrize("fmt", ["ASTC_6x6", "ASTC_4x4", "BC7", "BC3", "ETC2_R8G8B8A8"])
+def test_alpha_types_vs_oracle(cfx, oracle, fmt, alpha):
+    n = 96
+    img = oracle.gen_image("noise+grad", n, n, seed=77)
+    yy, xx = np.mgrid[0:n, 0:n].astype(np.float32)
+    img[..., 3] = np.clip(0.15 + 0.8*xx/n + 0.1*np.sin(yy*0.5), 0, 1)
+    if alpha == "PreMultiplied":
+        img[..., :3] *= img[..., 3:4]
+    src = oracle.to_rgba8(img)
+    img = src.astype(np.float32)/np.float32(255)
+    ref = oracle.encode(img, fmt, alpha=alpha)
+    got = cfx.encode(src, fmt, alpha=alpha)
+    d_gpu, d_ref = oracle.decode(got, fmt, n, n), oracle.decode(ref, fmt, n, n)
+    psnr = lambda d, nch: 10*np.log10(1/max(float(np.mean((d[..., :nch].astype(np.float64) - img[..., :nch])**2)), 1e-12))
+    assert psnr(d_gpu, 3) >= psnr(d_ref, 3) - PSNR_TOLERANCE_DB, "%s Alpha::%s RGB: gpu %.3f < reference %.3f - 0.1" % (
+        fmt, alpha, psnr(d_gpu, 3), psnr(d_ref, 3))
+    if alpha == "None" and fmt.startswith("ASTC"):
+        assert np.all(d_ref[..., 3] == 1.0) and np.all(d_gpu[..., 3] == 1.0)      # alpha is swizzled to one
+    else:
+        assert psnr(d_gpu, 4) >= psnr(d_ref, 4) - PSNR_TOLERANCE_DB, "%s Alpha::%s RGBA: gpu %.3f < reference %.3f - 0.1" % (
+            fmt, alpha, psnr(d_gpu, 4), psnr(d_ref, 4))
+
+
 # ---- ASTC on screenshot-like content (synth.ui_image: gray gradients, text-like strokes, soft discs): needs luminance
 # end points (with 1, 2 and 3 subsets), a quantisation estimate that knows bimodal weights and a partition ranking
 # that follows the clustering on gray content, and (large footprints) flat subsets that do not disturb a shared
