@@ -842,7 +842,7 @@ struct SlotView {           // what pack_block needs from a slot
 } // namespace
 
 template <int NT, int KS, int W, int CTAS, bool LOCK, bool HDR>
-__global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const EncodeParams p, const Tab3 tb, uint32_t n_exact, uint32_t refine)
+__global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant__ EncodeParams p, const __grid_constant__ Tab3 tb, uint32_t n_exact, uint32_t refine)
 {
     constexpr int K = (NT*8 + 31)/32;            // texels per lane
     constexpr int MW = (NT*8 + 63)/64;           // words per texel mask
