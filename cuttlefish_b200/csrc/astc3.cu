@@ -58,7 +58,7 @@ struct Slot3 {
 // points on every subset (CEM 6: e1 = (r, g, b), e0 = e1*s/256 -- a line through black, which is what shaded surfaces of
 // one material are; 4 / 8 / 12 stored values instead of 6 / 12 / 18 buy a finer weight grid or finer weights, and are
 // what makes multi-subset encodings affordable at all on the larger footprints: astcenc picks CEM 6 for 20-50 % of the
-// blocks of photographic content and on at least one subset of most of its two-subset blocks). Opaque blocks only.
+// blocks of photographic content and on at least one subset of most of its two-subset blocks). In blocks with alpha every subset keeps a direct alpha pair (CEM 10), which is also what makes three subsets possible there (18 values).
 // They are VIRTUAL: partition, ideal weights (A operand row), line lengths and the measured quantisation loss are those
 // of the RGB sibling slot -- where a subset suits a line through black its free line nearly is one -- and only the
 // error floor (distance from the through-black lines, Warp3T::scale_eline), the colour level class and the end point
@@ -100,6 +100,8 @@ struct Warp3T {
     float scale_eline[7];                   // error floor of the virtual slots 14..20
     uint32_t scale_valid[7];
     uint32_t mix_mask[2];                   // slots 19, 20: bit p = subset p takes the cheaper end point mode
+    uint32_t mix_kind[2];                   // ... in a block with alpha: 0 = the cheap subset is opaque (CEM 8 + 12), 1 = it goes
+                                            // through black with its own alpha pair (CEM 10 + 12)
     int sc[3], best_sc[3];                  // base + scale subsets: the quantised scale
     uint8_t part[4][TP];                    // subset of every texel for slots 1..4
     __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
@@ -240,7 +242,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     auto sub_mode = [&](uint32_t p) -> uint32_t {
         if (s < static_cast<uint32_t>(kScaleSlot)) return 0u;
         if (s < static_cast<uint32_t>(kMixSlot)) return 1u;
-        return (mixm >> p) & 1u ? (has_alpha ? 2u : 1u) : 0u;
+        return (mixm >> p) & 1u ? (has_alpha && ws.mix_kind[s - kMixSlot] == 0u ? 2u : 1u) : 0u;
     };
     const uint32_t T = c.tab.texels;
     const Slot3& slot = ws.slots[slot_base(s)];
@@ -1112,8 +1114,9 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 if (ws.slots[sl].valid) {
                     subset_line(moms[lane], -1, 6, lines[5 + lane]);
                     // for the base + scale siblings (slots 14..17): the subset's distance from its line through black
-                    lines[5 + lane].pad[0] = has_alpha ? 0.0f :
-                        origin_residual(moms[lane], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z));
+                    // (blocks with alpha, CEM 10: what the RGB part loses by going through black, on top of the RGBA line's floor)
+                    const float org = origin_residual(moms[lane], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z));
+                    lines[5 + lane].pad[0] = has_alpha ? fmaxf(org - rgb_free_residual(moms[lane]), 0.0f) : org;
                 }
             }
             __syncwarp();
@@ -1122,7 +1125,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 float e = 0.0f;
                 for (uint32_t q = 0; q < cnt; ++q) e += lines[first + q].pad[0];
                 ws.scale_eline[1 + lane] = e*ifx*ifx;
-                ws.scale_valid[1 + lane] = ws.slots[1 + lane].valid && !has_alpha && !HDR && !(tb.flags & 4u) ? 1u : 0u;
+                ws.scale_valid[1 + lane] = ws.slots[1 + lane].valid && !HDR && !(tb.flags & 4u) ? 1u : 0u;
             } else if (lane == 4) {
                 // one subset: CEM 6, or CEM 10 in a block with alpha (the alpha pair stays direct: what the RGB part
                 // loses by going through black comes on top of the RGBA line's floor)
@@ -1141,8 +1144,16 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                     e = (mask == 1u ? lines[first].pad[0] + lines[first + 1].resid : lines[first].resid + lines[first + 1].pad[0])*ifx*ifx;
                 } else {
                     mask = opq2[k];                                     // subsets whose alpha is 255 throughout
-                    if (mask != 1u && mask != 2u) ok = 0u;
-                    e = (lines[first].resid + lines[first + 1].resid)*ifx*ifx;
+                    uint32_t kind = 0u;
+                    e = lines[first].resid + lines[first + 1].resid;
+                    if (mask == 0u) {
+                        // no opaque subset: the one that loses least by it goes through black (CEM 10 + 12)
+                        kind = 1u;
+                        mask = lines[first].pad[0] <= lines[first + 1].pad[0] ? 1u : 2u;
+                        e += mask == 1u ? lines[first].pad[0] : lines[first + 1].pad[0];
+                    } else if (mask == 3u) ok = 0u;
+                    e *= ifx*ifx;
+                    ws.mix_kind[k] = kind;
                 }
                 ws.scale_eline[5 + k] = e; ws.scale_valid[5 + k] = ok; ws.mix_mask[k] = mask;
             }
@@ -1488,7 +1499,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 const uint32_t drow = slot_row(s);
                 const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
-                const float base = kLine*(virt ? ws.scale_eline[s - kScaleSlot] + (s == static_cast<uint32_t>(kScaleSlot) && has_alpha ? slot.e_line : 0.0f) : slot.e_line);
+                const float base = kLine*(virt ? ws.scale_eline[s - kScaleSlot] + (s < static_cast<uint32_t>(kMixSlot) && has_alpha ? slot.e_line : 0.0f) : slot.e_line);
                 const float l2sum = slot.len2[0] + slot.len2b;
                 // per-grid terms of this slot (lane = grid)
                 __syncwarp();
@@ -1646,7 +1657,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
             const bool virt = slot_is_scale(bs);
             for (uint32_t q = 0; q < bslot.pc; ++q) {
                 const bool cheap = bs >= static_cast<uint32_t>(kMixSlot) ? ((ws.mix_mask[bs - kMixSlot] >> q) & 1u) != 0u : virt;
-                cems[q] = static_cast<uint8_t>(!cheap ? (has_alpha ? 12 : 8) : (bs >= static_cast<uint32_t>(kMixSlot) && has_alpha ? 8 : (has_alpha ? 10 : 6)));
+                cems[q] = static_cast<uint8_t>(!cheap ? (has_alpha ? 12 : 8) : (bs >= static_cast<uint32_t>(kMixSlot) && has_alpha && ws.mix_kind[bs - kMixSlot] == 0u ? 8 : (has_alpha ? 10 : 6)));
             }
             *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr,
                 virt ? cems : nullptr, ws.best_sc);

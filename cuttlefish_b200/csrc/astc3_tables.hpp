@@ -211,7 +211,7 @@ inline Astc3Tab build_tables3(Built& b)
                 const int extra = type >= 10 ? 3*pc - 4 : 0;
                 const int avail = 128 - static_cast<int>(m.wbits) - (pc == 1 ? 17 : 29) - (type == 3 ? 2 : 0) - extra;
                 uint8_t cl = 0xFF;
-                const bool usable = !((type == 10 && alpha) || (type == 11 && !alpha) || ((type == 8 || type == 9) && alpha));
+                const bool usable = !((type == 10 && alpha) || (type == 11 && !alpha));     // types 8, 9 with alpha: CEM 10 on every subset
                 if (usable && (m.dual != 0) == (type == 3) && n_ints <= 18 && avail >= 0) cl = blob[t.off_clevel + (n_ints >> 1)*128 + avail];
                 blob[t3.off_modecl + (static_cast<size_t>(alpha)*kSlotTypes3 + type)*t3.n_modes + mi] = cl;
             }
