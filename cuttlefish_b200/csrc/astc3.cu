@@ -324,8 +324,10 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
             }
             if (lum) {
                 // gray end points: the least-squares solution is the mean of the per-channel ones (same system matrix)
+                // (blocks with alpha, CEM 4: the alpha pair keeps its own solution)
                 const uint32_t b4 = which*4u;
-                val = (__shfl_sync(0xFFu, val, b4) + __shfl_sync(0xFFu, val, b4 + 1u) + __shfl_sync(0xFFu, val, b4 + 2u))*(1.0f/3.0f);
+                const float gray = (__shfl_sync(0xFFu, val, b4) + __shfl_sync(0xFFu, val, b4 + 1u) + __shfl_sync(0xFFu, val, b4 + 2u))*(1.0f/3.0f);
+                if (ch < 3u) val = gray;
             }
             int q = 255;
             const uint32_t smode = sub_mode(p);
@@ -975,7 +977,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
         if (active && lane < kSlots3) {
             Slot3& sl = ws.slots[lane];
             sl.pc = 1; sl.seed = 0; sl.dual_ch = (lane >= 5 && lane < 9) ? static_cast<int32_t>(lane - 5) : -1;
-            sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !has_alpha && !(tb.flags & 1u) && !HDR) ? 1u : 0u;
+            sl.valid = lane == 0 || (lane >= 5 && lane < 9 && lane - 5 < nch) || (lane == kLumSlot && !(tb.flags & 1u) && !HDR) ? 1u : 0u;
             // (slots 10..13 are validated in setup 8, after the partitionings are known)
         }
         // ---- setup 3: cluster the texels into 2 and 3 groups, match the partition seeds against the clusters
@@ -1330,8 +1332,96 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 }
                 if (lane == 0) { sl.len2b = 0.0f; sl.e_line = chroma*ifx*ifx; }
             }
-        } else if (active && lane < 4) {
-            ws.slots[10 + lane].valid = 0;
+        } else if (active) {
+            // ---- setup 8a: blocks with alpha: LUMINANCE + ALPHA end points (CEM 4: L0 L1 A0 A1) for one subset (slot 9) and
+            //      the two-subset partitionings (slots 10, 11; the three-subset rows belong to the alpha dual-plane slot
+            //      here).  Gray content under a varying alpha -- smoke, glyphs, shadows -- is what astcenc spends this mode
+            //      on.  The weights run along the principal axis of the subset in the plane (sqrt(3) L, A): a unit of
+            //      luminance error is paid on three channels.
+            if (lane < 4) ws.slots[10 + lane].valid = 0;
+            float chroma = 0.0f;
+            for (uint32_t i = lane; i < T; i += 32) {
+                const int4 x = ws.v[i];
+                const float l = static_cast<float>(x.x + x.y + x.z)*(1.0f/3.0f);
+                const float d0 = static_cast<float>(x.x) - l, d1 = static_cast<float>(x.y) - l, d2 = static_cast<float>(x.z) - l;
+                chroma += d0*d0 + d1*d1 + d2*d2;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) chroma += __shfl_xor_sync(0xFFFFFFFFu, chroma, o);
+            // lane j < 5: axis of set j (0 = the whole block, 1..4 = the subsets of slots 1, 2) from its RGBA moments
+            float* ax = &ws.g[0][0];            // [set][8]: mean u, mean a, cos, sin, residual      (phase-2 scratch, free here)
+            __syncwarp();
+            if (lane < 5) {
+                const Mom& mo = moms[lane == 0 ? 10u : lane - 1u];
+                const float n = fmaxf(mo.n, 1.0f), in = 1.0f/n;
+                const float su = mo.s[0] + mo.s[1] + mo.s[2], sa = mo.s[3];
+                const float suu = mo.p[0] + mo.p[4] + mo.p[7] + 2.0f*(mo.p[1] + mo.p[2] + mo.p[5]) - su*su*in;
+                const float sua = mo.p[3] + mo.p[6] + mo.p[8] - su*sa*in;
+                const float saa = mo.p[9] - sa*sa*in;
+                const float xx = suu*(1.0f/3.0f), xa = sua*0.57735027f;
+                const float half_d = 0.5f*(xx - saa), r = sqrtf(half_d*half_d + xa*xa);
+                // eigenvector of the larger eigenvalue of [[xx, xa], [xa, saa]]
+                float cx = half_d + r, cy = xa;
+                if (cx*cx + cy*cy < 1e-12f*(xx + saa)*(xx + saa) + 1e-20f) { cx = xa; cy = r - half_d; }
+                float nn = cx*cx + cy*cy;
+                if (nn > 0.0f) { nn = rsqrtf(nn); cx *= nn; cy *= nn; } else { cx = 1.0f; cy = 0.0f; }
+                ax[lane*8u + 0u] = su*in + static_cast<float>(ctr.x + ctr.y + ctr.z);
+                ax[lane*8u + 1u] = sa*in + static_cast<float>(ctr.w);
+                ax[lane*8u + 2u] = cx; ax[lane*8u + 3u] = cy;
+                ax[lane*8u + 4u] = fmaxf(0.5f*(xx + saa) - r, 0.0f);
+            }
+            __syncwarp();
+            for (uint32_t job = 0; job < 3; ++job) {           // slot 9, 10, 11
+                const uint32_t sidx = job == 0 ? static_cast<uint32_t>(kLumSlot) : 9u + job;
+                Slot3& sl = ws.slots[sidx];
+                const bool ok = (job == 0 ? sl.valid != 0 : ws.slots[job].valid != 0) && !(tb.flags & 1u) && !HDR;
+                if (job > 0 && lane == 0) { sl.valid = ok ? 1u : 0u; sl.pc = 2u; sl.seed = ws.slots[job].seed; sl.dual_ch = -1; }
+                if (!ok) continue;
+                const uint32_t row = job == 0 ? static_cast<uint32_t>(kLumRow) : slot_row(sidx);
+                const uint32_t set0 = job == 0 ? 0u : 1u + 2u*(job - 1u);
+                float tl[K]; uint32_t ql[K];
+                float mn[2] = {3.0e38f, 3.0e38f}, mx[2] = {-3.0e38f, -3.0e38f};
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const uint32_t i = lane + 32u*r;
+                    tl[r] = 0.0f; ql[r] = 0u;
+                    if (i < T) {
+                        const uint32_t q = job == 0 ? 0u : ws.part[job - 1u][i];
+                        const float* a5 = ax + (set0 + q)*8u;
+                        const int4 x = ws.v[i];
+                        tl[r] = (static_cast<float>(x.x + x.y + x.z) - a5[0])*0.57735027f*a5[2] + (static_cast<float>(x.w) - a5[1])*a5[3];
+                        ql[r] = q;
+                        if (q == 0u) { mn[0] = fminf(mn[0], tl[r]); mx[0] = fmaxf(mx[0], tl[r]); }
+                        else { mn[1] = fminf(mn[1], tl[r]); mx[1] = fmaxf(mx[1], tl[r]); }
+                    }
+                }
+                float eline = chroma;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (job == 0 && q == 1) continue;
+                    float lo = warp_min_f(mn[q]), hi = warp_max_f(mx[q]);
+                    if (!(hi > lo)) { lo = 0.0f; hi = 0.0f; }
+                    const float range = hi - lo, irg = range > 1e-6f*FX ? 1.0f/range : 0.0f;
+#pragma unroll
+                    for (int r = 0; r < K; ++r) if (ql[r] == static_cast<uint32_t>(q) && lane + 32u*r < T) tl[r] = (tl[r] - lo)*irg;
+                    const float* a5 = ax + (set0 + static_cast<uint32_t>(q))*8u;
+                    eline += a5[4];
+                    if (lane == 0) {
+                        // back from (sqrt(3) L, A) to luminance and alpha, 0..255
+                        const float l0 = (a5[0] + lo*a5[2]*1.7320508f)*(ifx/3.0f), l1 = (a5[0] + hi*a5[2]*1.7320508f)*(ifx/3.0f);
+                        const float a0 = (a5[1] + lo*a5[3])*ifx, a1 = (a5[1] + hi*a5[3])*ifx;
+                        sl.e0[q] = make_float4(l0, l0, l0, a0); sl.e1[q] = make_float4(l1, l1, l1, a1);
+                        sl.len2[q] = range*range*ifx*ifx;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const uint32_t i = lane + 32u*r;
+                    if (i < T) ws.ta[row][i] = __float2half_rn(fminf(fmaxf(tl[r], 0.0f), 1.0f));
+                }
+                if (lane == 0) { sl.len2b = 0.0f; sl.e_line = eline*ifx*ifx; }
+            }
+            __syncwarp();
         }
         PHASE_SYNC();
 

@@ -671,7 +671,7 @@ CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo
     uint32_t cem[4];
     bool same = true;
     for (uint32_t s = 0; s < pc; ++s) {
-        cem[s] = cems ? cems[s] : (hdr_vals ? (has_alpha ? 14u : 11u) : (lum ? 0u : (has_alpha ? 12u : 8u)));
+        cem[s] = cems ? cems[s] : (hdr_vals ? (has_alpha ? 14u : 11u) : (lum ? (has_alpha ? 4u : 0u) : (has_alpha ? 12u : 8u)));
         same = same && cem[s] == cem[0];
     }
     b.put(0, m.mode_bits, 11);
@@ -710,6 +710,7 @@ CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo
         if (hdr_vals) val = static_cast<uint32_t>(hdr_vals[s*8u + k]) & 0xFFu;
         else if (cem[s] == 6u || cem[s] == 10u)       // R G B s (a0 a1)
             val = k < 3u ? (e.ep[s][1] >> (8u*k)) & 0xFFu : (k == 3u ? static_cast<uint32_t>(scales[s]) & 0xFFu : e.ep[s][k & 1u] >> 24);
+        else if (cem[s] == 4u) val = k < 2u ? e.ep[s][k] & 0xFFu : e.ep[s][k & 1u] >> 24;      // L0 L1 A0 A1
         else val = (e.ep[s][k & 1u] >> (8u*(k >> 1))) & 0xFFu;       // r0 r1 g0 g1 b0 b1 a0 a1 (luminance: the r pair)
         const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + val);
         return tab_u8(c, c.tab.off_cq_enc + cl*256u + rank);
