@@ -103,6 +103,7 @@ struct Warp3T {
     uint32_t mix_kind[2];                   // ... in a block with alpha: 0 = the cheap subset is opaque (CEM 8 + 12), 1 = it goes
                                             // through black with its own alpha pair (CEM 10 + 12)
     int sc[3], best_sc[3];                  // base + scale subsets: the quantised scale
+    uint32_t contr, best_contr;             // bit p: subset p's direct end points are stored blue-contracted (values in epv)
     uint8_t part[4][TP];                    // subset of every texel for slots 1..4
     __half ta[kRows3][TS];                  // A operand: ideal weights per slot plane (rows 0..8 first planes,
                                             // 9..12 second planes of slots 5..8, 13..15 luminance slots 9..11;
@@ -121,7 +122,8 @@ struct Warp3T {
     int ep[24];                             // quantised end points of the candidate: [subset][e0 rgba, e1 rgba]
     int best_ep[24];                        // (HDR: 12-bit values as end point mode 11 decodes them)
     float epf[24];                          // HDR: least-squares end points before mode-11 packing, 8-bit-like units
-    int epv[24], best_epv[24];              // HDR: per subset the six packed mode-11 values + two LDR alpha end points
+    int epv[24], best_epv[24];              // HDR: per subset the six packed mode-11 values + two LDR alpha end points;
+                                            // LDR: the stored values v0..v7 of a blue-contracted subset
     uint32_t hkey[28];                      // HDR: (error, sub-mode) keys of the 9 packing candidates per subset
     uint8_t su[2*TP];                       // candidate grid weights (unquantised values 0..64), bit-stream order
     uint8_t sk[2*TP];                       // ... and their rank in the quantisation level's value table
@@ -234,7 +236,7 @@ __device__ __forceinline__ void reweight_decimation(const Ctx& c, WS& ws, uint32
 // quantise = false: ws.su / ws.sk already hold the candidate's quantised weights (realign_weights).
 template <int K, bool hdr, typename WS>
 __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
-    uint32_t lane, bool quantise = true)
+    uint32_t lane, bool quantise = true, bool solve = true)
 {
     const bool lum = slot_is_lum(s);
     // per-subset end point mode: 0 = direct (RGB / RGBA), 1 = base + scale (+ alpha pair), 2 = RGB only in a block with alpha
@@ -254,8 +256,16 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
     // quantise (lane = grid weight)
     for (uint32_t pl = 0; quantise && pl < planes; ++pl)
         for (uint32_t j = lane; j < nw; j += 32) {
-            const int k = min(max(__float2int_rn(ws.g[pl][j]*nm1), 0), static_cast<int>(kWqN[L]) - 1);
-            ws.su[j*planes + pl] = static_cast<uint8_t>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(k)));
+            // nearest level by VALUE: the trit and quint levels are not evenly spaced (24 levels: 0 2 5 8 11 13 ...)
+            const float target = ws.g[pl][j]*64.0f;
+            int k = min(max(__float2int_rn(ws.g[pl][j]*nm1), 0), static_cast<int>(kWqN[L]) - 1);
+            int u = static_cast<int>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(k)));
+            if (kWqN[L] > 2u) {
+                const int kn = static_cast<float>(u) > target ? max(k - 1, 0) : min(k + 1, static_cast<int>(kWqN[L]) - 1);
+                const int un = static_cast<int>(tab_u8(c, c.tab.off_wq_val + L*32u + static_cast<uint32_t>(kn)));
+                if (fabsf(static_cast<float>(un) - target) < fabsf(static_cast<float>(u) - target)) { k = kn; u = un; }
+            }
+            ws.su[j*planes + pl] = static_cast<uint8_t>(u);
             ws.sk[j*planes + pl] = static_cast<uint8_t>(k);
         }
     __syncwarp();
@@ -281,8 +291,9 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
             w[k][pl] = static_cast<int>(acc >> 4);
         }
     }
-    // least-squares end points per subset from integer moment sums
-    for (uint32_t p = 0; p < pc; ++p) {
+    // least-squares end points per subset from integer moment sums (solve == false: ws.ep / ws.epv / ws.sc / ws.contr are
+    // kept as the caller left them and only the error is measured)
+    for (uint32_t p = 0; solve && p < pc; ++p) {
         int A = 0, B = 0, C = 0, P0 = 0, P1 = 0, P2 = 0, P3 = 0, Q0 = 0, Q1 = 0, Q2 = 0, Q3 = 0;
         int A2 = 0, B2 = 0, C2 = 0, PD = 0, QD = 0;
 #pragma unroll
@@ -362,6 +373,42 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
                 const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(iv));
                 q = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + rank));
             }
+            if (!hdr && !lum && smode != 1u) {
+                // BLUE CONTRACTION (ASTC spec, LDR RGB(A) direct; astcenc try_quantize_rgb_blue_contract,
+                // lib/astc-encoder/Source/astcenc_color_quantize.cpp): the end points may be stored as (2r - b, 2g - b, b)
+                // in swapped order -- the decoder recognises it by the order of the two sums and takes r = (r' + b) >> 1 --
+                // which halves the quantisation step of red and green wherever 2r - b and 2g - b stay inside 0..255,
+                // i.e. on near-gray colours.  Taken when it fits, keeps the order strict and reproduces the least-squares
+                // end points better than the direct values do.
+                const float bval = __shfl_sync(0xFFu, val, which*4u + 2u);
+                const float cval = ch < 2u ? 2.0f*val - bval : val;
+                const bool fits = ch >= 2u || (cval >= -0.5f && cval <= 255.5f);
+                int cq = q;
+                if (ch < 3u) {
+                    const int civ = min(max(__float2int_rn(cval), 0), 255);
+                    cq = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(civ))));
+                }
+                const int cqb = __shfl_sync(0xFFu, cq, which*4u + 2u);
+                const int dec = ch < 2u ? (cq + cqb) >> 1 : cq;
+                float dd = 0.0f, dq = 0.0f;
+                int ssum = 0;
+                if (ch < 3u) {
+                    dd = (static_cast<float>(dec) - val)*(static_cast<float>(dec) - val);
+                    dq = (static_cast<float>(q) - val)*(static_cast<float>(q) - val);
+                    ssum = cq;
+                }
+                ssum += __shfl_xor_sync(0xFFu, ssum, 1); ssum += __shfl_xor_sync(0xFFu, ssum, 2);      // per end point
+                const int osum = __shfl_xor_sync(0xFFu, ssum, 4);
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) { dd += __shfl_xor_sync(0xFFu, dd, o); dq += __shfl_xor_sync(0xFFu, dq, o); }
+                const bool order_ok = which ? ssum > osum : osum > ssum;       // stored sum of end point 1 strictly above end point 0's
+                const bool use = __ballot_sync(0xFFu, !fits) == 0u && order_ok && dd < dq;
+                if (use) {
+                    q = (ch < 3u || (has_alpha && smode != 2u)) ? dec : q;
+                    ws.epv[p*8u + 2u*ch + (which ? 0u : 1u)] = cq;      // end point 1 first: v0 v2 v4 (v6), then end point 0
+                }
+                if (lane == 0) ws.contr = use ? (ws.contr | (1u << p)) : (ws.contr & ~(1u << p));
+            } else if (lane == 0 && !hdr) ws.contr &= ~(1u << p);
             if (!hdr) ws.ep[p*8u + lane] = q;
         }
     }
@@ -405,7 +452,7 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
         __syncwarp();
     }
     // keep sum(e1.rgb) >= sum(e0.rgb) (otherwise the decoder would blue-contract): swap the end points
-    if (lane < pc && !lum && !hdr && sub_mode(lane) != 1u) {
+    if (lane < pc && !lum && !hdr && sub_mode(lane) != 1u && !((ws.contr >> lane) & 1u)) {
         int* e = ws.ep + lane*8u;
         if (e[4] + e[5] + e[6] < e[0] + e[1] + e[2]) {
 #pragma unroll
@@ -551,6 +598,7 @@ __device__ __forceinline__ void keep_best3(WS& ws, uint32_t nw, uint32_t planes,
     if (lane < pc*8u) ws.best_ep[lane] = ws.ep[lane];
     if (lane < pc*8u) ws.best_epv[lane] = ws.epv[lane];
     if (lane < 3u) ws.best_sc[lane] = ws.sc[lane];
+    if (lane == 0u) ws.best_contr = ws.contr;
     __syncwarp();
 }
 
@@ -1716,11 +1764,25 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
             if (realign) realign_weights(ctx, ws, s, m, has_alpha, lane);
             else decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
             if (!realign && NT > 8 && ws.slots[slot_base(s)].pc > 1 && m.nw < T && !(tb.flags & 32u)) reweight_decimation(ctx, ws, s, m.grid, m.nw, static_cast<uint32_t>(row0), lane);
-            const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane, !realign);
+            if (realign) {
+                // the realigned weights were chosen against the winner's end points: they are measured with exactly those
+                // (each accepted move lowered the exact error, so this can only improve on the winner); the next
+                // continuous round re-solves the end points for them
+                const uint32_t rpc = ws.slots[slot_base(s)].pc;
+                if (lane < rpc*8u) { ws.ep[lane] = ws.best_ep[lane]; ws.epv[lane] = ws.best_epv[lane]; }
+                if (lane < 3u) ws.sc[lane] = ws.best_sc[lane];
+                if (lane == 0u) ws.contr = ws.best_contr;
+                __syncwarp();
+            }
+            const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane, !realign, !realign);
 #ifdef CFX_ASTC3_TUNE
             if ((tb.flags & 256u) && lane == 0 && !refining)
                 printf("CAND blk %u slot %u mode %u nw %u level %u cl %u est %.1f exact %.1f\n", blk, s, code & 0xFFFFu, static_cast<uint32_t>(m.nw),
                     kWqN[m.level], cl, dbg_est, err/fx2);
+#endif
+#ifdef CFX_ASTC3_TUNE
+            if ((tb.flags & 256u) && lane == 0 && refining)
+                printf("REFINE blk %u round %u realign %d err %.1f best %.1f contr %u\n", blk, rounds, realign ? 1 : 0, err/fx2, best_err/fx2, ws.contr);
 #endif
             if (err < best_err) {
                 best_err = err; best_code = code; best_cl = cl; fails = 0;
@@ -1750,7 +1812,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 cems[q] = static_cast<uint8_t>(!cheap ? (has_alpha ? 12 : 8) : (bs >= static_cast<uint32_t>(kMixSlot) && has_alpha && ws.mix_kind[bs - kMixSlot] == 0u ? 8 : (has_alpha ? 10 : 6)));
             }
             *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr,
-                virt ? cems : nullptr, ws.best_sc);
+                virt ? cems : nullptr, ws.best_sc, HDR ? 0u : ws.best_contr, ws.best_epv);
         }
     }
 }

@@ -659,7 +659,8 @@ CFX_HD uint64_t bitrev64(uint64_t v)
 template <typename SlotT>
 CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo& m, const Enc& e, bool has_alpha,
     const uint8_t* u_scr, uint32_t lane, bool linear = false, const uint8_t* k_lin = nullptr, bool lum = false,
-    const int* hdr_vals = nullptr, const uint8_t* cems = nullptr, const int* scales = nullptr)
+    const int* hdr_vals = nullptr, const uint8_t* cems = nullptr, const int* scales = nullptr, uint32_t contracted = 0,
+    const int* raw_vals = nullptr)
 {
     Bits128 b; b.lo = b.hi = 0;
     const uint32_t pc = slot.pc;
@@ -668,6 +669,8 @@ CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo
     // followed by the two alpha end points.
     // cems (per subset, optional): 6 = RGB base + scale (R G B s), 10 = base + scale + alpha pair, 8, 12; the scale of
     // subset s is scales[s]. Subsets may differ (classes of adjacent numbers only: 6 with 8, 8 with 12).
+    // contracted (bit per subset) + raw_vals: the subset's RGB(A) direct end points are stored blue-contracted; raw_vals holds
+    // its values v0..v7 (stride 8) as they go into the block.
     uint32_t cem[4];
     bool same = true;
     for (uint32_t s = 0; s < pc; ++s) {
@@ -708,6 +711,7 @@ CFX_HD_NOINLINE uint4 pack_block(const Ctx& c, const SlotT& slot, const ModeInfo
         const uint32_t k = i - start[s];
         uint32_t val;
         if (hdr_vals) val = static_cast<uint32_t>(hdr_vals[s*8u + k]) & 0xFFu;
+        else if ((contracted >> s) & 1u) val = static_cast<uint32_t>(raw_vals[s*8u + k]) & 0xFFu;      // blue-contracted CEM 8 / 12: v0..v7 as stored
         else if (cem[s] == 6u || cem[s] == 10u)       // R G B s (a0 a1)
             val = k < 3u ? (e.ep[s][1] >> (8u*k)) & 0xFFu : (k == 3u ? static_cast<uint32_t>(scales[s]) & 0xFFu : e.ep[s][k & 1u] >> 24);
         else if (cem[s] == 4u) val = k < 2u ? e.ep[s][k] & 0xFFu : e.ep[s][k & 1u] >> 24;      // L0 L1 A0 A1

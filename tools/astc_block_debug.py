@@ -30,6 +30,11 @@ if os.environ.get("CFX_DEBUG_CHILD"):
 variants = [("free", {}), ("slot13", {"CFX_ASTC3_SLOT": "13"}), ("slot13 L6 nw36", {"CFX_ASTC3_SLOT": "13", "CFX_ASTC3_LEVEL": "6", "CFX_ASTC3_NW": "36"}),
             ("slot0", {"CFX_ASTC3_SLOT": "0"}), ("slot0 nw30", {"CFX_ASTC3_SLOT": "0", "CFX_ASTC3_NW": "30"}),
             ("slot14", {"CFX_ASTC3_SLOT": "14"}), ("slot1", {"CFX_ASTC3_SLOT": "1"}), ("free Highest", {"CFX_DEBUG_QUALITY": "Highest"})]
+if os.environ.get("CFX_DEBUG_VARIANTS"):      # "label:K=V,K=V;label2:..."
+    variants = []
+    for item in os.environ["CFX_DEBUG_VARIANTS"].split(";"):
+        label, _, kv = item.partition(":")
+        variants.append((label, dict(x.split("=") for x in kv.split(",") if x)))
 for label, env in variants:
     e = dict(os.environ, CFX_DEBUG_CHILD="1", **env)
     r = subprocess.run([sys.executable, __file__] + sys.argv[1:], env=e, capture_output=True, text=True)
