@@ -383,29 +383,34 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
                 const float bval = __shfl_sync(0xFFu, val, which*4u + 2u);
                 const float cval = ch < 2u ? 2.0f*val - bval : val;
                 const bool fits = ch >= 2u || (cval >= -0.5f && cval <= 255.5f);
-                int cq = q;
-                if (ch < 3u) {
-                    const int civ = min(max(__float2int_rn(cval), 0), 255);
-                    cq = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(civ))));
-                }
-                const int cqb = __shfl_sync(0xFFu, cq, which*4u + 2u);
-                const int dec = ch < 2u ? (cq + cqb) >> 1 : cq;
-                float dd = 0.0f, dq = 0.0f;
-                int ssum = 0;
-                if (ch < 3u) {
-                    dd = (static_cast<float>(dec) - val)*(static_cast<float>(dec) - val);
-                    dq = (static_cast<float>(q) - val)*(static_cast<float>(q) - val);
-                    ssum = cq;
-                }
-                ssum += __shfl_xor_sync(0xFFu, ssum, 1); ssum += __shfl_xor_sync(0xFFu, ssum, 2);      // per end point
-                const int osum = __shfl_xor_sync(0xFFu, ssum, 4);
+                bool use = false;
+                if (__ballot_sync(0xFFu, !fits) == 0u) {          // (uniform over the eight lanes; colourful blocks stop here)
+                    int cq = q;
+                    if (ch < 3u) {
+                        const int civ = min(max(__float2int_rn(cval), 0), 255);
+                        cq = static_cast<int>(tab_u8(c, c.tab.off_cq_val + cl*256u + tab_u8(c, c.tab.off_cq_near + cl*256u + static_cast<uint32_t>(civ))));
+                    }
+                    const int cqb = __shfl_sync(0xFFu, cq, which*4u + 2u);
+                    const int dec = ch < 2u ? (cq + cqb) >> 1 : cq;
+                    float dd = 0.0f, dq = 0.0f;
+                    int ssum = 0;
+                    if (ch < 3u) {
+                        dd = (static_cast<float>(dec) - val)*(static_cast<float>(dec) - val);
+                        dq = (static_cast<float>(q) - val)*(static_cast<float>(q) - val);
+                        ssum = cq;
+                    }
+                    ssum += __shfl_xor_sync(0xFFu, ssum, 1); ssum += __shfl_xor_sync(0xFFu, ssum, 2);      // per end point
+                    const int osum = __shfl_xor_sync(0xFFu, ssum, 4);
+                    // one reduction for both errors: their difference decides
+                    float diff = dd - dq;
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) { dd += __shfl_xor_sync(0xFFu, dd, o); dq += __shfl_xor_sync(0xFFu, dq, o); }
-                const bool order_ok = which ? ssum > osum : osum > ssum;       // stored sum of end point 1 strictly above end point 0's
-                const bool use = __ballot_sync(0xFFu, !fits) == 0u && order_ok && dd < dq;
-                if (use) {
-                    q = (ch < 3u || (has_alpha && smode != 2u)) ? dec : q;
-                    ws.epv[p*8u + 2u*ch + (which ? 0u : 1u)] = cq;      // end point 1 first: v0 v2 v4 (v6), then end point 0
+                    for (int o = 1; o < 8; o <<= 1) diff += __shfl_xor_sync(0xFFu, diff, o);
+                    const bool order_ok = which ? ssum > osum : osum > ssum;   // stored sum of end point 1 strictly above end point 0's
+                    use = order_ok && diff < 0.0f;
+                    if (use) {
+                        q = (ch < 3u || (has_alpha && smode != 2u)) ? dec : q;
+                        ws.epv[p*8u + 2u*ch + (which ? 0u : 1u)] = cq;      // end point 1 first: v0 v2 v4 (v6), then end point 0
+                    }
                 }
                 if (lane == 0) ws.contr = use ? (ws.contr | (1u << p)) : (ws.contr & ~(1u << p));
             } else if (lane == 0 && !hdr) ws.contr &= ~(1u << p);

@@ -30,22 +30,20 @@ def _cases():
 
 
 # Cases that MISS the 0.1 dB bar today, with the distance measured on the B200 (RGB / RGBA dB, `tools/real_report.py`,
-# round 2): the bar stays where north_star puts it and these are expected failures, not loosened tolerances.  All of
-# them are ASTC: our hypothesis set has no base + offset end points (CEM 9 / 13), no luminance + alpha (CEM 4) and,
-# in blocks with alpha, no base + scale subsets next to direct ones (CEM 10 + 12) -- astcenc uses these on 20-40 % of
-# the blocks of these images -- and at High / Highest the reference searches 4 partitions.
+# end of round 2): the bar stays where north_star puts it and these are expected failures, not loosened tolerances.
+# All of them are ASTC.  Blocks that end up in the same configuration as astcenc's are within 1.5 % of its error; what
+# is left is configuration choice: astcenc's base + offset end points (CEM 9 / 13) and luminance next to base + scale
+# (CEM 0 + 6) are not in our hypothesis set (the near-gray crop rgb09), its alpha weighting trades RGB for alpha on
+# rgba02 (three cases sit at the bar: -0.10 / -0.12 dB RGBA), and at High / Highest it searches 4 partitions and
+# refines more candidates.
 KNOWN_GAPS = {
-    ("rgb09", "ASTC_10x8", "Normal"): "-0.16", ("rgba01", "ASTC_10x8", "Normal"): "-0.19/-0.23",
-    ("rgb05", "ASTC_4x4", "Normal"): "-0.23", ("rgb09", "ASTC_4x4", "Normal"): "-0.34",
-    ("rgba00", "ASTC_4x4", "Normal"): "-0.27/-0.46", ("rgba01", "ASTC_4x4", "Normal"): "+0.05/-0.15",
-    ("rgba02", "ASTC_4x4", "Normal"): "-0.16/-0.22",
-    ("rgb00", "ASTC_6x6", "High"): "-0.31", ("rgb07", "ASTC_6x6", "High"): "-0.12", ("rgba01", "ASTC_6x6", "High"): "-0.16/-0.26",
-    ("rgb00", "ASTC_6x6", "Highest"): "-0.47", ("rgb07", "ASTC_6x6", "Highest"): "-0.34",
-    ("rgba01", "ASTC_6x6", "Highest"): "-0.20/-0.31", ("rgba01", "ASTC_6x6", "Low"): "-0.05/-0.15",
-    ("rgb09", "ASTC_6x6", "Normal"): "-0.23", ("rgba00", "ASTC_6x6", "Normal"): "-0.24/-0.42",
-    ("rgba01", "ASTC_6x6", "Normal"): "-0.13/-0.22", ("rgba02", "ASTC_6x6", "Normal"): "-0.10/-0.14",
-    ("rgb09", "ASTC_8x8", "Normal"): "-0.17", ("rgba00", "ASTC_8x8", "Normal"): "-0.11/-0.30",
-    ("rgba01", "ASTC_8x8", "Normal"): "-0.11/-0.17",
+    ("rgb09", "ASTC_4x4", "Normal"): "-0.18", ("rgb09", "ASTC_6x6", "Normal"): "-0.23",
+    ("rgb09", "ASTC_8x8", "Normal"): "-0.19", ("rgb09", "ASTC_10x8", "Normal"): "-0.16",
+    ("rgb05", "ASTC_4x4", "Normal"): "-0.12",
+    ("rgba02", "ASTC_4x4", "Normal"): "-0.02/-0.10", ("rgba02", "ASTC_6x6", "Normal"): "-0.07/-0.12",
+    ("rgba02", "ASTC_8x8", "Normal"): "-0.08/-0.10",
+    ("rgb00", "ASTC_6x6", "High"): "-0.29", ("rgb07", "ASTC_6x6", "High"): "-0.10",
+    ("rgb00", "ASTC_6x6", "Highest"): "-0.47", ("rgb07", "ASTC_6x6", "Highest"): "-0.32",
 }
 
 CASES = [pytest.param(*c, marks=pytest.mark.xfail(strict=False, reason="measured %s dB vs astcenc" % KNOWN_GAPS[c])) if c in KNOWN_GAPS else c
