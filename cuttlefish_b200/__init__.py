@@ -9,5 +9,5 @@ plus array-level helpers `encode()` (host buffers) and `encode_device()` (torch 
 All encoding happens in hand-written sm_100a kernels inside lib/libcfx.so; there is no CPU path.
 """
 from .api import (ALPHA, FILTERS, FORMATS, QUALITY, SRC_FORMATS, TYPES, CfxError, ColorMask, Texture,  # noqa: F401
-                  block_info, encode, encode_batch, encode_device, encode_mip_chain, encode_mip_chain_device, mip_levels, resize, encoded_size, format_is_exact, format_supported, init,
+                  block_info, container_header, encode_mip_chain_to_file, encode, encode_batch, encode_device, encode_mip_chain, encode_mip_chain_device, mip_levels, resize, encoded_size, format_is_exact, format_supported, init,
                   init_devices, set_devices, ipc_export, ipc_open, ipc_close, device_count, shutdown, kernel_launches, last_error, shard_block_rows, version)

@@ -42,6 +42,10 @@ SYMBOLS = [
     ("cfx_encode_mip_chain_device", ctypes.c_int, [ctypes.POINTER(SurfaceDesc), ctypes.c_void_p, ctypes.c_uint32,
                                                    ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p),
                                                    ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]),
+    ("cfx_dds_header", ctypes.c_size_t, [ctypes.POINTER(SurfaceDesc), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]),
+    ("cfx_ktx_header", ctypes.c_size_t, [ctypes.POINTER(SurfaceDesc), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]),
+    ("cfx_encode_mip_chain_to_file", ctypes.c_int, [ctypes.POINTER(SurfaceDesc), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                                    ctypes.c_uint32, ctypes.c_char_p]),
     ("cfx_ipc_export", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     ("cfx_ipc_open", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     ("cfx_ipc_close", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

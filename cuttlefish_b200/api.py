@@ -2,6 +2,7 @@
 encode calls, block-row sharding for multi-GPU runs, and a Texture class mirroring the part of
 cuttlefish::Texture that the convert path touches."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -332,6 +333,34 @@ def encode_mip_chain(img, fmt, filter="CatmullRom", levels=None, return_images=F
     mips = (ctypes.c_void_p * n)(*([None] + [m.ctypes.data for m in images[1:]])) if return_images else None
     _check(load().cfx_encode_mip_chain(ctypes.byref(d), img.ctypes.data, _enum(FILTERS, filter), n, dst, sizes, mips))
     return (outs, images) if return_images else outs
+
+
+CONTAINERS = {"DDS": 0, "KTX": 1}
+
+
+def container_header(container, fmt, width, height, mip_levels=1, array_size=0, **kw):
+    """The DDS (148 bytes) / KTX (64 bytes) file header the reference's Texture::save() writes for such a texture
+    (lib/src/SaveDds.cpp:565-683, lib/src/SaveKtx.cpp:1189-1214); None when the reference has no such file."""
+    d = make_desc(fmt, width, height, "RGBA32F", 16 * width, **kw)
+    buf = np.zeros(148, np.uint8)
+    fn = load().cfx_dds_header if _enum(CONTAINERS, container) == 0 else load().cfx_ktx_header
+    n = int(fn(ctypes.byref(d), int(mip_levels), int(array_size), buf.ctypes.data))
+    return buf[:n].copy() if n else None
+
+
+def encode_mip_chain_to_file(img, fmt, path, container=None, filter="CatmullRom", levels=None, **kw):
+    """generateMipmaps(filter, levels) + convert() + save(path): one call, the blocks land in a mapping of the file."""
+    img = np.asarray(img)
+    if img.dtype != np.uint8:
+        img = img.astype(np.float32, copy=False)
+    img = np.ascontiguousarray(img)
+    h, w, _ = img.shape
+    src_format, texel = _src_format_of(img.dtype)
+    if container is None:
+        container = "KTX" if str(path).lower().endswith(".ktx") else "DDS"
+    d = make_desc(fmt, w, h, src_format, w * texel, **kw)
+    _check(load().cfx_encode_mip_chain_to_file(ctypes.byref(d), img.ctypes.data, _enum(FILTERS, filter), int(levels or 0),
+                                              _enum(CONTAINERS, container), os.fsencode(path)))
 
 
 class Texture:

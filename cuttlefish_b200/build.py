@@ -24,6 +24,7 @@ NVCC_FLAGS = [
 UNITS = [
     ("cfx.cu", [], None),
     ("host_stage.cpp", [], None),
+    ("containers.cpp", [], None),
     ("resize.cu", ["-fmad=false", "-Xcompiler", "-ffp-contract=off"], None),
     ("bc4_bc5.cu", [], None),
     ("bc7.cu", [], "CFX_HAVE_BC7"),

@@ -173,6 +173,23 @@ int cfx_encode_mip_chain(const cfx_surface_desc* level0, const void* src, uint32
 int cfx_encode_mip_chain_device(const cfx_surface_desc* level0, const void* d_src, uint32_t filter, uint32_t levels,
                                 void* const* d_dsts, const size_t* dst_sizes, void* cuda_stream);
 
+/* Containers around the packed blocks, 2D textures and 2D arrays.
+ * cfx_dds_header / cfx_ktx_header write the file header the reference's writers produce for a texture of level0's format /
+ * type / colour space / alpha type and size with `mip_levels` levels (array_size 0 = not an array) -- saveDds(),
+ * lib/src/SaveDds.cpp:565-683 (magic + DDS_HEADER + DX10 header = 148 bytes), saveKtx(), lib/src/SaveKtx.cpp:1189-1214
+ * (64 bytes; every level is then a 32-bit imageSize followed by its blocks) -- and return its size, or 0 when the
+ * reference has no such file: DDS knows no ETC / EAC / ASTC format (isValidForDds), and Texture::convert() refuses an sRGB
+ * image for formats without an sRGB variant (BC4, BC5, BC6H, ETC1, EAC, ASTC HDR). `out` must hold 148 bytes.
+ * cfx_encode_mip_chain_to_file = generateMipmaps(filter, levels) + convert() + save(): the header is written into a
+ * mapping of the output file and every level's blocks are delivered straight into that mapping at their final offset
+ * (levels = 0: the full chain). Returns CFX_OK, CFX_ERR_UNSUPPORTED (no such container format / no GPU encoder) or the
+ * encode's error; the file is removed on failure. */
+enum { CFX_CONTAINER_DDS = 0, CFX_CONTAINER_KTX = 1 };
+size_t cfx_dds_header(const cfx_surface_desc* level0, uint32_t mip_levels, uint32_t array_size, void* out);
+size_t cfx_ktx_header(const cfx_surface_desc* level0, uint32_t mip_levels, uint32_t array_size, void* out);
+int cfx_encode_mip_chain_to_file(const cfx_surface_desc* level0, const void* src, uint32_t filter, uint32_t levels,
+                                 uint32_t container, const char* path);
+
 /* Cross-process peer memory, for hosts that run one PROCESS per GPU (bench.py under torchrun): the process
  * that is to own the assembled output exports the device buffer, the others open it and pass the mapped pointer plus
  * their slab's byte offset as d_dst of cfx_encode_device(). The encode kernel then stores its packed blocks straight
