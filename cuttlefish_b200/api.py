@@ -419,6 +419,10 @@ class Texture:
             return False
         if not format_supported(format, type):
             return False
+        # an sRGB texture converts only to formats with an sRGB variant (Texture::hasNativeSRGB, lib/src/Texture.cpp:421-468,
+        # checked at :1542): a container header exists exactly for those
+        if self.srgb and container_header("KTX", format, 4, 4, type=type, srgb=True) is None:
+            return False
         mask = colorMask if colorMask is not None else ColorMask()
         # one batch for every surface of the texture (the mip/depth loop of Converter::convert)
         flat = [image for level in self._images for image in level]

@@ -36,3 +36,11 @@ def test_file_sizes_follow_from_the_headers():
         levels = cfx.mip_levels(40, 24) if mips == "1" else 1
         blocks = sum(cfx.encoded_size(fmt, max(1, 40 >> i), max(1, 24 >> i)) for i in range(levels))
         assert int(z[k][0]) == (148 + blocks if ext == "dds" else 64 + 4 * levels + blocks), k
+
+
+def test_srgb_texture_refuses_formats_without_srgb_variant():
+    # Texture::convert(), lib/src/Texture.cpp:1542: sRGB textures convert only to formats with a native sRGB variant
+    tex = cfx.Texture(16, 16, srgb=True)
+    tex.setImage(np.zeros((16, 16, 4), np.float32))
+    for fmt, typ in (("BC4", "UNorm"), ("BC5", "SNorm"), ("BC6H", "UFloat"), ("ETC1", "UNorm"), ("EAC_R11", "UNorm"), ("ASTC_6x6", "UFloat")):
+        assert tex.convert(fmt, typ) is False and not tex.converted()
