@@ -896,6 +896,126 @@ struct SlotView {           // what pack_block needs from a slot
     int32_t dual_ch;
 };
 
+// ---- warp-cooperative block packing ----------------------------------------------------------------
+// The same 128 bits astc_core.cuh's pack_block() writes, but lane = value: every BISE element's position in the stream is
+// closed form (a trit group of five takes 5 b + 8 bits, a quint group of three 3 b + 7), so each lane places its own
+// element -- and its share of the group's trit / quint word -- into a private 128-bit word and four redux.or's merge
+// them.  The serial version was 2600 single-lane instructions per block behind a chain of dependent table loads.
+__device__ __forceinline__ void put128(uint64_t& lo, uint64_t& hi, uint32_t pos, uint32_t v, uint32_t n)
+{
+    if (n == 0) return;
+    const uint64_t vv = static_cast<uint64_t>(v) & ((1ull << n) - 1ull);
+    if (pos < 64) {
+        lo |= vv << pos;
+        if (pos + n > 64) hi |= vv >> (64u - pos);
+    } else hi |= vv << (pos - 64u);
+}
+
+// Element i of a BISE sequence of n values starting at bit pos0; E[] holds the encoded values (low `bits` bits = the
+// plain part, the rest = the trit / quint).
+__device__ __forceinline__ void ise_piece(const Ctx& c, const uint8_t* E, uint32_t i, uint32_t n, uint32_t pos0, uint32_t bits,
+    bool trits, bool quints, uint64_t& lo, uint64_t& hi)
+{
+    const uint32_t mask = (1u << bits) - 1u;
+    if (trits) {
+        const uint32_t g = i/5u, k = i - 5u*g;
+        uint32_t v[5];
+#pragma unroll
+        for (uint32_t q = 0; q < 5; ++q) v[q] = 5u*g + q < n ? E[5u*g + q] : 0u;
+        const uint32_t tw = tab_u8(c, c.tab.off_trit_enc + (v[0] >> bits) + 3u*(v[1] >> bits) + 9u*(v[2] >> bits) + 27u*(v[3] >> bits) +
+            81u*(v[4] >> bits));
+        const uint32_t sh = (0x75420u >> (4u*k)) & 15u, nb = (0x12122u >> (4u*k)) & 15u;
+        const uint32_t pos = pos0 + g*(5u*bits + 8u) + k*bits + sh;
+        put128(lo, hi, pos, E[i] & mask, bits);
+        put128(lo, hi, pos + bits, tw >> sh, nb);
+    } else if (quints) {
+        const uint32_t g = i/3u, k = i - 3u*g;
+        uint32_t v[3];
+#pragma unroll
+        for (uint32_t q = 0; q < 3; ++q) v[q] = 3u*g + q < n ? E[3u*g + q] : 0u;
+        const uint32_t qw = tab_u8(c, c.tab.off_quint_enc + (v[0] >> bits) + 5u*(v[1] >> bits) + 25u*(v[2] >> bits));
+        const uint32_t sh = (0x530u >> (4u*k)) & 15u, nb = (0x223u >> (4u*k)) & 15u;
+        const uint32_t pos = pos0 + g*(3u*bits + 7u) + k*bits + sh;
+        put128(lo, hi, pos, E[i] & mask, bits);
+        put128(lo, hi, pos + bits, qw >> sh, nb);
+    } else put128(lo, hi, pos0 + i*bits, E[i], bits);
+}
+
+// ep: [subset][e0 rgba, e1 rgba] (8 ints per subset); sk: the weights' ranks in bit-stream order; ecol / ewgt: scratch
+// for the encoded colour values (>= 18 bytes) and weights (>= nw*planes bytes).  The other arguments as pack_block().
+__device__ __forceinline__ uint4 pack_block_warp(const Ctx& c, const SlotView& slot, const ModeInfo& m, uint32_t cl, const int* ep,
+    bool has_alpha, const uint8_t* sk, bool lum, const int* hdr_vals, const uint8_t* cems, const int* scales, uint32_t contracted,
+    const int* raw_vals, uint8_t* ecol, uint8_t* ewgt, uint32_t lane)
+{
+    uint64_t lo = 0, hi = 0;
+    const uint32_t pc = slot.pc;
+    uint32_t cem[4];
+    bool same = true;
+    for (uint32_t s = 0; s < pc; ++s) {
+        cem[s] = cems ? cems[s] : (hdr_vals ? (has_alpha ? 14u : 11u) : (lum ? (has_alpha ? 4u : 0u) : (has_alpha ? 12u : 8u)));
+        same = same && cem[s] == cem[0];
+    }
+    // header (the same bits in every lane: or is idempotent)
+    put128(lo, hi, 0, m.mode_bits, 11);
+    put128(lo, hi, 11, pc - 1, 2);
+    uint32_t pos;
+    uint32_t below = 128u - m.wbits;                  // first free bit below the weights
+    if (pc == 1) { put128(lo, hi, 13, cem[0], 4); pos = 17; }
+    else {
+        put128(lo, hi, 13, slot.seed, 10);
+        if (same) put128(lo, hi, 25, cem[0], 4);
+        else {
+            uint32_t low = 4;
+            for (uint32_t s = 0; s < pc; ++s) low = low < (cem[s] >> 2) ? low : (cem[s] >> 2);
+            if (low == 3) low = 2;
+            uint32_t enc = low + 1u, bp = 2;
+            for (uint32_t s = 0; s < pc; ++s) enc |= ((cem[s] >> 2) - low) << bp++;
+            for (uint32_t s = 0; s < pc; ++s) { enc |= (cem[s] & 3u) << bp; bp += 2; }
+            const uint32_t hi_bits = 3u*pc - 4u;
+            put128(lo, hi, 23, enc & 0x3Fu, 6);
+            below -= hi_bits;
+            put128(lo, hi, below, enc >> 6, hi_bits);
+        }
+        pos = 29;
+    }
+    uint32_t start[5];                                  // first value of every subset
+    start[0] = 0;
+    for (uint32_t s = 0; s < pc; ++s) start[s + 1] = start[s] + ((cem[s] >> 2) + 1u)*2u;
+    const uint32_t ncol = start[pc];
+    const uint32_t planes = slot.dual_ch >= 0 ? 2u : 1u;
+    if (planes == 2) put128(lo, hi, below - 2u, static_cast<uint32_t>(slot.dual_ch), 2);
+    const uint32_t L = m.level, nwt = m.nw*planes;
+    // encoded values: lane = colour value, lane (+32) = weight
+    if (lane < ncol) {
+        uint32_t s = 0;
+        while (s + 1u < pc && lane >= start[s + 1]) ++s;
+        const uint32_t k = lane - start[s];
+        const int* e = ep + s*8u;
+        uint32_t val;
+        if (hdr_vals) val = static_cast<uint32_t>(hdr_vals[s*8u + k]) & 0xFFu;
+        else if ((contracted >> s) & 1u) val = static_cast<uint32_t>(raw_vals[s*8u + k]) & 0xFFu;
+        else if (cem[s] == 6u || cem[s] == 10u) val = static_cast<uint32_t>(k < 3u ? e[4u + k] : (k == 3u ? scales[s] : e[4u*(k & 1u) + 3u])) & 0xFFu;
+        else if (cem[s] == 4u) val = static_cast<uint32_t>(k < 2u ? e[4u*k] : e[4u*(k & 1u) + 3u]) & 0xFFu;
+        else val = static_cast<uint32_t>(e[4u*(k & 1u) + (k >> 1)]) & 0xFFu;
+        const uint32_t rank = tab_u8(c, c.tab.off_cq_near + cl*256u + val);
+        ecol[lane] = static_cast<uint8_t>(tab_u8(c, c.tab.off_cq_enc + cl*256u + rank));
+    }
+    for (uint32_t j = lane; j < nwt; j += 32) ewgt[j] = static_cast<uint8_t>(tab_u8(c, c.tab.off_wq_enc + L*32u + sk[j]));
+    __syncwarp();
+    if (lane < ncol) ise_piece(c, ecol, lane, ncol, pos, kCqBits[cl], kCqTrits[cl] != 0, kCqQuints[cl] != 0, lo, hi);
+    // weights: BISE from bit 0 of a scratch word, mirrored into the top of the block
+    uint64_t wlo = 0, whi = 0;
+    for (uint32_t j = lane; j < nwt; j += 32) ise_piece(c, ewgt, j, nwt, 0, kWqBits[L], kWqTrits[L] != 0, kWqQuints[L] != 0, wlo, whi);
+    hi |= (static_cast<uint64_t>(__brev(static_cast<uint32_t>(wlo))) << 32) | __brev(static_cast<uint32_t>(wlo >> 32));
+    lo |= (static_cast<uint64_t>(__brev(static_cast<uint32_t>(whi))) << 32) | __brev(static_cast<uint32_t>(whi >> 32));
+    uint4 out;
+    out.x = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(lo));
+    out.y = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(lo >> 32));
+    out.z = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(hi));
+    out.w = __reduce_or_sync(0xFFFFFFFFu, static_cast<uint32_t>(hi >> 32));
+    return out;
+}
+
 } // namespace
 
 template <int NT, int KS, int W, int CTAS, bool LOCK, bool HDR>
@@ -1527,6 +1647,18 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
             for (uint32_t k = 0; k < tb.t3.n_dec; ++k) {
                 const uint32_t g = __ldg(dec + k);
                 float acc0 = 0.0f, acc1 = 0.0f;
+                // the M fragments of this grid (second GEMM below): the dependent loads g -> fragment offset -> first tile
+                // are issued here, ahead of the R tiles' MMAs
+                const bool with_pen = !(tb.flags & 16u);
+                uint32_t ntw = 0;
+                const uint2* mf = nullptr;
+                uint2 mcur[KS];
+                if (with_pen) {
+                    ntw = (tab_u8(ctx, ctx.tab.off_grids + g*4u + 2u) + 7u) >> 3;          // GridInfo::nw in tiles of 8
+                    mf = reinterpret_cast<const uint2*>(ctx.blob + __ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_mfrag_idx) + g)) + lane;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) mcur[ks] = __ldg(mf + ks*32u);
+                }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     frag += KS*32;
@@ -1544,15 +1676,19 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 // + what clamping the least-squares grid weights into [0, 1] costs (see astc3_tables.hpp): M t on the
                 // tensor cores, overshoot^2 weighted by the weight's column energy
                 float pen0 = 0.0f, pen1 = 0.0f;
-                if (!(tb.flags & 16u)) {
-                    const uint32_t gnw = tab_u8(ctx, ctx.tab.off_grids + g*4u + 2u);          // GridInfo::nw
-                    const uint2* mf = reinterpret_cast<const uint2*>(ctx.blob + __ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_mfrag_idx) + g)) + lane;
-                    const uint32_t ntw = (gnw + 7u) >> 3;
+                if (with_pen) {
+                    // (one-tile prefetch, as for R above)
 #pragma unroll 1
                     for (uint32_t nt = 0; nt < ntw; ++nt) {
+                        uint2 mnext[KS];
+                        const uint32_t ntn = nt + 1u < ntw ? nt + 1u : nt;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) mnext[ks] = __ldg(mf + (ntn*KS + ks)*32u);
                         float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], __ldg(mf + (nt*KS + ks)*32u));
+                        for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], mcur[ks]);
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) mcur[ks] = mnext[ks];
                         const float2 ce = __ldg(reinterpret_cast<const float2*>(colen + g*64u + nt*8u + 2u*tq));
                         float o = c[0] - fminf(fmaxf(c[0], 0.0f), 1.0f); pen0 += ce.x*o*o;
                         o = c[1] - fminf(fmaxf(c[1], 0.0f), 1.0f); pen0 += ce.y*o*o;
@@ -1799,16 +1935,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
         const Slot3& bslot = ws.slots[slot_base(bs)];
         const ModeInfo bm = tab_mode(ctx, best_code & 0xFFFFu);
         PHASE_SYNC();       // (measured: without this barrier the warps drift apart and instruction fetch stalls cost 25 %)
-        if (active && lane == 0) {
-            Enc enc;
-            enc.clevel = best_cl; enc.err = best_err;
-            for (uint32_t s = 0; s < bslot.pc; ++s) {
-                const int* e = ws.best_ep + s*8u;
-                enc.ep[s][0] = static_cast<uint32_t>(e[0]) | (static_cast<uint32_t>(e[1]) << 8) | (static_cast<uint32_t>(e[2]) << 16) |
-                    (static_cast<uint32_t>(e[3]) << 24);
-                enc.ep[s][1] = static_cast<uint32_t>(e[4]) | (static_cast<uint32_t>(e[5]) << 8) | (static_cast<uint32_t>(e[6]) << 16) |
-                    (static_cast<uint32_t>(e[7]) << 24);
-            }
+        if (active) {
             SlotView sv; sv.pc = bslot.pc; sv.seed = bslot.seed; sv.dual_ch = bslot.dual_ch;
             uint8_t cems[4] = {0, 0, 0, 0};
             const bool virt = slot_is_scale(bs);
@@ -1816,8 +1943,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 const bool cheap = bs >= static_cast<uint32_t>(kMixSlot) ? ((ws.mix_mask[bs - kMixSlot] >> q) & 1u) != 0u : virt;
                 cems[q] = static_cast<uint8_t>(!cheap ? (has_alpha ? 12 : 8) : (bs >= static_cast<uint32_t>(kMixSlot) && has_alpha && ws.mix_kind[bs - kMixSlot] == 0u ? 8 : (has_alpha ? 10 : 6)));
             }
-            *dst = pack_block(ctx, sv, bm, enc, has_alpha, ws.best_su, 0, true, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr,
-                virt ? cems : nullptr, ws.best_sc, HDR ? 0u : ws.best_contr, ws.best_epv);
+            // (the candidate scratch ws.sk / ws.su is dead by now: it takes the encoded colour values and weights)
+            const uint4 packed = pack_block_warp(ctx, sv, bm, best_cl, ws.best_ep, has_alpha, ws.best_sk, slot_is_lum(bs), HDR ? ws.best_epv : nullptr,
+                virt ? cems : nullptr, ws.best_sc, HDR ? 0u : ws.best_contr, ws.best_epv, ws.sk, ws.su, lane);
+            if (lane == 0) *dst = packed;
         }
     }
 }
