@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcfx.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("CFX_BUILD_DIR", "lib"), "libcfx.so")      # (developer: a variant build)
 
 
 class SurfaceDesc(ctypes.Structure):

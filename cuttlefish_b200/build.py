@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "lib")
+OUT = os.path.join(HERE, os.environ.get("CFX_BUILD_DIR", "lib"))      # (developer: variant builds side by side)
 OBJ = os.path.join(OUT, "obj")
 LIB = os.path.join(OUT, "libcfx.so")
 
@@ -32,7 +32,7 @@ UNITS = [
     ("etc.cu", ["-fmad=false"], "CFX_HAVE_ETC"),
     ("bc6h.cu", [], "CFX_HAVE_BC6H"),
     ("astc_host.cu", [], "CFX_HAVE_ASTC"),
-    ("astc3.cu", ["-DCFX_ASTC3_TUNE=1"] if os.environ.get("CFX_ASTC3_TUNE") else [], None),
+    ("astc3.cu", (["-DCFX_ASTC3_TUNE=1"] if os.environ.get("CFX_ASTC3_TUNE") else []) + os.environ.get("CFX_ASTC3_DEFS", "").split(), None),
 ]
 
 

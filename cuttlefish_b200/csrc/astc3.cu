@@ -32,11 +32,19 @@ using namespace astc;
 
 namespace {
 
-// Launch shape: W warps per CTA, CTAS resident CTAs per SM (register budget = 64K/(W*32*CTAS)).  The kernel is ~9k SASS
-// instructions, far beyond the 32 KB instruction cache, so the warps of a CTA are kept in the same phase of the
-// search by CTA-wide barriers at the phase boundaries: one fetched instruction line then serves all of them.
-constexpr int kDefaultWarps = 12;
-constexpr int kDefaultCtasPerSm = 2;
+// Launch shape: W warps per CTA, CTAS resident CTAs per SM (register budget = 64K/(W*32*CTAS)); chosen per footprint in
+// launch_one().  The kernel is ~15k SASS instructions, far beyond the 32 KB instruction cache, so the warps of a CTA are
+// kept in the same phase of the search by CTA-wide barriers at the phase boundaries: one fetched instruction line then
+// serves all of them.
+// Finer-grained barriers were measured too (6x6): one per trip of the phase-2 loop is +10 % with two CTAs per SM but
+// -8 % with the single CTA the kernel now runs as (the trips differ in length: the sum of the slowest warps' trips
+// outweighs what the tighter lockstep saves), one per slot in the setup 7 / phase 1b' / 1c loops another -3 %.  Off.
+#ifndef CFX_ASTC3_LOOPSYNC
+#define CFX_ASTC3_LOOPSYNC 0
+#endif
+#ifndef CFX_ASTC3_SLOTSYNC
+#define CFX_ASTC3_SLOTSYNC 0
+#endif
 #define PHASE_SYNC() do { if (LOCK) __syncthreads(); else __syncwarp(); } while (0)
 constexpr int FX = 8;                          // texel fixed point scale
 constexpr int kMaxCand = 16;
@@ -1336,7 +1344,9 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
         __syncwarp();
         // ---- setup 7: per slot, project the texels on their subset's line -> ideal weights (fp16 A operand rows),
         //      end points, line lengths
-        for (uint32_t s = 0; active && s < kSlots; ++s) {
+        for (uint32_t s = 0; s < kSlots; ++s) {
+            if (CFX_ASTC3_SLOTSYNC) PHASE_SYNC();
+            if (!active) continue;
             Slot3& slot = ws.slots[s];
             if (!slot.valid) continue;
             const uint32_t pc = slot.pc;
@@ -1722,8 +1732,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
         }
         // ---- phase 1b': measured weight-quantisation loss of every slot at the coarse levels (lane = texel):
         //      qn[s][L] = sum_i len2_i (t_i - Q_L(t_i))^2 / sum_i len2_i, with the end point refit gain folded in
-        if (active) {
+        {
             for (uint32_t s = 0; s < kSlots3; ++s) {
+                if (CFX_ASTC3_SLOTSYNC) PHASE_SYNC();
+                if (!active) continue;
                 const Slot3& slot = ws.slots[s];
                 if (!slot.valid) continue;
                 const uint32_t row0 = slot_row(s);
@@ -1765,12 +1777,14 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
         // ---- phase 1c: estimate every (slot, mode); each lane keeps its three best
         float be0 = 3.0e38f, be1 = 3.0e38f, be2 = 3.0e38f;
         uint32_t bc0 = 0, bc1 = 0, bc2 = 0;
-        if (active) {
+        {
             const float tn = kColor*static_cast<float>(T*(has_alpha ? 4u : 3u));
             const float* ksum = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_ksum);
             float* gb = &ws.g[0][0];           // per grid: floor + decimation loss   (phase 2 scratch, free until then)
             float* gs = &ws.g[1][0];           // per grid: weight-quantisation scale
             for (uint32_t s = 0; s < kSlotsAll; ++s) {
+                if (CFX_ASTC3_SLOTSYNC) PHASE_SYNC();
+                if (!active) continue;
                 const Slot3& slot = ws.slots[slot_base(s)];
                 const bool virt = slot_is_scale(s);
                 if (virt ? !(ws.scale_valid[s - kScaleSlot] && slot.valid) : !slot.valid) continue;
@@ -1834,8 +1848,13 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
 #ifdef CFX_ASTC3_TUNE
         float dbg_est = 0.0f;
 #endif
+        // every trip of the loop starts at a CTA-wide barrier as well (LOCK): the body is ~2500 instructions, the warps
+        // take different branches of it and run different numbers of trips, and the instruction cache only keeps up while
+        // they stay together; a warp that is done keeps arriving until the whole CTA is
+        bool running = active;
 #pragma unroll 1
-        while (active) {
+        while (LOCK && CFX_ASTC3_LOOPSYNC ? __syncthreads_or(running ? 1 : 0) != 0 : running) {
+            if (!running) continue;
             uint32_t code = 0, cl = 0;
             int row0 = 0, row1 = -1;
             bool realign = false;
@@ -1869,7 +1888,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
             if (refining) {
                 // refinement alternates a continuous step (re-project on the quantised end points, re-decimate, re-solve)
                 // with a discrete one (realign_weights); it ends after `refine` pairs or two failures in a row
-                if (rounds >= 2u*refine || fails >= 2u || best_err <= 0.0f || best_err >= 3.0e38f) break;
+                if (rounds >= 2u*refine || fails >= 2u || best_err <= 0.0f || best_err >= 3.0e38f) { running = false; continue; }
                 realign = !HDR && (rounds & 1u) != 0u && !(tb.flags & 8u);
                 const bool skip = (rounds & 1u) != 0u && !realign;
                 ++rounds;
@@ -1980,14 +1999,24 @@ int launch_one(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t
     if (cfg == 1221) return launch_cfg<NT, KS, 12, 2, true>(p, tb, n_exact, refine, stream);
     if (cfg == 1611) return launch_cfg<NT, KS, 16, 1, true>(p, tb, n_exact, refine, stream);
     if (cfg == 2410) return launch_cfg<NT, KS, 24, 1, false>(p, tb, n_exact, refine, stream);
+    if (cfg == 2411) return launch_cfg<NT, KS, 24, 1, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 2011) return launch_cfg<NT, KS, 20, 1, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 1211) return launch_cfg<NT, KS, 12, 1, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 1411) return launch_cfg<NT, KS, 14, 1, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 1811) return launch_cfg<NT, KS, 18, 1, true>(p, tb, n_exact, refine, stream);
+    if (cfg == 1610) return launch_cfg<NT, KS, 16, 1, false>(p, tb, n_exact, refine, stream);
     }
 #endif
-    // above 64 texels the working set and the register file only allow 8 warps per SM
-    if constexpr (NT > 8) return launch_cfg<NT, KS, 8, 1, true>(p, tb, n_exact, refine, stream);
-    // 56- and 64-texel footprints: 9 warps per CTA so that two CTAs still fit an SM's shared memory
-    else if constexpr (NT >= 7) return launch_cfg<NT, KS, 9, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
-    else if constexpr (NT == 6) return launch_cfg<NT, KS, 11, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);   // 48 texels: same reason
-    else return launch_cfg<NT, KS, kDefaultWarps, kDefaultCtasPerSm, true>(p, tb, n_exact, refine, stream);
+    // ONE CTA per SM.  The kernel is ~15k SASS instructions and only runs well while all the warps of an SM walk the same
+    // part of it (measured at 6x6: 16 warps without the barriers 81 MTexel/s, with them 412): two CTAs per SM are two
+    // instruction streams competing for one instruction cache (12 warps x 2 CTAs: 359), one CTA of 20 warps is one stream,
+    // with 96 registers per thread instead of 80 (no spills) and 75 KB more L1 for the tables (428; 16 warps 412, 22
+    // warps 413, 24 warps 424).  The larger footprints take as many warps as their working set leaves room for, up to the
+    // count that measured best.
+    if constexpr (NT <= 6) return launch_cfg<NT, KS, 20, 1, true>(p, tb, n_exact, refine, stream);        // 4x4 ... 8x6: 5.5 - 10 KB per warp
+    else if constexpr (NT <= 8) return launch_cfg<NT, KS, 16, 1, true>(p, tb, n_exact, refine, stream);   // ... 8x8: 12.7 KB (18 warps: -9 %)
+    else if constexpr (NT <= 10) return launch_cfg<NT, KS, 12, 1, true>(p, tb, n_exact, refine, stream);  // 10x8: 18 KB (8 warps: -20 %)
+    else return launch_cfg<NT, KS, 8, 1, true>(p, tb, n_exact, refine, stream);                           // 10x10 (11 warps: the same) ... 12x12 (10 warps: -23 %)
 }
 
 

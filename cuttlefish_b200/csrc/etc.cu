@@ -48,7 +48,11 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
             if (live) reinterpret_cast<uint2*>(p.dst)[blk] = color;
             continue;
         }
+        // texels of a partial edge block that lie outside the image: clamp-to-edge replicas in xs, no weight in the search
+        // (EtcConverter hands etc2comp a smaller image for these blocks, lib/src/EtcConverter.cpp:122-150)
+        uint32_t vm = 0;
         for (uint32_t t = 0; t < 16; ++t) {
+            if (bx*4 + (t & 3) < p.width && by*4 + (t >> 2) < p.height) vm |= 1u << t;
             const uint32_t x = min(bx*4 + (t & 3), p.width - 1), y = min(by*4 + (t >> 2), p.height - 1);
             float4 v;
             if (p.src_format == SRC_RGBA8) {
@@ -65,18 +69,18 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
             etc::px(xs, lane, t, 0) = v.x; etc::px(xs, lane, t, 1) = v.y; etc::px(xs, lane, t, 2) = v.z; etc::px(xs, lane, t, 3) = v.w;
         }
         if (FORMAT == 41 || FORMAT == 42) {
-            const uint2 r = etc::encode_eac_r11<SIGNED>(xs, lane, 0, alpha_radius);
+            const uint2 r = etc::encode_eac_r11<SIGNED>(xs, lane, 0, alpha_radius, vm);
             if (FORMAT == 41) {
                 if (live) reinterpret_cast<uint2*>(p.dst)[blk] = r;
             } else {
-                const uint2 g = etc::encode_eac_r11<SIGNED>(xs, lane, 1, alpha_radius);
+                const uint2 g = etc::encode_eac_r11<SIGNED>(xs, lane, 1, alpha_radius, vm);
                 if (live) reinterpret_cast<uint4*>(p.dst)[blk] = make_uint4(r.x, r.y, g.x, g.y);
             }
             continue;
         }
-        const uint2 color = FORMAT == 39 ? etc::encode_color_a1(xs, lane, rounds) : etc::encode_color(xs, lane, FORMAT != 37, rounds);
+        const uint2 color = FORMAT == 39 ? etc::encode_color_a1(xs, lane, rounds, vm) : etc::encode_color(xs, lane, FORMAT != 37, rounds, vm);
         if (FORMAT == 40) {
-            const uint2 alpha = etc::encode_eac_alpha(xs, lane, alpha_radius);
+            const uint2 alpha = etc::encode_eac_alpha(xs, lane, alpha_radius, vm);
             if (live) reinterpret_cast<uint4*>(p.dst)[blk] = make_uint4(alpha.x, alpha.y, color.x, color.y);
         } else {
             if (live) reinterpret_cast<uint2*>(p.dst)[blk] = color;

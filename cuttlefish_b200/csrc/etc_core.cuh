@@ -10,6 +10,10 @@
 // descent around its mean over all 8 modifier tables with exact decoded error; ETC2 adds the planar
 // mode (least-squares plane per channel, 676 quantisation, +-1 descent) and the T / H modes
 // (two-colour clustering); EAC alpha searches table x multiplier x base around the block's range.
+// Partial edge blocks: `vm` (bit t = texel t lies inside the image) -- the reference hands etc2comp a smaller image for
+// them (lib/src/EtcConverter.cpp:122-150) and etc2comp gives the missing texels no weight (NaN alpha "border" pixels);
+// here the texels outside the image (clamp-to-edge replicas in xs) are left out of every mean and every error sum and
+// only receive selectors.
 // Compiles for the device and, through hostdev.h, for tools/emu_etc.cpp.
 #pragma once
 #include "hostdev.h"
@@ -189,15 +193,17 @@ struct ColorResult { float err; uint32_t hi, lo; };
 // ---- ETC1 part: both flips, differential and individual -----------------------------------------
 // diff_only: no individual (444+444) mode -- ETC2 RGB8A1, where that bit is the opaque flag.
 // tmask != 0: punch-through block of RGB8A1 (opaque flag clear, see half_fit).
-CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, bool diff_only = false, uint32_t tmask = 0)
+CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, bool diff_only = false, uint32_t tmask = 0,
+    uint32_t vm = 0xFFFFu)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
+    const uint32_t skip = tmask | (~vm & 0xFFFFu);       // texels without a say in the base colours
 #pragma unroll 1
     for (uint32_t flip = 0; flip < 2; ++flip) {
         const uint32_t maskA = flip ? 0x00FFu : 0x3333u, maskB = ~maskA & 0xFFFFu;
         float mA[3] = {0, 0, 0}, mB[3] = {0, 0, 0}, nA = 0.0f, nB = 0.0f;
         for (uint32_t t = 0; t < 16; ++t) {
-            if ((tmask >> t) & 1u) continue;
+            if ((skip >> t) & 1u) continue;
             const bool a = (maskA >> t) & 1u;
             if (a) nA += 1.0f; else nB += 1.0f;
 #pragma unroll
@@ -205,7 +211,7 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) { mA[c] *= nA > 0.0f ? 1.0f/nA : 0.0f; mB[c] *= nB > 0.0f ? 1.0f/nB : 0.0f; }
-        if (tmask) {                 // a half without opaque texels follows the other one
+        if (skip) {                  // a half without opaque (or inside-the-image) texels follows the other one
 #pragma unroll
             for (int c = 0; c < 3; ++c) { if (nA == 0.0f) mA[c] = mB[c]; if (nB == 0.0f) mB[c] = mA[c]; }
         }
@@ -228,12 +234,12 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
                 }
             }
             HalfFit fA, fB;
-            half_search(xs, lane, maskA, bits, qA, lo, hi, rounds, fA, tmask);
+            half_search(xs, lane, maskA & vm, bits, qA, lo, hi, rounds, fA, tmask);
             if (diff) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { lo[c] = max(qA[c] - 4, 0); hi[c] = min(qA[c] + 3, 31); }
             }
-            half_search(xs, lane, maskB, bits, qB, lo, hi, rounds, fB, tmask);
+            half_search(xs, lane, maskB & vm, bits, qB, lo, hi, rounds, fB, tmask);
             const float err = fA.err + fB.err;
             if (err < out.err) {
                 uint32_t h = 0, l = 0;
@@ -265,10 +271,11 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
 }
 
 // ---- ETC2 planar ---------------------------------------------------------------------------------
-CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, const int* V)
+CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, const int* V, uint32_t vm = 0xFFFFu)
 {
     float err = 0.0f;
     for (uint32_t t = 0; t < 16; ++t) {
+        if (!((vm >> t) & 1u)) continue;
         const int x = t & 3, y = t >> 2;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -280,7 +287,7 @@ CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, 
     return err;
 }
 
-CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out)
+CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out, uint32_t vm = 0xFFFFu)
 {
     int q[9];     // RO GO BO RH GH BH RV GV BV (6/7/6 bits)
 #pragma unroll
@@ -308,7 +315,7 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
         }
     };
     expand_all();
-    float best = planar_error(xs, lane, O, H, V);
+    float best = planar_error(xs, lane, O, H, V, vm);
     for (int round = 0; round < rounds && best > 0.0f; ++round) {
         bool improved = false;
 #pragma unroll 1
@@ -318,7 +325,7 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
             if (q[i] + d < 0 || q[i] + d > maxq) continue;
             q[i] += d;
             expand_all();
-            const float e = planar_error(xs, lane, O, H, V);
+            const float e = planar_error(xs, lane, O, H, V, vm);
             if (e < best) { best = e; improved = true; } else q[i] -= d;
         }
         if (!improved) break;
@@ -362,7 +369,8 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
 // Two 444 colours from a 2-means split of the block along its principal axis.
 // Error and selectors of one T / H configuration: kind 0: T with A single, B +-d; kind 1: T with B single, A +-d;
 // kind 2: H.  qA, qB: the two RGB444 colours; di: distance index.  Stops early once `limit` is exceeded.
-CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const int* qA, const int* qB, float limit, uint32_t& sel_out)
+CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const int* qA, const int* qB, float limit, uint32_t& sel_out,
+    uint32_t vm = 0xFFFFu)
 {
     const int d = kDist[di];
     int pal[4][3];
@@ -385,7 +393,8 @@ CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const
             const float e = d0*d0 + d1*d1 + d2*d2;
             if (e < be) { be = e; bk = k; }
         }
-        err += be; sel |= bk << (2*t);
+        if ((vm >> t) & 1u) err += be;
+        sel |= bk << (2*t);
     }
     sel_out = sel;
     return err;
@@ -395,7 +404,7 @@ CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const
 // (etc2comp widens its T / H search the same way in its later iterations, EtcBlock4x4Encoding_RGB8.cpp:370-...).
 // rounds: +-1 descent rounds over the two colours; the descent only runs while the T/H error is below `gate` (the short
 // searches pass a small multiple of the incumbent's error: a T/H block that far behind will not win).
-CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0, float gate = 3.0e38f)
+CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0, float gate = 3.0e38f, uint32_t vm = 0xFFFFu)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
     float m[3] = {0, 0, 0};
@@ -454,7 +463,7 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
 #pragma unroll 1
         for (uint32_t di = 0; di < 8; ++di) {
             uint32_t sel;
-            const float err = th_eval(xs, lane, kind, di, qA, qB, best, sel);
+            const float err = th_eval(xs, lane, kind, di, qA, qB, best, sel, vm);
             if (err < best) { best = err; best_kind = kind; best_d = di; best_sel = sel; }
         }
     }
@@ -472,7 +481,7 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
                 const int di = static_cast<int>(best_d) + dd;
                 if (di < 0 || di > 7) continue;
                 uint32_t sel;
-                const float err = th_eval(xs, lane, best_kind, static_cast<uint32_t>(di), tA, tB, best, sel);
+                const float err = th_eval(xs, lane, best_kind, static_cast<uint32_t>(di), tA, tB, best, sel, vm);
                 if (err < best) {
                     best = err; best_d = static_cast<uint32_t>(di); best_sel = sel; improved = true;
 #pragma unroll
@@ -527,10 +536,10 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
 }
 
 // ---- EAC alpha (ETC2 RGBA8) ----------------------------------------------------------------------
-CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius)
+CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius, uint32_t vm = 0xFFFFu)
 {
     float lo = 3.0e38f, hi = -3.0e38f;
-    for (uint32_t t = 0; t < 16; ++t) { const float a = px(xs, lane, t, 3); lo = fminf(lo, a); hi = fmaxf(hi, a); }
+    for (uint32_t t = 0; t < 16; ++t) { if (!((vm >> t) & 1u)) continue; const float a = px(xs, lane, t, 3); lo = fminf(lo, a); hi = fmaxf(hi, a); }
     uint32_t best_base = 255, best_mul = 1, best_tab = 13;
     float best = 3.0e38f;
     if (lo == hi && lo == 255.0f) {
@@ -553,6 +562,7 @@ CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius)
                     if (base < 0 || base > 255) continue;
                     float err = 0.0f;
                     for (uint32_t t = 0; t < 16 && err < best; ++t) {
+                        if (!((vm >> t) & 1u)) continue;
                         const float a = px(xs, lane, t, 3);
                         float be = 3.0e38f;
 #pragma unroll
@@ -593,7 +603,7 @@ CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius)
 // (same threshold, :96, :754).  Opaque blocks: the ETC2 RGB search without the individual mode (that bit is the
 // opaque flag); mixed blocks: differential mode with the opaque flag clear, transparent texels on selector 2 and the
 // others on {+0, +big, -big}; fully transparent blocks: selector 2 everywhere.  Our own search: PSNR parity.
-CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds)
+CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds, uint32_t vm = 0xFFFFu)
 {
     uint32_t tmask = 0;
     for (uint32_t t = 0; t < 16; ++t) if (px(xs, lane, t, 3) < 127.5f) tmask |= 1u << t;
@@ -603,13 +613,13 @@ CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds)
         for (uint32_t t = 0; t < 16; ++t) sel |= 2u << (2*t);
         return to_bytes(0u, pixel_bits(sel));
     }
-    encode_etc1(xs, lane, rounds, best, true, tmask);
+    encode_etc1(xs, lane, rounds, best, true, tmask, vm);
     if (tmask == 0 && best.err > 0.0f) {
         ColorResult r;
-        encode_planar(xs, lane, rounds, r);
+        encode_planar(xs, lane, rounds, r, vm);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE);
+            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm);
             if (r.err < best.err) best = r;
         }
     }
@@ -624,13 +634,13 @@ CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds)
 // clamp(base*8 + modifier*multiplier*8, -1023, 1023) / 1023 with an int8 base.  Our own search: PSNR parity.
 // xs channel `chan` holds v*255 with v clamped to [0,1] (unsigned) or [-1,1] (signed).
 template <bool SIGNED>
-CFX_HD uint2 encode_eac_r11(float* xs, uint32_t lane, uint32_t chan, int radius)
+CFX_HD uint2 encode_eac_r11(float* xs, uint32_t lane, uint32_t chan, int radius, uint32_t vm = 0xFFFFu)
 {
     const float scale = SIGNED ? 1023.0f/255.0f : 2047.0f/255.0f;
     const int off = SIGNED ? 0 : 4, vmin = SIGNED ? -1023 : 0, vmax = SIGNED ? 1023 : 2047;
     const int bmin = SIGNED ? -127 : 0, bmax = SIGNED ? 127 : 255;
     float lo = 3.0e38f, hi = -3.0e38f;
-    for (uint32_t t = 0; t < 16; ++t) { const float a = px(xs, lane, t, chan)*scale; lo = fminf(lo, a); hi = fmaxf(hi, a); }
+    for (uint32_t t = 0; t < 16; ++t) { if (!((vm >> t) & 1u)) continue; const float a = px(xs, lane, t, chan)*scale; lo = fminf(lo, a); hi = fmaxf(hi, a); }
     int best_base = 0, best_mul = 1;
     uint32_t best_tab = 13;
     float best = 3.0e38f;
@@ -650,6 +660,7 @@ CFX_HD uint2 encode_eac_r11(float* xs, uint32_t lane, uint32_t chan, int radius)
                 if (base < bmin || base > bmax) continue;
                 float err = 0.0f;
                 for (uint32_t t = 0; t < 16 && err < best; ++t) {
+                    if (!((vm >> t) & 1u)) continue;
                     const float a = px(xs, lane, t, chan)*scale;
                     float be = 3.0e38f;
 #pragma unroll
@@ -682,16 +693,16 @@ CFX_HD uint2 encode_eac_r11(float* xs, uint32_t lane, uint32_t chan, int radius)
 }
 
 // format: 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8 (colour part); returns the 8 colour bytes
-CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds)
+CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds, uint32_t vm = 0xFFFFu)
 {
     ColorResult best;
-    encode_etc1(xs, lane, rounds, best);
+    encode_etc1(xs, lane, rounds, best, false, 0, vm);
     if (etc2 && best.err > 0.0f) {
         ColorResult r;
-        encode_planar(xs, lane, rounds, r);
+        encode_planar(xs, lane, rounds, r, vm);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE);
+            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm);
             if (r.err < best.err) best = r;
         }
     }

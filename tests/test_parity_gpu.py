@@ -318,11 +318,12 @@ def test_ragged_and_tiny_surfaces(cfx, oracle, fmt):
         if fmt in EXACT_FORMATS:
             assert np.array_equal(got, ref)
         elif fmt.startswith("ETC"):
-            # the reference passes edge blocks to etc2comp as SMALLER images (EtcConverter.cpp:122-130);
-            # we clamp to edge like every other format, so only the visible texels are compared
+            # the reference passes edge blocks to etc2comp as SMALLER images (EtcConverter.cpp:122-130): texels outside the
+            # image carry no weight. Ours: the same (a validity mask per block, etc_core.cuh) -- the visible texels are held
+            # to the 0.1 dB bar (measured: 0.35 - 0.93 x the reference's error on the edge blocks)
             d_gpu, d_ref = oracle.decode(got, fmt, w, h), oracle.decode(ref, fmt, w, h)
             e = lambda d: float(np.mean((d[..., :3].astype(np.float64) - img[..., :3]) ** 2))
-            assert e(d_gpu) <= e(d_ref) * 1.6 + 1e-4
+            assert e(d_gpu) <= e(d_ref) * 10 ** (PSNR_TOLERANCE_DB / 10) + 1e-6, "%s %dx%d mse %.3g vs reference %.3g" % (fmt, w, h, e(d_gpu), e(d_ref))
         else:
             d_gpu, d_ref = oracle.decode(got, fmt, w, h), oracle.decode(ref, fmt, w, h)
             e = lambda d: float(np.mean((d[..., :3].astype(np.float64) - img[..., :3]) ** 2))
