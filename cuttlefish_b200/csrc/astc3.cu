@@ -39,6 +39,11 @@ namespace {
 // Finer-grained barriers were measured too (6x6): one per trip of the phase-2 loop is +10 % with two CTAs per SM but
 // -8 % with the single CTA the kernel now runs as (the trips differ in length: the sum of the slowest warps' trips
 // outweighs what the tighter lockstep saves), one per slot in the setup 7 / phase 1b' / 1c loops another -3 %.  Off.
+#ifdef CFX_ASTC3_TUNE
+#define CFX_ASTC3_TUNE_KEEP_ALL && !(tb.flags & 256u)      // developer: the candidate dump wants every slot's estimates
+#else
+#define CFX_ASTC3_TUNE_KEEP_ALL
+#endif
 #ifndef CFX_ASTC3_LOOPSYNC
 #define CFX_ASTC3_LOOPSYNC 0
 #endif
@@ -1038,6 +1043,9 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
     using WS = Warp3T<NT>;
     constexpr size_t kWsBytes = (sizeof(WS) + 15)/16*16;
     constexpr uint32_t TP = WS::TP;
+    // (keeping lane, warp and the working-set offset in registers behind an opaque asm -- the compiler re-reads the thread
+    // id and rebuilds smem + warp*kWsBytes + field in ~170 places, 8 % of the executed instructions -- was measured:
+    // 2 - 5 % slower, the three registers cost more in spills than the recomputation)
     WS& ws = *reinterpret_cast<WS*>(smem + warp*kWsBytes);
     __syncthreads();
     const Ctx& ctx = tb.ctx;
@@ -1757,8 +1765,11 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                     for (int L = 0; L < kDataLevels; ++L) {
                         constexpr int kLv[kDataLevels] = {2, 3, 4, 5, 6, 8};
                         const float nm1 = static_cast<float>(kLv[L] - 1), inm1 = 1.0f/nm1;   // compile-time constants
-                        const float d = fmaf(-rintf(t*nm1), inm1, t), d2 = fmaf(-rintf(t2*nm1), inm1, t2);
-                        e[L] += w*d*d + l2b*d2*d2;
+                        const float d = fmaf(-rintf(t*nm1), inm1, t);
+                        if (dual) {
+                            const float d2 = fmaf(-rintf(t2*nm1), inm1, t2);
+                            e[L] += w*d*d + l2b*d2*d2;
+                        } else e[L] = __fadd_rn(e[L], __fmul_rn(__fmul_rn(w, d), d));      // (the same roundings as the line above with l2b = 0)
                     }
                 }
                 // one integer reduction per level (the sums are scaled into 2^26)
@@ -1793,6 +1804,9 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 const uint4* list = reinterpret_cast<const uint4*>(ctx.blob + tb.t3.off_est[has_alpha ? 1 : 0][type]);
                 const uint32_t count = tb.t3.n_est[has_alpha ? 1 : 0][type];
                 const float base = kLine*(virt ? ws.scale_eline[s - kScaleSlot] + (s < static_cast<uint32_t>(kMixSlot) && has_alpha ? slot.e_line : 0.0f) : slot.e_line);
+                // every estimate of this slot is at least its floor: when n_exact lanes already hold something better, none
+                // of them can be among the n_exact candidates phase 2 looks at
+                if (static_cast<uint32_t>(__popc(__ballot_sync(0xFFFFFFFFu, be0 < base))) >= n_exact CFX_ASTC3_TUNE_KEEP_ALL) continue;
                 const float l2sum = slot.len2[0] + slot.len2b;
                 // per-grid terms of this slot (lane = grid)
                 __syncwarp();

@@ -23,7 +23,7 @@ constexpr int kBlkStride = 20;     // words per block in shared memory (16 texel
 
 template <int FORMAT>   // 29 BC1_RGB, 30 BC1_RGBA, 31 BC2, 32 BC3
 __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams p, int descent, uint32_t radius, uint32_t hq,
-    bool exact, bool both)
+    bool exact)
 {
     __shared__ __align__(16) uint32_t s_px[kBc1Warps][32*kBlkStride];
     __shared__ __align__(16) uint32_t s_tab[FORMAT == 32 ? kBc1Warps : 1][kBc4TableWords];
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
         if (FORMAT == 30) flags = bc1::kAllow3 | bc1::kPunchThrough;
         uint2 color;
 #ifdef CFX_HAVE_RGBCX_TABLES
-        // Quality::Normal: byte-exact rgbcx level 9 (bc1_exact.cuh).  BC1_RGBA blocks with a texel of
+        // Every Texture::Quality: byte-exact rgbcx levels 0 / 4 / 9 / 13 / 18 (bc1_exact.cuh).  BC1_RGBA blocks with a texel of
         // alpha < 0.5 go through libsquish in the reference (S3tcConverter.cpp:283-330); those keep our
         // punch-through search.
         bool transparent = false;
@@ -71,18 +71,10 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
             for (int i = 0; i < 16; ++i) transparent = transparent || (px[i] >> 24) < 128u;
         }
         if (exact && !transparent)
-            color = rgbcx9::encode_bc1_level9(px, FORMAT == 29 || FORMAT == 30, FORMAT == 29);
+            color = rgbcx9::encode_bc1_exact(px, p.quality, FORMAT == 29 || FORMAT == 30, FORMAT == 29);
         else
 #endif
             color = bc1::encode_color_block(px, flags, descent);
-#ifdef CFX_HAVE_RGBCX_TABLES
-        // High / Highest (rgbcx levels 13 / 18 in the reference: more orderings, more refinement): two independent
-        // searches, ours with its +-1 descent and the level-9 flow, and the block keeps the better one
-        if (both && !transparent) {
-            const uint2 alt = rgbcx9::encode_bc1_level9(px, FORMAT == 29 || FORMAT == 30, FORMAT == 29);
-            if (bc1::block_sse(px, alt, FORMAT >= 31) < bc1::block_sse(px, color, FORMAT >= 31)) color = alt;
-        }
-#endif
         if (FORMAT == 29 || FORMAT == 30) {
             if (lane < nblk) reinterpret_cast<uint2*>(p.dst)[first + lane] = color;
         } else if (FORMAT == 31) {
@@ -106,12 +98,12 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
     }
 }
 
-// Whether BC1-family colour blocks are byte-identical to rgbcx at this quality: only Normal (rgbcx level
-// 9) is restated, and only when the reference's tables were generated into the build.
+// Whether BC1-family colour blocks are byte-identical to rgbcx at this quality: all five levels (rgbcx levels 0, 4, 9,
+// 13, 18) are restated, but only when the reference's tables were generated into the build.
 bool bc1_color_is_exact(uint32_t quality)
 {
 #ifdef CFX_HAVE_RGBCX_TABLES
-    return quality == 2;
+    return quality <= 4;
 #else
     (void)quality;
     return false;
@@ -135,9 +127,8 @@ int launch_bc123(const EncodeParams& p, cudaStream_t stream)
     }
     const uint32_t grid = min(ctas, persistent_ctas(k, kBc1Warps*32));
     bool exact = bc1_color_is_exact(p.quality);
-    bool both = p.quality >= 3;
     void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&descent), const_cast<uint32_t*>(&radius),
-        const_cast<uint32_t*>(&hq), &exact, &both};
+        const_cast<uint32_t*>(&hq), &exact};
     if (cudaLaunchKernel(k, dim3(grid), dim3(kBc1Warps*32), args, 0, stream) != cudaSuccess) return -4;
     return 1;
 }

@@ -365,19 +365,23 @@ def test_color_mask_and_quality_levels(cfx, oracle):
         assert psnr[4] >= psnr[0] - 0.05 and psnr[2] >= psnr[0] - 0.05, "%s %s" % (fmt, psnr)
 
 
-# ---- BC1 family at Quality::Normal: byte-exact rgbcx level 9 when the build has the reference tables ----
+# ---- BC1 family at EVERY Texture::Quality: byte-exact rgbcx levels 0 / 4 / 9 / 13 / 18 when the build has the reference
+# tables (S3tcConverter.cpp:70 maps the five quality levels to those rgbcx levels) ----
+@pytest.mark.parametrize("quality", ["Normal", "Lowest", "Low", "High", "Highest"])
 @pytest.mark.parametrize("fmt", ["BC1_RGB", "BC1_RGBA", "BC2", "BC3"])
-def test_bc123_bit_exact_at_normal(cfx, oracle, fmt):
-    if not cfx.format_is_exact("BC1_RGB", quality="Normal"):
+def test_bc123_bit_exact_at_normal(cfx, oracle, fmt, quality):
+    if not cfx.format_is_exact("BC1_RGB", quality=quality):
         pytest.fail("libcfx.so was built without the reference's rgbcx tables (csrc/generated/rgbcx_tables.inc): the "
                     "bit-exact BC1/BC2/BC3 guarantee of north_star is gone -- rebuild where /root/reference is mounted")
-    for kind, w, h in [("noise+grad", 256, 256), ("gradient", 512, 512), ("gradient", 1024, 64), ("noise+grad", 97, 61)]:
-        img = oracle.gen_image(kind, w, h, seed=41)
-        ref = oracle.encode(img, fmt)
+    for kind, w, h in [("noise+grad", 256, 256), ("gradient", 512, 512), ("gradient", 1024, 64), ("noise+grad", 97, 61), ("ui", 288, 288)]:
+        img = oracle.gen_image(kind, w, h, seed=41) if kind != "ui" else oracle.gen_image(kind, w, h)
+        ref = oracle.encode(img, fmt, quality=quality)
         for src in (oracle.to_rgba8(img), img):                   # RGBA8 and RGBA32F source paths
-            got = cfx.encode(src, fmt)
+            got = cfx.encode(src, fmt, quality=quality)
             bad = block_mismatches(got, ref, cfx.block_info(fmt)[2])
-            assert bad.size == 0, "%s %s %dx%d: %d blocks differ, first %s" % (fmt, kind, w, h, bad.size, bad[:8])
+            assert bad.size == 0, "%s %s %s %dx%d: %d blocks differ, first %s" % (fmt, quality, kind, w, h, bad.size, bad[:8])
+    if quality != "Normal":
+        return
     # committed goldens (64x64 noise+grad, gradient, 30x22) are reference outputs too
     for name in golden_cases([fmt]):
         src, blocks, f, kw = load_golden(name)
@@ -398,9 +402,10 @@ def test_bc1_rgb_dark_and_gray_blocks_exact(cfx, oracle):
     img[32:48, :, :3] = dark                                       # near-black texels
     img[48:, :, :3] = (rng.integers(0, 256, (4, 16, 3)).repeat(4, axis=0).repeat(4, axis=1) / 255).astype(np.float32)  # solid blocks
     for fmt in ("BC1_RGB", "BC3"):
-        got = cfx.encode(oracle.to_rgba8(img), fmt)
-        bad = block_mismatches(got, oracle.encode(img, fmt), cfx.block_info(fmt)[2])
-        assert bad.size == 0, "%s: %d blocks differ, first %s" % (fmt, bad.size, bad[:8])
+        for quality in ("Lowest", "Low", "Normal", "High", "Highest"):
+            got = cfx.encode(oracle.to_rgba8(img), fmt, quality=quality)
+            bad = block_mismatches(got, oracle.encode(img, fmt, quality=quality), cfx.block_info(fmt)[2])
+            assert bad.size == 0, "%s %s: %d blocks differ, first %s" % (fmt, quality, bad.size, bad[:8])
 
 
 def test_etc1_bit_exact(cfx, oracle):
