@@ -44,6 +44,14 @@ namespace {
 #else
 #define CFX_ASTC3_TUNE_KEEP_ALL
 #endif
+// TMA-staged phase-1a operands (astc3_kernel<..., STAGE = true>: ONE thread fetches the R / M fragments of a weight grid
+// into shared memory with cp.async.bulk, double buffered on mbarriers, every warp's MMAs read them from there).  Measured
+// on the single-CTA launch shape (6x6, 4092^2): bit-identical output, 430.6 against 439.9 MTexel/s with every warp pulling
+// its own fragments through L1 (4x4 342 / 352, 8x6 445 / 462) -- the fragments hit in L1 (95 %) once one CTA owns the SM,
+// and the barrier per grid that hands the buffers back costs more than the long-scoreboard stalls it removes.  Off.
+#ifndef CFX_ASTC3_STAGE
+#define CFX_ASTC3_STAGE 0
+#endif
 #ifndef CFX_ASTC3_LOOPSYNC
 #define CFX_ASTC3_LOOPSYNC 0
 #endif
@@ -151,6 +159,34 @@ struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; float mis_w; i
 
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t redux_addu(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
+
+// ---- TMA bulk staging of the phase-1a operands (STAGE variant of the kernel) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a copy that never lands must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// One contiguous piece of the table blob -> shared memory (cp.async.bulk, the 1-D TMA copy); 16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint2 b)
 {
@@ -1031,7 +1067,7 @@ __device__ __forceinline__ uint4 pack_block_warp(const Ctx& c, const SlotView& s
 
 } // namespace
 
-template <int NT, int KS, int W, int CTAS, bool LOCK, bool HDR>
+template <int NT, int KS, int W, int CTAS, bool LOCK, bool HDR, bool STAGE>
 __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant__ EncodeParams p, const __grid_constant__ Tab3 tb, uint32_t n_exact, uint32_t refine)
 {
     constexpr int K = (NT*8 + 31)/32;            // texels per lane
@@ -1047,6 +1083,15 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
     // id and rebuilds smem + warp*kWsBytes + field in ~170 places, 8 % of the executed instructions -- was measured:
     // 2 - 5 % slower, the three registers cost more in spills than the recomputation)
     WS& ws = *reinterpret_cast<WS*>(smem + warp*kWsBytes);
+    // STAGE: behind the warps' working sets, two buffers of [R tiles | M tiles] of one weight grid and their mbarriers
+    constexpr uint32_t kTileBytes = NT*KS*256;                    // the R (or at most the M) fragments of one grid
+    uint8_t* const stage = smem + W*kWsBytes;
+    uint64_t* const stage_bar = reinterpret_cast<uint64_t*>(stage + 4*kTileBytes);
+    uint32_t staged = 0;                                          // grids staged so far by this CTA: buffer and parity
+    if (STAGE && threadIdx.x == 0) {
+        mbar_init(&stage_bar[0], 1); mbar_init(&stage_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const Ctx& ctx = tb.ctx;
     const uint32_t T = ctx.tab.texels, bw = ctx.tab.bw, bh = ctx.tab.bh;
@@ -1619,8 +1664,11 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
         // ---- phase 1a: decimation loss D[slot plane][grid] on the tensor cores
         uint32_t a[KS][4];
         load_a<KS>(ws, a, lane);
+        float lw[NT][2], lw2[NT][2];
+        float scale0 = 0.0f, scale1 = 0.0f, pscale0 = 0.0f, pscale1 = 0.0f;
+        const float* const colen = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_colenergy);
+        const uint8_t* const dec = ctx.blob + tb.t3.off_dec_list;
         if (active) {
-            float lw[NT][2], lw2[NT][2];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -1637,8 +1685,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                     if (gq == 4 && i < T && ws.slots[13].valid) wgt2 = ws.slots[13].len2[ws.part[3][i]];
                     lw2[nt][e] = wgt2;
                 }
-            const float scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
-            const float scale1 = gq == 0 ? (ws.slots[12].valid ? 1.0f : ws.slots[8].len2[0]) :
+            scale0 = gq == 0 ? ws.slots[0].len2[0] : (gq <= 4 ? 1.0f : ws.slots[gq].len2[0]);
+            scale1 = gq == 0 ? (ws.slots[12].valid ? 1.0f : ws.slots[8].len2[0]) :
                 (gq == 4 ? (ws.slots[13].valid ? 1.0f : ws.slots[8].len2b) :
                 (gq < 4 ? ws.slots[gq + 4].len2b : (gq == 5 ? ws.slots[kLumSlot].len2[0] : 1.0f)));
             // what one unit of clamped overshoot of a grid weight costs this row: its line length (multi-subset rows:
@@ -1647,17 +1695,78 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 const Slot3& q = ws.slots[sl];
                 return q.pc > 2 ? (q.len2[0] + q.len2[1] + q.len2[2])*(1.0f/3.0f) : (q.len2[0] + q.len2[1])*0.5f;
             };
-            const float pscale0 = gq >= 1 && gq <= 4 ? mean_len2(gq) : scale0;
-            const float pscale1 = gq == 0 && ws.slots[12].valid ? mean_len2(12) : (gq == 4 && ws.slots[13].valid ? mean_len2(13) :
+            pscale0 = gq >= 1 && gq <= 4 ? mean_len2(gq) : scale0;
+            pscale1 = gq == 0 && ws.slots[12].valid ? mean_len2(12) : (gq == 4 && ws.slots[13].valid ? mean_len2(13) :
                 (gq >= 6 ? mean_len2(gq + 4) : scale1));
-            const float* colen = reinterpret_cast<const float*>(ctx.blob + tb.t3.off_colenergy);
             // full-resolution grids lose nothing
             for (uint32_t g = lane; g < G; g += 32)
                 if (__ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_rfrag_idx) + g) == 0u)
                     for (uint32_t r = 0; r < 16; ++r) ws.u.est.D[r][g] = 0.0f;
+        }
+        if constexpr (STAGE) {
+            // The R and M fragments of a weight grid are the same for every block: ONE thread of the CTA fetches them into
+            // shared memory with two bulk copies (cp.async.bulk, the 1-D TMA path) per grid, double buffered on two mbarriers,
+            // and all the warps -- which walk the grids in step anyway -- feed their MMAs from there, instead of every
+            // warp pulling its own copy of the fragments through L1 (long-scoreboard stalls on the MMAs were 6 % of the
+            // kernel's samples with a one-tile register prefetch).
+            auto issue = [&](uint32_t k, uint32_t buf) {
+                const uint32_t g = __ldg(dec + k);
+                const uint32_t mbytes = ((tab_u8(ctx, ctx.tab.off_grids + g*4u + 2u) + 7u) >> 3)*(KS*256u);
+                uint8_t* dstb = stage + buf*2u*kTileBytes;
+                mbar_expect_tx(&stage_bar[buf], kTileBytes + mbytes);
+                bulk_load(dstb, ctx.blob + tb.t3.off_rstream + k*kTileBytes, kTileBytes, &stage_bar[buf]);
+                bulk_load(dstb + kTileBytes, ctx.blob + __ldg(reinterpret_cast<const uint32_t*>(ctx.blob + tb.t3.off_mfrag_idx) + g), mbytes, &stage_bar[buf]);
+            };
+            const uint32_t n_dec = tb.t3.n_dec;
+            if (threadIdx.x == 0 && n_dec) issue(0, staged & 1u);
+#pragma unroll 1
+            for (uint32_t k = 0; k < n_dec; ++k) {
+                const uint32_t buf = staged & 1u;
+                // the other buffer was last read one trip ago: every warp has passed that trip's closing barrier
+                if (threadIdx.x == 0 && k + 1u < n_dec) issue(k + 1u, buf ^ 1u);
+                mbar_wait(&stage_bar[buf], (staged >> 1) & 1u);
+                if (active) {
+                    const uint32_t g = __ldg(dec + k);
+                    const uint2* rf = reinterpret_cast<const uint2*>(stage + buf*2u*kTileBytes) + lane;
+                    const uint2* mfs = rf + kTileBytes/8u;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], rf[(nt*KS + ks)*32]);
+                        acc0 += lw[nt][0]*c[0]*c[0] + lw[nt][1]*c[1]*c[1];
+                        acc1 += lw2[nt][0]*c[2]*c[2] + lw2[nt][1]*c[3]*c[3];
+                    }
+                    float pen0 = 0.0f, pen1 = 0.0f;
+                    if (!(tb.flags & 16u)) {
+                        const uint32_t ntw = (tab_u8(ctx, ctx.tab.off_grids + g*4u + 2u) + 7u) >> 3;      // GridInfo::nw in tiles of 8
+#pragma unroll 1
+                        for (uint32_t nt = 0; nt < ntw; ++nt) {
+                            float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                            for (int ks = 0; ks < KS; ++ks) mma16816(c, a[ks], mfs[(nt*KS + ks)*32u]);
+                            const float2 ce = __ldg(reinterpret_cast<const float2*>(colen + g*64u + nt*8u + 2u*tq));
+                            float o = c[0] - fminf(fmaxf(c[0], 0.0f), 1.0f); pen0 += ce.x*o*o;
+                            o = c[1] - fminf(fmaxf(c[1], 0.0f), 1.0f); pen0 += ce.y*o*o;
+                            o = c[2] - fminf(fmaxf(c[2], 0.0f), 1.0f); pen1 += ce.x*o*o;
+                            o = c[3] - fminf(fmaxf(c[3], 0.0f), 1.0f); pen1 += ce.y*o*o;
+                        }
+                    }
+                    acc0 = acc0*scale0 + pen0*pscale0; acc1 = acc1*scale1 + pen1*pscale1;
+                    acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 1); acc0 += __shfl_xor_sync(0xFFFFFFFFu, acc0, 2);
+                    acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 1); acc1 += __shfl_xor_sync(0xFFFFFFFFu, acc1, 2);
+                    if (tq == 0) {
+                        ws.u.est.D[gq][g] = acc0;
+                        ws.u.est.D[gq + 8][g] = acc1;
+                    }
+                }
+                __syncthreads();
+                ++staged;
+            }
+        } else if (active) {
             // the decimated grids' R fragments are one contiguous stream: walk it with a one-tile prefetch
             const uint2* frag = reinterpret_cast<const uint2*>(ctx.blob + tb.t3.off_rstream) + lane;
-            const uint8_t* dec = ctx.blob + tb.t3.off_dec_list;
             uint2 bcur[KS];
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) bcur[ks] = __ldg(frag + ks*32);
@@ -1989,10 +2098,14 @@ namespace {
 template <int NT, int KS, int W, int CTAS, bool LOCK>
 int launch_cfg(const EncodeParams& p, const Tab3& tb, uint32_t n_exact, uint32_t refine, cudaStream_t stream)
 {
+    // the TMA-staged phase 1a needs one CTA per SM in lockstep and room for its two [R | M] buffers behind the working sets
+    constexpr size_t kWs = (sizeof(Warp3T<NT>) + 15)/16*16;
+    constexpr size_t kStageBytes = 4u*NT*KS*256u + 16u;
+    constexpr bool STAGE = CFX_ASTC3_STAGE && LOCK && CTAS == 1 && W*kWs + kStageBytes <= 232448u - 1024u;
     // the HDR variant is its own instantiation, so that the LDR kernel carries none of its code
-    const void* k = tb.hdr ? reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK, true>)
-                           : reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK, false>);
-    const size_t smem = W*((sizeof(Warp3T<NT>) + 15)/16*16);
+    const void* k = tb.hdr ? reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK, true, STAGE>)
+                           : reinterpret_cast<const void*>(&astc3_kernel<NT, KS, W, CTAS, LOCK, false, STAGE>);
+    const size_t smem = W*kWs + (STAGE ? kStageBytes : 0u);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) return -4;
     const uint32_t ctas_needed = (p.total_blocks + W - 1)/W;
     const uint32_t grid = min(ctas_needed, persistent_ctas(k, W*32, smem));
