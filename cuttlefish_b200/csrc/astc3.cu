@@ -1081,7 +1081,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
     constexpr uint32_t TP = WS::TP;
     // (keeping lane, warp and the working-set offset in registers behind an opaque asm -- the compiler re-reads the thread
     // id and rebuilds smem + warp*kWsBytes + field in ~170 places, 8 % of the executed instructions -- was measured:
-    // 2 - 5 % slower, the three registers cost more in spills than the recomputation)
+    // 2 - 5 % slower at 20 warps / 96 registers, the three registers cost more in spills than the recomputation; at 16
+    // warps / 128 registers it gains 3 %, which still leaves 16 warps 4 % behind 20)
     WS& ws = *reinterpret_cast<WS*>(smem + warp*kWsBytes);
     // STAGE: behind the warps' working sets, two buffers of [R tiles | M tiles] of one weight grid and their mbarriers
     constexpr uint32_t kTileBytes = NT*KS*256;                    // the R (or at most the M) fragments of one grid
