@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
         const uint32_t b = live ? blk : p.total_blocks - 1;
         const uint32_t by = b / p.blocks_x, bx = b - by*p.blocks_x;
         if (FORMAT == 37 && exact) {
-            // byte-exact etc2comp iteration 0 (etc1_exact.cuh): texels in the reference's column-major
+            // byte-exact etc2comp (etc1_exact.cuh): texels in the reference's column-major
             // block order, [0,1] floats, alpha forced to 1, texels outside the image marked with NaN alpha
             etc1x::Px src[16];
 #pragma unroll
@@ -44,7 +44,10 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
                     }
                     src[x*4 + y] = q;
                 }
-            const uint2 color = etc1x::encode_etc1_exact(src);
+            // etc2comp's effort for the quality level (lib/src/EtcConverter.cpp:34-51): up to Normal only encoding iteration 0
+            // runs, High (70) goes on to the radius-1 tries and the first degenerate set, Highest (100) runs all nine
+            const float effort = p.quality == 3u ? 70.0f : (p.quality >= 4u ? 100.0f : 40.0f);
+            const uint2 color = etc1x::encode_etc1_exact(src, effort);
             if (live) reinterpret_cast<uint2*>(p.dst)[blk] = color;
             continue;
         }
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
     }
 }
 
-bool etc1_is_exact(uint32_t quality) { return quality <= 2; }
+bool etc1_is_exact(uint32_t quality) { return quality <= 4; }       // every level (linear colour space)
 
 int launch_etc(const EncodeParams& p, cudaStream_t stream)
 {
@@ -109,7 +112,7 @@ int launch_etc(const EncodeParams& p, cudaStream_t stream)
         default: return -2;
     }
     const uint32_t grid = min(ctas, persistent_ctas(k, kEtcWarps*32));
-    // ETC1 at effort <= 40 (Lowest/Low/Normal) in linear colour space is the byte-exact restatement
+    // ETC1 in linear colour space is the byte-exact restatement at every quality level
     bool exact = etc1_is_exact(p.quality) && p.color_space == 0;
     void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&rounds), const_cast<int*>(&radius), &exact};
     if (cudaLaunchKernel(k, dim3(grid), dim3(kEtcWarps*32), args, 0, stream) != cudaSuccess) return -4;

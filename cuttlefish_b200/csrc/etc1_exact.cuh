@@ -1,12 +1,17 @@
-// Byte-exact ETC1 for Quality::Lowest / Low / Normal in linear colour space: a restatement of what
-// etc2comp computes when EtcConverter::process (lib/src/EtcConverter.cpp:120-152) encodes one block at
-// effort <= 40 -- only encoding iteration 0 runs (lib/etc2comp/EtcLib/Etc/EtcImage.cpp:282,
-// Block4x4Encoding_ETC1::PerformFirstIteration, EtcCodec/EtcBlock4x4Encoding_ETC1.cpp:311-338):
-//   source averages of the four halves (:402-410), most likely flip from "gray line" distances
-//   (:350-386, EtcBlock4x4Encoding_ETC1.h:138-152), then differential and individual tries at radius 0
-//   for that flip and for the other one (:545-690, :807-900; base colours from
-//   EtcDifferentialTrys.cpp:41-150 / EtcIndividualTrys.cpp:41-64), error metric RGBX
-//   (EtcBlock4x4Encoding.cpp:144-154), strict '<' everywhere, SetDoneIfPerfect early exits.
+// Byte-exact ETC1 in linear colour space, every Texture::Quality: a restatement of what etc2comp computes when
+// EtcConverter::process (lib/src/EtcConverter.cpp:120-152) encodes one block as its own Etc::Image.
+//   effort <= 40 (Lowest / Low / Normal): only encoding iteration 0 runs (lib/etc2comp/EtcLib/Etc/EtcImage.cpp:276-330 --
+//   with one block per image the effort percentage rounds to zero blocks; Block4x4Encoding_ETC1::PerformFirstIteration,
+//   EtcCodec/EtcBlock4x4Encoding_ETC1.cpp:311-338):
+//     source averages of the four halves (:402-410), most likely flip from "gray line" distances
+//     (:350-386, EtcBlock4x4Encoding_ETC1.h:138-152), then differential and individual tries at radius 0
+//     for that flip and for the other one (:545-690, :807-900; base colours from
+//     EtcDifferentialTrys.cpp:41-150 / EtcIndividualTrys.cpp:41-64), error metric RGBX
+//     (EtcBlock4x4Encoding.cpp:144-154), strict '<' everywhere, SetDoneIfPerfect early exits.
+//   effort 70 / 100 (High / Highest): the block is iterated until PerformIteration (:232-306) reports done -- radius-1
+//     differential and individual tries (27 base colours per half, the best pair within the differential range) on the
+//     likely flip and the other one, then the "degenerate" tries (:1000-1061: differential tries with gray offsets of
+//     2 and 4 on either base colour); High stops after the first degenerate set, Highest runs all four.
 // Byte parity needs the same IEEE single-precision operations in the same order and no fused
 // multiply-add: etc.cu is compiled with -fmad=false.  ONE LANE OWNS ONE BLOCK.
 #pragma once
@@ -39,9 +44,10 @@ CFX_HD float gray_distance2(const Px& p, const float* t)
 struct HalfTry { int r, g, b; uint32_t cw; uint32_t sel /* 2 bits x 8, pixel order of the half */; float err; };
 
 // TryDifferentialHalf / TryIndividualHalf at radius 0: one base colour, all 8 codewords
-CFX_HD void try_half(const Px* src, const uint32_t* mapping, float cr, float cg, float cb, HalfTry& t)
+CFX_HD_NOINLINE void try_half(const Px* src, const uint32_t* mapping, float cr, float cg, float cb, HalfTry& t)
 {
     t.err = 3.402823466e+38f; t.cw = 0; t.sel = 0;
+#pragma unroll 1
     for (uint32_t cw = 0; cw < 8; ++cw) {
         float sr[4], sg[4], sb[4];
         for (uint32_t k = 0; k < 4; ++k) {
@@ -70,11 +76,6 @@ CFX_HD void try_half(const Px* src, const uint32_t* mapping, float cr, float cg,
     }
 }
 
-CFX_HD int quant_component(float v, float scale)   // Quantize..().Int..(scale): round(clamp(v)*scale), expanded, back to int
-{
-    return static_cast<int>(roundf(scale*clamp01(v)));
-}
-
 struct Encoding { bool diff, flip; int r1, g1, b1, r2, g2, b2; uint32_t cw1, cw2, sel1, sel2; float err; };
 
 CFX_HD void bend(int& c1, int& c2)
@@ -84,11 +85,124 @@ CFX_HD void bend(int& c1, int& c2)
     else if (d < -4) { c1 += (d + 4)/2; c2 = c1 - 4; }
 }
 
-// src: 16 texels in the reference's block order (column-major: pixel = x*4 + y)
-CFX_HD uint2 encode_etc1_exact(const Px* src)
+CFX_HD int away_from_edge(int v, int radius, int top) { return v < radius ? radius : (v > top - radius ? top - radius : v); }
+
+// TryDifferentialHalf / TryIndividualHalf (EtcBlock4x4Encoding_ETC1.cpp:692-806, :885-998): the (2 radius + 1)^3 base colours
+// around (r, g, b), red outermost, each with its best codeword; returns the index of the first best try.
+struct TryRec { int r, g, b; uint32_t cw, sel; float err; };
+constexpr int kMaxTrys = 27;
+
+CFX_HD_NOINLINE int try_half_radius(const Px* src, const uint32_t* mapping, int r0, int g0, int b0, int radius, bool diff, TryRec* trys, int& count)
 {
-    const uint32_t mapL[8] = {0, 1, 2, 3, 4, 5, 6, 7}, mapR[8] = {8, 9, 10, 11, 12, 13, 14, 15};
-    const uint32_t mapT[8] = {0, 1, 4, 5, 8, 9, 12, 13}, mapB[8] = {2, 3, 6, 7, 10, 11, 14, 15};
+    int best = 0, n = 0;
+    float best_err = 3.402823466e+38f;
+#pragma unroll 1
+    for (int r = r0 - radius; r <= r0 + radius; ++r)
+#pragma unroll 1
+        for (int g = g0 - radius; g <= g0 + radius; ++g)
+#pragma unroll 1
+            for (int b = b0 - radius; b <= b0 + radius; ++b) {
+                // ConvertFromRGB5 / ConvertFromRGB4 on (unsigned char) components
+                const uint32_t ur = static_cast<unsigned char>(r), ug = static_cast<unsigned char>(g), ub = static_cast<unsigned char>(b);
+                const float fr = static_cast<float>(static_cast<unsigned char>(diff ? (ur << 3) + (ur >> 2) : (ur << 4) + ur))/255.0f;
+                const float fg = static_cast<float>(static_cast<unsigned char>(diff ? (ug << 3) + (ug >> 2) : (ug << 4) + ug))/255.0f;
+                const float fb = static_cast<float>(static_cast<unsigned char>(diff ? (ub << 3) + (ub >> 2) : (ub << 4) + ub))/255.0f;
+                HalfTry t;
+                try_half(src, mapping, fr, fg, fb, t);
+                TryRec& o = trys[n];
+                o.r = r; o.g = g; o.b = b; o.cw = t.cw; o.sel = t.sel; o.err = t.err;
+                if (t.err < best_err) { best_err = t.err; best = n; }
+                ++n;
+            }
+    count = n;
+    return best;
+}
+
+struct BlockCtx {
+    const Px* src;
+    float avgL[3], avgR[3], avgT[3], avgB[3];
+};
+CFX_CONST uint32_t kMapL[8] = {0, 1, 2, 3, 4, 5, 6, 7}, kMapR[8] = {8, 9, 10, 11, 12, 13, 14, 15};
+CFX_CONST uint32_t kMapT[8] = {0, 1, 4, 5, 8, 9, 12, 13}, kMapB[8] = {2, 3, 6, 7, 10, 11, 14, 15};
+
+// Block4x4Encoding_ETC1::TryDifferential (:544-690; base colours from DifferentialTrys, EtcDifferentialTrys.cpp:41-150):
+// both halves' tries, the best pair whose 5-bit deltas fit [-4, 3]; replaces `best` when strictly better.
+// (not inlined: the later iterations call it up to 18 times per block)
+CFX_HD_NOINLINE void try_differential(const BlockCtx& bc, bool flip, int radius, int gray1, int gray2, Encoding& best)
+{
+    const float* c1 = flip ? bc.avgT : bc.avgL;
+    const float* c2 = flip ? bc.avgB : bc.avgR;
+    const uint32_t* m1 = flip ? kMapT : kMapL;
+    const uint32_t* m2 = flip ? kMapB : kMapR;
+    int q1[3], q2[3];
+    for (int c = 0; c < 3; ++c) {
+        // QuantizeR5G5B5 then IntX(31): round(31*clamp(v)) -> expand -> *(1/255) -> round(*31)
+        const uint32_t a5 = static_cast<uint32_t>(roundf(31.0f*clamp01(c1[c]))), b5 = static_cast<uint32_t>(roundf(31.0f*clamp01(c2[c])));
+        const float fa = (1.0f/255.0f)*static_cast<float>((a5 << 3) + (a5 >> 2)), fb = (1.0f/255.0f)*static_cast<float>((b5 << 3) + (b5 >> 2));
+        q1[c] = away_from_edge(static_cast<int>(roundf(fa*31.0f)) + gray1, radius, 31);
+        q2[c] = away_from_edge(static_cast<int>(roundf(fb*31.0f)) + gray2, radius, 31);
+        bend(q1[c], q2[c]);
+    }
+    TryRec t1[kMaxTrys], t2[kMaxTrys];
+    int n1 = 0, n2 = 0;
+    int i1 = try_half_radius(bc.src, m1, q1[0], q1[1], q1[2], radius, true, t1, n1);
+    int i2 = try_half_radius(bc.src, m2, q2[0], q2[1], q2[2], radius, true, t2, n2);
+    float err = 3.402823466e+38f;
+    const int dr = t2[i2].r - t1[i1].r, dg = t2[i2].g - t1[i1].g, db = t2[i2].b - t1[i1].b;
+    if (dr >= -4 && dr <= 3 && dg >= -4 && dg <= 3 && db >= -4 && db <= 3) err = t1[i1].err + t2[i2].err;
+    else {
+#pragma unroll 1
+        for (int a = 0; a < n1; ++a)
+#pragma unroll 1
+            for (int b = 0; b < n2; ++b) {
+                const int er = t2[b].r - t1[a].r, eg = t2[b].g - t1[a].g, eb = t2[b].b - t1[a].b;
+                if (er <= 3 && er >= -4 && eg <= 3 && eg >= -4 && eb <= 3 && eb >= -4) {
+                    const float e = t1[a].err + t2[b].err;
+                    if (e < err) { err = e; i1 = a; i2 = b; }
+                }
+            }
+    }
+    if (err < best.err) {
+        best.err = t1[i1].err + t2[i2].err; best.diff = true; best.flip = flip;
+        best.r1 = t1[i1].r; best.g1 = t1[i1].g; best.b1 = t1[i1].b; best.r2 = t2[i2].r; best.g2 = t2[i2].g; best.b2 = t2[i2].b;
+        best.cw1 = t1[i1].cw; best.cw2 = t2[i2].cw; best.sel1 = t1[i1].sel; best.sel2 = t2[i2].sel;
+    }
+}
+
+// Block4x4Encoding_ETC1::TryIndividual (:807-883; IndividualTrys, EtcIndividualTrys.cpp:41-64): the best try of each half
+CFX_HD_NOINLINE void try_individual(const BlockCtx& bc, bool flip, int radius, Encoding& best)
+{
+    const float* c1 = flip ? bc.avgT : bc.avgL;
+    const float* c2 = flip ? bc.avgB : bc.avgR;
+    const uint32_t* m1 = flip ? kMapT : kMapL;
+    const uint32_t* m2 = flip ? kMapB : kMapR;
+    int q1[3], q2[3];
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t a4 = static_cast<uint32_t>(roundf(15.0f*clamp01(c1[c]))), b4 = static_cast<uint32_t>(roundf(15.0f*clamp01(c2[c])));
+        const float fa = (1.0f/255.0f)*static_cast<float>((a4 << 4) + a4), fb = (1.0f/255.0f)*static_cast<float>((b4 << 4) + b4);
+        q1[c] = away_from_edge(static_cast<int>(roundf(fa*15.0f)), radius, 15);
+        q2[c] = away_from_edge(static_cast<int>(roundf(fb*15.0f)), radius, 15);
+    }
+    TryRec t1[kMaxTrys], t2[kMaxTrys];
+    int n1 = 0, n2 = 0;
+    const int i1 = try_half_radius(bc.src, m1, q1[0], q1[1], q1[2], radius, false, t1, n1);
+    const int i2 = try_half_radius(bc.src, m2, q2[0], q2[1], q2[2], radius, false, t2, n2);
+    const float err = t1[i1].err + t2[i2].err;
+    if (err < best.err) {
+        best.err = err; best.diff = false; best.flip = flip;
+        best.r1 = t1[i1].r; best.g1 = t1[i1].g; best.b1 = t1[i1].b; best.r2 = t2[i2].r; best.g2 = t2[i2].g; best.b2 = t2[i2].b;
+        best.cw1 = t1[i1].cw; best.cw2 = t2[i2].cw; best.sel1 = t1[i1].sel; best.sel2 = t2[i2].sel;
+    }
+}
+
+// src: 16 texels in the reference's block order (column-major: pixel = x*4 + y).
+// effort: etc2comp's, as EtcConverter maps Texture::Quality to it (lib/src/EtcConverter.cpp:34-51: 0, 20, 40, 70, 100).  One
+// Etc::Image per block means the effort percentage of EtcImage.cpp:276-330 is all or nothing: up to 40 only encoding
+// iteration 0 runs, at 70 and 100 the block is iterated until Block4x4Encoding_ETC1::PerformIteration (:232-306) says done.
+CFX_HD uint2 encode_etc1_exact(const Px* src, float effort = 40.0f)
+{
+    BlockCtx bc;
+    bc.src = src;
     // CalculateSourceAverages (RGBX branch): quadrant sums, border texels count as (0,0,0)
     float ul[3], ll[3], ur[3], lr[3];
     {
@@ -99,65 +213,55 @@ CFX_HD uint2 encode_etc1_exact(const Px* src)
         };
         q(0, 1, 4, 5, ul); q(2, 3, 6, 7, ll); q(8, 9, 12, 13, ur); q(10, 11, 14, 15, lr);
     }
-    float avgL[3], avgR[3], avgT[3], avgB[3];
     for (int c = 0; c < 3; ++c) {
-        avgL[c] = (ul[c] + ll[c])*0.125f; avgR[c] = (ur[c] + lr[c])*0.125f;
-        avgT[c] = (ul[c] + ur[c])*0.125f; avgB[c] = (ll[c] + lr[c])*0.125f;
+        bc.avgL[c] = (ul[c] + ll[c])*0.125f; bc.avgR[c] = (ur[c] + lr[c])*0.125f;
+        bc.avgT[c] = (ul[c] + ur[c])*0.125f; bc.avgB[c] = (ll[c] + lr[c])*0.125f;
     }
     // CalculateMostLikelyFlip
     float eL = 0.0f, eR = 0.0f, eT = 0.0f, eB = 0.0f;
     for (uint32_t i = 0; i < 8; ++i) {
-        const float l = gray_distance2(src[i], avgL), r = gray_distance2(src[i + 8], avgR);
-        const float t = gray_distance2(src[mapT[i]], avgT), b = gray_distance2(src[mapB[i]], avgB);
+        const float l = gray_distance2(src[i], bc.avgL), r = gray_distance2(src[i + 8], bc.avgR);
+        const float t = gray_distance2(src[kMapT[i]], bc.avgT), b = gray_distance2(src[kMapB[i]], bc.avgB);
         eL += l; eR += r; eT += t; eB += b;
     }
-    const bool likely_flip = (eT + eB) < (eL + eR);
+    const bool likely = (eT + eB) < (eL + eR);
 
     Encoding best;
     best.err = 3.402823466e+38f; best.diff = true; best.flip = false;
     best.r1 = best.g1 = best.b1 = best.r2 = best.g2 = best.b2 = 0; best.cw1 = best.cw2 = best.sel1 = best.sel2 = 0;
-    for (int step = 0; step < 4; ++step) {
-        const bool flip = step < 2 ? likely_flip : !likely_flip;
-        const bool diff = (step & 1) == 0;
-        const float* c1 = flip ? avgT : avgL;
-        const float* c2 = flip ? avgB : avgR;
-        const uint32_t* m1 = flip ? mapT : mapL;
-        const uint32_t* m2 = flip ? mapB : mapR;
-        int q1[3], q2[3];
-        float f1[3], f2[3];
-        if (diff) {
-            for (int c = 0; c < 3; ++c) {
-                // QuantizeR5G5B5 then IntX(31): round(31*clamp(v)) -> expand -> *(1/255) -> round(*31)
-                const uint32_t a5 = static_cast<uint32_t>(roundf(31.0f*clamp01(c1[c]))), b5 = static_cast<uint32_t>(roundf(31.0f*clamp01(c2[c])));
-                const float fa = (1.0f/255.0f)*static_cast<float>((a5 << 3) + (a5 >> 2)), fb = (1.0f/255.0f)*static_cast<float>((b5 << 3) + (b5 >> 2));
-                q1[c] = min(max(static_cast<int>(roundf(fa*31.0f)), 0), 31);
-                q2[c] = min(max(static_cast<int>(roundf(fb*31.0f)), 0), 31);
-                bend(q1[c], q2[c]);
-                f1[c] = static_cast<float>(static_cast<unsigned char>((q1[c] << 3) + (q1[c] >> 2)))/255.0f;
-                f2[c] = static_cast<float>(static_cast<unsigned char>((q2[c] << 3) + (q2[c] >> 2)))/255.0f;
+    // encoding iteration 0 (PerformFirstIteration): radius 0, SetDoneIfPerfect after every try
+    try_differential(bc, likely, 0, 0, 0, best);
+    if (best.err != 0.0f) try_individual(bc, likely, 0, best);
+    if (best.err != 0.0f) try_differential(bc, !likely, 0, 0, 0, best);
+    if (best.err != 0.0f) try_individual(bc, !likely, 0, best);
+    // later iterations: radius 1 on both flips, then the "degenerate" tries (gray offsets on the base colours)
+    if (effort > 40.0f) {
+#pragma unroll 1
+        for (int it = 1; it <= 8 && best.err != 0.0f; ++it) {
+            bool done = false;
+            switch (it) {
+                case 1: try_differential(bc, likely, 1, 0, 0, best); break;
+                case 2: try_individual(bc, likely, 1, best); done = effort <= 49.5f; break;
+                case 3: try_differential(bc, !likely, 1, 0, 0, best); done = effort <= 59.5f; break;
+                case 4: try_individual(bc, !likely, 1, best); done = effort <= 69.5f; break;
+                case 5: case 6: case 7: case 8: {
+                    const bool f = it == 6 ? !likely : likely;
+                    const int m = it == 8 ? 4 : 2;
+                    if (it == 7) {
+                        try_differential(bc, f, 1, -2, -2, best); try_differential(bc, f, 1, -2, 2, best);
+                        try_differential(bc, f, 1, 2, -2, best); try_differential(bc, f, 1, 2, 2, best);
+                    } else {
+                        try_differential(bc, f, 1, -m, 0, best); try_differential(bc, f, 1, m, 0, best);
+                        try_differential(bc, f, 1, 0, m, best); try_differential(bc, f, 1, 0, -m, best);
+                    }
+                    done = it == 5 ? effort <= 79.5f : (it == 6 ? effort <= 89.5f : (it == 7 ? effort <= 99.5f : true));
+                    break;
+                }
             }
-        } else {
-            for (int c = 0; c < 3; ++c) {
-                const uint32_t a4 = static_cast<uint32_t>(roundf(15.0f*clamp01(c1[c]))), b4 = static_cast<uint32_t>(roundf(15.0f*clamp01(c2[c])));
-                const float fa = (1.0f/255.0f)*static_cast<float>((a4 << 4) + a4), fb = (1.0f/255.0f)*static_cast<float>((b4 << 4) + b4);
-                // IndividualTrys uses the same MoveAwayFromEdge (clamp to [0, 31]) as the differential path
-                q1[c] = min(max(static_cast<int>(roundf(fa*15.0f)), 0), 31);
-                q2[c] = min(max(static_cast<int>(roundf(fb*15.0f)), 0), 31);
-                f1[c] = static_cast<float>(static_cast<unsigned char>((q1[c] << 4) + q1[c]))/255.0f;
-                f2[c] = static_cast<float>(static_cast<unsigned char>((q2[c] << 4) + q2[c]))/255.0f;
-            }
+            if (done) break;
         }
-        HalfTry t1, t2;
-        try_half(src, m1, f1[0], f1[1], f1[2], t1);
-        try_half(src, m2, f2[0], f2[1], f2[2], t2);
-        const float err = t1.err + t2.err;
-        if (err < best.err) {
-            best.err = err; best.diff = diff; best.flip = flip;
-            best.r1 = q1[0]; best.g1 = q1[1]; best.b1 = q1[2]; best.r2 = q2[0]; best.g2 = q2[1]; best.b2 = q2[2];
-            best.cw1 = t1.cw; best.cw2 = t2.cw; best.sel1 = t1.sel; best.sel2 = t2.sel;
-        }
-        if (best.err == 0.0f) break;                                 // SetDoneIfPerfect
     }
+    const uint32_t* mapL = kMapL; const uint32_t* mapR = kMapR; const uint32_t* mapT = kMapT; const uint32_t* mapB = kMapB;
 
     // SetEncodingBits
     uint32_t hi = 0;
