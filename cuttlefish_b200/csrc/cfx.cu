@@ -925,7 +925,7 @@ int cfx_format_is_exact(uint32_t format, uint32_t type, uint32_t quality)
         case CFX_FORMAT_BC1_RGB: case CFX_FORMAT_BC2: case CFX_FORMAT_BC3: return bc1_color_is_exact(quality) ? 1 : 0;
 #endif
 #ifdef CFX_HAVE_ETC
-        case CFX_FORMAT_ETC1: return etc1_is_exact(quality) ? 1 : 0;       // linear colour space
+        case CFX_FORMAT_ETC1: return etc1_is_exact(quality) ? 1 : 0;       // linear and sRGB (RGBX / REC709 metric)
 #endif
         default: return 0;
     }

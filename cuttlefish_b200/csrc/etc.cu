@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
             // etc2comp's effort for the quality level (lib/src/EtcConverter.cpp:34-51): up to Normal only encoding iteration 0
             // runs, High (70) goes on to the radius-1 tries and the first degenerate set, Highest (100) runs all nine
             const float effort = p.quality == 3u ? 70.0f : (p.quality >= 4u ? 100.0f : 40.0f);
-            const uint2 color = etc1x::encode_etc1_exact(src, effort);
+            // sRGB textures: etc2comp's REC709 metric instead of RGBX (lib/src/EtcConverter.cpp:61-64)
+            const uint2 color = etc1x::encode_etc1_exact(src, effort, p.color_space == 1u);
             if (live) reinterpret_cast<uint2*>(p.dst)[blk] = color;
             continue;
         }
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
     }
 }
 
-bool etc1_is_exact(uint32_t quality) { return quality <= 4; }       // every level (linear colour space)
+bool etc1_is_exact(uint32_t quality) { return quality <= 4; }       // every level, linear and sRGB
 
 int launch_etc(const EncodeParams& p, cudaStream_t stream)
 {
@@ -112,8 +113,8 @@ int launch_etc(const EncodeParams& p, cudaStream_t stream)
         default: return -2;
     }
     const uint32_t grid = min(ctas, persistent_ctas(k, kEtcWarps*32));
-    // ETC1 in linear colour space is the byte-exact restatement at every quality level
-    bool exact = etc1_is_exact(p.quality) && p.color_space == 0;
+    // ETC1 is the byte-exact restatement at every quality level, in both colour spaces
+    bool exact = etc1_is_exact(p.quality);
     void* args[] = {const_cast<EncodeParams*>(&p), const_cast<int*>(&rounds), const_cast<int*>(&radius), &exact};
     if (cudaLaunchKernel(k, dim3(grid), dim3(kEtcWarps*32), args, 0, stream) != cudaSuccess) return -4;
     return 1;

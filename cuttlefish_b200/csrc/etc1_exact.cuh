@@ -1,4 +1,4 @@
-// Byte-exact ETC1 in linear colour space, every Texture::Quality: a restatement of what etc2comp computes when
+// Byte-exact ETC1, every Texture::Quality, linear and sRGB colour space (etc2comp's RGBX / REC709 error metric): a restatement of what etc2comp computes when
 // EtcConverter::process (lib/src/EtcConverter.cpp:120-152) encodes one block as its own Etc::Image.
 //   effort <= 40 (Lowest / Low / Normal): only encoding iteration 0 runs (lib/etc2comp/EtcLib/Etc/EtcImage.cpp:276-330 --
 //   with one block per image the effort percentage rounds to zero blocks; Block4x4Encoding_ETC1::PerformFirstIteration,
@@ -44,7 +44,21 @@ CFX_HD float gray_distance2(const Px& p, const float* t)
 struct HalfTry { int r, g, b; uint32_t cw; uint32_t sel /* 2 bits x 8, pixel order of the half */; float err; };
 
 // TryDifferentialHalf / TryIndividualHalf at radius 0: one base colour, all 8 codewords
-CFX_HD_NOINLINE void try_half(const Px* src, const uint32_t* mapping, float cr, float cg, float cb, HalfTry& t)
+// rec709: the REC709 error metric etc2comp uses for sRGB textures (Block4x4Encoding::CalcPixelError,
+// EtcBlock4x4Encoding.cpp:157-180: luma weighted 3, blue chroma 0.5; source and decoded alpha are 1 for ETC1)
+CFX_HD float pixel_error_rec709(float dr, float dg, float db, const Px& s)
+{
+    const float luma1 = s.r*0.2126f + s.g*0.7152f + s.b*0.0722f;
+    const float cr1 = 0.5f*((s.r - luma1)*(1.0f/(1.0f - 0.2126f)));
+    const float cb1 = 0.5f*((s.b - luma1)*(1.0f/(1.0f - 0.0722f)));
+    const float luma2 = dr*0.2126f + dg*0.7152f + db*0.0722f;
+    const float cr2 = 0.5f*((dr - luma2)*(1.0f/(1.0f - 0.2126f)));
+    const float cb2 = 0.5f*((db - luma2)*(1.0f/(1.0f - 0.0722f)));
+    const float dl = s.a*luma1 - 1.0f*luma2, dcr = s.a*cr1 - 1.0f*cr2, dcb = s.a*cb1 - 1.0f*cb2, da = 1.0f - s.a;
+    return 3.0f*dl*dl + dcr*dcr + 0.5f*dcb*dcb + da*da;
+}
+
+CFX_HD_NOINLINE void try_half(const Px* src, const uint32_t* mapping, float cr, float cg, float cb, HalfTry& t, bool rec709 = false)
 {
     t.err = 3.402823466e+38f; t.cw = 0; t.sel = 0;
 #pragma unroll 1
@@ -63,6 +77,7 @@ CFX_HD_NOINLINE void try_half(const Px* src, const uint32_t* mapping, float cr, 
             for (uint32_t k = 0; k < 4; ++k) {
                 float e;
                 if (s.a != s.a) e = 0.0f;                       // border texel
+                else if (rec709) e = pixel_error_rec709(sr[k], sg[k], sb[k], s);
                 else {
                     const float dr = sr[k] - s.r, dg = sg[k] - s.g, db = sb[k] - s.b, da = 1.0f - s.a;
                     e = dr*dr + dg*dg + db*db + da*da;
@@ -92,7 +107,8 @@ CFX_HD int away_from_edge(int v, int radius, int top) { return v < radius ? radi
 struct TryRec { int r, g, b; uint32_t cw, sel; float err; };
 constexpr int kMaxTrys = 27;
 
-CFX_HD_NOINLINE int try_half_radius(const Px* src, const uint32_t* mapping, int r0, int g0, int b0, int radius, bool diff, TryRec* trys, int& count)
+CFX_HD_NOINLINE int try_half_radius(const Px* src, const uint32_t* mapping, int r0, int g0, int b0, int radius, bool diff, TryRec* trys, int& count,
+    bool rec709)
 {
     int best = 0, n = 0;
     float best_err = 3.402823466e+38f;
@@ -108,7 +124,7 @@ CFX_HD_NOINLINE int try_half_radius(const Px* src, const uint32_t* mapping, int 
                 const float fg = static_cast<float>(static_cast<unsigned char>(diff ? (ug << 3) + (ug >> 2) : (ug << 4) + ug))/255.0f;
                 const float fb = static_cast<float>(static_cast<unsigned char>(diff ? (ub << 3) + (ub >> 2) : (ub << 4) + ub))/255.0f;
                 HalfTry t;
-                try_half(src, mapping, fr, fg, fb, t);
+                try_half(src, mapping, fr, fg, fb, t, rec709);
                 TryRec& o = trys[n];
                 o.r = r; o.g = g; o.b = b; o.cw = t.cw; o.sel = t.sel; o.err = t.err;
                 if (t.err < best_err) { best_err = t.err; best = n; }
@@ -120,6 +136,7 @@ CFX_HD_NOINLINE int try_half_radius(const Px* src, const uint32_t* mapping, int 
 
 struct BlockCtx {
     const Px* src;
+    bool rec709;
     float avgL[3], avgR[3], avgT[3], avgB[3];
 };
 CFX_CONST uint32_t kMapL[8] = {0, 1, 2, 3, 4, 5, 6, 7}, kMapR[8] = {8, 9, 10, 11, 12, 13, 14, 15};
@@ -145,8 +162,8 @@ CFX_HD_NOINLINE void try_differential(const BlockCtx& bc, bool flip, int radius,
     }
     TryRec t1[kMaxTrys], t2[kMaxTrys];
     int n1 = 0, n2 = 0;
-    int i1 = try_half_radius(bc.src, m1, q1[0], q1[1], q1[2], radius, true, t1, n1);
-    int i2 = try_half_radius(bc.src, m2, q2[0], q2[1], q2[2], radius, true, t2, n2);
+    int i1 = try_half_radius(bc.src, m1, q1[0], q1[1], q1[2], radius, true, t1, n1, bc.rec709);
+    int i2 = try_half_radius(bc.src, m2, q2[0], q2[1], q2[2], radius, true, t2, n2, bc.rec709);
     float err = 3.402823466e+38f;
     const int dr = t2[i2].r - t1[i1].r, dg = t2[i2].g - t1[i1].g, db = t2[i2].b - t1[i1].b;
     if (dr >= -4 && dr <= 3 && dg >= -4 && dg <= 3 && db >= -4 && db <= 3) err = t1[i1].err + t2[i2].err;
@@ -185,8 +202,8 @@ CFX_HD_NOINLINE void try_individual(const BlockCtx& bc, bool flip, int radius, E
     }
     TryRec t1[kMaxTrys], t2[kMaxTrys];
     int n1 = 0, n2 = 0;
-    const int i1 = try_half_radius(bc.src, m1, q1[0], q1[1], q1[2], radius, false, t1, n1);
-    const int i2 = try_half_radius(bc.src, m2, q2[0], q2[1], q2[2], radius, false, t2, n2);
+    const int i1 = try_half_radius(bc.src, m1, q1[0], q1[1], q1[2], radius, false, t1, n1, bc.rec709);
+    const int i2 = try_half_radius(bc.src, m2, q2[0], q2[1], q2[2], radius, false, t2, n2, bc.rec709);
     const float err = t1[i1].err + t2[i2].err;
     if (err < best.err) {
         best.err = err; best.diff = false; best.flip = flip;
@@ -199,10 +216,10 @@ CFX_HD_NOINLINE void try_individual(const BlockCtx& bc, bool flip, int radius, E
 // effort: etc2comp's, as EtcConverter maps Texture::Quality to it (lib/src/EtcConverter.cpp:34-51: 0, 20, 40, 70, 100).  One
 // Etc::Image per block means the effort percentage of EtcImage.cpp:276-330 is all or nothing: up to 40 only encoding
 // iteration 0 runs, at 70 and 100 the block is iterated until Block4x4Encoding_ETC1::PerformIteration (:232-306) says done.
-CFX_HD uint2 encode_etc1_exact(const Px* src, float effort = 40.0f)
+CFX_HD uint2 encode_etc1_exact(const Px* src, float effort = 40.0f, bool rec709 = false)
 {
     BlockCtx bc;
-    bc.src = src;
+    bc.src = src; bc.rec709 = rec709;
     // CalculateSourceAverages (RGBX branch): quadrant sums, border texels count as (0,0,0)
     float ul[3], ll[3], ur[3], lr[3];
     {
@@ -213,6 +230,31 @@ CFX_HD uint2 encode_etc1_exact(const Px* src, float effort = 40.0f)
         };
         q(0, 1, 4, 5, ul); q(2, 3, 6, 7, ll); q(8, 9, 12, 13, ur); q(10, 11, 14, 15, lr);
     }
+    bool partial = false;
+    for (int i = 0; i < 16; ++i) partial = partial || src[i].a != src[i].a;
+    if (rec709 && partial) {
+        // a block with border texels is "translucent" under every metric but RGBX: alpha-weighted averages, NaN alpha
+        // counts as 0 (CalculateSourceAverages, :413-520); the border texels are (0, 0, 0), so the sums above stand
+        auto wq = [&](int a, int b, int c, int d) {
+            const float w0 = src[a].a != src[a].a ? 0.0f : src[a].a, w1 = src[b].a != src[b].a ? 0.0f : src[b].a;
+            const float w2 = src[c].a != src[c].a ? 0.0f : src[c].a, w3 = src[d].a != src[d].a ? 0.0f : src[d].a;
+            return ((w0 + w1) + w2) + w3;
+        };
+        const float wul = wq(0, 1, 4, 5), wll = wq(2, 3, 6, 7), wur = wq(8, 9, 12, 13), wlr = wq(10, 11, 14, 15);
+        const float wL = wul + wll, wR = wur + wlr, wT = wul + wur, wB = wll + wlr;
+        for (int c = 0; c < 3; ++c) {
+            if (wL > 0.0f) bc.avgL[c] = (ul[c] + ll[c])*(1.0f/wL);
+            if (wR > 0.0f) bc.avgR[c] = (ur[c] + lr[c])*(1.0f/wR);
+            if (wT > 0.0f) bc.avgT[c] = (ul[c] + ur[c])*(1.0f/wT);
+            if (wB > 0.0f) bc.avgB[c] = (ll[c] + lr[c])*(1.0f/wB);
+        }
+        for (int c = 0; c < 3; ++c) {
+            if (wL == 0.0f) bc.avgL[c] = bc.avgR[c];
+            if (wR == 0.0f) bc.avgR[c] = bc.avgL[c];
+            if (wT == 0.0f) bc.avgT[c] = bc.avgB[c];
+            if (wB == 0.0f) bc.avgB[c] = bc.avgT[c];
+        }
+    } else
     for (int c = 0; c < 3; ++c) {
         bc.avgL[c] = (ul[c] + ll[c])*0.125f; bc.avgR[c] = (ur[c] + lr[c])*0.125f;
         bc.avgT[c] = (ul[c] + ur[c])*0.125f; bc.avgB[c] = (ll[c] + lr[c])*0.125f;

@@ -430,6 +430,13 @@ def test_etc1_bit_exact(cfx, oracle):
     for name in golden_cases(["ETC1"]):
         src, blocks, f, kw = load_golden(name)
         assert np.array_equal(cfx.encode(src, f, **kw), blocks), name
+    # sRGB textures: etc2comp's REC709 metric (lib/src/EtcConverter.cpp:61-64), partial blocks with alpha-weighted averages
+    for kind, w, h in [("noise+grad", 128, 128), ("noise+grad", 97, 61), ("ui", 96, 96)]:
+        img = oracle.gen_image(kind, w, h, seed=61) if kind != "ui" else oracle.gen_image(kind, w, h)
+        for q in ("Normal", "High", "Highest"):
+            ref = oracle.encode(img, "ETC1", quality=q, srgb=True)
+            bad = block_mismatches(cfx.encode(oracle.to_rgba8(img), "ETC1", quality=q, srgb=True), ref, 8)
+            assert bad.size == 0, "ETC1 sRGB %s %dx%d %s: %d blocks differ, first %s" % (kind, w, h, q, bad.size, bad[:8])
 
 
 # ---- BC4 / BC5 SNorm (Compressonator in the reference): our own search in a biased domain, PSNR parity ----

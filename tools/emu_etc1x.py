@@ -12,7 +12,7 @@ so = os.path.join(out, "libemu_etc1x.so")
 subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++",
                        os.path.join(ROOT, "tools", "emu_etc1x.cpp"), "-o", so])
 lib = ctypes.CDLL(so)
-lib.emu_etc1x_encode.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_float]
+lib.emu_etc1x_encode.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_float, ctypes.c_int]
 EFFORT = {"Lowest": 0.0, "Low": 20.0, "Normal": 40.0, "High": 70.0, "Highest": 100.0}
 levels = sys.argv[1:] or list(EFFORT)
 inputs = [(k + " %d" % n, oracle.gen_image(k, n, n)) for k, n in (("noise+grad", 128), ("gradient", 128), ("ui", 96))]
@@ -26,10 +26,11 @@ for name, img in inputs:
     img = np.ascontiguousarray(img, np.float32)
     h, w, _ = img.shape
     for quality in levels:
+      for srgb in (False, True):
         got = np.zeros(((h + 3)//4)*((w + 3)//4)*8, np.uint8)
-        lib.emu_etc1x_encode(img.ctypes.data, w, h, got.ctypes.data, EFFORT[quality])
-        ref = oracle.encode(img, "ETC1", quality=quality)
+        lib.emu_etc1x_encode(img.ctypes.data, w, h, got.ctypes.data, EFFORT[quality], 1 if srgb else 0)
+        ref = oracle.encode(img, "ETC1", quality=quality, srgb=srgb)
         n = int(np.sum(np.any(got.reshape(-1, 8) != ref.reshape(-1, 8), axis=1)))
         bad += n
-        print("%-18s ETC1 %-7s mismatching blocks %d of %d" % (name, quality, n, got.size//8), flush=True)
+        print("%-18s ETC1 %-7s %-6s mismatching blocks %d of %d" % (name, quality, "sRGB" if srgb else "linear", n, got.size//8), flush=True)
 print("TOTAL mismatches", bad)
