@@ -31,7 +31,7 @@ LDR = [("rgb00", SMALL + "LDR-RGB/ldr-rgb-00.png", (32, 32)), ("rgb03", SMALL + 
 FORMATS_NORMAL = ["BC1_RGB", "BC3", "BC7", "ETC1", "ETC2_R8G8B8", "ETC2_R8G8B8A8", "ASTC_4x4", "ASTC_6x6", "ASTC_8x8", "ASTC_10x8"]
 # the other Texture::Quality levels, on a subset (astcenc's exhaustive preset takes ~20 s per crop)
 LEVEL_IMAGES = ["rgb00", "rgb07", "rgba01"]
-LEVEL_FORMATS = ["BC7", "ASTC_6x6", "ETC2_R8G8B8A8", "BC1_RGB"]
+LEVEL_FORMATS = ["BC7", "ASTC_6x6", "ETC2_R8G8B8A8", "BC1_RGB", "ETC1"]
 LEVELS = ["Lowest", "Low", "High", "Highest"]
 
 
@@ -73,12 +73,20 @@ def main():
         assert src.shape == (N, N, 4), (name, rgba.shape)
         img = src.astype(np.float32) / np.float32(255.0)
         arrays = {"src": src}
+        # (variants already in the file are kept: adding a format does not re-run astcenc's exhaustive preset)
+        path_out = os.path.join(HERE, "real", name + ".npz")
+        if os.path.exists(path_out):
+            old = np.load(path_out)
+            if np.array_equal(old["src"], src):
+                arrays.update({k: old[k] for k in old.files})
         for fmt in FORMATS_NORMAL:
-            arrays["blocks__%s__Normal" % fmt] = oracle.encode_glue(img, fmt, threads=0)
+            if "blocks__%s__Normal" % fmt not in arrays:
+                arrays["blocks__%s__Normal" % fmt] = oracle.encode_glue(img, fmt, threads=0)
         if name in LEVEL_IMAGES:
             for fmt in LEVEL_FORMATS:
                 for q in LEVELS:
-                    arrays["blocks__%s__%s" % (fmt, q)] = oracle.encode_glue(img, fmt, threads=0, quality=q)
+                    if "blocks__%s__%s" % (fmt, q) not in arrays:
+                        arrays["blocks__%s__%s" % (fmt, q)] = oracle.encode_glue(img, fmt, threads=0, quality=q)
         np.savez_compressed(os.path.join(HERE, "real", name + ".npz"), **arrays)
         print(name, len(arrays) - 1, "variants", flush=True)
     hdr = read_rgbe(SMALL + "HDR-RGB/hdr-rgb-00.hdr")
