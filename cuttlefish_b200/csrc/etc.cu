@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
             }
             continue;
         }
-        const uint2 color = FORMAT == 39 ? etc::encode_color_a1(xs, lane, rounds, vm) : etc::encode_color(xs, lane, FORMAT != 37, rounds, vm);
+        // sRGB textures: the reference's perceptual (REC709) colour error instead of plain squared RGB distance
+        const bool perc = p.color_space == 1u;
+        const uint2 color = FORMAT == 39 ? etc::encode_color_a1(xs, lane, rounds, vm, perc) : etc::encode_color(xs, lane, FORMAT != 37, rounds, vm, perc);
         if (FORMAT == 40) {
             const uint2 alpha = etc::encode_eac_alpha(xs, lane, alpha_radius, vm);
             if (live) reinterpret_cast<uint4*>(p.dst)[blk] = make_uint4(alpha.x, alpha.y, color.x, color.y);

@@ -52,6 +52,28 @@ CFX_HD int expand7(int v) { return (v << 1) | (v >> 6); }
 #endif
 struct HalfFit { float err; uint32_t table; };
 
+// The colour error metric.  Linear textures: plain squared RGB distance (etc2comp's RGBX).  sRGB textures (`perc`): the
+// reference switches etc2comp to REC709 (lib/src/EtcConverter.cpp:61-88; Block4x4Encoding::CalcPixelError,
+// EtcBlock4x4Encoding.cpp:157-180): 3 dL^2 + dCr^2 + 0.5 dCb^2 with L = 0.2126 r + 0.7152 g + 0.0722 b,
+// Cr = 0.5 (r - L)/(1 - 0.2126), Cb = 0.5 (b - L)/(1 - 0.0722) -- a quadratic form d^T A d of the RGB difference d,
+// A = M^T diag(3, 1, 0.5) M; its six coefficients below.  The search is the same, every error sum is taken in this metric.
+namespace rec709 {
+constexpr double kLr = 0.2126, kLg = 0.7152, kLb = 0.0722;
+constexpr double kCr = 0.5/(1.0 - kLr), kCb = 0.5/(1.0 - kLb);
+// rows of M: luma, chroma red, chroma blue
+constexpr double m[3][3] = {{kLr, kLg, kLb}, {kCr*(1.0 - kLr), -kCr*kLg, -kCr*kLb}, {-kCb*kLr, -kCb*kLg, kCb*(1.0 - kLb)}};
+constexpr double w[3] = {3.0, 1.0, 0.5};
+constexpr double a(int i, int j) { return w[0]*m[0][i]*m[0][j] + w[1]*m[1][i]*m[1][j] + w[2]*m[2][i]*m[2][j]; }
+constexpr float a00 = static_cast<float>(a(0, 0)), a11 = static_cast<float>(a(1, 1)), a22 = static_cast<float>(a(2, 2));
+constexpr float a01 = static_cast<float>(a(0, 1)), a02 = static_cast<float>(a(0, 2)), a12 = static_cast<float>(a(1, 2));
+}
+// d^T A d
+CFX_HD float perc_norm(float d0, float d1, float d2)
+{
+    return rec709::a00*d0*d0 + rec709::a11*d1*d1 + rec709::a22*d2*d2 + 2.0f*(rec709::a01*d0*d1 + rec709::a02*d0*d2 + rec709::a12*d1*d2);
+}
+CFX_HD float color_err(float d0, float d1, float d2, bool perc) { return perc ? perc_norm(d0, d1, d2) : d0*d0 + d1*d1 + d2*d2; }
+
 // The four colours of modifier table tb around an 8-bit base colour (clamped), kept as -2 p_k and |p_k|^2: the error of
 // texel x to colour k is |x|^2 + (|p_k|^2 - 2 p_k.x), three multiply-adds per candidate. For 8-bit sources every term is
 // an integer below 2^24, so this is exactly the sum of squared differences.
@@ -59,7 +81,7 @@ struct HalfFit { float err; uint32_t table; };
 // (transparent) at no cost, the others choose among {+0, +big, -big} (selectors 0, 1, 3).
 struct TableColours { float n0[4], n1[4], n2[4], cc[4]; };
 
-CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours& p)
+CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours& p, bool perc = false)
 {
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {
@@ -67,6 +89,14 @@ CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours
         if (punch && k == 0u) m = 0;
         const float p0 = static_cast<float>(clamp255(base[0] + m)), p1 = static_cast<float>(clamp255(base[1] + m)),
             p2 = static_cast<float>(clamp255(base[2] + m));
+        if (perc) {
+            // |p - x|_A^2 = p^T A p - 2 (A p).x + x^T A x
+            const float q0 = rec709::a00*p0 + rec709::a01*p1 + rec709::a02*p2, q1 = rec709::a01*p0 + rec709::a11*p1 + rec709::a12*p2,
+                q2 = rec709::a02*p0 + rec709::a12*p1 + rec709::a22*p2;
+            p.n0[k] = -2.0f*q0; p.n1[k] = -2.0f*q1; p.n2[k] = -2.0f*q2;
+            p.cc[k] = p0*q0 + p1*q1 + p2*q2;
+            continue;
+        }
         p.n0[k] = -2.0f*p0; p.n1[k] = -2.0f*p1; p.n2[k] = -2.0f*p2;
         p.cc[k] = p0*p0 + p1*p1 + p2*p2;
     }
@@ -75,13 +105,13 @@ CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours
 // Best modifier table (of tb0 .. tb1) of one half (texel mask) for an 8-bit base colour, and its error. The selectors are
 // not kept: most fits lose, half_selectors() recomputes them for the one that ends up in the block.
 CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask = 0,
-    uint32_t tb0 = 0, uint32_t tb1 = 7)
+    uint32_t tb0 = 0, uint32_t tb1 = 7, bool perc = false)
 {
     out.err = 3.0e38f; out.table = 0;
 #pragma unroll 1
     for (uint32_t tb = tb0; tb <= tb1; ++tb) {
         TableColours p;
-        table_colours(base, tb, tmask != 0, p);
+        table_colours(base, tb, tmask != 0, p, perc);
         float err = 0.0f;
         for (uint32_t left = mask & ~tmask; left; left &= left - 1u) {
             const uint32_t t = static_cast<uint32_t>(__ffs(left)) - 1u;
@@ -92,7 +122,7 @@ CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, f
                 if (tmask && k == 2u) continue;
                 be = fminf(be, p.cc[k] + p.n0[k]*x0 + p.n1[k]*x1 + p.n2[k]*x2);
             }
-            err += fmaxf(be + (x0*x0 + x1*x1 + x2*x2), 0.0f);
+            err += fmaxf(be + (perc ? perc_norm(x0, x1, x2) : x0*x0 + x1*x1 + x2*x2), 0.0f);
             if (err >= out.err || err >= limit) break;
         }
         if (err < out.err) { out.err = err; out.table = tb; }
@@ -100,10 +130,10 @@ CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, f
 }
 
 // Selectors (2 bits per texel t, only the half's texels) of a base colour and table: the first minimum over k.
-CFX_HD uint32_t half_selectors(float* xs, uint32_t lane, uint32_t mask, const int* base, uint32_t tb, uint32_t tmask = 0)
+CFX_HD uint32_t half_selectors(float* xs, uint32_t lane, uint32_t mask, const int* base, uint32_t tb, uint32_t tmask = 0, bool perc = false)
 {
     TableColours p;
-    table_colours(base, tb, tmask != 0, p);
+    table_colours(base, tb, tmask != 0, p, perc);
     uint32_t sel = 0;
     for (uint32_t left = mask; left; left &= left - 1u) {
         const uint32_t t = static_cast<uint32_t>(__ffs(left)) - 1u;
@@ -124,12 +154,12 @@ CFX_HD uint32_t half_selectors(float* xs, uint32_t lane, uint32_t mask, const in
 
 // Descent of one half's quantised base colour (bits = 4 or 5) within [lo, hi] per channel.
 CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* q /* in/out */, const int* lo, const int* hi,
-    int rounds, HalfFit& best, uint32_t tmask = 0)
+    int rounds, HalfFit& best, uint32_t tmask = 0, bool perc = false)
 {
     int base[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { q[c] = min(max(q[c], lo[c]), hi[c]); base[c] = bits == 5 ? expand5(q[c]) : expand4(q[c]); }
-    half_fit(xs, lane, mask, base, 3.0e38f, best, tmask);
+    half_fit(xs, lane, mask, base, 3.0e38f, best, tmask, 0, 7, perc);
     for (int round = 0; round < rounds && best.err > 0.0f; ++round) {
         bool improved = false;
 #pragma unroll 1
@@ -152,7 +182,7 @@ CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* 
             // (up to Quality::Normal) only look at the incumbent's neighbours, the long ones at all eight
             const bool narrow = CFX_ETC_NARROW && rounds <= 1;
             half_fit(xs, lane, mask, base, best.err, f, tmask, narrow ? (best.table ? best.table - 1u : 0u) : 0u,
-                narrow ? min(best.table + 1u, 7u) : 7u);
+                narrow ? min(best.table + 1u, 7u) : 7u, perc);
             if (f.err < best.err) { best = f; q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; improved = true; }
         }
         if (!improved) break;
@@ -194,7 +224,7 @@ struct ColorResult { float err; uint32_t hi, lo; };
 // diff_only: no individual (444+444) mode -- ETC2 RGB8A1, where that bit is the opaque flag.
 // tmask != 0: punch-through block of RGB8A1 (opaque flag clear, see half_fit).
 CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, bool diff_only = false, uint32_t tmask = 0,
-    uint32_t vm = 0xFFFFu)
+    uint32_t vm = 0xFFFFu, bool perc = false)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
     const uint32_t skip = tmask | (~vm & 0xFFFFu);       // texels without a say in the base colours
@@ -234,12 +264,12 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
                 }
             }
             HalfFit fA, fB;
-            half_search(xs, lane, maskA & vm, bits, qA, lo, hi, rounds, fA, tmask);
+            half_search(xs, lane, maskA & vm, bits, qA, lo, hi, rounds, fA, tmask, perc);
             if (diff) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { lo[c] = max(qA[c] - 4, 0); hi[c] = min(qA[c] + 3, 31); }
             }
-            half_search(xs, lane, maskB & vm, bits, qB, lo, hi, rounds, fB, tmask);
+            half_search(xs, lane, maskB & vm, bits, qB, lo, hi, rounds, fB, tmask, perc);
             const float err = fA.err + fB.err;
             if (err < out.err) {
                 uint32_t h = 0, l = 0;
@@ -263,7 +293,7 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
                 int bA[3], bB[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { bA[c] = diff ? expand5(qA[c]) : expand4(qA[c]); bB[c] = diff ? expand5(qB[c]) : expand4(qB[c]); }
-                l = pixel_bits(half_selectors(xs, lane, maskA, bA, fA.table, tmask) | half_selectors(xs, lane, maskB, bB, fB.table, tmask));
+                l = pixel_bits(half_selectors(xs, lane, maskA, bA, fA.table, tmask, perc) | half_selectors(xs, lane, maskB, bB, fB.table, tmask, perc));
                 out.err = err; out.hi = h; out.lo = l;
             }
         }
@@ -271,23 +301,25 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
 }
 
 // ---- ETC2 planar ---------------------------------------------------------------------------------
-CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, const int* V, uint32_t vm = 0xFFFFu)
+CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, const int* V, uint32_t vm = 0xFFFFu, bool perc = false)
 {
     float err = 0.0f;
     for (uint32_t t = 0; t < 16; ++t) {
         if (!((vm >> t) & 1u)) continue;
         const int x = t & 3, y = t >> 2;
+        float d[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const int v = clamp255((x*(H[c] - O[c]) + y*(V[c] - O[c]) + 4*O[c] + 2) >> 2);
-            const float d = static_cast<float>(v) - px(xs, lane, t, c);
-            err += d*d;
+            d[c] = static_cast<float>(v) - px(xs, lane, t, c);
+            if (!perc) err += d[c]*d[c];
         }
+        if (perc) err += perc_norm(d[0], d[1], d[2]);
     }
     return err;
 }
 
-CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out, uint32_t vm = 0xFFFFu)
+CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out, uint32_t vm = 0xFFFFu, bool perc = false)
 {
     int q[9];     // RO GO BO RH GH BH RV GV BV (6/7/6 bits)
 #pragma unroll
@@ -315,7 +347,7 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
         }
     };
     expand_all();
-    float best = planar_error(xs, lane, O, H, V, vm);
+    float best = planar_error(xs, lane, O, H, V, vm, perc);
     for (int round = 0; round < rounds && best > 0.0f; ++round) {
         bool improved = false;
 #pragma unroll 1
@@ -325,7 +357,7 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
             if (q[i] + d < 0 || q[i] + d > maxq) continue;
             q[i] += d;
             expand_all();
-            const float e = planar_error(xs, lane, O, H, V, vm);
+            const float e = planar_error(xs, lane, O, H, V, vm, perc);
             if (e < best) { best = e; improved = true; } else q[i] -= d;
         }
         if (!improved) break;
@@ -370,7 +402,7 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
 // Error and selectors of one T / H configuration: kind 0: T with A single, B +-d; kind 1: T with B single, A +-d;
 // kind 2: H.  qA, qB: the two RGB444 colours; di: distance index.  Stops early once `limit` is exceeded.
 CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const int* qA, const int* qB, float limit, uint32_t& sel_out,
-    uint32_t vm = 0xFFFFu)
+    uint32_t vm = 0xFFFFu, bool perc = false)
 {
     const int d = kDist[di];
     int pal[4][3];
@@ -390,7 +422,7 @@ CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const
         for (uint32_t k = 0; k < 4; ++k) {
             const float d0 = static_cast<float>(pal[k][0]) - px(xs, lane, t, 0), d1 = static_cast<float>(pal[k][1]) - px(xs, lane, t, 1),
                 d2 = static_cast<float>(pal[k][2]) - px(xs, lane, t, 2);
-            const float e = d0*d0 + d1*d1 + d2*d2;
+            const float e = color_err(d0, d1, d2, perc);
             if (e < be) { be = e; bk = k; }
         }
         if ((vm >> t) & 1u) err += be;
@@ -404,7 +436,7 @@ CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const
 // (etc2comp widens its T / H search the same way in its later iterations, EtcBlock4x4Encoding_RGB8.cpp:370-...).
 // rounds: +-1 descent rounds over the two colours; the descent only runs while the T/H error is below `gate` (the short
 // searches pass a small multiple of the incumbent's error: a T/H block that far behind will not win).
-CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0, float gate = 3.0e38f, uint32_t vm = 0xFFFFu)
+CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0, float gate = 3.0e38f, uint32_t vm = 0xFFFFu, bool perc = false)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
     float m[3] = {0, 0, 0};
@@ -463,7 +495,7 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
 #pragma unroll 1
         for (uint32_t di = 0; di < 8; ++di) {
             uint32_t sel;
-            const float err = th_eval(xs, lane, kind, di, qA, qB, best, sel, vm);
+            const float err = th_eval(xs, lane, kind, di, qA, qB, best, sel, vm, perc);
             if (err < best) { best = err; best_kind = kind; best_d = di; best_sel = sel; }
         }
     }
@@ -481,7 +513,7 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
                 const int di = static_cast<int>(best_d) + dd;
                 if (di < 0 || di > 7) continue;
                 uint32_t sel;
-                const float err = th_eval(xs, lane, best_kind, static_cast<uint32_t>(di), tA, tB, best, sel, vm);
+                const float err = th_eval(xs, lane, best_kind, static_cast<uint32_t>(di), tA, tB, best, sel, vm, perc);
                 if (err < best) {
                     best = err; best_d = static_cast<uint32_t>(di); best_sel = sel; improved = true;
 #pragma unroll
@@ -603,7 +635,7 @@ CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius, uint32_t vm 
 // (same threshold, :96, :754).  Opaque blocks: the ETC2 RGB search without the individual mode (that bit is the
 // opaque flag); mixed blocks: differential mode with the opaque flag clear, transparent texels on selector 2 and the
 // others on {+0, +big, -big}; fully transparent blocks: selector 2 everywhere.  Our own search: PSNR parity.
-CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds, uint32_t vm = 0xFFFFu)
+CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds, uint32_t vm = 0xFFFFu, bool perc = false)
 {
     uint32_t tmask = 0;
     for (uint32_t t = 0; t < 16; ++t) if (px(xs, lane, t, 3) < 127.5f) tmask |= 1u << t;
@@ -613,13 +645,13 @@ CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds, uint32_t vm =
         for (uint32_t t = 0; t < 16; ++t) sel |= 2u << (2*t);
         return to_bytes(0u, pixel_bits(sel));
     }
-    encode_etc1(xs, lane, rounds, best, true, tmask, vm);
+    encode_etc1(xs, lane, rounds, best, true, tmask, vm, perc);
     if (tmask == 0 && best.err > 0.0f) {
         ColorResult r;
-        encode_planar(xs, lane, rounds, r, vm);
+        encode_planar(xs, lane, rounds, r, vm, perc);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm);
+            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm, perc);
             if (r.err < best.err) best = r;
         }
     }
@@ -693,16 +725,16 @@ CFX_HD uint2 encode_eac_r11(float* xs, uint32_t lane, uint32_t chan, int radius,
 }
 
 // format: 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8 (colour part); returns the 8 colour bytes
-CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds, uint32_t vm = 0xFFFFu)
+CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds, uint32_t vm = 0xFFFFu, bool perc = false)
 {
     ColorResult best;
-    encode_etc1(xs, lane, rounds, best, false, 0, vm);
+    encode_etc1(xs, lane, rounds, best, false, 0, vm, perc);
     if (etc2 && best.err > 0.0f) {
         ColorResult r;
-        encode_planar(xs, lane, rounds, r, vm);
+        encode_planar(xs, lane, rounds, r, vm, perc);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm);
+            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm, perc);
             if (r.err < best.err) best = r;
         }
     }
