@@ -155,7 +155,7 @@ struct Warp3T {
 // model constants (fitted on the host with tools/emu_astc3.py)
 constexpr float kLine = 1.1f, kDec = 1.0f, kQuant = 0.9f, kColor = 0.5f;
 
-struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; float mis_w; int dbg_slot, dbg_level, dbg_nw; };   // dbg_*: developer builds only (-1 = any)   // hdr: Texture::Type::UFloat (texels searched as LNS, end point mode 11)   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
+struct Tab3 { Ctx ctx; Astc3Tab t3; uint32_t flags; uint32_t hdr; float mis_w; int dbg_slot, dbg_level, dbg_nw; uint32_t cw; float4 sw, isw; };   // sw / isw: square roots of the channel weights and their reciprocals (kernel parameters: constant-bank operands, no registers)   // cw: channel error weights r, g, b, a in sixteenths, one byte each (0x10101010 = plain squared error)   // dbg_*: developer builds only (-1 = any)   // hdr: Texture::Type::UFloat (texels searched as LNS, end point mode 11)   // flags (developer): 1 = no luminance slot, 2 = model-only quantisation term
 
 __device__ __forceinline__ int redux_add(int v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 __device__ __forceinline__ uint32_t redux_addu(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
@@ -285,7 +285,7 @@ __device__ __forceinline__ void reweight_decimation(const Ctx& c, WS& ws, uint32
 // quantise = false: ws.su / ws.sk already hold the candidate's quantised weights (realign_weights).
 template <int K, bool hdr, typename WS>
 __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, uint32_t cl, bool has_alpha,
-    uint32_t lane, bool quantise = true, bool solve = true)
+    uint32_t lane, bool quantise = true, bool solve = true, uint32_t cw = 0x10101010u)
 {
     const bool lum = slot_is_lum(s);
     // per-subset end point mode: 0 = direct (RGB / RGBA), 1 = base + scale (+ alpha pair), 2 = RGB only in a block with alpha
@@ -542,11 +542,12 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
         const int* e = ws.ep + part[k]*8u;
         const int4 x = ws.v[lane + 32u*k];
         const int w0 = w[k][0], w1 = w[k][1];
-        int d = ((e[0]*FX*(64 - (dc == 0 ? w1 : w0)) + e[4]*FX*(dc == 0 ? w1 : w0) + 32) >> 6) - x.x; err += static_cast<uint32_t>(d*d);
-        d = ((e[1]*FX*(64 - (dc == 1 ? w1 : w0)) + e[5]*FX*(dc == 1 ? w1 : w0) + 32) >> 6) - x.y; err += static_cast<uint32_t>(d*d);
-        d = ((e[2]*FX*(64 - (dc == 2 ? w1 : w0)) + e[6]*FX*(dc == 2 ? w1 : w0) + 32) >> 6) - x.z; err += static_cast<uint32_t>(d*d);
+        // (channel weights in sixteenths: 16 = the plain squared error, bit for bit)
+        int d = ((e[0]*FX*(64 - (dc == 0 ? w1 : w0)) + e[4]*FX*(dc == 0 ? w1 : w0) + 32) >> 6) - x.x; err += (static_cast<uint32_t>(d*d)*(cw & 0xFFu)) >> 4;
+        d = ((e[1]*FX*(64 - (dc == 1 ? w1 : w0)) + e[5]*FX*(dc == 1 ? w1 : w0) + 32) >> 6) - x.y; err += (static_cast<uint32_t>(d*d)*((cw >> 8) & 0xFFu)) >> 4;
+        d = ((e[2]*FX*(64 - (dc == 2 ? w1 : w0)) + e[6]*FX*(dc == 2 ? w1 : w0) + 32) >> 6) - x.z; err += (static_cast<uint32_t>(d*d)*((cw >> 16) & 0xFFu)) >> 4;
         if (has_alpha) {
-            d = ((e[3]*FX*(64 - (dc == 3 ? w1 : w0)) + e[7]*FX*(dc == 3 ? w1 : w0) + 32) >> 6) - x.w; err += static_cast<uint32_t>(d*d);
+            d = ((e[3]*FX*(64 - (dc == 3 ? w1 : w0)) + e[7]*FX*(dc == 3 ? w1 : w0) + 32) >> 6) - x.w; err += (static_cast<uint32_t>(d*d)*(cw >> 24)) >> 4;
         }
     }
     err = redux_addu(err);
@@ -562,7 +563,8 @@ __device__ __forceinline__ float evaluate3(const Ctx& c, WS& ws, uint32_t s, con
 // four parity classes are swept one after the other, each class in parallel. LDR only. Leaves the result in
 // ws.su / ws.sk; the caller re-solves the end points and measures (evaluate3 with quantise = false).
 template <typename WS>
-__device__ __forceinline__ void realign_weights(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, bool has_alpha, uint32_t lane)
+__device__ __forceinline__ void realign_weights(const Ctx& c, WS& ws, uint32_t s, const ModeInfo& m, bool has_alpha, uint32_t lane,
+    uint32_t cw = 0x10101010u)
 {
     constexpr uint32_t TP = WS::TP;
     const uint32_t T = c.tab.texels;
@@ -622,9 +624,10 @@ __device__ __forceinline__ void realign_weights(const Ctx& c, WS& ws, uint32_t s
                         // this plane's channels only: the dual channel rides the second plane
                         if (dc >= 0 && (ch == dc) != (pl == 1u)) continue;
                         const int a = ep[ch]*FX, b = ep[4 + ch]*FX, xv = xs[ch];
-                        int d = ((a*(64 - w0) + b*w0 + 32) >> 6) - xv; c0 += d*d;
-                        d = ((a*(64 - wd) + b*wd + 32) >> 6) - xv; cd += d*d;
-                        d = ((a*(64 - wu) + b*wu + 32) >> 6) - xv; cu += d*d;
+                        const int wc = static_cast<int>((cw >> (8*ch)) & 0xFFu);
+                        int d = ((a*(64 - w0) + b*w0 + 32) >> 6) - xv; c0 += (d*d*wc) >> 4;
+                        d = ((a*(64 - wd) + b*wd + 32) >> 6) - xv; cd += (d*d*wc) >> 4;
+                        d = ((a*(64 - wu) + b*wu + 32) >> 6) - xv; cu += (d*d*wc) >> 4;
                     }
                     d_dn += cd - c0; d_up += cu - c0;
                 }
@@ -763,19 +766,32 @@ __device__ __noinline__ float rgb_free_residual(const Mom& mo)
 }
 
 // Residual only, moments passed in registers (integer sums about the block centre).
+// Channel error weights (sRGB textures, see launch_astc3): the hypotheses are built in the WEIGHTED colour space
+// x'_c = sw_c x_c (sw = square roots of the weights; all 1.0f -- exact -- for linear textures).  The integer moments stay
+// plain; they are scaled where they become floats: entry k of (n, s0..s3, p00 p01 p02 p03 p11 p12 p13 p22 p23 p33).
+__device__ __forceinline__ float mom_scale(int k, float4 sw)
+{
+    const float a[4] = {sw.x, sw.y, sw.z, sw.w};
+    if (k == 0) return 1.0f;
+    if (k < 5) return a[k - 1];
+    const int i = k < 9 ? 0 : (k < 12 ? 1 : (k < 14 ? 2 : 3));
+    const int j = k < 9 ? k - 5 : (k < 12 ? k - 8 : (k < 14 ? k - 10 : 3));
+    return a[i]*a[j];
+}
+
 __device__ __noinline__ float subset_resid(int n, int s0, int s1, int s2, int s3, int p0, int p1, int p2, int p3, int p4, int p5,
-    int p6, int p7, int p8, int p9)
+    int p6, int p7, int p8, int p9, float4 sw)
 {
     Mom mo;
     mo.n = static_cast<float>(n);
-    mo.s[0] = static_cast<float>(s0); mo.s[1] = static_cast<float>(s1); mo.s[2] = static_cast<float>(s2); mo.s[3] = static_cast<float>(s3);
-    mo.p[0] = static_cast<float>(p0); mo.p[1] = static_cast<float>(p1); mo.p[2] = static_cast<float>(p2); mo.p[3] = static_cast<float>(p3);
-    mo.p[4] = static_cast<float>(p4); mo.p[5] = static_cast<float>(p5); mo.p[6] = static_cast<float>(p6); mo.p[7] = static_cast<float>(p7);
-    mo.p[8] = static_cast<float>(p8); mo.p[9] = static_cast<float>(p9);
+    mo.s[0] = static_cast<float>(s0)*sw.x; mo.s[1] = static_cast<float>(s1)*sw.y; mo.s[2] = static_cast<float>(s2)*sw.z; mo.s[3] = static_cast<float>(s3)*sw.w;
+    mo.p[0] = static_cast<float>(p0)*(sw.x*sw.x); mo.p[1] = static_cast<float>(p1)*(sw.x*sw.y); mo.p[2] = static_cast<float>(p2)*(sw.x*sw.z); mo.p[3] = static_cast<float>(p3)*(sw.x*sw.w);
+    mo.p[4] = static_cast<float>(p4)*(sw.y*sw.y); mo.p[5] = static_cast<float>(p5)*(sw.y*sw.z); mo.p[6] = static_cast<float>(p6)*(sw.y*sw.w); mo.p[7] = static_cast<float>(p7)*(sw.z*sw.z);
+    mo.p[8] = static_cast<float>(p8)*(sw.z*sw.w); mo.p[9] = static_cast<float>(p9)*(sw.w*sw.w);
     float m[4], v[4];
     return line_core(mo, -1, 4, m, v);
 }
-#define CFX_RESID15(a) subset_resid(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14])
+#define CFX_RESID15(a) subset_resid(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], sw)
 
 // A set of texels: one bit per texel, MW 64-bit words (footprints above 64 texels need 2 or 3).
 template <int MW> struct TexelMask { uint64_t w[MW]; };
@@ -1098,6 +1114,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
     const uint32_t T = ctx.tab.texels, bw = ctx.tab.bw, bh = ctx.tab.bh;
     const uint32_t G = ctx.tab.n_grids;
     const bool alpha_off = p.alpha_type == 0;
+    // square roots of the channel error weights and their reciprocals (1.0f for linear textures): read from the kernel
+    // parameters wherever they are used -- as locals they cost 8 registers the kernel does not have (-8 % throughput)
+    const float4& sw = tb.sw;
+    const float4& isw = tb.isw;
     const float fx2 = static_cast<float>(FX*FX);
     const float ifx = 1.0f/static_cast<float>(FX);
     // setup scratch lives where phase 1 later writes D
@@ -1205,7 +1225,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
         // ---- setup 2: lines of the single-subset slot (lane 0) and of the four dual-plane slots (lanes 1..4)
         if (active) {
 #pragma unroll
-            for (int k = 0; k < 15; ++k) if (lane == static_cast<uint32_t>(k)) (&moms[10].n)[k] = static_cast<float>(tot[k]);
+            for (int k = 0; k < 15; ++k) if (lane == static_cast<uint32_t>(k)) (&moms[10].n)[k] = static_cast<float>(tot[k])*mom_scale(k, sw);
             __syncwarp();
             if (lane < 5) subset_line(moms[10], static_cast<int>(lane) - 1, 6, lines[lane]);
         }
@@ -1329,7 +1349,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
 #pragma unroll
                 for (int f = 0; f < 15; ++f) {
                     const int t = redux_add(acc[f]);
-                    if (lane == static_cast<uint32_t>(f)) (&moms[job].n)[f] = static_cast<float>(t);
+                    if (lane == static_cast<uint32_t>(f)) (&moms[job].n)[f] = static_cast<float>(t)*mom_scale(f, sw);
                 }
             }
             __syncwarp();
@@ -1352,7 +1372,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                     subset_line(moms[lane], -1, 6, lines[5 + lane]);
                     // for the base + scale siblings (slots 14..17): the subset's distance from its line through black
                     // (blocks with alpha, CEM 10: what the RGB part loses by going through black, on top of the RGBA line's floor)
-                    const float org = origin_residual(moms[lane], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z));
+                    const float org = origin_residual(moms[lane], sw.x*static_cast<float>(ctr.x), sw.y*static_cast<float>(ctr.y), sw.z*static_cast<float>(ctr.z));
                     lines[5 + lane].pad[0] = has_alpha ? fmaxf(org - rgb_free_residual(moms[lane]), 0.0f) : org;
                 }
             }
@@ -1366,7 +1386,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
             } else if (lane == 4) {
                 // one subset: CEM 6, or CEM 10 in a block with alpha (the alpha pair stays direct: what the RGB part
                 // loses by going through black comes on top of the RGBA line's floor)
-                const float org = origin_residual(moms[10], static_cast<float>(ctr.x), static_cast<float>(ctr.y), static_cast<float>(ctr.z));
+                const float org = origin_residual(moms[10], sw.x*static_cast<float>(ctr.x), sw.y*static_cast<float>(ctr.y), sw.z*static_cast<float>(ctr.z));
                 ws.scale_eline[0] = org*ifx*ifx;
                 ws.scale_valid[0] = !HDR && !(tb.flags & 4u) ? 1u : 0u;
                 if (has_alpha) ws.scale_eline[0] = fmaxf(org - rgb_free_residual(moms[10]), 0.0f)*ifx*ifx;     // + slot 0's floor, added in phase 1c
@@ -1415,8 +1435,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                     const uint32_t q = pc > 1 ? ws.part[s - 1][i] : 0u;
                     const LineFit& lf = lines[base + q];
                     const int4 x = ws.v[i];
-                    tl[r] = (static_cast<float>(x.x - ctr.x) - lf.m[0])*lf.v[0] + (static_cast<float>(x.y - ctr.y) - lf.m[1])*lf.v[1] +
-                        (static_cast<float>(x.z - ctr.z) - lf.m[2])*lf.v[2] + (static_cast<float>(x.w - ctr.w) - lf.m[3])*lf.v[3];
+                    tl[r] = (sw.x*static_cast<float>(x.x - ctr.x) - lf.m[0])*lf.v[0] + (sw.y*static_cast<float>(x.y - ctr.y) - lf.m[1])*lf.v[1] +
+                        (sw.z*static_cast<float>(x.z - ctr.z) - lf.m[2])*lf.v[2] + (sw.w*static_cast<float>(x.w - ctr.w) - lf.m[3])*lf.v[3];
                     ql[r] = q;
                 }
             }
@@ -1438,10 +1458,12 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 const LineFit& lf = lines[base + q];
                 eline += lf.resid;
                 if (lane == 0) {
-                    const float c0 = static_cast<float>(ctr.x) + lf.m[0], c1 = static_cast<float>(ctr.y) + lf.m[1];
-                    const float c2 = static_cast<float>(ctr.z) + lf.m[2], c3 = static_cast<float>(ctr.w) + lf.m[3];
-                    slot.e0[q] = make_float4((c0 + mn*lf.v[0])*ifx, (c1 + mn*lf.v[1])*ifx, (c2 + mn*lf.v[2])*ifx, (c3 + mn*lf.v[3])*ifx);
-                    slot.e1[q] = make_float4((c0 + mx*lf.v[0])*ifx, (c1 + mx*lf.v[1])*ifx, (c2 + mx*lf.v[2])*ifx, (c3 + mx*lf.v[3])*ifx);
+                    // (back from the weighted space: isw = 1/sw, exactly 1.0f for linear textures)
+                    const float c0 = static_cast<float>(ctr.x), c1 = static_cast<float>(ctr.y), c2 = static_cast<float>(ctr.z), c3 = static_cast<float>(ctr.w);
+                    slot.e0[q] = make_float4((c0 + (lf.m[0] + mn*lf.v[0])*isw.x)*ifx, (c1 + (lf.m[1] + mn*lf.v[1])*isw.y)*ifx,
+                        (c2 + (lf.m[2] + mn*lf.v[2])*isw.z)*ifx, (c3 + (lf.m[3] + mn*lf.v[3])*isw.w)*ifx);
+                    slot.e1[q] = make_float4((c0 + (lf.m[0] + mx*lf.v[0])*isw.x)*ifx, (c1 + (lf.m[1] + mx*lf.v[1])*isw.y)*ifx,
+                        (c2 + (lf.m[2] + mx*lf.v[2])*isw.z)*ifx, (c3 + (lf.m[3] + mx*lf.v[3])*isw.w)*ifx);
                     slot.len2[q] = range*range*ifx*ifx;
                 }
             }
@@ -1457,8 +1479,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                     const float rq = ql[r] == 0 ? rg0 : (ql[r] == 1 ? rg1 : rg2);
                     if (i < T && ql[r] != qd && rq*8.0f < dom_rg) {
                         const int4 x = ws.v[i];
-                        const float t = (static_cast<float>(x.x - ctr.x) - ld.m[0])*ld.v[0] + (static_cast<float>(x.y - ctr.y) - ld.m[1])*ld.v[1] +
-                            (static_cast<float>(x.z - ctr.z) - ld.m[2])*ld.v[2] + (static_cast<float>(x.w - ctr.w) - ld.m[3])*ld.v[3];
+                        const float t = (sw.x*static_cast<float>(x.x - ctr.x) - ld.m[0])*ld.v[0] + (sw.y*static_cast<float>(x.y - ctr.y) - ld.m[1])*ld.v[1] +
+                            (sw.z*static_cast<float>(x.z - ctr.z) - ld.m[2])*ld.v[2] + (sw.w*static_cast<float>(x.w - ctr.w) - ld.m[3])*ld.v[3];
                         tl[r] = fminf(fmaxf((t - dom_mn)*dir, 0.0f), 1.0f);
                     }
                 }
@@ -1486,7 +1508,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                     for (int k = 0; k < 4; ++k) if (k == dc) { a4[k] = static_cast<float>(lo)*ifx; b4[k] = static_cast<float>(hi)*ifx; }
                     slot.e0[0] = make_float4(a4[0], a4[1], a4[2], a4[3]);
                     slot.e1[0] = make_float4(b4[0], b4[1], b4[2], b4[3]);
-                    const float d = static_cast<float>(hi - lo)*ifx;
+                    const float d = static_cast<float>(hi - lo)*ifx*(dc == 0 ? sw.x : (dc == 1 ? sw.y : (dc == 2 ? sw.z : sw.w)));
                     slot.len2b = d*d;
                 }
             }
@@ -1589,7 +1611,10 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
             float* ax = &ws.g[0][0];            // [set][8]: mean u, mean a, cos, sin, residual      (phase-2 scratch, free here)
             __syncwarp();
             if (lane < 5) {
-                const Mom& mo = moms[lane == 0 ? 10u : lane - 1u];
+                Mom mo = moms[lane == 0 ? 10u : lane - 1u];
+                // (this axis lives in the plain (sqrt(3) L, A) plane: undo the channel scaling of the moments)
+#pragma unroll
+                for (int k = 1; k < 15; ++k) (&mo.n)[k] *= 1.0f/mom_scale(k, sw);
                 const float n = fmaxf(mo.n, 1.0f), in = 1.0f/n;
                 const float su = mo.s[0] + mo.s[1] + mo.s[2], sa = mo.s[3];
                 const float suu = mo.p[0] + mo.p[4] + mo.p[7] + 2.0f*(mo.p[1] + mo.p[2] + mo.p[5]) - su*su*in;
@@ -2034,7 +2059,8 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                         if (c4 == 3 && !has_alpha) continue;
                         const float es = c4 < 3 ? escale : (HDR ? kHdrAlphaScale : 1.0f);
                         const float a0 = static_cast<float>(e[c4])*es, d = static_cast<float>(e[4 + c4])*es - a0;
-                        if (c4 == dc) { num1 += (xs[c4] - a0)*d; den1 += d*d; } else { num0 += (xs[c4] - a0)*d; den0 += d*d; }
+                        const float w4 = c4 == 0 ? sw.x*sw.x : (c4 == 1 ? sw.y*sw.y : (c4 == 2 ? sw.z*sw.z : sw.w*sw.w));
+                        if (c4 == dc) { num1 += w4*((xs[c4] - a0)*d); den1 += w4*(d*d); } else { num0 += w4*((xs[c4] - a0)*d); den0 += w4*(d*d); }
                     }
                     ws.ta[0][i] = __float2half_rn(den0 > 0.0f ? fminf(fmaxf(num0/den0, 0.0f), 1.0f) : 0.0f);
                     ws.ta[1][i] = __float2half_rn(den1 > 0.0f ? fminf(fmaxf(num1/den1, 0.0f), 1.0f) : 0.0f);
@@ -2045,7 +2071,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
             }
             const uint32_t s = code >> 16;
             const ModeInfo m = tab_mode(ctx, code & 0xFFFFu);
-            if (realign) realign_weights(ctx, ws, s, m, has_alpha, lane);
+            if (realign) realign_weights(ctx, ws, s, m, has_alpha, lane, tb.cw);
             else decimate_mma<KS>(tb, ws, a, m.grid, m.nw, row0, row1, lane);
             if (!realign && NT > 8 && ws.slots[slot_base(s)].pc > 1 && m.nw < T && !(tb.flags & 32u)) reweight_decimation(ctx, ws, s, m.grid, m.nw, static_cast<uint32_t>(row0), lane);
             if (realign) {
@@ -2058,7 +2084,7 @@ __global__ void __launch_bounds__(W*32, CTAS) astc3_kernel(const __grid_constant
                 if (lane == 0u) ws.contr = ws.best_contr;
                 __syncwarp();
             }
-            const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane, !realign, !realign);
+            const float err = evaluate3<K, HDR>(ctx, ws, s, m, cl, has_alpha, lane, !realign, !realign, tb.cw);
 #ifdef CFX_ASTC3_TUNE
             if ((tb.flags & 256u) && lane == 0 && !refining)
                 printf("CAND blk %u slot %u mode %u nw %u level %u cl %u est %.1f exact %.1f\n", blk, s, code & 0xFFFFu, static_cast<uint32_t>(m.nw),
@@ -2177,6 +2203,18 @@ int launch_astc3(const EncodeParams& p, const Ctx& ctx, const Astc3Tab& t3, cuda
     tb.dbg_slot = tb.dbg_level = tb.dbg_nw = -1;
 #endif
     tb.hdr = p.type == 4u ? 1u : 0u;                      // Texture::Type::UFloat
+    // sRGB textures: astcenc runs with ASTCENC_FLG_USE_PERCEPTUAL (lib/src/AstcConverter.cpp:171-172), i.e. channel error
+    // weights 0.30 / 0.59 / 0.11 x 2.25 against 1 for alpha (astcenc_entry.cpp:644-649): 10.8 / 21.2 / 4.0 / 16 sixteenths.
+    // They weigh the exact error of phase 2 (which candidate wins, which refinement step is kept), and the hypotheses are
+    // built in the weighted colour space (moments, principal lines, ideal weights, line lengths: `sw` in the kernel); the
+    // luminance slots, k-means and the colour quantisation term of the estimates stay in plain RGB.
+    tb.cw = p.color_space == 1u && !tb.hdr ? 0x1004150Bu : 0x10101010u;
+    {
+        const float w[4] = {static_cast<float>(tb.cw & 0xFFu)/16.0f, static_cast<float>((tb.cw >> 8) & 0xFFu)/16.0f,
+            static_cast<float>((tb.cw >> 16) & 0xFFu)/16.0f, static_cast<float>(tb.cw >> 24)/16.0f};
+        tb.sw = make_float4(sqrtf(w[0]), sqrtf(w[1]), sqrtf(w[2]), sqrtf(w[3]));
+        tb.isw = make_float4(1.0f/tb.sw.x, 1.0f/tb.sw.y, 1.0f/tb.sw.z, 1.0f/tb.sw.w);
+    }
     const uint32_t NT = t3.NT, KS = t3.KS;
     if (NT == 2 && KS == 1) return launch_one<2, 1>(p, tb, n_exact, refine, stream);
     if (NT == 3 && KS == 2) return launch_one<3, 2>(p, tb, n_exact, refine, stream);
