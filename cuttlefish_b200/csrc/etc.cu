@@ -15,7 +15,9 @@ namespace cfx {
 
 namespace { constexpr int kEtcWarps = 4; }
 
-template <int FORMAT, bool SIGNED = false>   // 37 ETC1, 38 ETC2 RGB, 39 ETC2 RGB8A1, 40 ETC2 RGBA8, 41 EAC R11, 42 EAC RG11
+// PERC: the sRGB instantiation of the ETC2 colour search (REC709 error, etc_core.cuh) -- its own kernel, so that the linear
+// one carries none of its code (both searches in one kernel cost the linear path 5 %)
+template <int FORMAT, bool SIGNED = false, bool PERC = false>   // 37 ETC1, 38 ETC2 RGB, 39 ETC2 RGB8A1, 40 ETC2 RGBA8, 41 EAC R11, 42 EAC RG11
 __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p, int rounds, int alpha_radius, bool exact)
 {
     __shared__ float s_x[kEtcWarps][16*4*32];
@@ -82,9 +84,8 @@ __global__ void __launch_bounds__(kEtcWarps*32) etc_kernel(const EncodeParams p,
             }
             continue;
         }
-        // sRGB textures: the reference's perceptual (REC709) colour error instead of plain squared RGB distance
-        const bool perc = p.color_space == 1u;
-        const uint2 color = FORMAT == 39 ? etc::encode_color_a1(xs, lane, rounds, vm, perc) : etc::encode_color(xs, lane, FORMAT != 37, rounds, vm, perc);
+        // (PERC, sRGB textures: the reference's perceptual REC709 colour error instead of plain squared RGB distance)
+        const uint2 color = FORMAT == 39 ? etc::encode_color_a1<PERC>(xs, lane, rounds, vm) : etc::encode_color<PERC>(xs, lane, FORMAT != 37, rounds, vm);
         if (FORMAT == 40) {
             const uint2 alpha = etc::encode_eac_alpha(xs, lane, alpha_radius, vm);
             if (live) reinterpret_cast<uint4*>(p.dst)[blk] = make_uint4(alpha.x, alpha.y, color.x, color.y);
@@ -104,12 +105,13 @@ int launch_etc(const EncodeParams& p, cudaStream_t stream)
     const uint32_t groups = (p.total_blocks + 31)/32;
     const uint32_t ctas = (groups + kEtcWarps - 1)/kEtcWarps;
     const bool sn = p.type == 1;                          // Texture::Type::SNorm
+    const bool srgb = p.color_space == 1;                 // the REC709 instantiation of the colour search
     const void* k = nullptr;
     switch (p.format) {
-        case 37: k = reinterpret_cast<const void*>(&etc_kernel<37>); break;
-        case 38: k = reinterpret_cast<const void*>(&etc_kernel<38>); break;
-        case 39: k = reinterpret_cast<const void*>(&etc_kernel<39>); break;
-        case 40: k = reinterpret_cast<const void*>(&etc_kernel<40>); break;
+        case 37: k = srgb ? reinterpret_cast<const void*>(&etc_kernel<37, false, true>) : reinterpret_cast<const void*>(&etc_kernel<37>); break;
+        case 38: k = srgb ? reinterpret_cast<const void*>(&etc_kernel<38, false, true>) : reinterpret_cast<const void*>(&etc_kernel<38>); break;
+        case 39: k = srgb ? reinterpret_cast<const void*>(&etc_kernel<39, false, true>) : reinterpret_cast<const void*>(&etc_kernel<39>); break;
+        case 40: k = srgb ? reinterpret_cast<const void*>(&etc_kernel<40, false, true>) : reinterpret_cast<const void*>(&etc_kernel<40>); break;
         case 41: k = sn ? reinterpret_cast<const void*>(&etc_kernel<41, true>) : reinterpret_cast<const void*>(&etc_kernel<41, false>); break;
         case 42: k = sn ? reinterpret_cast<const void*>(&etc_kernel<42, true>) : reinterpret_cast<const void*>(&etc_kernel<42, false>); break;
         default: return -2;

@@ -81,7 +81,8 @@ CFX_HD float color_err(float d0, float d1, float d2, bool perc) { return perc ? 
 // (transparent) at no cost, the others choose among {+0, +big, -big} (selectors 0, 1, 3).
 struct TableColours { float n0[4], n1[4], n2[4], cc[4]; };
 
-CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours& p, bool perc = false)
+template <bool PERC>
+CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours& p)
 {
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {
@@ -89,7 +90,7 @@ CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours
         if (punch && k == 0u) m = 0;
         const float p0 = static_cast<float>(clamp255(base[0] + m)), p1 = static_cast<float>(clamp255(base[1] + m)),
             p2 = static_cast<float>(clamp255(base[2] + m));
-        if (perc) {
+        if (PERC) {
             // |p - x|_A^2 = p^T A p - 2 (A p).x + x^T A x
             const float q0 = rec709::a00*p0 + rec709::a01*p1 + rec709::a02*p2, q1 = rec709::a01*p0 + rec709::a11*p1 + rec709::a12*p2,
                 q2 = rec709::a02*p0 + rec709::a12*p1 + rec709::a22*p2;
@@ -104,14 +105,16 @@ CFX_HD void table_colours(const int* base, uint32_t tb, bool punch, TableColours
 
 // Best modifier table (of tb0 .. tb1) of one half (texel mask) for an 8-bit base colour, and its error. The selectors are
 // not kept: most fits lose, half_selectors() recomputes them for the one that ends up in the block.
-CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask = 0,
-    uint32_t tb0 = 0, uint32_t tb1 = 7, bool perc = false)
+// (PERC is a template parameter: as a run-time flag in this loop it cost the linear path 11 %)
+template <bool PERC>
+CFX_HD void half_fit_t(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask,
+    uint32_t tb0, uint32_t tb1)
 {
     out.err = 3.0e38f; out.table = 0;
 #pragma unroll 1
     for (uint32_t tb = tb0; tb <= tb1; ++tb) {
         TableColours p;
-        table_colours(base, tb, tmask != 0, p, perc);
+        table_colours<PERC>(base, tb, tmask != 0, p);
         float err = 0.0f;
         for (uint32_t left = mask & ~tmask; left; left &= left - 1u) {
             const uint32_t t = static_cast<uint32_t>(__ffs(left)) - 1u;
@@ -122,18 +125,26 @@ CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, f
                 if (tmask && k == 2u) continue;
                 be = fminf(be, p.cc[k] + p.n0[k]*x0 + p.n1[k]*x1 + p.n2[k]*x2);
             }
-            err += fmaxf(be + (perc ? perc_norm(x0, x1, x2) : x0*x0 + x1*x1 + x2*x2), 0.0f);
+            err += fmaxf(be + (PERC ? perc_norm(x0, x1, x2) : x0*x0 + x1*x1 + x2*x2), 0.0f);
             if (err >= out.err || err >= limit) break;
         }
         if (err < out.err) { out.err = err; out.table = tb; }
     }
 }
 
+CFX_HD void half_fit(float* xs, uint32_t lane, uint32_t mask, const int* base, float limit, HalfFit& out, uint32_t tmask = 0,
+    uint32_t tb0 = 0, uint32_t tb1 = 7, bool perc = false)
+{
+    if (perc) half_fit_t<true>(xs, lane, mask, base, limit, out, tmask, tb0, tb1);
+    else half_fit_t<false>(xs, lane, mask, base, limit, out, tmask, tb0, tb1);
+}
+
 // Selectors (2 bits per texel t, only the half's texels) of a base colour and table: the first minimum over k.
-CFX_HD uint32_t half_selectors(float* xs, uint32_t lane, uint32_t mask, const int* base, uint32_t tb, uint32_t tmask = 0, bool perc = false)
+template <bool PERC = false>
+CFX_HD uint32_t half_selectors(float* xs, uint32_t lane, uint32_t mask, const int* base, uint32_t tb, uint32_t tmask = 0)
 {
     TableColours p;
-    table_colours(base, tb, tmask != 0, p, perc);
+    table_colours<PERC>(base, tb, tmask != 0, p);
     uint32_t sel = 0;
     for (uint32_t left = mask; left; left &= left - 1u) {
         const uint32_t t = static_cast<uint32_t>(__ffs(left)) - 1u;
@@ -153,13 +164,14 @@ CFX_HD uint32_t half_selectors(float* xs, uint32_t lane, uint32_t mask, const in
 }
 
 // Descent of one half's quantised base colour (bits = 4 or 5) within [lo, hi] per channel.
+template <bool PERC = false>
 CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* q /* in/out */, const int* lo, const int* hi,
-    int rounds, HalfFit& best, uint32_t tmask = 0, bool perc = false)
+    int rounds, HalfFit& best, uint32_t tmask = 0)
 {
     int base[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { q[c] = min(max(q[c], lo[c]), hi[c]); base[c] = bits == 5 ? expand5(q[c]) : expand4(q[c]); }
-    half_fit(xs, lane, mask, base, 3.0e38f, best, tmask, 0, 7, perc);
+    half_fit_t<PERC>(xs, lane, mask, base, 3.0e38f, best, tmask, 0, 7);
     for (int round = 0; round < rounds && best.err > 0.0f; ++round) {
         bool improved = false;
 #pragma unroll 1
@@ -181,8 +193,8 @@ CFX_HD void half_search(float* xs, uint32_t lane, uint32_t mask, int bits, int* 
             // a one-step move of the base colour rarely changes the best table by more than one: the short descents
             // (up to Quality::Normal) only look at the incumbent's neighbours, the long ones at all eight
             const bool narrow = CFX_ETC_NARROW && rounds <= 1;
-            half_fit(xs, lane, mask, base, best.err, f, tmask, narrow ? (best.table ? best.table - 1u : 0u) : 0u,
-                narrow ? min(best.table + 1u, 7u) : 7u, perc);
+            half_fit_t<PERC>(xs, lane, mask, base, best.err, f, tmask, narrow ? (best.table ? best.table - 1u : 0u) : 0u,
+                narrow ? min(best.table + 1u, 7u) : 7u);
             if (f.err < best.err) { best = f; q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; improved = true; }
         }
         if (!improved) break;
@@ -223,8 +235,9 @@ struct ColorResult { float err; uint32_t hi, lo; };
 // ---- ETC1 part: both flips, differential and individual -----------------------------------------
 // diff_only: no individual (444+444) mode -- ETC2 RGB8A1, where that bit is the opaque flag.
 // tmask != 0: punch-through block of RGB8A1 (opaque flag clear, see half_fit).
+template <bool PERC = false>
 CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, bool diff_only = false, uint32_t tmask = 0,
-    uint32_t vm = 0xFFFFu, bool perc = false)
+    uint32_t vm = 0xFFFFu)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
     const uint32_t skip = tmask | (~vm & 0xFFFFu);       // texels without a say in the base colours
@@ -264,12 +277,12 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
                 }
             }
             HalfFit fA, fB;
-            half_search(xs, lane, maskA & vm, bits, qA, lo, hi, rounds, fA, tmask, perc);
+            half_search<PERC>(xs, lane, maskA & vm, bits, qA, lo, hi, rounds, fA, tmask);
             if (diff) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { lo[c] = max(qA[c] - 4, 0); hi[c] = min(qA[c] + 3, 31); }
             }
-            half_search(xs, lane, maskB & vm, bits, qB, lo, hi, rounds, fB, tmask, perc);
+            half_search<PERC>(xs, lane, maskB & vm, bits, qB, lo, hi, rounds, fB, tmask);
             const float err = fA.err + fB.err;
             if (err < out.err) {
                 uint32_t h = 0, l = 0;
@@ -293,7 +306,7 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
                 int bA[3], bB[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { bA[c] = diff ? expand5(qA[c]) : expand4(qA[c]); bB[c] = diff ? expand5(qB[c]) : expand4(qB[c]); }
-                l = pixel_bits(half_selectors(xs, lane, maskA, bA, fA.table, tmask, perc) | half_selectors(xs, lane, maskB, bB, fB.table, tmask, perc));
+                l = pixel_bits(half_selectors<PERC>(xs, lane, maskA, bA, fA.table, tmask) | half_selectors<PERC>(xs, lane, maskB, bB, fB.table, tmask));
                 out.err = err; out.hi = h; out.lo = l;
             }
         }
@@ -301,7 +314,8 @@ CFX_HD void encode_etc1(float* xs, uint32_t lane, int rounds, ColorResult& out, 
 }
 
 // ---- ETC2 planar ---------------------------------------------------------------------------------
-CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, const int* V, uint32_t vm = 0xFFFFu, bool perc = false)
+template <bool PERC>
+CFX_HD float planar_error_t(float* xs, uint32_t lane, const int* O, const int* H, const int* V, uint32_t vm)
 {
     float err = 0.0f;
     for (uint32_t t = 0; t < 16; ++t) {
@@ -312,14 +326,20 @@ CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, 
         for (int c = 0; c < 3; ++c) {
             const int v = clamp255((x*(H[c] - O[c]) + y*(V[c] - O[c]) + 4*O[c] + 2) >> 2);
             d[c] = static_cast<float>(v) - px(xs, lane, t, c);
-            if (!perc) err += d[c]*d[c];
+            if (!PERC) err += d[c]*d[c];
         }
-        if (perc) err += perc_norm(d[0], d[1], d[2]);
+        if (PERC) err += perc_norm(d[0], d[1], d[2]);
     }
     return err;
 }
 
-CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out, uint32_t vm = 0xFFFFu, bool perc = false)
+CFX_HD float planar_error(float* xs, uint32_t lane, const int* O, const int* H, const int* V, uint32_t vm = 0xFFFFu, bool perc = false)
+{
+    return perc ? planar_error_t<true>(xs, lane, O, H, V, vm) : planar_error_t<false>(xs, lane, O, H, V, vm);
+}
+
+template <bool PERC = false>
+CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out, uint32_t vm = 0xFFFFu)
 {
     int q[9];     // RO GO BO RH GH BH RV GV BV (6/7/6 bits)
 #pragma unroll
@@ -347,7 +367,7 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
         }
     };
     expand_all();
-    float best = planar_error(xs, lane, O, H, V, vm, perc);
+    float best = planar_error_t<PERC>(xs, lane, O, H, V, vm);
     for (int round = 0; round < rounds && best > 0.0f; ++round) {
         bool improved = false;
 #pragma unroll 1
@@ -357,7 +377,7 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
             if (q[i] + d < 0 || q[i] + d > maxq) continue;
             q[i] += d;
             expand_all();
-            const float e = planar_error(xs, lane, O, H, V, vm, perc);
+            const float e = planar_error_t<PERC>(xs, lane, O, H, V, vm);
             if (e < best) { best = e; improved = true; } else q[i] -= d;
         }
         if (!improved) break;
@@ -401,8 +421,9 @@ CFX_HD void encode_planar(float* xs, uint32_t lane, int rounds, ColorResult& out
 // Two 444 colours from a 2-means split of the block along its principal axis.
 // Error and selectors of one T / H configuration: kind 0: T with A single, B +-d; kind 1: T with B single, A +-d;
 // kind 2: H.  qA, qB: the two RGB444 colours; di: distance index.  Stops early once `limit` is exceeded.
-CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const int* qA, const int* qB, float limit, uint32_t& sel_out,
-    uint32_t vm = 0xFFFFu, bool perc = false)
+template <bool PERC>
+CFX_HD float th_eval_t(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const int* qA, const int* qB, float limit, uint32_t& sel_out,
+    uint32_t vm)
 {
     const int d = kDist[di];
     int pal[4][3];
@@ -422,7 +443,7 @@ CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const
         for (uint32_t k = 0; k < 4; ++k) {
             const float d0 = static_cast<float>(pal[k][0]) - px(xs, lane, t, 0), d1 = static_cast<float>(pal[k][1]) - px(xs, lane, t, 1),
                 d2 = static_cast<float>(pal[k][2]) - px(xs, lane, t, 2);
-            const float e = color_err(d0, d1, d2, perc);
+            const float e = PERC ? perc_norm(d0, d1, d2) : d0*d0 + d1*d1 + d2*d2;
             if (e < be) { be = e; bk = k; }
         }
         if ((vm >> t) & 1u) err += be;
@@ -432,11 +453,18 @@ CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const
     return err;
 }
 
+CFX_HD float th_eval(float* xs, uint32_t lane, uint32_t kind, uint32_t di, const int* qA, const int* qB, float limit, uint32_t& sel_out,
+    uint32_t vm = 0xFFFFu, bool perc = false)
+{
+    return perc ? th_eval_t<true>(xs, lane, kind, di, qA, qB, limit, sel_out, vm) : th_eval_t<false>(xs, lane, kind, di, qA, qB, limit, sel_out, vm);
+}
+
 // rounds > 0 (Quality::High and up): +-1 descent on the six RGB444 components of the winner, distance index +-1
 // (etc2comp widens its T / H search the same way in its later iterations, EtcBlock4x4Encoding_RGB8.cpp:370-...).
 // rounds: +-1 descent rounds over the two colours; the descent only runs while the T/H error is below `gate` (the short
 // searches pass a small multiple of the incumbent's error: a T/H block that far behind will not win).
-CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0, float gate = 3.0e38f, uint32_t vm = 0xFFFFu, bool perc = false)
+template <bool PERC = false>
+CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0, float gate = 3.0e38f, uint32_t vm = 0xFFFFu)
 {
     out.err = 3.0e38f; out.hi = out.lo = 0;
     float m[3] = {0, 0, 0};
@@ -495,7 +523,7 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
 #pragma unroll 1
         for (uint32_t di = 0; di < 8; ++di) {
             uint32_t sel;
-            const float err = th_eval(xs, lane, kind, di, qA, qB, best, sel, vm, perc);
+            const float err = th_eval_t<PERC>(xs, lane, kind, di, qA, qB, best, sel, vm);
             if (err < best) { best = err; best_kind = kind; best_d = di; best_sel = sel; }
         }
     }
@@ -513,7 +541,7 @@ CFX_HD void encode_th(float* xs, uint32_t lane, ColorResult& out, int rounds = 0
                 const int di = static_cast<int>(best_d) + dd;
                 if (di < 0 || di > 7) continue;
                 uint32_t sel;
-                const float err = th_eval(xs, lane, best_kind, static_cast<uint32_t>(di), tA, tB, best, sel, vm, perc);
+                const float err = th_eval_t<PERC>(xs, lane, best_kind, static_cast<uint32_t>(di), tA, tB, best, sel, vm);
                 if (err < best) {
                     best = err; best_d = static_cast<uint32_t>(di); best_sel = sel; improved = true;
 #pragma unroll
@@ -635,7 +663,8 @@ CFX_HD uint2 encode_eac_alpha(float* xs, uint32_t lane, int radius, uint32_t vm 
 // (same threshold, :96, :754).  Opaque blocks: the ETC2 RGB search without the individual mode (that bit is the
 // opaque flag); mixed blocks: differential mode with the opaque flag clear, transparent texels on selector 2 and the
 // others on {+0, +big, -big}; fully transparent blocks: selector 2 everywhere.  Our own search: PSNR parity.
-CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds, uint32_t vm = 0xFFFFu, bool perc = false)
+template <bool PERC = false>
+CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds, uint32_t vm = 0xFFFFu)
 {
     uint32_t tmask = 0;
     for (uint32_t t = 0; t < 16; ++t) if (px(xs, lane, t, 3) < 127.5f) tmask |= 1u << t;
@@ -645,13 +674,13 @@ CFX_HD uint2 encode_color_a1(float* xs, uint32_t lane, int rounds, uint32_t vm =
         for (uint32_t t = 0; t < 16; ++t) sel |= 2u << (2*t);
         return to_bytes(0u, pixel_bits(sel));
     }
-    encode_etc1(xs, lane, rounds, best, true, tmask, vm, perc);
+    encode_etc1<PERC>(xs, lane, rounds, best, true, tmask, vm);
     if (tmask == 0 && best.err > 0.0f) {
         ColorResult r;
-        encode_planar(xs, lane, rounds, r, vm, perc);
+        encode_planar<PERC>(xs, lane, rounds, r, vm);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm, perc);
+            encode_th<PERC>(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm);
             if (r.err < best.err) best = r;
         }
     }
@@ -725,16 +754,17 @@ CFX_HD uint2 encode_eac_r11(float* xs, uint32_t lane, uint32_t chan, int radius,
 }
 
 // format: 37 ETC1, 38 ETC2 RGB, 40 ETC2 RGBA8 (colour part); returns the 8 colour bytes
-CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds, uint32_t vm = 0xFFFFu, bool perc = false)
+template <bool PERC = false>
+CFX_HD uint2 encode_color(float* xs, uint32_t lane, bool etc2, int rounds, uint32_t vm = 0xFFFFu)
 {
     ColorResult best;
-    encode_etc1(xs, lane, rounds, best, false, 0, vm, perc);
+    encode_etc1<PERC>(xs, lane, rounds, best, false, 0, vm);
     if (etc2 && best.err > 0.0f) {
         ColorResult r;
-        encode_planar(xs, lane, rounds, r, vm, perc);
+        encode_planar<PERC>(xs, lane, rounds, r, vm);
         if (r.err < best.err) best = r;
         if (best.err > 0.0f) {
-            encode_th(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm, perc);
+            encode_th<PERC>(xs, lane, r, rounds >= (CFX_ETC_TH_AT_NORMAL ? 1 : 2) ? rounds : 0, rounds >= 2 ? 3.0e38f : best.err*CFX_ETC_TH_GATE, vm);
             if (r.err < best.err) best = r;
         }
     }

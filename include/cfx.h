@@ -122,8 +122,8 @@ void cfx_shutdown(void);
 /* 1 if the (format,type) pair has a GPU encoder, else 0. */
 int cfx_format_supported(uint32_t format, uint32_t type);
 /* 1 if the GPU encoder's bytes are IDENTICAL to the reference CPU encoder's for this (format, type,
- * quality) -- BC4/BC5 always; BC1_RGB/BC2/BC3 at CFX_QUALITY_NORMAL when the library was built with the
- * reference's rgbcx tables (tools/gen_rgbcx_tables.py); ETC1 at CFX_QUALITY_LOWEST..NORMAL in linear
+ * quality) -- BC4/BC5 UNorm always; BC1_RGB/BC2/BC3 at every quality level when the library was built with
+ * the reference's rgbcx tables (tools/gen_rgbcx_tables.py); ETC1 at every quality level, linear and sRGB
  * colour space -- else 0: the format is held to PSNR parity.
  * No reference analogue; lets an integrator (and the tests) know which guarantee applies. */
 int cfx_format_is_exact(uint32_t format, uint32_t type, uint32_t quality);
