@@ -25,11 +25,11 @@ struct Px { float r, g, b, a; };      // a = NaN marks a border texel (outside t
 CFX_HD float clamp01(float v) { if (v < 0.0f) v = 0.0f; if (v > 1.0f) v = 1.0f; return v; }
 
 // codeword table entries as the reference's compile-time floats k/255
+CFX_CONST float kCwSmall[8] = {2.0f/255.0f, 5.0f/255.0f, 9.0f/255.0f, 13.0f/255.0f, 18.0f/255.0f, 24.0f/255.0f, 33.0f/255.0f, 47.0f/255.0f};
+CFX_CONST float kCwLarge[8] = {8.0f/255.0f, 17.0f/255.0f, 29.0f/255.0f, 42.0f/255.0f, 60.0f/255.0f, 80.0f/255.0f, 106.0f/255.0f, 183.0f/255.0f};
 CFX_HD float cw_delta(uint32_t cw, uint32_t sel)
 {
-    const float s[8] = {2.0f/255.0f, 5.0f/255.0f, 9.0f/255.0f, 13.0f/255.0f, 18.0f/255.0f, 24.0f/255.0f, 33.0f/255.0f, 47.0f/255.0f};
-    const float l[8] = {8.0f/255.0f, 17.0f/255.0f, 29.0f/255.0f, 42.0f/255.0f, 60.0f/255.0f, 80.0f/255.0f, 106.0f/255.0f, 183.0f/255.0f};
-    const float v = (sel & 1u) ? l[cw] : s[cw];
+    const float v = (sel & 1u) ? kCwLarge[cw] : kCwSmall[cw];
     return (sel & 2u) ? -v : v;
 }
 
@@ -58,29 +58,45 @@ CFX_HD float pixel_error_rec709(float dr, float dg, float db, const Px& s)
     return 3.0f*dl*dl + dcr*dcr + 0.5f*dcb*dcb + da*da;
 }
 
-CFX_HD_NOINLINE void try_half(const Px* src, const uint32_t* mapping, float cr, float cg, float cb, HalfTry& t, bool rec709 = false)
+// The half's eight texels are read once into registers (this function is the whole cost of the later iterations: 54 calls
+// per differential try, 8 tables x 8 texels x 4 selectors each); same operations in the same order as the loops in
+// TryDifferentialHalf / TryIndividualHalf.
+template <bool REC709>
+CFX_HD_NOINLINE void try_half_t(const Px* src, const uint32_t* mapping, float cr, float cg, float cb, HalfTry& t)
 {
+    Px px[8];
+    float a2[8];
+    bool border[8];
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+        px[i] = src[mapping[i]];
+        border[i] = px[i].a != px[i].a;
+        const float da = 1.0f - px[i].a;
+        a2[i] = da*da;
+    }
     t.err = 3.402823466e+38f; t.cw = 0; t.sel = 0;
 #pragma unroll 1
     for (uint32_t cw = 0; cw < 8; ++cw) {
         float sr[4], sg[4], sb[4];
+#pragma unroll
         for (uint32_t k = 0; k < 4; ++k) {
             const float d = cw_delta(cw, k);
             sr[k] = clamp01(cr + d); sg[k] = clamp01(cg + d); sb[k] = clamp01(cb + d);
         }
         uint32_t sels = 0;
         float cw_err = 0.0f;
+#pragma unroll
         for (uint32_t i = 0; i < 8; ++i) {
-            const Px& s = src[mapping[i]];
             float best = 3.402823466e+38f;
             uint32_t bsel = 0;
+#pragma unroll
             for (uint32_t k = 0; k < 4; ++k) {
                 float e;
-                if (s.a != s.a) e = 0.0f;                       // border texel
-                else if (rec709) e = pixel_error_rec709(sr[k], sg[k], sb[k], s);
+                if (border[i]) e = 0.0f;                        // border texel
+                else if (REC709) e = pixel_error_rec709(sr[k], sg[k], sb[k], px[i]);
                 else {
-                    const float dr = sr[k] - s.r, dg = sg[k] - s.g, db = sb[k] - s.b, da = 1.0f - s.a;
-                    e = dr*dr + dg*dg + db*db + da*da;
+                    const float dr = sr[k] - px[i].r, dg = sg[k] - px[i].g, db = sb[k] - px[i].b;
+                    e = dr*dr + dg*dg + db*db + a2[i];
                 }
                 if (e < best) { best = e; bsel = k; }
             }
@@ -89,6 +105,11 @@ CFX_HD_NOINLINE void try_half(const Px* src, const uint32_t* mapping, float cr, 
         }
         if (cw_err < t.err) { t.cw = cw; t.sel = sels; t.err = cw_err; }
     }
+}
+
+CFX_HD void try_half(const Px* src, const uint32_t* mapping, float cr, float cg, float cb, HalfTry& t, bool rec709 = false)
+{
+    if (rec709) try_half_t<true>(src, mapping, cr, cg, cb, t); else try_half_t<false>(src, mapping, cr, cg, cb, t);
 }
 
 struct Encoding { bool diff, flip; int r1, g1, b1, r2, g2, b2; uint32_t cw1, cw2, sel1, sel2; float err; };
