@@ -85,8 +85,8 @@ __device__ __forceinline__ void bc4_sorted_palette(uint32_t mode, uint32_t elo, 
 // tau_c = floor((q_c + q_{c+1})/2) (ties are equidistant, so they do not change the SSE), and summing
 // n_c q_c^2 - 2 q_c S1_c over the clusters by parts gives
 //     SSE - sum v^2 = sum_{c<7} (q_c - q_{c+1}) (N(tau_c) (q_c + q_{c+1}) - D(tau_c)) + 16 q_7^2 - D(255) q_7,
-// i.e. 7 table look-ups per trial.  The table (indexed by q_c + q_{c+1}, 512 entries of D | N << 16) is built once per
-// block with 16 shared-memory atomics and a warp scan.  Trials keep the reference's order (mode, lo_delta, hi_delta)
+// i.e. 7 table look-ups per trial.  The table (indexed by s = q_c + q_{c+1}, 512 entries holding the inner term
+// N(s >> 1) s - D(s >> 1) itself) is built once per block with 16 shared-memory atomics and a warp scan.  Trials keep the reference's order (mode, lo_delta, hi_delta)
 // and the lexicographic (SSE, trial) minimum is the serial loop's first minimum; the selectors are then computed for
 // the winner only, with the reference's first-smallest-index tie rule.
 template <bool SIGNED = false>
@@ -123,7 +123,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
 
     if (mx == mn) return make_uint2(stored(mn) | (stored(mn) << 8), 0u);
 
-    // ---- threshold table: T[x] = D(x) | N(x) << 16 for x = 0..255, stored twice (index q_c + q_{c+1}) ----
+    // ---- threshold table: D(x) | N(x) << 16 for x = 0..255 by histogram + scan, expanded to N s - D for s = 0..511 ----
     uint32_t dtot;
     {
         uint4* z = reinterpret_cast<uint4*>(s_tab) + lane*2;           // histogram lives in the first 256 words
@@ -143,9 +143,18 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
         dtot = __shfl_sync(0xFFFFFFFFu, run, 31) & 0xFFFFu;
         a.x += base; a.y += base; a.z += base; a.w += base; b.x += base; b.y += base; b.z += base; b.w += base;
         __syncwarp();                                                  // every lane has read its histogram words
+        // entry s (= q_c + q_{c+1}, tau = s >> 1) holds the whole inner term N(tau) s - D(tau)
         uint4* o4 = reinterpret_cast<uint4*>(s_tab) + lane*4;
-        o4[0] = make_uint4(a.x, a.x, a.y, a.y); o4[1] = make_uint4(a.z, a.z, a.w, a.w);
-        o4[2] = make_uint4(b.x, b.x, b.y, b.y); o4[3] = make_uint4(b.z, b.z, b.w, b.w);
+        const uint32_t s0 = lane*16u;
+        auto pair = [](uint32_t w, uint32_t s, uint32_t& even, uint32_t& odd) {
+            const uint32_t cnt = w >> 16;
+            even = cnt*s - (w & 0xFFFFu); odd = even + cnt;
+        };
+        uint4 o;
+        pair(a.x, s0,      o.x, o.y); pair(a.y, s0 + 2,  o.z, o.w); o4[0] = o;
+        pair(a.z, s0 + 4,  o.x, o.y); pair(a.w, s0 + 6,  o.z, o.w); o4[1] = o;
+        pair(b.x, s0 + 8,  o.x, o.y); pair(b.y, s0 + 10, o.z, o.w); o4[2] = o;
+        pair(b.z, s0 + 12, o.x, o.y); pair(b.w, s0 + 14, o.z, o.w); o4[3] = o;
         __syncwarp();
     }
 
@@ -164,9 +173,7 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
             int acc = static_cast<int>(q[7]*(16u*q[7] - dtot));
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
-                const uint32_t s = q[c] + q[c + 1];
-                const uint32_t w = s_tab[s];
-                const int inner = static_cast<int>((w >> 16)*s) - static_cast<int>(w & 0xFFFFu);
+                const int inner = static_cast<int>(s_tab[q[c] + q[c + 1]]);
                 acc += (static_cast<int>(q[c]) - static_cast<int>(q[c + 1]))*inner;
             }
             if (acc < best_err) { best_err = acc; best_t = mode*nn + r; }
