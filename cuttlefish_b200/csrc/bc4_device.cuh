@@ -36,14 +36,15 @@ __device__ __forceinline__ void bc4_palette(uint32_t e0, uint32_t e1, uint32_t& 
 }
 
 template <bool SIGNED = false>
-__device__ __forceinline__ void bc4_trial_endpoints(uint32_t t, uint32_t n, int rad, uint32_t mn,
+__device__ __forceinline__ void bc4_trial_endpoints(uint32_t t, uint32_t n, uint32_t inv, int rad, uint32_t mn,
     uint32_t mx, uint32_t& e0, uint32_t& e1, bool& valid)
 {
     uint32_t nn = n*n;
     uint32_t mode = t >= nn ? 1u : 0u;
     uint32_t rem = t - mode*nn;
-    int lo_d = static_cast<int>(rem / n) - rad;
-    int hi_d = static_cast<int>(rem % n) - rad;
+    uint32_t lo_i = (rem*inv) >> 20;                                   // rem / n, inv = ceil(2^20 / n)
+    int lo_d = static_cast<int>(lo_i) - rad;
+    int hi_d = static_cast<int>(rem - lo_i*n) - rad;
     e0 = static_cast<uint32_t>(min(max(static_cast<int>(mx) + hi_d, SIGNED ? 1 : 0), 255));
     e1 = static_cast<uint32_t>(min(max(static_cast<int>(mn) + lo_d, SIGNED ? 1 : 0), 255));
     valid = e0 != e1;
@@ -161,29 +162,35 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     const uint32_t n = 2*radius + 1, nn = n*n;
     const uint32_t inv = ((1u << 20) + n - 1)/n;                       // r / n == (r*inv) >> 20 for r < n*n <= 4225
     const int lowest = SIGNED ? 1 : 0;
-    int best_err = 0x7FFFFFFF; uint32_t best_t = 0xFFFFFFFFu;
-    for (uint32_t mode = 0; mode < 2; ++mode) {
-        for (uint32_t r = lane; r < nn; r += 32) {
-            const uint32_t lo_i = (r*inv) >> 20, hi_i = r - lo_i*n;
-            const int a = min(max(static_cast<int>(mx + hi_i) - static_cast<int>(radius), lowest), 255);
-            const int b = min(max(static_cast<int>(mn + lo_i) - static_cast<int>(radius), lowest), 255);
-            if (a == b) continue;
+    // both modes of an end point pair in one pass; the lane's first minimum in the reference's order (mode, lo, hi)
+    // is mode 0's unless mode 1 is strictly better
+    int best_err = 0x7FFFFFFF, best_err1 = 0x7FFFFFFF; uint32_t best_t = 0xFFFFFFFFu, best_t1 = 0xFFFFFFFFu;
+    for (uint32_t r = lane; r < nn; r += 32) {
+        const uint32_t lo_i = (r*inv) >> 20, hi_i = r - lo_i*n;
+        const int a = min(max(static_cast<int>(mx + hi_i) - static_cast<int>(radius), lowest), 255);
+        const int b = min(max(static_cast<int>(mn + lo_i) - static_cast<int>(radius), lowest), 255);
+        if (a == b) continue;
+        const uint32_t elo = static_cast<uint32_t>(min(a, b)), ehi = static_cast<uint32_t>(max(a, b));
+#pragma unroll
+        for (uint32_t mode = 0; mode < 2; ++mode) {
             uint32_t q[8];
-            bc4_sorted_palette<SIGNED>(mode, static_cast<uint32_t>(min(a, b)), static_cast<uint32_t>(max(a, b)), q);
+            bc4_sorted_palette<SIGNED>(mode, elo, ehi, q);
             int acc = static_cast<int>(q[7]*(16u*q[7] - dtot));
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
                 const int inner = static_cast<int>(s_tab[q[c] + q[c + 1]]);
                 acc += (static_cast<int>(q[c]) - static_cast<int>(q[c + 1]))*inner;
             }
-            if (acc < best_err) { best_err = acc; best_t = mode*nn + r; }
+            if (mode == 0) { if (acc < best_err) { best_err = acc; best_t = r; } }
+            else if (acc < best_err1) { best_err1 = acc; best_t1 = nn + r; }
         }
     }
+    if (best_err1 < best_err) { best_err = best_err1; best_t = best_t1; }
     const int werr = __reduce_min_sync(0xFFFFFFFFu, best_err);
     const uint32_t wt = __reduce_min_sync(0xFFFFFFFFu, best_err == werr ? best_t : 0xFFFFFFFFu);
 
     uint32_t e0, e1; bool valid;
-    bc4_trial_endpoints<SIGNED>(wt, n, static_cast<int>(radius), mn, mx, e0, e1, valid);
+    bc4_trial_endpoints<SIGNED>(wt, n, inv, static_cast<int>(radius), mn, mx, e0, e1, valid);
     uint32_t lo4, hi4;
     bc4_palette<SIGNED>(e0, e1, lo4, hi4);
     uint32_t sel = 0;
