@@ -14,8 +14,15 @@ namespace cfx {
 
 constexpr int kTile = 64;
 
+// Resident CTAs per SM the kernels are compiled for (measured on 8192^2, radius 5): BC4 is fastest at 48 registers /
+// 5 CTAs (17.5 GTexel/s; 17.3 at 6, 16.8 at 8 CTAs of 32 registers), BC5 at 40 registers / 6 CTAs (9.4; 8.9 at 4 CTAs
+// of 59 registers, 8.7 at 8).
+#ifndef CFX_BC45_MINB
+#define CFX_BC45_MINB(channels) ((channels) == 2 ? 6 : 5)
+#endif
+
 template <int CHANNELS, bool SIGNED>
-__global__ void __launch_bounds__(kThreads) bc45_kernel(const EncodeParams p, uint32_t radius, uint32_t hq)
+__global__ void __launch_bounds__(kThreads, CFX_BC45_MINB(CHANNELS)) bc45_kernel(const EncodeParams p, uint32_t radius, uint32_t hq)
 {
     __shared__ __align__(16) uint32_t s_px[kTile*16];
     __shared__ __align__(16) uint32_t s_out[kTile*2*CHANNELS];
@@ -79,7 +86,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 } // namespace
 
 template <int CHANNELS>
-__global__ void __launch_bounds__(kThreads) bc45_tma_kernel(const EncodeParams p, const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kThreads, CFX_BC45_MINB(CHANNELS)) bc45_tma_kernel(const EncodeParams p, const __grid_constant__ CUtensorMap tmap,
     uint32_t radius, uint32_t hq)
 {
     __shared__ __align__(128) uint32_t s_px[2][kTile*16];          // two 256 x 4 texel boxes
