@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
     const uint32_t lane = lane_id(), warp = warp_id();
     uint32_t* sp = s_px[warp];
     const uint32_t groups = (p.total_blocks + 31)/32;
+    const uint32_t inv = bc4_trial_inv(radius);
     for (uint32_t grp = blockIdx.x*kBc1Warps + warp; grp < groups; grp += gridDim.x*kBc1Warps) {
         const uint32_t first = grp*32;
         const uint32_t nblk = min(32u, p.total_blocks - first);
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kBc1Warps*32) bc123_kernel(const EncodeParams 
         } else {
             uint2 mine = make_uint2(0, 0);
             for (uint32_t b = 0; b < nblk; ++b) {
-                const uint2 a = bc4_encode_warp(sp + b*kBlkStride, 3, radius, hq != 0, s_tab[FORMAT == 32 ? warp : 0]);
+                const uint2 a = bc4_encode_warp(sp + b*kBlkStride, 3, radius, inv, hq != 0, s_tab[FORMAT == 32 ? warp : 0]);
                 if (b == lane) mine = a;
             }
             if (lane < nblk) reinterpret_cast<uint4*>(p.dst)[first + lane] = make_uint4(mine.x, mine.y, color.x, color.y);

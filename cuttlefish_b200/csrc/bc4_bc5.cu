@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(kThreads, CFX_BC45_MINB(CHANNELS)) bc45_kernel
     __shared__ __align__(16) uint32_t s_out[kTile*2*CHANNELS];
     __shared__ __align__(16) uint32_t s_tab[kWarps][kBc4TableWords];
     const uint32_t tiles = (p.total_blocks + kTile - 1)/kTile;
+    const uint32_t inv = bc4_trial_inv(radius);
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         uint32_t first = tile*kTile;
         uint32_t n = min(static_cast<uint32_t>(kTile), p.total_blocks - first);
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(kThreads, CFX_BC45_MINB(CHANNELS)) bc45_kernel
         for (uint32_t b = warp_id(); b < n; b += kWarps) {
 #pragma unroll
             for (int c = 0; c < CHANNELS; ++c) {
-                uint2 r = bc4_encode_warp<SIGNED>(s_px + b*16, c, radius, hq != 0, s_tab[warp_id()]);
+                uint2 r = bc4_encode_warp<SIGNED>(s_px + b*16, c, radius, inv, hq != 0, s_tab[warp_id()]);
                 if (lane_id() == 0) {
                     s_out[(b*CHANNELS + c)*2] = r.x;
                     s_out[(b*CHANNELS + c)*2 + 1] = r.y;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kThreads, CFX_BC45_MINB(CHANNELS)) bc45_tma_ke
     __shared__ __align__(16) uint32_t s_tab[kWarps][kBc4TableWords];
     const uint32_t tiles = p.total_blocks/kTile;                   // the launcher guarantees whole tiles
     const uint32_t tiles_x = p.blocks_x/kTile;
+    const uint32_t inv = bc4_trial_inv(radius);
     constexpr uint32_t kBoxBytes = kTile*16*4;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, CFX_BC45_MINB(CHANNELS)) bc45_tma_ke
         for (uint32_t b = warp_id(); b < kTile; b += kWarps) {
 #pragma unroll
             for (int c = 0; c < CHANNELS; ++c) {
-                uint2 r = bc4_encode_warp<false>(s_px[buf] + b*4, c, radius, hq != 0, s_tab[warp_id()], kTile*4);
+                uint2 r = bc4_encode_warp<false>(s_px[buf] + b*4, c, radius, inv, hq != 0, s_tab[warp_id()], kTile*4);
                 if (lane_id() == 0) {
                     s_out[(b*CHANNELS + c)*2] = r.x;
                     s_out[(b*CHANNELS + c)*2 + 1] = r.y;

@@ -90,8 +90,15 @@ __device__ __forceinline__ void bc4_sorted_palette(uint32_t mode, uint32_t elo, 
 // N(s >> 1) s - D(s >> 1) itself) is built once per block with 16 shared-memory atomics and a warp scan.  Trials keep the reference's order (mode, lo_delta, hi_delta)
 // and the lexicographic (SSE, trial) minimum is the serial loop's first minimum; the selectors are then computed for
 // the winner only, with the reference's first-smallest-index tie rule.
+// ceil(2^20 / n) for n = 2 radius + 1: r / n == (r*inv) >> 20 for r < n*n <= 4225.  One division per kernel, not per block.
+__device__ __forceinline__ uint32_t bc4_trial_inv(uint32_t radius)
+{
+    const uint32_t n = 2*radius + 1;
+    return ((1u << 20) + n - 1)/n;
+}
+
 template <bool SIGNED = false>
-__device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t chan, uint32_t radius,
+__device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t chan, uint32_t radius, uint32_t inv,
     bool hq, uint32_t* s_tab, uint32_t row_stride = 4)
 {
     auto texel = [&](uint32_t i) -> uint32_t { return s_blk[(i >> 2)*row_stride + (i & 3u)]; };
@@ -160,7 +167,6 @@ __device__ __forceinline__ uint2 bc4_encode_warp(const uint32_t* s_blk, uint32_t
     }
 
     const uint32_t n = 2*radius + 1, nn = n*n;
-    const uint32_t inv = ((1u << 20) + n - 1)/n;                       // r / n == (r*inv) >> 20 for r < n*n <= 4225
     const int lowest = SIGNED ? 1 : 0;
     // both modes of an end point pair in one pass; the lane's first minimum in the reference's order (mode, lo, hi)
     // is mode 0's unless mode 1 is strictly better
